@@ -1,0 +1,183 @@
+/* mvosr.h -- C ABI of the B200 scale-recovery library (libmvosr.so).
+ *
+ * Drop-in boundary for the per-frame scale-recovery path of TimingSpace/MVOScaleRecovery.
+ * The reference is pure Python and has no FFI; each entry point below names the reference
+ * call it replaces (file:line into the reference tree).  Signatures are plain C: pointers,
+ * sizes, a POD config, an opaque handle and a CUDA stream passed as void*.  No torch types.
+ *
+ * Memory: unless a name ends in _host, every data pointer is a DEVICE pointer owned by the
+ * caller (e.g. torch tensors); the library owns only its internal workspace.  Kernels are
+ * enqueued on the given stream and the call returns without synchronising (the _host entry
+ * points synchronise before returning because they copy results to host memory).
+ *
+ * Threading: a handle may be used by one host thread at a time.
+ * Errors: every function returns MVOSR_OK (0) or a negative MVOSR_E_* code; per-frame
+ * conditions are reported in the status byte of each frame, never as a call failure.
+ *
+ * Data layout ("frame batch"): F frames packed CSR-style.  offsets[f]..offsets[f+1] delimit
+ * the features of frame f inside structure-of-arrays float32 buffers (x[], y[], z[], u[], v[]
+ * for triangulated features; cur_u[], cur_v[], ref_u[], ref_v[] for tracked correspondences).
+ */
+#ifndef MVOSR_H
+#define MVOSR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVOSR_VERSION 100
+
+/* ---- return codes ---- */
+#define MVOSR_OK                 0
+#define MVOSR_E_INVALID         -1   /* bad argument */
+#define MVOSR_E_CUDA            -2   /* CUDA runtime error (see mvosr_last_cuda_error) */
+#define MVOSR_E_NOMEM           -3
+#define MVOSR_E_CAPACITY        -4   /* max_features exceeds what the fused kernel supports */
+#define MVOSR_E_NO_DEVICE       -5
+
+/* ---- per-frame status byte (bit flags) ---- */
+#define MVOSR_ST_UPDATED      0x01   /* RANSAC ran (N_sel >= 12): raw_scale is valid (rescale.py:152) */
+#define MVOSR_ST_SECOND_DT    0x02   /* graph check kept > 10 features -> second Delaunay (rescale.py:133) */
+#define MVOSR_ST_FEW_ROI      0x04   /* < 3 ROI features or all collinear: reference raises QhullError */
+#define MVOSR_ST_NO_MODEL     0x08   /* every hypothesis had 0 inliers: reference crashes in np.matrix(None) */
+#define MVOSR_ST_BAD_INPUT    0x10   /* |u|,|v| >= 4096 or non-finite pixel coordinate in the ROI */
+#define MVOSR_ST_OVERFLOW     0x20   /* frame exceeds the kernel capacity (ROI features or star degree) */
+#define MVOSR_ST_SKIPPED      0x40   /* frame not processed (not moving / too few features, main_offline.py:64,73) */
+
+/* ---- configuration (POD). Defaults = the constants hard-coded in the reference. ---- */
+typedef struct mvosr_config {
+    double  absolute_reference;   /* camera height in metres; main.py:55 passes param.camera_h (1.75); harness uses 1.7 */
+    double  fx, fy, cx, cy;       /* src/param.py:30-35 */
+    float   vanish;               /* ROI row, features with v > vanish are kept (rescale.py:30,115) = 185 */
+    int32_t min_features;         /* estimator is called only if n > this (param.py:37, main_offline.py:73) = 100 */
+    int32_t min_kept;             /* second Delaunay only if kept > this (rescale.py:133) = 10 */
+    int32_t min_selected;         /* RANSAC only if N_sel >= this (rescale.py:152) = 12 */
+    double  sin_loose;            /* largest s with asin(s)*180/pi < -80 (rescale.py:85): loose <=> s <= sin_loose */
+    double  sin_tight;            /* same for -85 (rescale.py:86) */
+    double  height_level_factor;  /* 0.9 (rescale.py:91) */
+    int32_t ransac_iterations;    /* 100 (rescale.py:155) */
+    int32_t ransac_stop_at_goal;  /* 1: stop at first ic > goal (ransac.py:20); 0: evaluate all (sweep config C5) */
+    double  ransac_threshold;     /* 0.005 (rescale.py:155) */
+    double  ransac_goal_fraction; /* 0.8 (estimate_road_norm.py:68) */
+    uint32_t graph_pass_mask;     /* 24-bit table: bit (idx*3+k) set <=> p_k(idx) > 0.6 (graph.py:131-145) for the
+                                     canonical (ascending) vertex order; default from [[3,1],[2,2],[2,2],[0,4]] */
+    double  slew_limit;           /* 0.3 (rescale.py:169-172) */
+    int32_t window_size;          /* 5: both mains pass window_size=5 (main.py:55); class default is 6 */
+    double  triangulation_max_depth; /* distanceThresh=100 (visual_odometry.py:133) */
+    int32_t reserved[8];
+} mvosr_config;
+
+/* ---- per-frame counters (parity probes and logging; mirrors the reference's prints) ---- */
+typedef struct mvosr_frame_stats {
+    int32_t n_features;     /* features in the frame after the triangulation mask (pre-ROI) */
+    int32_t n_roi;          /* after v > vanish */
+    int32_t n_dup;          /* exact duplicate 2-D points dropped from Delaunay #1 (Qhull: .coplanar) */
+    int32_t n_kept;         /* graph-check survivors ("feature left", rescale.py:132) */
+    int32_t n_tri;          /* triangles fed to flat_selection (Delaunay #2, or #1 if not re-triangulated) */
+    int32_t n_loose;        /* pitch < -80 ("triangle left", rescale.py:88) */
+    int32_t n_tight;        /* pitch < -85 */
+    int32_t n_valid;        /* tight & height > level ("triangle left final", rescale.py:97); N_sel = 3*n_valid */
+    int32_t best_hyp;       /* index of the returned hypothesis, -1 if none */
+    int32_t best_ic;        /* its inlier count over the vertex list with multiplicity (ransac.py:13-16) */
+    int32_t hyps_used;      /* hypotheses the sequential loop would have evaluated (ransac.py:9,20) */
+    int32_t n_degenerate;   /* evaluated hypotheses whose 3 positions do not span a plane (reference: LAPACK-arbitrary) */
+    int32_t n_deferred;     /* stars finished by the warp-cooperative path (Delaunay #1 + #2) */
+    int32_t n_exact;        /* predicate evaluations that fell through to exact arithmetic */
+    double  height_level;   /* 0.9 * median(height[loose]) (rescale.py:91) */
+    double  model[4];       /* returned plane (a,b,c,d), unit 4-norm, sign normalised so that b >= 0 */
+    double  height;         /* h_bar / |n| (rescale.py:157-164) */
+} mvosr_frame_stats;
+
+/* ---- optional dense per-frame debug outputs (device pointers, any may be NULL) ----
+ * Frame f writes at row offset offsets[f] (feature-indexed arrays) or 2*offsets[f] (triangle-indexed). */
+typedef struct mvosr_debug_buffers {
+    int32_t *tri1;          /* [2*M][3] canonical triangles of Delaunay #1, indices into the ROI-compacted frame */
+    int32_t *n_tri1;        /* [F] */
+    uint8_t *keep;          /* [M] graph-check keep flag per ROI feature (graph.py:33-36) */
+    int32_t *tri2;          /* [2*M][3] canonical triangles fed to flat_selection, indices after keep-compaction */
+    uint8_t *tri_flags;     /* [2*M] bit0 loose, bit1 tight, bit2 valid */
+    double  *tri_height;    /* [2*M] 1/|n| per triangle */
+    uint8_t *inlier;        /* [M] inlier flag of the returned model per kept feature (only selected vertices count) */
+    int32_t *data_id;       /* [6*M] the vertex list handed to RANSAC (rescale.py:101), 3*n_valid entries */
+} mvosr_debug_buffers;
+
+typedef struct mvosr_handle mvosr_handle;
+
+int  mvosr_version(void);
+const char *mvosr_error_string(int code);
+const char *mvosr_last_cuda_error(void);
+
+/* Fill cfg with the reference's constants (see field comments). */
+int  mvosr_default_config(mvosr_config *cfg);
+
+/* Replaces ScaleEstimator.__init__ (src/rescale.py:23-35) for a batch context on CUDA device `device`. */
+int  mvosr_create(const mvosr_config *cfg, int device, mvosr_handle **out);
+int  mvosr_destroy(mvosr_handle *h);
+int  mvosr_get_config(const mvosr_handle *h, mvosr_config *cfg);
+
+/* Stage 1 -- replaces the triangulation inside cv2.recoverPose(..., distanceThresh=100) +
+ * dehomogenisation (src/thirdparty/MonocularVO/visual_odometry.py:129-147) and the reprojection of
+ * src/main.py:102-104.  poses: [F][12] float64 row-major [R|t], x_ref = R x_cur + t.
+ * e_mask: optional per-correspondence uint8 (the findEssentialMat inlier mask, :134-136), may be NULL.
+ * Outputs are written order-preserving and compacted at offsets[f]; n_out[f] = surviving features. */
+int  mvosr_triangulate_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                              const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                              const uint8_t *e_mask, const double *poses,
+                              float *x, float *y, float *z, float *u, float *v, int32_t *n_out,
+                              void *stream);
+
+/* Stages 2-5 -- replaces ScaleEstimator.feature_selection + the RANSAC/height/scale part of
+ * scale_calculation_ransac (src/rescale.py:113-167) for F frames at once; the temporal state
+ * (:168-178) is applied by mvosr_filter_sequences.  counts may be NULL (then offsets[f+1]-offsets[f]).
+ * frame_index0 / seq_id / seed select the Philox hypothesis stream: hypothesis i of frame f uses
+ * counter (i, frame_index0+f, seq_id, 0) and key (seed lo, seed hi).  max_features = upper bound on the
+ * features of any frame (sizes the shared-memory staging).  raw_scale[f] = absolute_reference / height
+ * when status has MVOSR_ST_UPDATED, NaN otherwise. */
+int  mvosr_scale_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets, const int32_t *counts,
+                        const float *x, const float *y, const float *z, const float *u, const float *v,
+                        int32_t max_features, int32_t frame_index0, int32_t seq_id, uint64_t seed,
+                        double *raw_scale, uint8_t *status, mvosr_frame_stats *stats,
+                        const mvosr_debug_buffers *debug, void *stream);
+
+/* Stages 1-5 fused: tracked correspondences + relative poses in, raw scales out; triangulated
+ * features never leave the SM.  n_features[f] receives the post-mask feature count (needed by the
+ * n > min_features gate of main.py:110).  Same stream/seed conventions as mvosr_scale_frames. */
+int  mvosr_scale_frames_from_correspondences(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                        const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                        const uint8_t *e_mask, const double *poses,
+                        int32_t max_features, int32_t frame_index0, int32_t seq_id, uint64_t seed,
+                        double *raw_scale, uint8_t *status, int32_t *n_features, mvosr_frame_stats *stats,
+                        void *stream);
+
+/* Stage 6 -- replaces the driver gating of src/main_offline.py:57-88 and the temporal state of
+ * src/rescale.py:168-178 (slew limiter + median of the last window_size states), then
+ * filter(data, 10) of script/evaluate_scale.py:25-29.  One thread per sequence; seq_offsets: [S+1]
+ * frame ranges.  move_flags may be NULL (all moving).  n_features may be NULL (all above the gate).
+ * scale_out[f] = what main_offline appends to `scales` (scales[1:]); filter10_out may be NULL. */
+int  mvosr_filter_sequences(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets,
+                            const double *raw_scale, const uint8_t *status, const uint8_t *move_flags,
+                            const int32_t *n_features, double *scale_out, double *filter10_out, void *stream);
+
+/* Canonical Delaunay triangles of F point sets (the replacement of scipy.spatial.Delaunay(...).simplices
+ * at src/rescale.py:124-125, rows ascending, rows lexsorted).  tri: [2*M][3] written at 2*offsets[f]. */
+int  mvosr_delaunay_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                           const float *u, const float *v, int32_t max_features,
+                           int32_t *tri, int32_t *n_tri, uint8_t *status, void *stream);
+
+/* Host-buffer convenience used for end-to-end timing and by callers without device memory: all pointers
+ * are HOST pointers (pinned for full speed); copies, stages 1-6 and the copy back happen inside. */
+int  mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t *offsets_host,
+                        const float *cur_u_host, const float *cur_v_host, const float *ref_u_host, const float *ref_v_host,
+                        const double *poses_host, const uint8_t *move_flags_host,
+                        int32_t max_features, int32_t seq_id, uint64_t seed,
+                        double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host);
+
+/* Number of kernels the library has launched on this handle since creation (bench.py's gpu_launches). */
+int64_t mvosr_launch_count(const mvosr_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVOSR_H */

@@ -1,0 +1,211 @@
+"""Batched host API: PyTorch tensors as the frame-batch container, libmvosr.so as the engine.
+
+``ScaleRecovery`` owns one native handle (one CUDA device).  Inputs are CSR-packed frames
+(structure-of-arrays float32 CUDA tensors + int32 offsets); every method enqueues the
+CUDA kernels on torch's current stream and returns CUDA tensors without synchronising.
+
+Reference path replaced: the per-frame loop of src/main_offline.py:57-88 around
+rescale.ScaleEstimator.scale_calculation (src/rescale.py:113-178, 191-193) -- see
+include/mvosr.h for the call-by-call mapping.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t: torch.Tensor, dtype, name: str, device):
+    if t.dtype != dtype or not t.is_contiguous() or t.device != device:
+        raise ValueError("%s must be a contiguous %s tensor on %s (got %s, %s)" % (name, dtype, device, t.dtype, t.device))
+
+
+class ScaleRecovery:
+    """Batch engine for stages 1-6.  ``config`` overrides fields of the reference defaults
+    (``mvosr_default_config``), e.g. ``absolute_reference=1.7, ransac_iterations=256``."""
+
+    def __init__(self, device: Optional[int] = None, **config):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mvoscalerecovery_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = N.lib()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        cfg = N.default_config()
+        for k, v in config.items():
+            if not hasattr(cfg, k):
+                raise TypeError("unknown config field %r" % k)
+            setattr(cfg, k, v)
+        self.config = cfg
+        h = C.c_void_p()
+        N.check(self.lib.mvosr_create(C.byref(cfg), self.device_index, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mvosr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mvosr_launch_count(self._h))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ stage 1
+    def triangulate_frames(self, offsets, cur_u, cur_v, ref_u, ref_v, poses, e_mask=None):
+        """Replaces cv2.recoverPose's triangulation + main.py:102-104. Returns dict(x,y,z,u,v,n_out)."""
+        dev = self.device
+        F = offsets.numel() - 1
+        _chk(offsets, torch.int32, "offsets", dev)
+        for n, t in (("cur_u", cur_u), ("cur_v", cur_v), ("ref_u", ref_u), ("ref_v", ref_v)):
+            _chk(t, torch.float32, n, dev)
+        _chk(poses, torch.float64, "poses", dev)
+        M = cur_u.numel()
+        out = {k: torch.empty(M, dtype=torch.float32, device=dev) for k in "xyzuv"}
+        n_out = torch.zeros(F, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_triangulate_frames(self._h, F, _ptr(offsets), _ptr(cur_u), _ptr(cur_v), _ptr(ref_u), _ptr(ref_v),
+                                                      _ptr(e_mask), _ptr(poses), _ptr(out["x"]), _ptr(out["y"]), _ptr(out["z"]),
+                                                      _ptr(out["u"]), _ptr(out["v"]), _ptr(n_out), self._stream()))
+        out["n_out"] = n_out
+        return out
+
+    # ------------------------------------------------------------------ stages 2-5
+    def scale_frames(self, offsets, x, y, z, u, v, max_features: int, counts=None, frame_index0: int = 0, seq_id: int = 0,
+                     seed: int = 0, stats: bool = True, debug: bool = False):
+        """Replaces feature_selection + RANSAC + height/scale of rescale.py:113-167 for F frames.
+        Returns dict(raw_scale f64[F], status u8[F], stats (structured numpy view factory), debug buffers)."""
+        dev = self.device
+        F = offsets.numel() - 1
+        _chk(offsets, torch.int32, "offsets", dev)
+        for n, t in (("x", x), ("y", y), ("z", z), ("u", u), ("v", v)):
+            _chk(t, torch.float32, n, dev)
+        M = x.numel()
+        raw = torch.empty(F, dtype=torch.float64, device=dev)
+        status = torch.zeros(F, dtype=torch.uint8, device=dev)
+        st = torch.zeros(F * C.sizeof(N.FrameStats), dtype=torch.uint8, device=dev) if stats else None
+        dbg_struct = None
+        dbg = {}
+        if debug:
+            dbg = dict(tri1=torch.full((2 * M, 3), -1, dtype=torch.int32, device=dev), n_tri1=torch.zeros(F, dtype=torch.int32, device=dev),
+                       keep=torch.zeros(M, dtype=torch.uint8, device=dev), tri2=torch.full((2 * M, 3), -1, dtype=torch.int32, device=dev),
+                       tri_flags=torch.zeros(2 * M, dtype=torch.uint8, device=dev), tri_height=torch.zeros(2 * M, dtype=torch.float64, device=dev),
+                       inlier=torch.zeros(M, dtype=torch.uint8, device=dev), data_id=torch.full((6 * M,), -1, dtype=torch.int32, device=dev))
+            dbg_struct = N.DebugBuffers(*[dbg[k].data_ptr() for k in ("tri1", "n_tri1", "keep", "tri2", "tri_flags", "tri_height", "inlier", "data_id")])
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_scale_frames(self._h, F, _ptr(offsets), _ptr(counts), _ptr(x), _ptr(y), _ptr(z), _ptr(u), _ptr(v),
+                                                int(max_features), int(frame_index0), int(seq_id), C.c_uint64(int(seed)),
+                                                _ptr(raw), _ptr(status), _ptr(st), C.byref(dbg_struct) if dbg_struct else None,
+                                                self._stream()))
+        return dict(raw_scale=raw, status=status, stats=st, debug=dbg)
+
+    def scale_frames_from_correspondences(self, offsets, cur_u, cur_v, ref_u, ref_v, poses, max_features: int, e_mask=None,
+                                          frame_index0: int = 0, seq_id: int = 0, seed: int = 0, stats: bool = False):
+        """Stages 1-5 fused (correspondences + poses -> raw scales)."""
+        dev = self.device
+        F = offsets.numel() - 1
+        _chk(offsets, torch.int32, "offsets", dev)
+        for n, t in (("cur_u", cur_u), ("cur_v", cur_v), ("ref_u", ref_u), ("ref_v", ref_v)):
+            _chk(t, torch.float32, n, dev)
+        _chk(poses, torch.float64, "poses", dev)
+        raw = torch.empty(F, dtype=torch.float64, device=dev)
+        status = torch.zeros(F, dtype=torch.uint8, device=dev)
+        nfeat = torch.zeros(F, dtype=torch.int32, device=dev)
+        st = torch.zeros(F * C.sizeof(N.FrameStats), dtype=torch.uint8, device=dev) if stats else None
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_scale_frames_from_correspondences(
+                self._h, F, _ptr(offsets), _ptr(cur_u), _ptr(cur_v), _ptr(ref_u), _ptr(ref_v), _ptr(e_mask), _ptr(poses),
+                int(max_features), int(frame_index0), int(seq_id), C.c_uint64(int(seed)), _ptr(raw), _ptr(status), _ptr(nfeat), _ptr(st),
+                self._stream()))
+        return dict(raw_scale=raw, status=status, n_features=nfeat, stats=st)
+
+    # ------------------------------------------------------------------ stage 6
+    def filter_sequences(self, seq_offsets, raw_scale, status, move_flags=None, n_features=None, filter10: bool = True):
+        """Replaces the gating of main_offline.py:57-88 + rescale.py:168-178, then evaluate_scale.filter(...,10)."""
+        dev = self.device
+        _chk(seq_offsets, torch.int32, "seq_offsets", dev)
+        _chk(raw_scale, torch.float64, "raw_scale", dev)
+        _chk(status, torch.uint8, "status", dev)
+        S = seq_offsets.numel() - 1
+        F = raw_scale.numel()
+        out = torch.empty(F, dtype=torch.float64, device=dev)
+        f10 = torch.empty(F, dtype=torch.float64, device=dev) if filter10 else None
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_filter_sequences(self._h, S, _ptr(seq_offsets), _ptr(raw_scale), _ptr(status), _ptr(move_flags),
+                                                    _ptr(n_features), _ptr(out), _ptr(f10), self._stream()))
+        return dict(scale=out, filter10=f10)
+
+    # ------------------------------------------------------------------ Delaunay alone
+    def delaunay_frames(self, offsets, u, v, max_features: int):
+        """Canonical triangles per frame (replacement of scipy.spatial.Delaunay(...).simplices)."""
+        dev = self.device
+        F = offsets.numel() - 1
+        _chk(offsets, torch.int32, "offsets", dev)
+        _chk(u, torch.float32, "u", dev)
+        _chk(v, torch.float32, "v", dev)
+        M = u.numel()
+        tri = torch.full((2 * M, 3), -1, dtype=torch.int32, device=dev)
+        ntri = torch.zeros(F, dtype=torch.int32, device=dev)
+        status = torch.zeros(F, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_delaunay_frames(self._h, F, _ptr(offsets), _ptr(u), _ptr(v), int(max_features), _ptr(tri), _ptr(ntri),
+                                                   _ptr(status), self._stream()))
+        return dict(tri=tri, n_tri=ntri, status=status)
+
+    # ------------------------------------------------------------------ host buffers end to end
+    def recover_scales_host(self, offsets: np.ndarray, cur_u, cur_v, ref_u, ref_v, poses, move_flags=None, max_features: int = 0,
+                            seq_id: int = 0, seed: int = 0, out=None):
+        """Host (ideally pinned) numpy/torch-CPU buffers in, filtered scales out: copies + stages 1-6 inside."""
+        def hp(a):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                return C.c_void_p(a.data_ptr())
+            return C.c_void_p(a.ctypes.data)
+        F = int(offsets.shape[0] - 1)
+        if out is None:
+            out = dict(scale=np.empty(F, np.float64), raw_scale=np.empty(F, np.float64), status=np.empty(F, np.uint8))
+        if not max_features:
+            o = offsets.numpy() if isinstance(offsets, torch.Tensor) else offsets
+            max_features = int(np.max(np.diff(o))) if F else 0
+        with torch.cuda.device(self.device):
+            N.check(self.lib.mvosr_recover_scales_host(self._h, F, hp(offsets), hp(cur_u), hp(cur_v), hp(ref_u), hp(ref_v), hp(poses),
+                                                       hp(move_flags), int(max_features), int(seq_id), C.c_uint64(int(seed)),
+                                                       hp(out["scale"]), hp(out["raw_scale"]), hp(out["status"])))
+        return out
+
+
+def stats_to_numpy(stats_tensor: torch.Tensor) -> np.ndarray:
+    """View the per-frame mvosr_frame_stats bytes as a numpy structured array."""
+    dt = np.dtype([(n, np.int32) for n in ("n_features", "n_roi", "n_dup", "n_kept", "n_tri", "n_loose", "n_tight", "n_valid",
+                                           "best_hyp", "best_ic", "hyps_used", "n_degenerate", "n_deferred", "n_exact")]
+                  + [("height_level", np.float64), ("model", np.float64, (4,)), ("height", np.float64)])
+    assert dt.itemsize == C.sizeof(N.FrameStats)
+    return stats_tensor.cpu().numpy().view(dt)
+
+
+def pack_frames(f3_list, f2_list, device):
+    """Pack per-frame (n,3)/(n,2) arrays into the CSR float32 structure-of-arrays batch."""
+    sizes = [int(a.shape[0]) for a in f3_list]
+    off = np.zeros(len(sizes) + 1, np.int32)
+    np.cumsum(sizes, out=off[1:])
+    f3 = np.concatenate([np.asarray(a, np.float32).reshape(-1, 3) for a in f3_list], 0) if sizes else np.zeros((0, 3), np.float32)
+    f2 = np.concatenate([np.asarray(a, np.float32).reshape(-1, 2) for a in f2_list], 0) if sizes else np.zeros((0, 2), np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    return dict(offsets=t(off), x=t(f3[:, 0]), y=t(f3[:, 1]), z=t(f3[:, 2]), u=t(f2[:, 0]), v=t(f2[:, 1]),
+                max_features=max(sizes) if sizes else 0)

@@ -1,0 +1,406 @@
+// libmvosr.so -- host side of the C ABI declared in include/mvosr.h, plus the small kernels
+// (stand-alone stage 1, temporal filter).  Built for sm_100a only; there is no CPU fallback:
+// every entry point either runs the CUDA kernels or returns an error code.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "frame_kernel.cuh"
+
+using namespace mvosr;
+
+static thread_local char g_cuda_err[256] = "";
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return MVOSR_E_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+struct mvosr_handle {
+    mvosr_config cfg;
+    int device;
+    int num_sms;
+    int smem_optin;
+    int cap_max;
+    int *work_counter;           // device
+    int64_t launches;
+    // host-API staging (grown on demand)
+    void *d_stage; size_t stage_bytes;
+};
+
+// -------------------------------------------------------------------------------------------------
+// small kernels
+// -------------------------------------------------------------------------------------------------
+namespace mvosr {
+
+// Stage 1 alone: one CTA per frame (grid-stride), order-preserving compaction of the surviving features.
+__global__ void __launch_bounds__(256) triangulate_kernel(int n_frames, const int32_t *offsets,
+        const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v, const uint8_t *e_mask,
+        const double *poses, mvosr_config cfg, float *x, float *y, float *z, float *u, float *v, int32_t *n_out) {
+    __shared__ int wcnt[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const int base = offsets[f], n = offsets[f + 1] - base;
+        Pose pose;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) pose.R[i] = poses[12 * f + (i / 3) * 4 + (i % 3)];
+        pose.t[0] = poses[12 * f + 3]; pose.t[1] = poses[12 * f + 7]; pose.t[2] = poses[12 * f + 11];
+        int total = 0;
+        for (int c0 = 0; c0 < n; c0 += 256) {
+            int i = c0 + tid;
+            bool ok = false; double X = 0, Y = 0, Z = 0, uu = 0, vv = 0;
+            if (i < n) {
+                ok = triangulate_point(cur_u[base + i], cur_v[base + i], ref_u[base + i], ref_v[base + i], pose,
+                                       cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.triangulation_max_depth, X, Y, Z, uu, vv);
+                if (e_mask) ok = ok && e_mask[base + i] != 0;
+            }
+            unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+            if (lane == 0) wcnt[warp] = __popc(bal);
+            __syncthreads();
+            int woff = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { int c = wcnt[w]; if (w < warp) woff += c; tot += c; }
+            if (ok) {
+                // destination index <= source index and earlier chunks are already consumed: in-place safe
+                int pos = base + total + woff + __popc(bal & ((1u << lane) - 1u));
+                x[pos] = (float)X; y[pos] = (float)Y; z[pos] = (float)Z; u[pos] = (float)uu; v[pos] = (float)vv;
+            }
+            total += tot;
+            __syncthreads();
+        }
+        if (tid == 0) n_out[f] = total;
+    }
+}
+
+__device__ __forceinline__ double median_small(const double *q, int n) {
+    double s[32];
+    for (int i = 0; i < n; ++i) { double v = q[i]; int j = i; while (j > 0 && s[j - 1] > v) { s[j] = s[j - 1]; --j; } s[j] = v; }
+    return (n & 1) ? s[n / 2] : (s[n / 2 - 1] + s[n / 2]) / 2.0;      // np.median: mean of the two middle values
+}
+
+// Stage 6a: driver gating (main_offline.py:57-88) + slew limiter + deque median (rescale.py:168-178).
+// The recurrence is strictly sequential per sequence: one thread per sequence.
+__global__ void filter_kernel(int n_seq, const int32_t *seq_offsets, const double *raw, const uint8_t *status,
+                              const uint8_t *move, const int32_t *n_features, mvosr_config cfg, double *out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    double scale = 1.0;                  // self.scale = 1 (rescale.py:27)
+    double q[32]; int qn = 0;            // scale_queue
+    int win = cfg.window_size < 1 ? 1 : (cfg.window_size > 31 ? 31 : cfg.window_size);
+    double last = 0.0;                   // scales = [0] (main_offline.py:45)
+    for (int f = seq_offsets[s]; f < seq_offsets[s + 1]; ++f) {
+        double o;
+        if (move && !move[f]) o = 0.0;                                               // :64-68
+        else if (n_features && n_features[f] <= cfg.min_features) o = last;          // :73,84-86
+        else {
+            if (status[f] & MVOSR_ST_UPDATED) {
+                double r = raw[f];
+                if (r - scale > cfg.slew_limit) scale += cfg.slew_limit;
+                else if (r - scale < -cfg.slew_limit) scale -= cfg.slew_limit;
+                else scale = r;
+            }
+            q[qn++] = scale;
+            if (qn > win) { for (int i = 1; i < qn; ++i) q[i - 1] = q[i]; --qn; }
+            o = median_small(q, qn);
+        }
+        out[f] = o; last = o;
+    }
+}
+
+// Stage 6b: filter(data, window=10) of script/evaluate_scale.py:25-29 -- causal running median; thread per frame.
+__global__ void filter10_kernel(int n_seq, const int32_t *seq_offsets, const double *in, double *out) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = seq_offsets[n_seq];
+    if (f >= total) return;
+    int lo = 0, hi = n_seq;              // sequence containing f
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (seq_offsets[mid] <= f) lo = mid; else hi = mid; }
+    int s0 = seq_offsets[lo];
+    int a = f - 9 < s0 ? s0 : f - 9;
+    out[f] = median_small(in + a, f - a + 1);
+}
+
+}  // namespace mvosr
+
+// -------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mvosr_version(void) { return MVOSR_VERSION; }
+
+const char *mvosr_error_string(int code) {
+    switch (code) {
+        case MVOSR_OK: return "ok";
+        case MVOSR_E_INVALID: return "invalid argument";
+        case MVOSR_E_CUDA: return "CUDA error";
+        case MVOSR_E_NOMEM: return "out of memory";
+        case MVOSR_E_CAPACITY: return "frame exceeds kernel capacity";
+        case MVOSR_E_NO_DEVICE: return "no CUDA device";
+        default: return "unknown error";
+    }
+}
+
+const char *mvosr_last_cuda_error(void) { return g_cuda_err; }
+
+static double sin_threshold(double deg) {
+    // largest double s with asin(s)*180/pi < deg (deg < 0), by bisection on the monotone libm asin
+    double lo = -1.0, hi = 0.0;          // lo satisfies, hi does not
+    for (int i = 0; i < 200; ++i) {
+        double mid = 0.5 * (lo + hi);
+        if (mid == lo || mid == hi) break;
+        if (asin(mid) * 180.0 / M_PI < deg) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+static uint32_t default_pass_mask(void) {
+    // graph.py:6-17,134-145 with edge potential [[3,1],[2,2],[2,2],[0,4]]: bit (idx*3+k) <=> p_k(idx) > 0.6
+    const double ep[4][2] = { {3, 1}, {2, 2}, {2, 2}, {0, 4} };
+    double tp[8][8];
+    for (int row = 0; row < 8; ++row)
+        for (int col = 0; col < 8; ++col) {
+            int r0 = (row >> 2) & 1, r1 = (row >> 1) & 1, r2 = row & 1, c0 = (col >> 2) & 1, c1 = (col >> 1) & 1, c2 = col & 1;
+            tp[row][col] = ep[r0 * 2 + r1][c0] * ep[r1 * 2 + r2][c1] * ep[r0 * 2 + r2][c2];
+        }
+    uint32_t m = 0;
+    for (int idx = 0; idx < 8; ++idx) {
+        double z = 0, pk[3] = { 0, 0, 0 };
+        for (int row = 0; row < 8; ++row) {
+            z += tp[row][idx];
+            if (row & 4) pk[0] += tp[row][idx];
+            if (row & 2) pk[1] += tp[row][idx];
+            if (row & 1) pk[2] += tp[row][idx];
+        }
+        for (int k = 0; k < 3; ++k) if (pk[k] / z > 0.6) m |= 1u << (idx * 3 + k);
+    }
+    return m;
+}
+
+int mvosr_default_config(mvosr_config *c) {
+    if (!c) return MVOSR_E_INVALID;
+    memset(c, 0, sizeof(*c));
+    c->absolute_reference = 1.75;        // src/param.py:36
+    c->fx = 718.856; c->fy = 718.856; c->cx = 607.1928; c->cy = 185.2157;
+    c->vanish = 185.0f;
+    c->min_features = 100; c->min_kept = 10; c->min_selected = 12;
+    c->sin_loose = sin_threshold(-80.0);
+    c->sin_tight = sin_threshold(-85.0);
+    c->height_level_factor = 0.9;
+    c->ransac_iterations = 100; c->ransac_stop_at_goal = 1;
+    c->ransac_threshold = 0.005; c->ransac_goal_fraction = 0.8;
+    c->graph_pass_mask = default_pass_mask();
+    c->slew_limit = 0.3; c->window_size = 5;
+    c->triangulation_max_depth = 100.0;
+    return MVOSR_OK;
+}
+
+int mvosr_create(const mvosr_config *cfg, int device, mvosr_handle **out) {
+    if (!out) return MVOSR_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MVOSR_E_NO_DEVICE;
+    if (device < 0 || device >= ndev) return MVOSR_E_INVALID;
+    CK(cudaSetDevice(device));
+    mvosr_handle *h = new (std::nothrow) mvosr_handle();
+    if (!h) return MVOSR_E_NOMEM;
+    memset(h, 0, sizeof(*h));
+    if (cfg) h->cfg = *cfg; else mvosr_default_config(&h->cfg);
+    h->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    int cap = 256;
+    while (make_plan(cap + 64).total + (int)sizeof(Ctl) + 1024 <= h->smem_optin) cap += 64;
+    h->cap_max = cap;
+    CK(cudaMalloc(&h->work_counter, sizeof(int)));
+    CK(cudaFuncSetAttribute(frame_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512));
+    CK(cudaFuncSetAttribute(frame_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512));
+    *out = h;
+    return MVOSR_OK;
+}
+
+int mvosr_destroy(mvosr_handle *h) {
+    if (!h) return MVOSR_OK;
+    cudaSetDevice(h->device);
+    if (h->work_counter) cudaFree(h->work_counter);
+    if (h->d_stage) cudaFree(h->d_stage);
+    delete h;
+    return MVOSR_OK;
+}
+
+int mvosr_get_config(const mvosr_handle *h, mvosr_config *cfg) {
+    if (!h || !cfg) return MVOSR_E_INVALID;
+    *cfg = h->cfg;
+    return MVOSR_OK;
+}
+
+int64_t mvosr_launch_count(const mvosr_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"
+
+static int pick_cap(const mvosr_handle *h, int max_features) {
+    int cap = (max_features + 63) / 64 * 64;
+    if (cap < 256) cap = 256;
+    if (cap > h->cap_max) cap = h->cap_max;
+    return cap;
+}
+
+template <bool FROM_CORR>
+static int launch_frames(mvosr_handle *h, FrameParams &P, int max_features, cudaStream_t st) {
+    if (P.n_frames <= 0) return MVOSR_OK;
+    P.cap = pick_cap(h, max_features);
+    P.cfg = h->cfg;
+    P.work_counter = h->work_counter;
+    SmemPlan pl = make_plan(P.cap);
+    CK(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
+    int grid = P.n_frames < h->num_sms ? P.n_frames : h->num_sms;
+    frame_kernel<FROM_CORR><<<grid, NT, pl.total, st>>>(P);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return MVOSR_OK;
+}
+
+extern "C" {
+
+int mvosr_triangulate_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                             const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                             const uint8_t *e_mask, const double *poses,
+                             float *x, float *y, float *z, float *u, float *v, int32_t *n_out, void *stream) {
+    if (!h || n_frames < 0 || !offsets || !cur_u || !cur_v || !ref_u || !ref_v || !poses || !x || !y || !z || !u || !v || !n_out)
+        return MVOSR_E_INVALID;
+    if (n_frames == 0) return MVOSR_OK;
+    CK(cudaSetDevice(h->device));
+    int grid = n_frames < 8 * h->num_sms ? n_frames : 8 * h->num_sms;
+    triangulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_frames, offsets, cur_u, cur_v, ref_u, ref_v, e_mask, poses,
+                                                                  h->cfg, x, y, z, u, v, n_out);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return MVOSR_OK;
+}
+
+int mvosr_scale_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets, const int32_t *counts,
+                       const float *x, const float *y, const float *z, const float *u, const float *v,
+                       int32_t max_features, int32_t frame_index0, int32_t seq_id, uint64_t seed,
+                       double *raw_scale, uint8_t *status, mvosr_frame_stats *stats,
+                       const mvosr_debug_buffers *debug, void *stream) {
+    if (!h || n_frames < 0 || !offsets || !x || !y || !z || !u || !v || !raw_scale || !status || max_features < 0)
+        return MVOSR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    FrameParams P; memset(&P, 0, sizeof(P));
+    P.n_frames = n_frames; P.offsets = offsets; P.counts = counts;
+    P.x = x; P.y = y; P.z = z; P.u = u; P.v = v;
+    P.mode = MODE_FULL; P.gate = 0;
+    P.frame_index0 = frame_index0; P.seq_id = seq_id; P.seed = seed;
+    P.raw_scale = raw_scale; P.status = status; P.stats = stats;
+    if (debug) { P.dbg = *debug; P.has_dbg = 1; }
+    return launch_frames<false>(h, P, max_features, (cudaStream_t)stream);
+}
+
+int mvosr_scale_frames_from_correspondences(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                       const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                       const uint8_t *e_mask, const double *poses,
+                       int32_t max_features, int32_t frame_index0, int32_t seq_id, uint64_t seed,
+                       double *raw_scale, uint8_t *status, int32_t *n_features, mvosr_frame_stats *stats, void *stream) {
+    if (!h || n_frames < 0 || !offsets || !cur_u || !cur_v || !ref_u || !ref_v || !poses || !raw_scale || !status || max_features < 0)
+        return MVOSR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    FrameParams P; memset(&P, 0, sizeof(P));
+    P.n_frames = n_frames; P.offsets = offsets;
+    P.cur_u = cur_u; P.cur_v = cur_v; P.ref_u = ref_u; P.ref_v = ref_v; P.e_mask = e_mask; P.poses = poses;
+    P.mode = MODE_FULL; P.gate = 1;
+    P.frame_index0 = frame_index0; P.seq_id = seq_id; P.seed = seed;
+    P.raw_scale = raw_scale; P.status = status; P.n_features = n_features; P.stats = stats;
+    return launch_frames<true>(h, P, max_features, (cudaStream_t)stream);
+}
+
+int mvosr_delaunay_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets, const float *u, const float *v,
+                          int32_t max_features, int32_t *tri, int32_t *n_tri, uint8_t *status, void *stream) {
+    if (!h || n_frames < 0 || !offsets || !u || !v || !tri || !n_tri || max_features < 0) return MVOSR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    FrameParams P; memset(&P, 0, sizeof(P));
+    P.n_frames = n_frames; P.offsets = offsets; P.u = u; P.v = v;
+    P.mode = MODE_DT_ONLY;
+    P.tri_out = tri; P.n_tri_out = n_tri; P.status = status;
+    return launch_frames<false>(h, P, max_features, (cudaStream_t)stream);
+}
+
+int mvosr_filter_sequences(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets,
+                           const double *raw_scale, const uint8_t *status, const uint8_t *move_flags,
+                           const int32_t *n_features, double *scale_out, double *filter10_out, void *stream) {
+    if (!h || n_sequences < 0 || !seq_offsets || !raw_scale || !status || !scale_out) return MVOSR_E_INVALID;
+    if (n_sequences == 0) return MVOSR_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    filter_kernel<<<(n_sequences + 31) / 32, 32, 0, st>>>(n_sequences, seq_offsets, raw_scale, status, move_flags, n_features,
+                                                           h->cfg, scale_out);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    if (filter10_out) {
+        int total = 0;
+        // the frame count is seq_offsets[n_sequences] (device memory): size the grid from a bounded copy
+        CK(cudaMemcpyAsync(&total, seq_offsets + n_sequences, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (total > 0) {
+            filter10_kernel<<<(total + 127) / 128, 128, 0, st>>>(n_sequences, seq_offsets, scale_out, filter10_out);
+            CK(cudaGetLastError());
+            h->launches += 1;
+        }
+    }
+    return MVOSR_OK;
+}
+
+int mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t *offsets_host,
+                       const float *cur_u_host, const float *cur_v_host, const float *ref_u_host, const float *ref_v_host,
+                       const double *poses_host, const uint8_t *move_flags_host,
+                       int32_t max_features, int32_t seq_id, uint64_t seed,
+                       double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host) {
+    if (!h || n_frames < 0 || !offsets_host || !cur_u_host || !cur_v_host || !ref_u_host || !ref_v_host || !poses_host || !scale_out_host)
+        return MVOSR_E_INVALID;
+    if (n_frames == 0) return MVOSR_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t M = (size_t)offsets_host[n_frames];
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t o_off = 0, o_cu = o_off + al(4 * (size_t)(n_frames + 1)), o_cv = o_cu + al(4 * M), o_ru = o_cv + al(4 * M),
+           o_rv = o_ru + al(4 * M), o_pose = o_rv + al(4 * M), o_move = o_pose + al(96 * (size_t)n_frames),
+           o_raw = o_move + al((size_t)n_frames), o_st = o_raw + al(8 * (size_t)n_frames), o_nf = o_st + al((size_t)n_frames),
+           o_out = o_nf + al(4 * (size_t)n_frames), o_seq = o_out + al(8 * (size_t)n_frames), total = o_seq + 256;
+    if (total > h->stage_bytes) {
+        if (h->d_stage) cudaFree(h->d_stage);
+        h->d_stage = nullptr; h->stage_bytes = 0;
+        if (cudaMalloc(&h->d_stage, total) != cudaSuccess) { cudaGetLastError(); return MVOSR_E_NOMEM; }
+        h->stage_bytes = total;
+    }
+    char *d = (char *)h->d_stage;
+    cudaStream_t st = 0;
+    CK(cudaMemcpyAsync(d + o_off, offsets_host, 4 * (size_t)(n_frames + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_cu, cur_u_host, 4 * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_cv, cur_v_host, 4 * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_ru, ref_u_host, 4 * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_rv, ref_v_host, 4 * M, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_pose, poses_host, 96 * (size_t)n_frames, cudaMemcpyHostToDevice, st));
+    if (move_flags_host) CK(cudaMemcpyAsync(d + o_move, move_flags_host, (size_t)n_frames, cudaMemcpyHostToDevice, st));
+    int32_t seqo[2] = { 0, n_frames };
+    CK(cudaMemcpyAsync(d + o_seq, seqo, sizeof(seqo), cudaMemcpyHostToDevice, st));
+    int rc = mvosr_scale_frames_from_correspondences(h, n_frames, (const int32_t *)(d + o_off), (const float *)(d + o_cu),
+                (const float *)(d + o_cv), (const float *)(d + o_ru), (const float *)(d + o_rv), nullptr, (const double *)(d + o_pose),
+                max_features, 0, seq_id, seed, (double *)(d + o_raw), (uint8_t *)(d + o_st), (int32_t *)(d + o_nf), nullptr, st);
+    if (rc != MVOSR_OK) return rc;
+    rc = mvosr_filter_sequences(h, 1, (const int32_t *)(d + o_seq), (const double *)(d + o_raw), (const uint8_t *)(d + o_st),
+                                move_flags_host ? (const uint8_t *)(d + o_move) : nullptr, (const int32_t *)(d + o_nf),
+                                (double *)(d + o_out), nullptr, st);
+    if (rc != MVOSR_OK) return rc;
+    CK(cudaMemcpyAsync(scale_out_host, d + o_out, 8 * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+    if (raw_scale_out_host) CK(cudaMemcpyAsync(raw_scale_out_host, d + o_raw, 8 * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+    if (status_out_host) CK(cudaMemcpyAsync(status_out_host, d + o_st, (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MVOSR_OK;
+}
+
+}  // extern "C"

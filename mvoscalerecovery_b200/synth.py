@@ -141,13 +141,13 @@ def make_frame(seed: int, seq: int, frame: int, n_corr: int, true_scale: float,
 
 def make_sequence(seed: int, n_frames: int, n_corr: int = 2500, seq: int = 0,
                   cam: Camera = Camera(), camera_h: float = 1.7, outlier_frac: float = 0.1,
-                  n_jitter: float = 0.05, still_every: int = 0, **kw) -> CorrespondenceBatch:
+                  n_jitter: float = 0.05, still_every: int = 0, scales=None, **kw) -> CorrespondenceBatch:
     """A CSR batch of ``n_frames`` frames; frame sizes jitter by +-n_jitter around n_corr.
 
     ``still_every`` > 0 marks every k-th frame as "not moving" (move_flag 0, no
     correspondences), the case of src/main_offline.py:64-68.
     """
-    scales = true_scale_profile(n_frames, seed, seq)
+    scales = true_scale_profile(n_frames, seed, seq) if scales is None else np.asarray(scales, dtype=np.float64)
     rng = np.random.Generator(np.random.Philox(key=[seed & 0xFFFFFFFFFFFFFFFF, 0xC0FFEE + seq]))
     sizes = np.maximum(8, np.round(n_corr * (1 + rng.uniform(-n_jitter, n_jitter, n_frames)))).astype(np.int64)
     move = np.ones(n_frames, dtype=np.uint8)

@@ -1,0 +1,194 @@
+"""Parity of the CUDA path (through the C ABI) against the reference's own outputs (goldens) and the oracle.
+
+Tolerances: index / mask / triangle-set work is compared bit-exactly; floating point within 1e-9
+relative (the north star allows 1e-5 on height and scale; FP64 closed forms vs LAPACK agree far tighter)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _run_golden(engine, g, debug=True):
+    from mvoscalerecovery_b200.batch import pack_frames, stats_to_numpy
+    torch = _torch()
+    f3 = [g.f3(f) for f in range(g.n_frames)]
+    f2 = [g.f2(f) for f in range(g.n_frames)]
+    b = pack_frames(f3, f2, engine.device)
+    out = engine.scale_frames(b["offsets"], b["x"], b["y"], b["z"], b["u"], b["v"], b["max_features"], seed=g.seed, debug=debug)
+    torch.cuda.synchronize()
+    res = dict(raw=out["raw_scale"].cpu().numpy(), status=out["status"].cpu().numpy(), stats=stats_to_numpy(out["stats"]),
+               off=b["offsets"].cpu().numpy(), batch=b)
+    if debug:
+        res["dbg"] = {k: v.cpu().numpy() for k, v in out["debug"].items()}
+    return res
+
+
+def test_delaunay_frames_vs_reference_qhull(engine, golden):
+    """DT #1 of every golden frame through mvosr_delaunay_frames == canonicalised Qhull simplices (rescale.py:124)."""
+    torch = _torch()
+    g = golden
+    frames = [f for f in range(g.n_frames) if g.called(f)]
+    pts = []
+    for f in frames:
+        f2 = g.f2(f)
+        pts.append(f2[f2[:, 1] > 185])
+    off = np.zeros(len(pts) + 1, np.int32)
+    np.cumsum([p.shape[0] for p in pts], out=off[1:])
+    allp = np.concatenate(pts, 0)
+    dev = engine.device
+    out = engine.delaunay_frames(torch.from_numpy(off).to(dev), torch.from_numpy(np.ascontiguousarray(allp[:, 0])).to(dev),
+                                 torch.from_numpy(np.ascontiguousarray(allp[:, 1])).to(dev), int(np.max(np.diff(off))))
+    torch.cuda.synchronize()
+    tri = out["tri"].cpu().numpy(); ntri = out["n_tri"].cpu().numpy(); st = out["status"].cpu().numpy()
+    for i, f in enumerate(frames):
+        ref = g.get(f, "tri1").astype(np.int32)
+        assert st[i] == 0, (f, st[i])
+        got = tri[2 * off[i]: 2 * off[i] + ntri[i]]
+        assert ntri[i] == ref.shape[0], (f, ntri[i], ref.shape[0])
+        assert np.array_equal(got, ref), "frame %d triangle set differs" % f
+
+
+def test_scale_frames_vs_reference(engine, golden):
+    """Every intermediate of rescale.ScaleEstimator.scale_calculation, frame by frame."""
+    from mvoscalerecovery_b200 import _native as N
+    g = golden
+    r = _run_golden(engine, g)
+    off, dbg, stats = r["off"], r["dbg"], r["stats"]
+    n_checked = 0
+    for f in range(g.n_frames):
+        if not g.called(f):
+            continue
+        sc = g.scalars(f)
+        a, T0 = off[f], 2 * off[f]
+        st = int(r["status"][f])
+        assert not (st & (N.ST_BAD_INPUT | N.ST_OVERFLOW | N.ST_FEW_ROI)), (f, st)
+        tri1 = g.get(f, "tri1").astype(np.int32)
+        assert dbg["n_tri1"][f] == tri1.shape[0]
+        assert np.array_equal(dbg["tri1"][T0:T0 + tri1.shape[0]], tri1), "frame %d DT#1" % f
+        keep = g.get(f, "keep")
+        assert np.array_equal(dbg["keep"][a:a + keep.shape[0]].astype(bool), keep), "frame %d graph keep mask" % f
+        assert stats["n_kept"][f] == keep.sum()
+        assert bool(st & N.ST_SECOND_DT) == sc["second_dt"]
+        tri2 = g.get(f, "tri2").astype(np.int32)
+        assert stats["n_tri"][f] == tri2.shape[0]
+        assert np.array_equal(dbg["tri2"][T0:T0 + tri2.shape[0]], tri2), "frame %d DT#2" % f
+        flags = g.get(f, "flags")
+        assert np.array_equal(dbg["tri_flags"][T0:T0 + flags.shape[0]], flags), "frame %d loose/tight/valid masks" % f
+        np.testing.assert_allclose(dbg["tri_height"][T0:T0 + flags.shape[0]], g.get(f, "heights"), rtol=1e-7)
+        np.testing.assert_allclose(stats["height_level"][f], sc["height_level"], rtol=RTOL)
+        data_id = g.get(f, "data_id").astype(np.int32)
+        assert 3 * stats["n_valid"][f] == data_id.shape[0]
+        assert np.array_equal(dbg["data_id"][6 * a: 6 * a + data_id.shape[0]], data_id), "frame %d vertex list" % f
+        assert bool(st & N.ST_UPDATED) == sc["updated"]
+        if sc["updated"]:
+            hyp = g.get(f, "hyp_log")
+            assert stats["hyps_used"][f] == hyp.shape[0], (f, stats["hyps_used"][f], hyp.shape[0])
+            assert stats["best_ic"][f] == sc["best_ic"], (f, stats["best_ic"][f], sc["best_ic"])
+            m_ref = g.get(f, "model")
+            m_ref = m_ref * (1.0 if m_ref[1] >= 0 else -1.0)
+            np.testing.assert_allclose(stats["model"][f], m_ref, rtol=1e-8, atol=1e-11)
+            np.testing.assert_allclose(stats["height"][f], sc["height"], rtol=RTOL)
+            np.testing.assert_allclose(r["raw"][f], sc["raw_scale"], rtol=RTOL)
+        n_checked += 1
+    assert n_checked > 0
+
+
+def test_filter_vs_reference(engine, golden):
+    """Temporal state + driver gating + filter_10 on the GPU's own raw scales == reference outputs."""
+    torch = _torch()
+    g = golden
+    r = _run_golden(engine, g, debug=False)
+    dev = engine.device
+    nfeat = torch.from_numpy(np.array([g.f3(f).shape[0] for f in range(g.n_frames)], np.int32)).to(dev)
+    move = torch.from_numpy(g.z["move_flags"].astype(np.uint8)).to(dev)
+    seq = torch.tensor([0, g.n_frames], dtype=torch.int32, device=dev)
+    out = engine.filter_sequences(seq, torch.from_numpy(r["raw"]).to(dev), torch.from_numpy(r["status"]).to(dev), move, nfeat)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out["scale"].cpu().numpy(), g.z["scales"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(out["filter10"].cpu().numpy(), g.z["filter10"], rtol=RTOL, atol=1e-12)
+
+
+def test_stage1_vs_opencv(engine, golden):
+    """Per-point DLT vs cv2.recoverPose's triangulation (visual_odometry.py:132-147)."""
+    torch = _torch()
+    g = golden
+    dev = engine.device
+    z = g.z
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = engine.triangulate_frames(t(z["offsets"]), t(z["cur_u"]), t(z["cur_v"]), t(z["ref_u"]), t(z["ref_v"]), t(z["poses"]))
+    torch.cuda.synchronize()
+    n_out = out["n_out"].cpu().numpy()
+    X = np.stack([out[k].cpu().numpy() for k in "xyz"], 1); uv = np.stack([out[k].cpu().numpy() for k in "uv"], 1)
+    off = z["offsets"]
+    checked = 0
+    for f in range(g.n_frames):
+        f3, f2 = g.f3(f), g.f2(f)
+        assert n_out[f] == f3.shape[0], (f, n_out[f], f3.shape[0])         # identical mask
+        got3 = X[off[f]: off[f] + n_out[f]]; got2 = uv[off[f]: off[f] + n_out[f]]
+        # float32 outputs: equal up to the last float32 bit (float64 results agree to ~1e-12 relative)
+        ulp3 = np.abs(got3 - f3) / np.maximum(np.abs(np.spacing(f3)), 1e-30)
+        ulp2 = np.abs(got2 - f2) / np.maximum(np.abs(np.spacing(f2)), 1e-30)
+        assert ulp3.size == 0 or ulp3.max() <= 1.0, (f, ulp3.max())
+        assert ulp2.size == 0 or ulp2.max() <= 1.0, (f, ulp2.max())
+        if ulp3.size:
+            assert (ulp3 > 0).mean() < 0.01 and (ulp2 > 0).mean() < 0.01
+        checked += 1
+    assert checked
+
+
+def test_fused_path_matches_staged_path(engine, golden):
+    """Fused correspondences->scale kernel == stand-alone stage 1 followed by the staged kernel, bit for bit."""
+    torch = _torch()
+    g = golden
+    dev = engine.device
+    z = g.z
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    off = t(z["offsets"])
+    args = (t(z["cur_u"]), t(z["cur_v"]), t(z["ref_u"]), t(z["ref_v"]), t(z["poses"]))
+    maxf = int(np.max(np.diff(z["offsets"])))
+    fused = engine.scale_frames_from_correspondences(off, *args, max_features=maxf, seed=g.seed)
+    s1 = engine.triangulate_frames(off, *args)
+    staged = engine.scale_frames(off, s1["x"], s1["y"], s1["z"], s1["u"], s1["v"], maxf, counts=s1["n_out"], seed=g.seed)
+    torch.cuda.synchronize()
+    a = fused["raw_scale"].cpu().numpy(); b = staged["raw_scale"].cpu().numpy()
+    sa = fused["status"].cpu().numpy(); sb = staged["status"].cpu().numpy()
+    nf = fused["n_features"].cpu().numpy()
+    gate = nf <= 100
+    assert np.array_equal(sa[~gate], sb[~gate])
+    assert np.array_equal(a[~gate], b[~gate], equal_nan=True)
+    assert np.all(sa[gate] & 64)
+    # and against the reference end to end (stage-1 outputs differ from OpenCV's in the last float32 bit of a
+    # fraction of a percent of values, hence the north star's 1e-5 tolerance here rather than 1e-9)
+    seq = torch.tensor([0, g.n_frames], dtype=torch.int32, device=dev)
+    out = engine.filter_sequences(seq, fused["raw_scale"], fused["status"], t(z["move_flags"].astype(np.uint8)), fused["n_features"])
+    torch.cuda.synchronize()
+    got = out["scale"].cpu().numpy()
+    ref = z["scales"]
+    close = np.isclose(got, ref, rtol=1e-5, atol=1e-12)
+    assert close.mean() >= 0.9, (g.name, close.mean(), got[~close][:5], ref[~close][:5])
+
+
+def test_host_api_end_to_end(engine, golden):
+    """mvosr_recover_scales_host (host buffers in, filtered scales out) == device-resident path."""
+    torch = _torch()
+    g = golden
+    z = g.z
+    dev = engine.device
+    out = engine.recover_scales_host(np.ascontiguousarray(z["offsets"]), np.ascontiguousarray(z["cur_u"]), np.ascontiguousarray(z["cur_v"]),
+                                     np.ascontiguousarray(z["ref_u"]), np.ascontiguousarray(z["ref_v"]), np.ascontiguousarray(z["poses"]),
+                                     np.ascontiguousarray(z["move_flags"].astype(np.uint8)), seed=g.seed)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    fused = engine.scale_frames_from_correspondences(t(z["offsets"]), t(z["cur_u"]), t(z["cur_v"]), t(z["ref_u"]), t(z["ref_v"]), t(z["poses"]),
+                                                     max_features=int(np.max(np.diff(z["offsets"]))), seed=g.seed)
+    seq = torch.tensor([0, g.n_frames], dtype=torch.int32, device=dev)
+    f = engine.filter_sequences(seq, fused["raw_scale"], fused["status"], t(z["move_flags"].astype(np.uint8)), fused["n_features"])
+    torch.cuda.synchronize()
+    assert np.array_equal(out["scale"], f["scale"].cpu().numpy())
+    assert np.array_equal(out["raw_scale"], fused["raw_scale"].cpu().numpy(), equal_nan=True)
