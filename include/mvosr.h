@@ -174,6 +174,11 @@ int  mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t 
                         int32_t max_features, int32_t seq_id, uint64_t seed,
                         double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host);
 
+/* Profiling aid: when set (device pointer, [F][16] int64), the fused kernel stores per-frame SM cycles per phase:
+ * 0 load+stage1+ROI, 1 grid#1, 2/3 stars#1 thread/warp path, 6 compaction+grid#2, 7/8 stars#2 thread/warp path,
+ * 10 planes, 11 median, 12 valid list, 13 RANSAC. Pass NULL to disable. */
+int  mvosr_set_phase_timing(mvosr_handle *h, int64_t *phase_cycles_device);
+
 /* Number of kernels the library has launched on this handle since creation (bench.py's gpu_launches). */
 int64_t mvosr_launch_count(const mvosr_handle *h);
 

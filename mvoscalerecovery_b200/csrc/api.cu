@@ -33,6 +33,7 @@ struct mvosr_handle {
     int64_t launches;
     // host-API staging (grown on demand)
     void *d_stage; size_t stage_bytes;
+    long long *phase_cycles;     // optional profiling sink (device), set by mvosr_set_phase_timing
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -243,6 +244,12 @@ int mvosr_get_config(const mvosr_handle *h, mvosr_config *cfg) {
 
 int64_t mvosr_launch_count(const mvosr_handle *h) { return h ? h->launches : 0; }
 
+int mvosr_set_phase_timing(mvosr_handle *h, int64_t *phase_cycles_device) {
+    if (!h) return MVOSR_E_INVALID;
+    h->phase_cycles = (long long *)phase_cycles_device;
+    return MVOSR_OK;
+}
+
 }  // extern "C"
 
 static int pick_cap(const mvosr_handle *h, int max_features) {
@@ -258,6 +265,7 @@ static int launch_frames(mvosr_handle *h, FrameParams &P, int max_features, cuda
     P.cap = pick_cap(h, max_features);
     P.cfg = h->cfg;
     P.work_counter = h->work_counter;
+    P.phase_cycles = h->phase_cycles;
     SmemPlan pl = make_plan(P.cap);
     CK(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
     int grid = P.n_frames < h->num_sms ? P.n_frames : h->num_sms;

@@ -10,7 +10,7 @@
 //   RANSAC   get_pitch_ransac / run_ransac                    estimate_road_norm.py:8-18,66-70, thirdparty/Ransac/ransac.py:3-23
 //   scale    height = h_bar/|n|, scale = ref/height           rescale.py:156-167
 //
-// Shared-memory plan for capacity `cap` ROI features (bytes): px,py 8cap | X,Y,Z 12cap | pflag cap |
+// Shared-memory plan for capacity `cap` ROI features (bytes): px,py 16cap (float64 copies: no conversions in the hot loops) | X,Y,Z 12cap | pflag cap |
 // cell_start/cell_n/cell_pts 6cap(+) | u32 scratch 4cap (cell counters, later canonical offsets) |
 // tri list 12cap | tbase,tcnt 3cap | mult 2cap | region A = max(star storage, 16cap heights) | flags 2cap.
 #pragma once
@@ -18,6 +18,7 @@
 #include <math_constants.h>
 #include "../../include/mvosr.h"
 #include "star.cuh"
+#include "gstar.cuh"
 #include "philox.cuh"
 #include "triangulate.cuh"
 
@@ -50,6 +51,7 @@ struct FrameParams {
     // DT-only mode outputs
     int32_t *tri_out; int32_t *n_tri_out;
     int *work_counter;              // dynamic frame scheduler
+    long long *phase_cycles;        // optional [F][16] per-phase SM cycles (profiling aid)
 };
 
 struct SmemPlan {
@@ -61,8 +63,8 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 __host__ __device__ inline SmemPlan make_plan(int cap) {
     SmemPlan p; p.cap = cap; int o = 0;
-    p.off_px = o; o = align16(o + 4 * cap);
-    p.off_py = o; o = align16(o + 4 * cap);
+    p.off_px = o; o = align16(o + 8 * cap);
+    p.off_py = o; o = align16(o + 8 * cap);
     p.off_X = o; o = align16(o + 4 * cap);
     p.off_Y = o; o = align16(o + 4 * cap);
     p.off_Z = o; o = align16(o + 4 * cap);
@@ -76,7 +78,7 @@ __host__ __device__ inline SmemPlan make_plan(int cap) {
     p.off_tcnt = o; o = align16(o + cap);
     p.off_mult = o; o = align16(o + 2 * cap + 4);
     p.off_defer = o; o = align16(o + 2 * cap);
-    int star_bytes = MAXDEG_T * NT * 2 + NWARP * (MAXDEG_W * 2 + 3 * MAXDEG_W * 8);
+    int star_bytes = NWARP * WARPSTAR_BYTES;
     int a_bytes = 16 * cap > star_bytes ? 16 * cap : star_bytes;
     p.off_A = o; o = align16(o + a_bytes);
     p.off_flags = o; o = align16(o + 2 * cap);
@@ -85,6 +87,7 @@ __host__ __device__ inline SmemPlan make_plan(int cap) {
 }
 
 struct Ctl {                         // static shared control block
+    int next_pos;
     int n_roi, n_feat, n2, status, bad, n_dup, n_dup1, n_kept, T, n_defer, n_exact, n_deferred_total;
     int n_loose, n_tight, n_valid, best_hyp, best_ic, hyps_used, n_degenerate, err;
     int warp_cnt[NWARP], warp_cnt2[NWARP];
@@ -94,6 +97,7 @@ struct Ctl {                         // static shared control block
     unsigned hist[256];
     unsigned long long sel_prefix; int sel_k; unsigned long long sel_val[2];
     int frame;
+    long long tphase[16];
     int round_ic[NWARP];
     double round_model[NWARP][5];
 };
@@ -126,13 +130,13 @@ __device__ __forceinline__ void block_excl_scan(uint32_t *a, int n, int *warp_tm
     __syncthreads();
 }
 
-__device__ __forceinline__ bool edge_consistent(const float *py, const float *Z, int a, int b) {
+__device__ __forceinline__ bool edge_consistent(const double *py, const float *Z, int a, int b) {
     // check_triangle (graph.py:124-129): (v_a - v_b) * (d_a - d_b) < 0, float64 on float32-exact values
-    return ((double)py[a] - (double)py[b]) * ((double)Z[a] - (double)Z[b]) < 0.0;
+    return (py[a] - py[b]) * ((double)Z[a] - (double)Z[b]) < 0.0;
 }
 
 // graph vote of one star triangle (p,qa,qb) for vertex p under the canonical (ascending) vertex order
-__device__ __forceinline__ int graph_vote(const float *py, const float *Z, int p, int qa, int qb, uint32_t pass_mask) {
+__device__ __forceinline__ int graph_vote(const double *py, const float *Z, int p, int qa, int qb, uint32_t pass_mask) {
     int i0 = p, i1 = qa, i2 = qb;
     if (i0 > i1) { int t = i0; i0 = i1; i1 = t; }
     if (i1 > i2) { int t = i1; i1 = i2; i2 = t; }
@@ -147,7 +151,8 @@ __device__ __forceinline__ int graph_vote(const float *py, const float *Z, int p
 // star consumers
 // ---------------------------------------------------------------------------------------------
 struct FrameView {
-    float *px, *py, *X, *Y, *Z;
+    double *px, *py;                 // 2-D pixel coordinates (float32-exact values)
+    float *X, *Y, *Z;
     uint8_t *pflag;                  // bit0 duplicate, bit1 keep
     uint16_t *tri;                   // [T][3]
     uint16_t *tbase; uint8_t *tcnt;
@@ -203,12 +208,12 @@ __device__ __forceinline__ void consume_emit(const Star &st, int d, int p, Frame
 // ---------------------------------------------------------------------------------------------
 struct GridArrays { uint16_t *cell_start, *cell_n, *cell_pts; uint32_t *scr; };
 
-__device__ __forceinline__ bool build_grid(int n, const float *px, const float *py, uint8_t *pflag, GridArrays ga,
+__device__ __forceinline__ bool build_grid(int n, const double *px, const double *py, uint8_t *pflag, GridArrays ga,
                                            int cap, Ctl *ctl, Grid &g) {
     int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float xmn = CUDART_INF_F, xmx = -CUDART_INF_F, ymn = CUDART_INF_F, ymx = -CUDART_INF_F;
     for (int i = tid; i < n; i += NT) {
-        float a = px[i], b = py[i];
+        float a = (float)px[i], b = (float)py[i];      // exact: the values are float32
         xmn = fminf(xmn, a); xmx = fmaxf(xmx, a); ymn = fminf(ymn, b); ymx = fmaxf(ymx, b);
     }
 #pragma unroll
@@ -236,7 +241,7 @@ __device__ __forceinline__ bool build_grid(int n, const float *px, const float *
         if (gxd * gyd <= (double)cap) { gx = (int)gxd; gy = (int)gyd; break; }
         h *= 1.25;
     }
-    g.xmin = xmn; g.ymin = ymn; g.h = h; g.inv_h = 1.0 / h; g.gx = gx; g.gy = gy;
+    g.xmin = (double)xmn; g.ymin = (double)ymn; g.h = h; g.inv_h = 1.0 / h; g.gx = gx; g.gy = gy;
     int ncell = gx * gy;
     for (int i = tid; i <= ncell; i += NT) ga.scr[i] = 0;
     __syncthreads();
@@ -276,42 +281,77 @@ __device__ __forceinline__ bool build_grid(int n, const float *px, const float *
     return true;
 }
 
+// lane-parallel consumers of a register-resident group star (lane i owns star triangle i)
+__device__ __forceinline__ void g_consume_vote(const GCtx &c, FrameView &fv) {
+    bool fin = c.gl < c.d && c.sid != INF16 && c.nid != INF16;
+    int v = fin ? graph_vote(fv.py, fv.Z, c.p, c.sid, c.nid, fv.pass_mask) : 0;
+    unsigned mf = gballot(c, fin), mv = gballot(c, fin && v);
+    // keep = (#incident triangles with p>0.6)/(#incident) > 0.5 (graph.py:33-35,131-132); 0/0 -> False
+    if (c.gl == 0 && 2 * __popc(mv) > __popc(mf)) fv.pflag[c.p] |= 2;
+}
+
+__device__ __forceinline__ void g_consume_emit(const GCtx &c, FrameView &fv, int tri_cap) {
+    bool fin = c.gl < c.d && c.sid != INF16 && c.nid != INF16;
+    bool em = fin && c.sid > c.p && c.nid > c.p;
+    int a = min(c.sid, c.nid), b = max(c.sid, c.nid);
+    unsigned key = em ? (((unsigned)a << 16) | (unsigned)b) : 0xFFFFFFFFu;
+    unsigned me = gballot(c, em);
+    int k = __popc(me);
+    if (!k) return;
+    int base = 0;
+    if (c.gl == 0) base = atomicAdd(&fv.ctl->T, k);
+    base = gshfl(c, base, 0);
+    if (base + k > tri_cap) { if (c.gl == 0) atomicOr(&fv.ctl->status, MVOSR_ST_OVERFLOW); return; }
+    int rank = 0;
+    unsigned m2 = me;
+    while (m2) { int j = __ffs(m2) - 1; m2 &= m2 - 1; unsigned kj = gshfl(c, key, j); rank += (kj < key); }
+    if (em) { uint16_t *t = fv.tri + 3 * (base + rank); t[0] = (uint16_t)c.p; t[1] = (uint16_t)a; t[2] = (uint16_t)b; }
+    if (c.gl == 0) { fv.tbase[c.p] = (uint16_t)base; fv.tcnt[c.p] = (uint8_t)k; }
+}
+
 // ---------------------------------------------------------------------------------------------
 // all stars of the staged point set; EMIT selects the consumer
 // ---------------------------------------------------------------------------------------------
-template <bool EMIT>
-__device__ __forceinline__ void run_stars(int n, const PointSet &ps, FrameView &fv, uint16_t *star_mem, unsigned char *warp_mem,
-                                          uint16_t *defer, int tri_cap) {
+// (not a template and not inlined: one copy of the star builder in the kernel, whatever the number of call sites)
+__device__ __noinline__ void run_stars(const bool EMIT, int n, const PointSet &ps, FrameView &fv, uint16_t *star_mem, unsigned char *warp_mem,
+                                       uint16_t *defer, int tri_cap, int tslot) {
     int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Ctl *ctl = fv.ctl;
     int n_exact = 0;
-    if (EMIT) {
-        for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
-        __syncthreads();
-    }
-    ThreadStar ts; ts.base = star_mem + tid;
-    for (int pos = tid; pos < n; pos += NT) {
-        int p = ps.cell_pts[pos];
-        if (p == INF16) { if (EMIT) { /* duplicate: emits nothing */ } continue; }
-        int d;
-        int r = build_star_thread(ts, d, p, ps, n_exact);
-        if (r == STAR_OK) {
-            if (EMIT) consume_emit(ts, d, p, fv, tri_cap); else consume_vote(ts, d, p, fv);
-        } else if (r == STAR_DEFER) {
-            int slot = atomicAdd(&ctl->n_defer, 1);
-            defer[slot] = (uint16_t)p;
-        } else if (r == STAR_NONE) {
-            if (EMIT) { fv.tcnt[p] = 0; fv.tbase[p] = 0; }
-        } else {
-            atomicOr(&ctl->status, MVOSR_ST_OVERFLOW);
-            if (EMIT) { fv.tcnt[p] = 0; fv.tbase[p] = 0; }
+    long long tc0 = clock64();
+    if (EMIT) for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
+    if (tid == 0) ctl->next_pos = 0;
+    __syncthreads();
+    // one 16-lane group per point, points fetched dynamically in cell order (spatially coherent)
+    {
+        GCtx c;
+        c.gl = tid & (GL - 1);
+        c.gmask = (lane & GL) ? 0xFFFF0000u : 0x0000FFFFu;
+        c.n_exact = 0;
+        for (;;) {
+            int pos = 0;
+            if (c.gl == 0) pos = atomicAdd(&ctl->next_pos, 1);
+            pos = gshfl(c, pos, 0);
+            if (pos >= n) break;
+            int p = ps.cell_pts[pos];
+            if (p == INF16) continue;                     // duplicate: in no triangle
+            int r = g_build(c, p, ps);
+            if (r == STAR_OK) {
+                if (EMIT) g_consume_emit(c, fv, tri_cap); else g_consume_vote(c, fv);
+            } else if (r != STAR_NONE) {
+                // degree > 16 (or an inconsistency): the sequential-rule warp builder takes the point
+                if (c.gl == 0) { int slot = atomicAdd(&ctl->n_defer, 1); defer[slot] = (uint16_t)p; }
+            }
         }
+        n_exact += c.n_exact;
     }
     __syncthreads();
+    long long tc1 = clock64();
     int nd = ctl->n_defer;
     WarpStar ws;
-    unsigned char *wm = warp_mem + warp * (MAXDEG_W * 2 + 3 * MAXDEG_W * 8);
-    ws.qx = (double *)wm; ws.qy = ws.qx + MAXDEG_W; ws.ql = ws.qy + MAXDEG_W; ws.id = (uint16_t *)(ws.ql + MAXDEG_W);
+    unsigned char *wm = warp_mem + warp * WARPSTAR_BYTES;
+    ws.qx = (double *)wm; ws.qy = ws.qx + MAXDEG_W; ws.ql = ws.qy + MAXDEG_W; ws.vx = ws.ql + MAXDEG_W; ws.vy = ws.vx + MAXDEG_W;
+    ws.r2 = ws.vy + MAXDEG_W; ws.id = (uint16_t *)(ws.r2 + MAXDEG_W);
     for (int k = warp; k < nd; k += NWARP) {
         int p = defer[k];
         int d;
@@ -329,7 +369,11 @@ __device__ __forceinline__ void run_stars(int n, const PointSet &ps, FrameView &
     }
     if (n_exact) atomicAdd(&ctl->n_exact, n_exact);
     __syncthreads();
-    if (tid == 0) { ctl->n_deferred_total += nd; ctl->n_defer = 0; }
+    if (tid == 0) {
+        ctl->n_deferred_total += nd; ctl->n_defer = 0;
+        long long tc2 = clock64();
+        ctl->tphase[tslot] += tc1 - tc0; ctl->tphase[tslot + 1] += tc2 - tc1;
+    }
     __syncthreads();
 }
 
@@ -395,7 +439,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
     const int cap = P.cap;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     FrameView fv;
-    fv.px = (float *)(smem + pl.off_px); fv.py = (float *)(smem + pl.off_py);
+    fv.px = (double *)(smem + pl.off_px); fv.py = (double *)(smem + pl.off_py);
     fv.X = (float *)(smem + pl.off_X); fv.Y = (float *)(smem + pl.off_Y); fv.Z = (float *)(smem + pl.off_Z);
     fv.pflag = smem + pl.off_pflag;
     fv.tri = (uint16_t *)(smem + pl.off_tri);
@@ -407,12 +451,14 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
     uint16_t *mult = (uint16_t *)(smem + pl.off_mult);
     uint16_t *defer = (uint16_t *)(smem + pl.off_defer);
     uint16_t *star_mem = (uint16_t *)(smem + pl.off_A);
-    unsigned char *warp_mem = smem + pl.off_A + MAXDEG_T * NT * 2;
+    unsigned char *warp_mem = smem + pl.off_A;
     double *theight = (double *)(smem + pl.off_A);          // aliases the star storage (dead by then)
     uint8_t *tflags = smem + pl.off_flags;
     const int tri_cap = 2 * cap;
     const mvosr_config &cfg = P.cfg;
 
+    long long tlast = 0;
+#define TMARK(k) do { if (tid == 0) { long long tn_ = clock64(); ctl.tphase[k] += tn_ - tlast; tlast = tn_; } } while (0)
     for (;;) {
         __syncthreads();
         if (tid == 0) ctl.frame = atomicAdd(P.work_counter, 1);
@@ -424,6 +470,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             ctl.n_defer = ctl.n_exact = ctl.n_deferred_total = 0;
             ctl.n_loose = ctl.n_tight = ctl.n_valid = 0; ctl.best_hyp = -1; ctl.best_ic = 0; ctl.hyps_used = 0;
             ctl.n_degenerate = 0; ctl.err = 0; ctl.height_level = CUDART_NAN;
+            for (int k = 0; k < 16; ++k) ctl.tphase[k] = 0;
+            tlast = clock64();
         }
         __syncthreads();
         const int base = P.offsets[f];
@@ -470,12 +518,13 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 if (fabsf(fu) < 7.62939453125e-06f) fu = 0.f;       // 2^-17: keeps every difference exact in float64
                 if (fabsf(fv_) < 7.62939453125e-06f) fv_ = 0.f;
                 if (pos < cap) {
-                    fv.px[pos] = fu; fv.py[pos] = fv_; fv.X[pos] = fx3; fv.Y[pos] = fy3; fv.Z[pos] = fz3; fv.pflag[pos] = 0;
+                    fv.px[pos] = (double)fu; fv.py[pos] = (double)fv_; fv.X[pos] = fx3; fv.Y[pos] = fy3; fv.Z[pos] = fz3; fv.pflag[pos] = 0;
                 }
             }
             total += tot; total_feat += totf;
             __syncthreads();
         }
+        TMARK(0);
         const int n_feat = total_feat;
         int n = total;
         int status = 0;
@@ -492,13 +541,15 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         if (!status) {
             // ---------------- Delaunay #1 -> graph vote (or triangles in DT-only mode) ----------------
             build_grid(n, fv.px, fv.py, fv.pflag, ga, cap, &ctl, g);
+            TMARK(1);
             ps.g = g;
             if (P.mode == MODE_DT_ONLY) {
-                run_stars<true>(n, ps, fv, star_mem, warp_mem, defer, tri_cap);
+                run_stars(true, n, ps, fv, star_mem, warp_mem, defer, tri_cap, 2);
             } else {
-                run_stars<false>(n, ps, fv, star_mem, warp_mem, defer, tri_cap);
+                run_stars(false, n, ps, fv, star_mem, warp_mem, defer, tri_cap, 2);
             }
             status |= ctl.status;
+            if (tid == 0) tlast = clock64();
         }
         if (!status && P.mode == MODE_DT_ONLY) {
             write_canonical(n, fv, ga.scr, ctl.warp_cnt, P.tri_out + 3 * (size_t)(2 * base), P.n_tri_out + f);
@@ -517,7 +568,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             second = n_kept > cfg.min_kept;
             if (P.has_dbg && P.dbg.tri1) {
                 // parity probe: also materialise Delaunay #1 (re-runs the stars in emit mode)
-                run_stars<true>(n, ps, fv, star_mem, warp_mem, defer, tri_cap);
+                run_stars(true, n, ps, fv, star_mem, warp_mem, defer, tri_cap, 14);
                 write_canonical(n, fv, ga.scr, ctl.warp_cnt, P.dbg.tri1 + 3 * (size_t)(2 * base), P.dbg.n_tri1 ? P.dbg.n_tri1 + f : nullptr);
                 if (tid == 0) ctl.T = 0;
                 __syncthreads();
@@ -528,7 +579,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 for (int c0 = 0; c0 < n; c0 += NT) {
                     int i = c0 + tid;
                     bool k = i < n && (fv.pflag[i] & 2);
-                    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+                    double a0 = 0, a1 = 0; float a2 = 0, a3 = 0, a4 = 0;
                     if (k) { a0 = fv.px[i]; a1 = fv.py[i]; a2 = fv.X[i]; a3 = fv.Y[i]; a4 = fv.Z[i]; }
                     unsigned bal = __ballot_sync(0xFFFFFFFFu, k);
                     if (lane == 0) ctl.warp_cnt[warp] = __popc(bal);
@@ -554,8 +605,10 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 __syncthreads();
             }
             // ---------------- Delaunay #2 (or #1 again) with triangle emission ----------------
-            run_stars<true>(n, ps, fv, star_mem, warp_mem, defer, tri_cap);
+            TMARK(6);
+            run_stars(true, n, ps, fv, star_mem, warp_mem, defer, tri_cap, 7);
             status |= ctl.status;
+            if (tid == 0) tlast = clock64();
         }
         const int T = ctl.T;
         if (!status && P.mode == MODE_FULL) {
@@ -587,6 +640,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             }
             if (lane == 0) { atomicAdd(&ctl.n_loose, c_loose); atomicAdd(&ctl.n_tight, c_tight); }
             __syncthreads();
+            TMARK(10);
             const int n_loose = ctl.n_loose;
             // height_level = 0.9 * median(height[loose])  (np.median: mean of the two middle values for even counts)
             double level = CUDART_NAN;
@@ -601,6 +655,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 level = cfg.height_level_factor * med;
             }
             if (tid == 0) ctl.height_level = level;
+            TMARK(11);
             // ---------------- valid triangles -> canonical vertex list, multiplicities ----------------
             for (int i = tid; i < n + 2; i += NT) mult[i] = 0;
             __syncthreads();
@@ -627,6 +682,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             __syncthreads();
             if (tid == 0) ctl.n_valid = n_valid;
             const int n_sel = 3 * n_valid;
+            TMARK(12);
 
             // ---------------- RANSAC over the vertex list (ransac.py:3-23) ----------------
             // One warp per hypothesis, NWARP hypotheses per round; after each round every thread replays the
@@ -718,6 +774,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 }
                 if (tid == 0) { ctl.best_hyp = best; ctl.best_ic = best_ic; ctl.hyps_used = used; ctl.n_degenerate = ndeg; }
             }
+            TMARK(13);
             // ---------------- probes that need the final flags ----------------
             if (P.has_dbg) {
                 if (P.dbg.data_id) {
@@ -787,6 +844,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 s.best_hyp = ctl.best_hyp; s.best_ic = ctl.best_ic; s.hyps_used = ctl.hyps_used; s.n_degenerate = ctl.n_degenerate;
                 s.n_deferred = ctl.n_deferred_total; s.n_exact = ctl.n_exact; s.height_level = ctl.height_level;
             }
+            if (P.phase_cycles) for (int k = 0; k < 16; ++k) P.phase_cycles[16 * (size_t)f + k] = ctl.tphase[k];
         }
     }
 }

@@ -17,10 +17,10 @@ struct HostStar {
 };
 
 // mirrors build_grid() of frame_kernel.cuh (sequential)
-static void host_grid(int n, const float *px, const float *py, int cap, Grid &g, std::vector<uint16_t> &cell_start,
+static void host_grid(int n, const double *px, const double *py, int cap, Grid &g, std::vector<uint16_t> &cell_start,
                       std::vector<uint16_t> &cell_n, std::vector<uint16_t> &cell_pts, std::vector<uint8_t> &dup) {
     float xmn = INFINITY, xmx = -INFINITY, ymn = INFINITY, ymx = -INFINITY;
-    for (int i = 0; i < n; ++i) { xmn = fminf(xmn, px[i]); xmx = fmaxf(xmx, px[i]); ymn = fminf(ymn, py[i]); ymx = fmaxf(ymx, py[i]); }
+    for (int i = 0; i < n; ++i) { xmn = fminf(xmn, (float)px[i]); xmx = fmaxf(xmx, (float)px[i]); ymn = fminf(ymn, (float)py[i]); ymx = fmaxf(ymx, (float)py[i]); }
     double w = (double)xmx - xmn, hgt = (double)ymx - ymn, h;
     if (w > 0 && hgt > 0) h = sqrt(2.0 * w * hgt / n); else h = fmax(w, hgt) * 2.0 / n;
     h = fmax(h, fmax(sqrt(w * hgt / cap), fmax(w, hgt) / cap));
@@ -48,7 +48,9 @@ static void host_grid(int n, const float *px, const float *py, int cap, Grid &g,
 }
 
 // Canonical Delaunay triangles via the product's thread-path stars. defer_cells<0 disables deferral.
-extern "C" int host_sim_delaunay(const float *px, const float *py, int n, int cap, int32_t *tri_out, int *n_defer_out, int *n_exact_out) {
+extern "C" int host_sim_delaunay(const float *fx, const float *fy, int n, int cap, int32_t *tri_out, int *n_defer_out, int *n_exact_out) {
+    std::vector<double> vx(fx, fx + n), vy(fy, fy + n);
+    const double *px = vx.data(), *py = vy.data();
     Grid g; std::vector<uint16_t> cs, cn, cp; std::vector<uint8_t> dup;
     host_grid(n, px, py, cap, g, cs, cn, cp, dup);
     PointSet ps; ps.px = px; ps.py = py; ps.cell_start = cs.data(); ps.cell_n = cn.data(); ps.cell_pts = cp.data(); ps.g = g;

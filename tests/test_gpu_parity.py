@@ -192,3 +192,53 @@ def test_host_api_end_to_end(engine, golden):
     torch.cuda.synchronize()
     assert np.array_equal(out["scale"], f["scale"].cpu().numpy())
     assert np.array_equal(out["raw_scale"], fused["raw_scale"].cpu().numpy(), equal_nan=True)
+
+
+def _degenerate_sets():
+    rng = np.random.default_rng(12345)
+    sets = {}
+    sets["grid8x6"] = np.stack(np.meshgrid(np.arange(8.), 190 + np.arange(6.)), -1).reshape(-1, 2)
+    sets["grid40x30"] = np.stack(np.meshgrid(np.arange(40.) * 3, 190 + np.arange(30.) * 2), -1).reshape(-1, 2)
+    sets["collinear_dup"] = np.array([[0, 200], [1, 200], [2, 200], [3, 200], [1, 200], [1.5, 201]])
+    sets["all_collinear"] = np.array([[0, 200], [1, 200], [2, 200], [3, 200], [10, 200]])
+    th = np.linspace(0, 2 * np.pi, 20, endpoint=False)
+    sets["circle_centre"] = np.vstack([np.stack([500 + 64 * np.cos(th), 250 + 64 * np.sin(th)], 1), [[500, 250]]])
+    sets["circle_only"] = np.stack([500 + 64 * np.cos(th), 250 + 64 * np.sin(th)], 1)
+    sets["int_pixels"] = np.round(np.stack([rng.uniform(0, 1241, 2000), rng.uniform(186, 376, 2000)], 1))
+    sets["half_pixels"] = np.round(np.stack([rng.uniform(0, 300, 1500), rng.uniform(186, 376, 1500)], 1) * 2) / 2
+    sets["skewed"] = np.stack([rng.normal(600, 30, 1500), 186 + rng.exponential(8, 1500)], 1)
+    sets["clusters"] = np.vstack([rng.normal([200, 250], 3, (300, 2)), rng.normal([900, 300], 40, (300, 2)), rng.uniform([0, 186], [1241, 376], (200, 2))])
+    sets["three"] = np.array([[10, 200], [20, 210], [15, 250]])
+    sets["four_square"] = np.array([[0, 190], [1, 190], [1, 191], [0, 191]])
+    sets["hub"] = np.vstack([[[600, 280]], np.stack([600 + 80 * np.cos(np.linspace(0, 2 * np.pi, 40, endpoint=False) + 0.01),
+                                                     280 + 80 * np.sin(np.linspace(0, 2 * np.pi, 40, endpoint=False) + 0.01)], 1)])
+    sets["random3000"] = np.stack([rng.uniform(0, 1241, 3000), rng.uniform(186, 376, 3000)], 1)
+    return {k: v.astype(np.float32) for k, v in sets.items()}
+
+
+def test_delaunay_degenerate_inputs_vs_exact_oracle(engine):
+    """Co-circular, collinear, duplicate and clustered inputs: the CUDA triangulation must equal the exact
+    oracle's (same symbolic tie-break), and be A valid Delaunay triangulation by the independent exact validator."""
+    torch = _torch()
+    from oracle import exact
+    sets = _degenerate_sets()
+    names = list(sets)
+    off = np.zeros(len(names) + 1, np.int32)
+    np.cumsum([sets[k].shape[0] for k in names], out=off[1:])
+    allp = np.concatenate([sets[k] for k in names], 0)
+    dev = engine.device
+    out = engine.delaunay_frames(torch.from_numpy(off).to(dev), torch.from_numpy(np.ascontiguousarray(allp[:, 0])).to(dev),
+                                 torch.from_numpy(np.ascontiguousarray(allp[:, 1])).to(dev), int(np.max(np.diff(off))))
+    torch.cuda.synchronize()
+    tri = out["tri"].cpu().numpy(); ntri = out["n_tri"].cpu().numpy(); st = out["status"].cpu().numpy()
+    for i, k in enumerate(names):
+        ref, dup = exact.delaunay_exact(sets[k])
+        got = tri[2 * off[i]: 2 * off[i] + ntri[i]]
+        if ref.shape[0] == 0:
+            assert ntri[i] == 0 and (st[i] & 4), (k, ntri[i], st[i])        # FEW_ROI: nothing to triangulate
+            continue
+        assert st[i] == 0, (k, st[i])
+        assert ntri[i] == ref.shape[0], (k, ntri[i], ref.shape[0])
+        assert np.array_equal(got, ref), "set %s differs from the exact oracle" % k
+        ok, msg, _ = exact.validate_delaunay(sets[k], got, dup)
+        assert ok, (k, msg)
