@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmvosr.so")
 SOURCES = ["api.cu"]
-HEADERS = ["frame_kernel.cuh", "star.cuh", "predicates.cuh", "philox.cuh", "triangulate.cuh",
+HEADERS = ["frame_kernel.cuh", "gstar.cuh", "predicates.cuh", "philox.cuh", "triangulate.cuh",
            os.path.join("..", "..", "include", "mvosr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -25,7 +25,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = os.environ.get("MVOSR_NVCC_EXTRA", "").split()          # e.g. -DMVOSR_STAR_COUNTERS -DMVOSR_DEBUG_PRINT (profiling / debugging builds)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

@@ -10,14 +10,16 @@
 //   RANSAC   get_pitch_ransac / run_ransac                    estimate_road_norm.py:8-18,66-70, thirdparty/Ransac/ransac.py:3-23
 //   scale    height = h_bar/|n|, scale = ref/height           rescale.py:156-167
 //
-// Shared-memory plan for capacity `cap` ROI features (bytes): px,py 16cap (float64 copies: no conversions in the hot loops) | X,Y,Z 12cap | pflag cap |
-// cell_start/cell_n/cell_pts 6cap(+) | u32 scratch 4cap (cell counters, later canonical offsets) |
-// tri list 12cap | tbase,tcnt 3cap | mult 2cap | region A = max(star storage, 16cap heights) | flags 2cap.
+// Shared-memory plan for capacity `cap` ROI features, 52 bytes per feature:
+//   X,Y,Z 12cap (float32, feature order) | region T 12cap: U,V (float32 pixel coordinates, feature order) until the last
+//   grid build of the frame, then the triangle list (uint16 x 3 x 2cap) | region H 16cap: the cell-sorted copy of the
+//   points (x,y float32, orig uint16), cell_start, the deferred-star queue during the Delaunay passes, then the triangle
+//   heights (float64 x 2cap) | scr 4cap (uint32: cell counters, later scans) | tbase 2cap | tcnt cap | pflag cap |
+//   mult 2cap | tflags 2cap.
 #pragma once
 #include <stdint.h>
 #include <math_constants.h>
 #include "../../include/mvosr.h"
-#include "star.cuh"
 #include "gstar.cuh"
 #include "philox.cuh"
 #include "triangulate.cuh"
@@ -55,51 +57,48 @@ struct FrameParams {
 };
 
 struct SmemPlan {
-    int cap, off_px, off_py, off_X, off_Y, off_Z, off_pflag, off_cell_start, off_cell_n, off_cell_pts, off_scr,
-        off_tri, off_tbase, off_tcnt, off_mult, off_A, off_flags, off_defer, total;
+    int cap, off_X, off_Y, off_Z, off_T, off_H, off_scr, off_tbase, off_tcnt, off_pflag, off_mult, off_tflags, total;
+    // inside region T / H
+    int t_U, t_V, h_sx, h_sy, h_sorig, h_cell_start, h_defer;
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline SmemPlan make_plan(int cap) {
+__host__ __device__ inline SmemPlan make_plan(int cap) {   // cap: multiple of 64
     SmemPlan p; p.cap = cap; int o = 0;
-    p.off_px = o; o = align16(o + 8 * cap);
-    p.off_py = o; o = align16(o + 8 * cap);
-    p.off_X = o; o = align16(o + 4 * cap);
-    p.off_Y = o; o = align16(o + 4 * cap);
-    p.off_Z = o; o = align16(o + 4 * cap);
-    p.off_pflag = o; o = align16(o + cap);
-    p.off_cell_start = o; o = align16(o + 2 * (cap + 2));
-    p.off_cell_n = o; o = align16(o + 2 * (cap + 2));
-    p.off_cell_pts = o; o = align16(o + 2 * cap);
-    p.off_scr = o; o = align16(o + 4 * (cap + 2));
-    p.off_tri = o; o = align16(o + 12 * cap);
-    p.off_tbase = o; o = align16(o + 2 * cap);
-    p.off_tcnt = o; o = align16(o + cap);
-    p.off_mult = o; o = align16(o + 2 * cap + 4);
-    p.off_defer = o; o = align16(o + 2 * cap);
-    int star_bytes = NWARP * WARPSTAR_BYTES;
-    int a_bytes = 16 * cap > star_bytes ? 16 * cap : star_bytes;
-    p.off_A = o; o = align16(o + a_bytes);
-    p.off_flags = o; o = align16(o + 2 * cap);
-    p.total = o;
+    p.off_X = o; o += 4 * cap;
+    p.off_Y = o; o += 4 * cap;
+    p.off_Z = o; o += 4 * cap;
+    p.off_T = o; o += 12 * cap;
+    p.off_H = o; o += 16 * cap;
+    p.off_scr = o; o += 4 * cap + 16;
+    p.off_tbase = o; o += 2 * cap;
+    p.off_tcnt = o; o += cap;
+    p.off_pflag = o; o += cap;
+    p.off_mult = o; o += 2 * cap + 16;
+    p.off_tflags = o; o += 2 * cap;
+    p.total = align16(o);
+    p.t_U = p.off_T; p.t_V = p.off_T + 4 * cap;
+    p.h_sx = p.off_H; p.h_sy = p.off_H + 4 * cap; p.h_sorig = p.off_H + 8 * cap;
+    p.h_cell_start = p.off_H + 10 * cap;           // at most cap - 1 cells: cap uint16 entries
+    p.h_defer = p.off_H + 12 * cap;                // 2cap bytes: ends at 14cap <= 16cap
     return p;
 }
 
 struct Ctl {                         // static shared control block
-    int next_pos;
-    int n_roi, n_feat, n2, status, bad, n_dup, n_dup1, n_kept, T, n_defer, n_exact, n_deferred_total;
-    int n_loose, n_tight, n_valid, best_hyp, best_ic, hyps_used, n_degenerate, err;
+    StarCtl sc;
+    int n_roi, n_feat, status, bad, n_dup, n_dup1, n_kept, T, n_exact, n_deferred_total;
+    int n_loose, n_tight, n_valid, best_hyp, best_ic, hyps_used, n_degenerate;
     int warp_cnt[NWARP], warp_cnt2[NWARP];
-    float bb[4];
     float red[4][NWARP];
     double height_level;
     unsigned hist[256];
-    unsigned long long sel_prefix; int sel_k; unsigned long long sel_val[2];
+    unsigned long long sel_prefix; int sel_k;
     int frame;
     long long tphase[16];
     int round_ic[NWARP];
     double round_model[NWARP][5];
+    SortedSet ps;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -109,6 +108,14 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += t; }
     return v;
+}
+
+// per-warp counts already stored in cnt[0..NWARP): this warp's exclusive offset and the block total
+__device__ __forceinline__ void warp_offsets(const int *cnt, int warp, int lane, int &woff, int &tot) {
+    int c = lane < NWARP ? cnt[lane] : 0;                 // NWARP == 32
+    int inc = warp_incl_scan(c, lane);
+    tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    woff = __shfl_sync(0xFFFFFFFFu, inc - c, warp);
 }
 
 // exclusive scan of a[0..n) (uint32) in shared memory, in place; a[n] receives the total. Block-wide.
@@ -121,99 +128,24 @@ __device__ __forceinline__ void block_excl_scan(uint32_t *a, int n, int *warp_tm
     int inc = warp_incl_scan(sum, lane);
     if (lane == 31) warp_tmp[warp] = inc;
     __syncthreads();
-    int woff = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) { int c = warp_tmp[w]; if (w < warp) woff += c; tot += c; }
+    int woff, tot;
+    warp_offsets(warp_tmp, warp, lane, woff, tot);
     int run = woff + inc - sum;
     for (int i = b; i < e; ++i) { int t = (int)a[i]; a[i] = (uint32_t)run; run += t; }
     if (tid == 0) a[n] = (uint32_t)tot;
     __syncthreads();
 }
 
-__device__ __forceinline__ bool edge_consistent(const double *py, const float *Z, int a, int b) {
-    // check_triangle (graph.py:124-129): (v_a - v_b) * (d_a - d_b) < 0, float64 on float32-exact values
-    return (py[a] - py[b]) * ((double)Z[a] - (double)Z[b]) < 0.0;
-}
-
-// graph vote of one star triangle (p,qa,qb) for vertex p under the canonical (ascending) vertex order
-__device__ __forceinline__ int graph_vote(const double *py, const float *Z, int p, int qa, int qb, uint32_t pass_mask) {
-    int i0 = p, i1 = qa, i2 = qb;
-    if (i0 > i1) { int t = i0; i0 = i1; i1 = t; }
-    if (i1 > i2) { int t = i1; i1 = i2; i2 = t; }
-    if (i0 > i1) { int t = i0; i0 = i1; i1 = t; }
-    int a = edge_consistent(py, Z, i0, i1), b = edge_consistent(py, Z, i1, i2), c = edge_consistent(py, Z, i0, i2);
-    int idx = a * 4 + b * 2 + c;
-    int k = (p == i0) ? 0 : (p == i1 ? 1 : 2);
-    return (pass_mask >> (idx * 3 + k)) & 1u;
-}
-
 // ---------------------------------------------------------------------------------------------
-// star consumers
+// grid build: cell-sorted copy (sx, sy, sorig, cell_start) of the n points in U,V
 // ---------------------------------------------------------------------------------------------
-struct FrameView {
-    double *px, *py;                 // 2-D pixel coordinates (float32-exact values)
-    float *X, *Y, *Z;
-    uint8_t *pflag;                  // bit0 duplicate, bit1 keep
-    uint16_t *tri;                   // [T][3]
-    uint16_t *tbase; uint8_t *tcnt;
-    Ctl *ctl;
-    uint32_t pass_mask;
-};
+struct GridArrays { float *sx, *sy; uint16_t *sorig, *cell_start; uint32_t *scr; };
 
-template <class Star>
-__device__ __forceinline__ void consume_vote(const Star &st, int d, int p, FrameView &fv) {
-    int total = 0, pass = 0;
-    for (int i = 0; i < d; ++i) {
-        int qa = st.get(i), qb = st.get(i + 1 < d ? i + 1 : 0);
-        if (qa == INF16 || qb == INF16) continue;
-        ++total;
-        pass += graph_vote(fv.py, fv.Z, p, qa, qb, fv.pass_mask);
-    }
-    // keep = (#incident triangles with p>0.6)/(#incident) > 0.5 (graph.py:33-35,131-132); 0/0 -> False
-    if (2 * pass > total) fv.pflag[p] |= 2;
-}
-
-template <class Star>
-__device__ __forceinline__ void consume_emit(const Star &st, int d, int p, FrameView &fv, int tri_cap) {
-    int k = 0;
-    for (int i = 0; i < d; ++i) {
-        int qa = st.get(i), qb = st.get(i + 1 < d ? i + 1 : 0);
-        if (qa == INF16 || qb == INF16) continue;
-        if (qa > p && qb > p) ++k;
-    }
-    fv.tcnt[p] = (uint8_t)k;
-    if (!k) { fv.tbase[p] = 0; return; }
-    int base = atomicAdd(&fv.ctl->T, k);
-    if (base + k > tri_cap) { atomicOr(&fv.ctl->status, MVOSR_ST_OVERFLOW); fv.tcnt[p] = 0; return; }
-    fv.tbase[p] = (uint16_t)base;
-    int w = 0;
-    for (int i = 0; i < d; ++i) {
-        int qa = st.get(i), qb = st.get(i + 1 < d ? i + 1 : 0);
-        if (qa == INF16 || qb == INF16) continue;
-        if (!(qa > p && qb > p)) continue;
-        int a = min(qa, qb), b = max(qa, qb);
-        // insertion sort by (a,b) inside this point's block
-        int j = w++;
-        uint16_t *t = fv.tri + 3 * base;
-        while (j > 0 && (t[3 * (j - 1) + 1] > a || (t[3 * (j - 1) + 1] == a && t[3 * (j - 1) + 2] > b))) {
-            t[3 * j + 1] = t[3 * (j - 1) + 1]; t[3 * j + 2] = t[3 * (j - 1) + 2]; --j;
-        }
-        t[3 * j + 0] = (uint16_t)p; t[3 * j + 1] = (uint16_t)a; t[3 * j + 2] = (uint16_t)b;
-    }
-    for (int j = 0; j < k; ++j) fv.tri[3 * (base + j)] = (uint16_t)p;
-}
-
-// ---------------------------------------------------------------------------------------------
-// grid build over the n points currently staged in px/py
-// ---------------------------------------------------------------------------------------------
-struct GridArrays { uint16_t *cell_start, *cell_n, *cell_pts; uint32_t *scr; };
-
-__device__ __forceinline__ bool build_grid(int n, const double *px, const double *py, uint8_t *pflag, GridArrays ga,
-                                           int cap, Ctl *ctl, Grid &g) {
-    int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void build_grid(int n, const float *U, const float *V, uint8_t *pflag, GridArrays ga, int cap, Ctl *ctl) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float xmn = CUDART_INF_F, xmx = -CUDART_INF_F, ymn = CUDART_INF_F, ymx = -CUDART_INF_F;
     for (int i = tid; i < n; i += NT) {
-        float a = (float)px[i], b = (float)py[i];      // exact: the values are float32
+        float a = U[i], b = V[i];
         xmn = fminf(xmn, a); xmx = fmaxf(xmx, a); ymn = fminf(ymn, b); ymx = fmaxf(ymx, b);
     }
 #pragma unroll
@@ -223,30 +155,38 @@ __device__ __forceinline__ bool build_grid(int n, const double *px, const double
     }
     if (lane == 0) { ctl->red[0][warp] = xmn; ctl->red[1][warp] = xmx; ctl->red[2][warp] = ymn; ctl->red[3][warp] = ymx; }
     __syncthreads();
-    xmn = ctl->red[0][0]; xmx = ctl->red[1][0]; ymn = ctl->red[2][0]; ymx = ctl->red[3][0];
+    if (warp == 0) {
+        xmn = ctl->red[0][lane]; xmx = ctl->red[1][lane]; ymn = ctl->red[2][lane]; ymx = ctl->red[3][lane];     // NWARP == 32
 #pragma unroll
-    for (int w = 1; w < NWARP; ++w) {
-        xmn = fminf(xmn, ctl->red[0][w]); xmx = fmaxf(xmx, ctl->red[1][w]);
-        ymn = fminf(ymn, ctl->red[2][w]); ymx = fmaxf(ymx, ctl->red[3][w]);
+        for (int o = 16; o; o >>= 1) {
+            xmn = fminf(xmn, __shfl_xor_sync(0xFFFFFFFFu, xmn, o)); xmx = fmaxf(xmx, __shfl_xor_sync(0xFFFFFFFFu, xmx, o));
+            ymn = fminf(ymn, __shfl_xor_sync(0xFFFFFFFFu, ymn, o)); ymx = fmaxf(ymx, __shfl_xor_sync(0xFFFFFFFFu, ymx, o));
+        }
+        if (lane == 0) {
+            const int max_cells = cap - 1;
+            float w = xmx - xmn, hgt = ymx - ymn, h;
+            if (w > 0.f && hgt > 0.f) h = sqrtf(GRID_DENSITY * w * hgt / (float)n);
+            else h = fmaxf(w, hgt) * 2.f / (float)n;
+            if (!(h > 0.f)) h = 1.f;
+            int gx, gy; float inv_h;
+            for (;;) {
+                inv_h = 1.f / h;
+                gx = (int)((xmx - xmn) * inv_h) + 1; gy = (int)((ymx - ymn) * inv_h) + 1;     // same expression as cell_of
+                if ((long long)gx * gy <= max_cells) break;
+                h *= 1.25f;
+            }
+            SortedSet &ps = ctl->ps;
+            ps.x = ga.sx; ps.y = ga.sy; ps.orig = ga.sorig; ps.cell_start = ga.cell_start; ps.n = n;
+            ps.xmin = xmn; ps.ymin = ymn; ps.h = h; ps.inv_h = inv_h; ps.gx = gx; ps.gy = gy;
+        }
     }
-    double w = (double)xmx - (double)xmn, hgt = (double)ymx - (double)ymn;
-    double h;
-    if (w > 0 && hgt > 0) h = sqrt(2.0 * w * hgt / (double)n);
-    else h = fmax(w, hgt) * 2.0 / (double)n;
-    h = fmax(h, fmax(sqrt(w * hgt / (double)cap), fmax(w, hgt) / (double)cap));
-    if (!(h > 0)) h = 1.0;
-    int gx, gy;
-    for (;;) {
-        double gxd = floor(w / h) + 1.0, gyd = floor(hgt / h) + 1.0;
-        if (gxd * gyd <= (double)cap) { gx = (int)gxd; gy = (int)gyd; break; }
-        h *= 1.25;
-    }
-    g.xmin = (double)xmn; g.ymin = (double)ymn; g.h = h; g.inv_h = 1.0 / h; g.gx = gx; g.gy = gy;
-    int ncell = gx * gy;
+    __syncthreads();
+    const float xmin = ctl->ps.xmin, ymin = ctl->ps.ymin, inv_h = ctl->ps.inv_h;
+    const int gx = ctl->ps.gx, gy = ctl->ps.gy, ncell = gx * gy;
     for (int i = tid; i <= ncell; i += NT) ga.scr[i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += NT) {
-        int c = cell_coord(px[i], g.xmin, g.inv_h, gx) + gx * cell_coord(py[i], g.ymin, g.inv_h, gy);
+        int c = cell_of(U[i], xmin, inv_h, gx) + gx * cell_of(V[i], ymin, inv_h, gy);
         atomicAdd(&ga.scr[c], 1u);
     }
     __syncthreads();
@@ -254,125 +194,35 @@ __device__ __forceinline__ bool build_grid(int n, const double *px, const double
     for (int i = tid; i <= ncell; i += NT) ga.cell_start[i] = (uint16_t)ga.scr[i];
     __syncthreads();
     for (int i = tid; i < n; i += NT) {
-        int c = cell_coord(px[i], g.xmin, g.inv_h, gx) + gx * cell_coord(py[i], g.ymin, g.inv_h, gy);
+        int c = cell_of(U[i], xmin, inv_h, gx) + gx * cell_of(V[i], ymin, inv_h, gy);
         unsigned pos = atomicAdd(&ga.scr[c], 1u);
-        ga.cell_pts[pos] = (uint16_t)i;
+        ga.sorig[pos] = (uint16_t)i;
     }
     __syncthreads();
-    // per cell: sort ids ascending (determinism), drop exact duplicates (lowest index kept; Qhull drops them too)
+    // per cell: sort by feature index (determinism; lowest index first), turn exact duplicates into holes at the
+    // tail (the lowest index is kept; Qhull drops duplicates too, into .coplanar)
+    int ndup = 0;
     for (int c = tid; c < ncell; c += NT) {
-        int b = ga.cell_start[c], e = ga.cell_start[c + 1];
+        const int b = ga.cell_start[c], e = ga.cell_start[c + 1];
         for (int i = b + 1; i < e; ++i) {
-            uint16_t v = ga.cell_pts[i]; int j = i;
-            while (j > b && ga.cell_pts[j - 1] > v) { ga.cell_pts[j] = ga.cell_pts[j - 1]; --j; }
-            ga.cell_pts[j] = v;
+            uint16_t v = ga.sorig[i]; int j = i;
+            while (j > b && ga.sorig[j - 1] > v) { ga.sorig[j] = ga.sorig[j - 1]; --j; }
+            ga.sorig[j] = v;
         }
         int m = b;
         for (int i = b; i < e; ++i) {
-            int s = ga.cell_pts[i]; bool dup = false;
-            for (int j = b; j < m; ++j) { int q = ga.cell_pts[j]; if (px[q] == px[s] && py[q] == py[s]) { dup = true; break; } }
-            if (dup) { pflag[s] |= 1; atomicAdd(&ctl->n_dup, 1); }
-            else ga.cell_pts[m++] = (uint16_t)s;
+            const int s = ga.sorig[i]; bool dup = false;
+            for (int j = b; j < m; ++j) { int q = ga.sorig[j]; if (U[q] == U[s] && V[q] == V[s]) { dup = true; break; } }
+            if (dup) { pflag[s] |= 1; ++ndup; }
+            else ga.sorig[m++] = (uint16_t)s;
         }
-        ga.cell_n[c] = (uint16_t)(m - b);
-        for (int i = m; i < e; ++i) ga.cell_pts[i] = INF16;
+        for (int i = m; i < e; ++i) ga.sorig[i] = INF16;
     }
+    if (ndup) atomicAdd(&ctl->n_dup, ndup);
     __syncthreads();
-    return true;
-}
-
-// lane-parallel consumers of a register-resident group star (lane i owns star triangle i)
-__device__ __forceinline__ void g_consume_vote(const GCtx &c, FrameView &fv) {
-    bool fin = c.gl < c.d && c.sid != INF16 && c.nid != INF16;
-    int v = fin ? graph_vote(fv.py, fv.Z, c.p, c.sid, c.nid, fv.pass_mask) : 0;
-    unsigned mf = gballot(c, fin), mv = gballot(c, fin && v);
-    // keep = (#incident triangles with p>0.6)/(#incident) > 0.5 (graph.py:33-35,131-132); 0/0 -> False
-    if (c.gl == 0 && 2 * __popc(mv) > __popc(mf)) fv.pflag[c.p] |= 2;
-}
-
-__device__ __forceinline__ void g_consume_emit(const GCtx &c, FrameView &fv, int tri_cap) {
-    bool fin = c.gl < c.d && c.sid != INF16 && c.nid != INF16;
-    bool em = fin && c.sid > c.p && c.nid > c.p;
-    int a = min(c.sid, c.nid), b = max(c.sid, c.nid);
-    unsigned key = em ? (((unsigned)a << 16) | (unsigned)b) : 0xFFFFFFFFu;
-    unsigned me = gballot(c, em);
-    int k = __popc(me);
-    if (!k) return;
-    int base = 0;
-    if (c.gl == 0) base = atomicAdd(&fv.ctl->T, k);
-    base = gshfl(c, base, 0);
-    if (base + k > tri_cap) { if (c.gl == 0) atomicOr(&fv.ctl->status, MVOSR_ST_OVERFLOW); return; }
-    int rank = 0;
-    unsigned m2 = me;
-    while (m2) { int j = __ffs(m2) - 1; m2 &= m2 - 1; unsigned kj = gshfl(c, key, j); rank += (kj < key); }
-    if (em) { uint16_t *t = fv.tri + 3 * (base + rank); t[0] = (uint16_t)c.p; t[1] = (uint16_t)a; t[2] = (uint16_t)b; }
-    if (c.gl == 0) { fv.tbase[c.p] = (uint16_t)base; fv.tcnt[c.p] = (uint8_t)k; }
-}
-
-// ---------------------------------------------------------------------------------------------
-// all stars of the staged point set; EMIT selects the consumer
-// ---------------------------------------------------------------------------------------------
-// (not a template and not inlined: one copy of the star builder in the kernel, whatever the number of call sites)
-__device__ __noinline__ void run_stars(const bool EMIT, int n, const PointSet &ps, FrameView &fv, uint16_t *star_mem, unsigned char *warp_mem,
-                                       uint16_t *defer, int tri_cap, int tslot) {
-    int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    Ctl *ctl = fv.ctl;
-    int n_exact = 0;
-    long long tc0 = clock64();
-    if (EMIT) for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
-    if (tid == 0) ctl->next_pos = 0;
-    __syncthreads();
-    // one 16-lane group per point, points fetched dynamically in cell order (spatially coherent)
-    {
-        GCtx c;
-        c.gl = tid & (GL - 1);
-        c.gmask = (lane & GL) ? 0xFFFF0000u : 0x0000FFFFu;
-        c.n_exact = 0;
-        for (;;) {
-            int pos = 0;
-            if (c.gl == 0) pos = atomicAdd(&ctl->next_pos, 1);
-            pos = gshfl(c, pos, 0);
-            if (pos >= n) break;
-            int p = ps.cell_pts[pos];
-            if (p == INF16) continue;                     // duplicate: in no triangle
-            int r = g_build(c, p, ps);
-            if (r == STAR_OK) {
-                if (EMIT) g_consume_emit(c, fv, tri_cap); else g_consume_vote(c, fv);
-            } else if (r != STAR_NONE) {
-                // degree > 16 (or an inconsistency): the sequential-rule warp builder takes the point
-                if (c.gl == 0) { int slot = atomicAdd(&ctl->n_defer, 1); defer[slot] = (uint16_t)p; }
-            }
-        }
-        n_exact += c.n_exact;
-    }
-    __syncthreads();
-    long long tc1 = clock64();
-    int nd = ctl->n_defer;
-    WarpStar ws;
-    unsigned char *wm = warp_mem + warp * WARPSTAR_BYTES;
-    ws.qx = (double *)wm; ws.qy = ws.qx + MAXDEG_W; ws.ql = ws.qy + MAXDEG_W; ws.vx = ws.ql + MAXDEG_W; ws.vy = ws.vx + MAXDEG_W;
-    ws.r2 = ws.vy + MAXDEG_W; ws.id = (uint16_t *)(ws.r2 + MAXDEG_W);
-    for (int k = warp; k < nd; k += NWARP) {
-        int p = defer[k];
-        int d;
-        int r = build_star_warp(ws, d, p, ps, lane, n_exact);
-        __syncwarp();
-        if (lane == 0) {
-            if (r == STAR_OK) {
-                if (EMIT) consume_emit(ws, d, p, fv, tri_cap); else consume_vote(ws, d, p, fv);
-            } else {
-                if (r != STAR_NONE) atomicOr(&ctl->status, MVOSR_ST_OVERFLOW);
-                if (EMIT) { fv.tcnt[p] = 0; fv.tbase[p] = 0; }
-            }
-        }
-        __syncwarp();
-    }
-    if (n_exact) atomicAdd(&ctl->n_exact, n_exact);
-    __syncthreads();
-    if (tid == 0) {
-        ctl->n_deferred_total += nd; ctl->n_defer = 0;
-        long long tc2 = clock64();
-        ctl->tphase[tslot] += tc1 - tc0; ctl->tphase[tslot + 1] += tc2 - tc1;
+    for (int i = tid; i < n; i += NT) {
+        const int o = ga.sorig[i];
+        ga.sx[i] = o != INF16 ? U[o] : 0.f; ga.sy[i] = o != INF16 ? V[o] : 0.f;
     }
     __syncthreads();
 }
@@ -438,23 +288,20 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
     const SmemPlan pl = make_plan(P.cap);
     const int cap = P.cap;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    FrameView fv;
-    fv.px = (double *)(smem + pl.off_px); fv.py = (double *)(smem + pl.off_py);
-    fv.X = (float *)(smem + pl.off_X); fv.Y = (float *)(smem + pl.off_Y); fv.Z = (float *)(smem + pl.off_Z);
-    fv.pflag = smem + pl.off_pflag;
-    fv.tri = (uint16_t *)(smem + pl.off_tri);
-    fv.tbase = (uint16_t *)(smem + pl.off_tbase); fv.tcnt = smem + pl.off_tcnt;
-    fv.ctl = &ctl; fv.pass_mask = P.cfg.graph_pass_mask;
+    float *X = (float *)(smem + pl.off_X), *Y = (float *)(smem + pl.off_Y), *Z = (float *)(smem + pl.off_Z);
+    float *U = (float *)(smem + pl.t_U), *V = (float *)(smem + pl.t_V);
+    uint8_t *pflag = smem + pl.off_pflag;
     GridArrays ga;
-    ga.cell_start = (uint16_t *)(smem + pl.off_cell_start); ga.cell_n = (uint16_t *)(smem + pl.off_cell_n);
-    ga.cell_pts = (uint16_t *)(smem + pl.off_cell_pts); ga.scr = (uint32_t *)(smem + pl.off_scr);
+    ga.sx = (float *)(smem + pl.h_sx); ga.sy = (float *)(smem + pl.h_sy); ga.sorig = (uint16_t *)(smem + pl.h_sorig);
+    ga.cell_start = (uint16_t *)(smem + pl.h_cell_start); ga.scr = (uint32_t *)(smem + pl.off_scr);
+    uint16_t *defer = (uint16_t *)(smem + pl.h_defer);
     uint16_t *mult = (uint16_t *)(smem + pl.off_mult);
-    uint16_t *defer = (uint16_t *)(smem + pl.off_defer);
-    uint16_t *star_mem = (uint16_t *)(smem + pl.off_A);
-    unsigned char *warp_mem = smem + pl.off_A;
-    double *theight = (double *)(smem + pl.off_A);          // aliases the star storage (dead by then)
-    uint8_t *tflags = smem + pl.off_flags;
-    const int tri_cap = 2 * cap;
+    double *theight = (double *)(smem + pl.off_H);           // aliases the sorted copy (dead by then)
+    uint8_t *tflags = smem + pl.off_tflags;
+    FrameView fv;
+    fv.Z = Z; fv.pflag = pflag; fv.tri = (uint16_t *)(smem + pl.off_T);
+    fv.tbase = (uint16_t *)(smem + pl.off_tbase); fv.tcnt = smem + pl.off_tcnt;
+    fv.T = &ctl.T; fv.status = &ctl.status; fv.pass_mask = P.cfg.graph_pass_mask; fv.tri_cap = 2 * cap;
     const mvosr_config &cfg = P.cfg;
 
     long long tlast = 0;
@@ -466,11 +313,12 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         const int f = ctl.frame;
         if (f >= P.n_frames) break;
         if (tid == 0) {
-            ctl.n_roi = ctl.n_feat = ctl.n2 = ctl.status = ctl.bad = ctl.n_dup = ctl.n_kept = ctl.T = 0; ctl.n_dup1 = -1;
-            ctl.n_defer = ctl.n_exact = ctl.n_deferred_total = 0;
+            ctl.n_roi = ctl.n_feat = ctl.status = ctl.bad = ctl.n_dup = ctl.n_kept = ctl.T = 0; ctl.n_dup1 = -1;
+            ctl.n_exact = ctl.n_deferred_total = 0;
             ctl.n_loose = ctl.n_tight = ctl.n_valid = 0; ctl.best_hyp = -1; ctl.best_ic = 0; ctl.hyps_used = 0;
-            ctl.n_degenerate = 0; ctl.err = 0; ctl.height_level = CUDART_NAN;
+            ctl.n_degenerate = 0; ctl.height_level = CUDART_NAN;
             for (int k = 0; k < 16; ++k) ctl.tphase[k] = 0;
+            for (int k = 0; k < 8; ++k) ctl.sc.cnt[k] = 0;
             tlast = clock64();
         }
         __syncthreads();
@@ -491,11 +339,11 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             float fu = 0, fv_ = 0, fx3 = 0, fy3 = 0, fz3 = 0;
             if (i < n_in) {
                 if (FROM_CORR) {
-                    double X, Y, Z, uu, vv;
+                    double X3, Y3, Z3, uu, vv;
                     feat = triangulate_point(P.cur_u[base + i], P.cur_v[base + i], P.ref_u[base + i], P.ref_v[base + i], pose,
-                                             cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.triangulation_max_depth, X, Y, Z, uu, vv);
+                                             cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.triangulation_max_depth, X3, Y3, Z3, uu, vv);
                     if (P.e_mask) feat = feat && P.e_mask[base + i] != 0;
-                    fx3 = (float)X; fy3 = (float)Y; fz3 = (float)Z; fu = (float)uu; fv_ = (float)vv;
+                    fx3 = (float)X3; fy3 = (float)Y3; fz3 = (float)Z3; fu = (float)uu; fv_ = (float)vv;
                 } else {
                     feat = true;
                     fv_ = P.v[base + i];
@@ -509,17 +357,15 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             unsigned bal = __ballot_sync(0xFFFFFFFFu, ok), balf = __ballot_sync(0xFFFFFFFFu, feat);
             if (lane == 0) { ctl.warp_cnt[warp] = __popc(bal); ctl.warp_cnt2[warp] = __popc(balf); }
             __syncthreads();
-            int woff = 0, tot = 0, totf = 0;
-#pragma unroll
-            for (int w = 0; w < NWARP; ++w) { int c = ctl.warp_cnt[w]; if (w < warp) woff += c; tot += c; totf += ctl.warp_cnt2[w]; }
+            int woff, tot, woff2, totf;
+            warp_offsets(ctl.warp_cnt, warp, lane, woff, tot);
+            warp_offsets(ctl.warp_cnt2, warp, lane, woff2, totf);
             if (ok) {
                 int pos = total + woff + __popc(bal & ((1u << lane) - 1u));
                 if (!(fabsf(fu) < 4096.f) || !(fabsf(fv_) < 4096.f)) ctl.bad = 1;
                 if (fabsf(fu) < 7.62939453125e-06f) fu = 0.f;       // 2^-17: keeps every difference exact in float64
                 if (fabsf(fv_) < 7.62939453125e-06f) fv_ = 0.f;
-                if (pos < cap) {
-                    fv.px[pos] = (double)fu; fv.py[pos] = (double)fv_; fv.X[pos] = fx3; fv.Y[pos] = fy3; fv.Z[pos] = fz3; fv.pflag[pos] = 0;
-                }
+                if (pos < cap) { U[pos] = fu; V[pos] = fv_; X[pos] = fx3; Y[pos] = fy3; Z[pos] = fz3; pflag[pos] = 0; }
             }
             total += tot; total_feat += totf;
             __syncthreads();
@@ -533,23 +379,25 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         if (ctl.bad) status |= MVOSR_ST_BAD_INPUT;
         if (n < 3) status |= MVOSR_ST_FEW_ROI;
 
-        Grid g;
-        PointSet ps;
-        ps.px = fv.px; ps.py = fv.py; ps.cell_start = ga.cell_start; ps.cell_n = ga.cell_n; ps.cell_pts = ga.cell_pts;
         bool second = false;
-        int n1 = n;
+        const int n1 = n;
+        int n_exact = 0;
         if (!status) {
             // ---------------- Delaunay #1 -> graph vote (or triangles in DT-only mode) ----------------
-            build_grid(n, fv.px, fv.py, fv.pflag, ga, cap, &ctl, g);
+            build_grid(n, U, V, pflag, ga, cap, &ctl);
             TMARK(1);
-            ps.g = g;
             if (P.mode == MODE_DT_ONLY) {
-                run_stars(true, n, ps, fv, star_mem, warp_mem, defer, tri_cap, 2);
+                for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
+                __syncthreads();
+                int nd = run_stars<true>(ctl.ps, fv, &ctl.sc, defer, n_exact);
+                if (tid == 0) ctl.n_deferred_total += nd;
             } else {
-                run_stars(false, n, ps, fv, star_mem, warp_mem, defer, tri_cap, 2);
+                int nd = run_stars<false>(ctl.ps, fv, &ctl.sc, defer, n_exact);
+                if (tid == 0) ctl.n_deferred_total += nd;
             }
+            __syncthreads();
             status |= ctl.status;
-            if (tid == 0) tlast = clock64();
+            TMARK(2);
         }
         if (!status && P.mode == MODE_DT_ONLY) {
             write_canonical(n, fv, ga.scr, ctl.warp_cnt, P.tri_out + 3 * (size_t)(2 * base), P.n_tri_out + f);
@@ -558,19 +406,23 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         if (!status && P.mode == MODE_FULL) {
             // ---------------- keep mask, survivor rule (rescale.py:131-137) ----------------
             int cnt = 0;
-            for (int i = tid; i < n; i += NT) cnt += (fv.pflag[i] >> 1) & 1;
+            for (int i = tid; i < n; i += NT) cnt += (pflag[i] >> 1) & 1;
 #pragma unroll
             for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-            if (lane == 0) atomicAdd(&ctl.n_kept, cnt);
+            if (lane == 0 && cnt) atomicAdd(&ctl.n_kept, cnt);
             __syncthreads();
             const int n_kept = ctl.n_kept;
-            if (P.has_dbg && P.dbg.keep) for (int i = tid; i < n; i += NT) P.dbg.keep[base + i] = (fv.pflag[i] >> 1) & 1;
+            if (P.has_dbg && P.dbg.keep) for (int i = tid; i < n; i += NT) P.dbg.keep[base + i] = (pflag[i] >> 1) & 1;
             second = n_kept > cfg.min_kept;
             if (P.has_dbg && P.dbg.tri1) {
-                // parity probe: also materialise Delaunay #1 (re-runs the stars in emit mode)
-                run_stars(true, n, ps, fv, star_mem, warp_mem, defer, tri_cap, 14);
+                // parity probe: also materialise Delaunay #1 (re-runs the stars in emit mode; the triangle list
+                // overwrites U,V, which are restored from the sorted copy afterwards)
+                for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
+                __syncthreads();
+                run_stars<true>(ctl.ps, fv, &ctl.sc, defer, n_exact);
                 write_canonical(n, fv, ga.scr, ctl.warp_cnt, P.dbg.tri1 + 3 * (size_t)(2 * base), P.dbg.n_tri1 ? P.dbg.n_tri1 + f : nullptr);
                 if (tid == 0) ctl.T = 0;
+                for (int i = tid; i < n; i += NT) { int o = ga.sorig[i]; if (o != INF16) { U[o] = ga.sx[i]; V[o] = ga.sy[i]; } }
                 __syncthreads();
             }
             if (second) {
@@ -578,37 +430,39 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 int run = 0;
                 for (int c0 = 0; c0 < n; c0 += NT) {
                     int i = c0 + tid;
-                    bool k = i < n && (fv.pflag[i] & 2);
-                    double a0 = 0, a1 = 0; float a2 = 0, a3 = 0, a4 = 0;
-                    if (k) { a0 = fv.px[i]; a1 = fv.py[i]; a2 = fv.X[i]; a3 = fv.Y[i]; a4 = fv.Z[i]; }
+                    bool k = i < n && (pflag[i] & 2);
+                    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+                    if (k) { a0 = U[i]; a1 = V[i]; a2 = X[i]; a3 = Y[i]; a4 = Z[i]; }
                     unsigned bal = __ballot_sync(0xFFFFFFFFu, k);
                     if (lane == 0) ctl.warp_cnt[warp] = __popc(bal);
                     __syncthreads();
-                    int woff = 0, tot = 0;
-#pragma unroll
-                    for (int w = 0; w < NWARP; ++w) { int c = ctl.warp_cnt[w]; if (w < warp) woff += c; tot += c; }
+                    int woff, tot;
+                    warp_offsets(ctl.warp_cnt, warp, lane, woff, tot);
                     if (k) {
                         int pos = run + woff + __popc(bal & ((1u << lane) - 1u));
-                        fv.px[pos] = a0; fv.py[pos] = a1; fv.X[pos] = a2; fv.Y[pos] = a3; fv.Z[pos] = a4;
+                        U[pos] = a0; V[pos] = a1; X[pos] = a2; Y[pos] = a3; Z[pos] = a4;
                     }
                     run += tot;
                     __syncthreads();
                 }
                 n = n_kept;
-                for (int i = tid; i < n; i += NT) fv.pflag[i] = 0;
+                for (int i = tid; i < n; i += NT) pflag[i] = 0;
                 if (tid == 0) { ctl.n_dup1 = ctl.n_dup; ctl.n_dup = 0; }
                 __syncthreads();
-                build_grid(n, fv.px, fv.py, fv.pflag, ga, cap, &ctl, g);
-                ps.g = g;
+                build_grid(n, U, V, pflag, ga, cap, &ctl);
             } else {
-                for (int i = tid; i < n; i += NT) fv.pflag[i] &= 1;
+                for (int i = tid; i < n; i += NT) pflag[i] &= 1;
                 __syncthreads();
             }
             // ---------------- Delaunay #2 (or #1 again) with triangle emission ----------------
+            for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
+            __syncthreads();
             TMARK(6);
-            run_stars(true, n, ps, fv, star_mem, warp_mem, defer, tri_cap, 7);
+            int nd = run_stars<true>(ctl.ps, fv, &ctl.sc, defer, n_exact);
+            if (tid == 0) ctl.n_deferred_total += nd;
+            __syncthreads();
             status |= ctl.status;
-            if (tid == 0) tlast = clock64();
+            TMARK(7);
         }
         const int T = ctl.T;
         if (!status && P.mode == MODE_FULL) {
@@ -619,9 +473,9 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             int c_loose = 0, c_tight = 0;
             for (int t = tid; t < T; t += NT) {
                 int i0 = fv.tri[3 * t], i1 = fv.tri[3 * t + 1], i2 = fv.tri[3 * t + 2];
-                double p0x = fv.X[i0], p0y = fv.Y[i0], p0z = fv.Z[i0];
-                double e1x = (double)fv.X[i1] - p0x, e1y = (double)fv.Y[i1] - p0y, e1z = (double)fv.Z[i1] - p0z;
-                double e2x = (double)fv.X[i2] - p0x, e2y = (double)fv.Y[i2] - p0y, e2z = (double)fv.Z[i2] - p0z;
+                double p0x = X[i0], p0y = Y[i0], p0z = Z[i0];
+                double e1x = (double)X[i1] - p0x, e1y = (double)Y[i1] - p0y, e1z = (double)Z[i1] - p0z;
+                double e2x = (double)X[i2] - p0x, e2y = (double)Y[i2] - p0y, e2z = (double)Z[i2] - p0z;
                 // n = P^-1 . 1 = (e1 x e2) / (p0 . (e1 x e2))
                 double cx = e1y * e2z - e1z * e2y, cy = e1z * e2x - e1x * e2z, cz = e1x * e2y - e1y * e2x;
                 double det = p0x * cx + p0y * cy + p0z * cz;
@@ -716,9 +570,9 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                         }
                         int ic = 0;
                         bool degenerate = (vtx[0] == vtx[1]) || (vtx[0] == vtx[2]) || (vtx[1] == vtx[2]);
-                        double p0x = fv.X[vtx[0]], p0y = fv.Y[vtx[0]], p0z = fv.Z[vtx[0]];
-                        double e1x = (double)fv.X[vtx[1]] - p0x, e1y = (double)fv.Y[vtx[1]] - p0y, e1z = (double)fv.Z[vtx[1]] - p0z;
-                        double e2x = (double)fv.X[vtx[2]] - p0x, e2y = (double)fv.Y[vtx[2]] - p0y, e2z = (double)fv.Z[vtx[2]] - p0z;
+                        double p0x = X[vtx[0]], p0y = Y[vtx[0]], p0z = Z[vtx[0]];
+                        double e1x = (double)X[vtx[1]] - p0x, e1y = (double)Y[vtx[1]] - p0y, e1z = (double)Z[vtx[1]] - p0z;
+                        double e2x = (double)X[vtx[2]] - p0x, e2y = (double)Y[vtx[2]] - p0y, e2z = (double)Z[vtx[2]] - p0z;
                         // null vector of [p 1] (3x4) in closed form: (n, -n.p0), n = e1 x e2 (estimate_road_norm.py:13-15)
                         nx = e1y * e2z - e1z * e2y; ny = e1z * e2x - e1x * e2z; nz = e1x * e2y - e1y * e2x;
                         dd = -(nx * p0x + ny * p0y + nz * p0z);
@@ -729,7 +583,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                             for (int q = lane; q < n; q += 32) {
                                 int w = mult[q];
                                 if (!w) continue;
-                                double r = nx * (double)fv.X[q] + ny * (double)fv.Y[q] + nz * (double)fv.Z[q] + dd;
+                                double r = nx * (double)X[q] + ny * (double)Y[q] + nz * (double)Z[q] + dd;
                                 if (fabs(r) < thr) ic += w;
                             }
 #pragma unroll
@@ -765,7 +619,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                     if (P.has_dbg && P.dbg.inlier) {
                         const double thr = cfg.ransac_threshold * b_n4;
                         for (int q = tid; q < n; q += NT) {
-                            double r = b_nx * (double)fv.X[q] + b_ny * (double)fv.Y[q] + b_nz * (double)fv.Z[q] + b_dd;
+                            double r = b_nx * (double)X[q] + b_ny * (double)Y[q] + b_nz * (double)Z[q] + b_dd;
                             P.dbg.inlier[base + q] = (mult[q] && fabs(r) < thr) ? 1 : 0;
                         }
                     }
@@ -792,11 +646,11 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 __syncthreads();
                 if (P.dbg.tri2 || P.dbg.tri_flags || P.dbg.tri_height) {
                     // canonical offsets over ALL triangles: scan tcnt (scr is free again after the probes above)
-                    for (int i = tid; i < n; i += NT) ga.scr[i] = (fv.pflag[i] & 1) ? 0u : fv.tcnt[i];
+                    for (int i = tid; i < n; i += NT) ga.scr[i] = (pflag[i] & 1) ? 0u : fv.tcnt[i];
                     __syncthreads();
                     block_excl_scan(ga.scr, n, ctl.warp_cnt);
                     for (int p = tid; p < n; p += NT) {
-                        if (fv.pflag[p] & 1) continue;
+                        if (pflag[p] & 1) continue;
                         int k = fv.tcnt[p], b = fv.tbase[p], o = (int)ga.scr[p];
                         for (int j = 0; j < k; ++j) {
                             size_t row = (size_t)(2 * base) + o + j;
@@ -832,6 +686,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             }
         }
         if (second) status |= MVOSR_ST_SECOND_DT;
+        if (n_exact) atomicAdd(&ctl.n_exact, n_exact);
         __syncthreads();
         if (tid == 0) {
             if (P.status) P.status[f] = (uint8_t)status;
@@ -844,6 +699,10 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 s.best_hyp = ctl.best_hyp; s.best_ic = ctl.best_ic; s.hyps_used = ctl.hyps_used; s.n_degenerate = ctl.n_degenerate;
                 s.n_deferred = ctl.n_deferred_total; s.n_exact = ctl.n_exact; s.height_level = ctl.height_level;
             }
+#ifdef MVOSR_STAR_COUNTERS
+            ctl.tphase[3] = ctl.sc.cnt[0]; ctl.tphase[4] = ctl.sc.cnt[1]; ctl.tphase[5] = ctl.sc.cnt[2]; ctl.tphase[8] = ctl.sc.cnt[3];
+            ctl.tphase[9] = ctl.sc.cnt[4]; ctl.tphase[14] = ctl.sc.cnt[5]; ctl.tphase[15] = ctl.sc.cnt[6]; ctl.tphase[1] = ctl.sc.cnt[7];
+#endif
             if (P.phase_cycles) for (int k = 0; k < 16; ++k) P.phase_cycles[16 * (size_t)f + k] = ctl.tphase[k];
         }
     }

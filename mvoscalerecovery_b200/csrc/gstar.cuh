@@ -1,354 +1,608 @@
-// Half-warp ("group") star builder: the production path of the per-frame Delaunay stage.
+// Per-site Delaunay stars over a cell-sorted point set staged in shared memory (device code, sm_100a).
 //
-// One group of 16 lanes builds the star of one point; two groups share a warp and run the same loop.
-// The star lives in REGISTERS: lane i of the group holds neighbour slot i (id, coordinates relative to
-// p, lift), a copy of slot i+1, and the cached circumdisk of star triangle i = (p, slot i, slot i+1).
-//   * candidates are spread over the lanes (one each), sorted nearest-first with a 16-lane bitonic
-//     network, pre-filtered in parallel against the cached circumdisks (conservative), and only the
-//     flagged ones are inserted, one at a time;
-//   * an insertion evaluates the EXACT conflict (in-circle with symbolic tie-break / ghost orientation,
-//     predicates.cuh) of the candidate against all star triangles at once, lane i testing triangle i;
-//     the conflicting arc is removed and the candidate spliced in with shuffles;
-//   * levels: the 3x3 cell block, then ring 2 (5x5), each followed by the finality test "every
-//     unexamined point is farther than twice the largest circumradius"; stars that are still not final
-//     (hull / near-hull) run a directed search: the cell range R covering all current circumdisks (the
-//     whole grid while the star is open) is swept in 8x8-cell blocks, blocks and then cells being culled
-//     against the disks and ghost half-planes.  The union of the disks only shrinks as the star is
-//     clipped, so one sweep of R suffices.
-// Same rules, same predicates and therefore the same (unique) triangulation as star.cuh's sequential
-// builder, which remains the host-simulated reference and the device fallback for stars of degree > 16.
+// Replaces scipy.spatial.Delaunay(feature2d).simplices (Qhull 8.0.2) at reference
+// src/rescale.py:124-125,136-137, per frame.
+//
+// Method (no shared mutable mesh, no inter-thread ordering): the Delaunay star of every point p -- the
+// cyclic counter-clockwise list of its neighbours -- is built independently by Bowyer-Watson insertion
+// restricted to that one star.  A candidate s changes the star iff it lies inside the circumcircle of some
+// star triangle (p,q_i,q_i+1); the triangles in conflict form one contiguous arc (their Voronoi vertices are
+// the vertices of p's cell cut off by the bisector of p,s), which is removed and replaced by s.  Hull points
+// carry one INF slot standing for the two ghost triangles (p,q,inf),(p,inf,q); their conflict is an
+// orientation test.  Exact predicates with a symbolic tie-break (predicates.cuh) make the triangulation
+// unique, so independently built stars agree; triangle (a<b<c) is emitted by the star of a.
+//
+// Fast path (stars_fast): one half-warp of 16 lanes per star, the star in REGISTERS -- lane i holds
+// neighbour slot i and, for star triangle i, the three cofactors (m0,m1,m2) of the in-circle determinant
+// with their error weights, so that a candidate is tested against ALL triangles of the star by
+//     det = m0*|s|^2 + m1*s.x + m2*s.y,   err = e0*|s|^2 + e1*|s.x| + e2*|s.y|      (float32, 6 FMA per lane)
+// and one ballot.  |det| > err certifies the sign (forward error bound, KERR below); otherwise the group
+// re-evaluates that candidate with the exact float64/integer predicates.  Candidates come from the grid:
+// first the 3x3 block of cells around p, then a sweep over grid rows outwards from p's row in which every
+// row contributes only the cell interval covered by the union of the star's current circumdisks (ghost
+// triangles: half-planes).  That union only shrinks as the star is clipped, so one sweep suffices and a
+// star is final when the sweep has left the union.  The two half-warps of a warp run in lock step on
+// different stars: test and splice are executed warp-convergently under predication, only the refill of
+// a group's candidate batch is divergent.
+//
+// Fallback (fb_build): anything the fast path does not handle -- more than 16 neighbours, a collinear
+// bootstrap, an inconsistent arc -- is queued and rebuilt by one full warp (32 slots) with exact
+// predicates only, scanning the grid ring by ring (nearest first) until every unexamined point is farther
+// than twice the largest circumradius.  Slow and simple; a handful of stars per frame at most.
 #pragma once
-#include "star.cuh"
+#include <stdint.h>
+#include <math_constants.h>
+#include <stdio.h>
+#include "predicates.cuh"
 
 namespace mvosr {
 
-constexpr int GL = 16;                   // lanes per group
-constexpr int NGROUP = NT / GL;
-constexpr double GINF = 1.0e300;
+constexpr int NT = 1024;                 // threads per CTA of the fused frame kernel
+constexpr int NWARP = NT / 32;
+constexpr int GL = 16;                   // lanes per star on the fast path
+constexpr uint16_t INF16 = 0xFFFF;
+constexpr float GRID_DENSITY = 1.5f;     // mean points per grid cell
+// Forward error bound of the float32 in-circle evaluation: inputs are float32 roundings of exact
+// differences (relative error u = 2^-24); every term of the expanded determinant accumulates at most
+// 11u (4 inputs, <= 7 roundings), so |det_fl - det| <= 11u * perm.  KERR = 16u leaves room for the
+// rounding of the bound itself.
+constexpr float KERR = 9.5367431640625e-07f;   // 2^-20
 
-struct GCtx {                            // group-uniform + per-lane registers
-    unsigned gmask;                      // lanes of this group inside the warp
-    int gl;                              // lane inside the group
-    int p, d;
-    double ppx, ppy, reach2;
-    int sid; double sqx, sqy, sql;       // slot gl
-    int nid; double nqx, nqy, nql;       // slot gl+1 (cyclic)
-    double vx, vy, r2;                   // triangle gl: circumcentre rel. p and inflated radius^2 (r2 >= 0);
-                                         // ghost (p,q,inf): (vx,vy)=q, r2=-1; ghost (p,inf,q): r2=-2; unused lane: r2=-3;
-                                         // r2 = GINF: finite but too flat to bound -> always "may conflict"
-    double tr4;                          // (2 * circumradius)^2 upper bound, GINF for ghost / unknown
-    int n_exact;
+enum { STAR_OK = 0, STAR_DEFER = 1, STAR_OVERFLOW = 2, STAR_INCONSISTENT = 3, STAR_NONE = 4 };
+
+// The staged point set: entries sorted by grid cell (row-major), inside a cell by original index;
+// exact duplicates of an earlier point are holes (orig == INF16) at the tail of their cell.
+struct SortedSet {
+    const float *x, *y;                  // [n] pixel coordinates (float32; |x| < 4096, multiples of 2^-40)
+    const uint16_t *orig;                // [n] index in the frame's feature order, INF16 for a hole
+    const uint16_t *cell_start;          // [gx*gy+1]
+    int n;
+    float xmin, ymin, h, inv_h;
+    int gx, gy;
 };
 
-template <class T> __device__ __forceinline__ T gshfl(const GCtx &c, T v, int src) { return __shfl_sync(c.gmask, v, src, GL); }
-__device__ __forceinline__ unsigned gballot(const GCtx &c, bool pred) {
-    return (__ballot_sync(c.gmask, pred) >> (c.gmask & 0x10000u ? 16 : 0)) & 0xFFFFu;
-}
-__device__ __forceinline__ double gmax(const GCtx &c, double v) {
-#pragma unroll
-    for (int o = 8; o; o >>= 1) v = fmax(v, __shfl_xor_sync(c.gmask, v, o, GL));
-    return v;
-}
-__device__ __forceinline__ int gmin_i(const GCtx &c, int v) {
-#pragma unroll
-    for (int o = 8; o; o >>= 1) v = min(v, __shfl_xor_sync(c.gmask, v, o, GL));
-    return v;
-}
-__device__ __forceinline__ int gmax_i(const GCtx &c, int v) {
-#pragma unroll
-    for (int o = 8; o; o >>= 1) v = max(v, __shfl_xor_sync(c.gmask, v, o, GL));
-    return v;
+__device__ __forceinline__ int cell_of(float v, float vmin, float inv_h, int g) {
+    int c = (int)((v - vmin) * inv_h);
+    return c < 0 ? 0 : (c >= g ? g - 1 : c);
 }
 
-// Refresh the copy of the next slot and the triangle cache after any change of the star.
-__device__ __forceinline__ void g_refresh(GCtx &c) {
-    int nx = c.gl + 1 < c.d ? c.gl + 1 : 0;
-    c.nid = gshfl(c, c.sid, nx); c.nqx = gshfl(c, c.sqx, nx); c.nqy = gshfl(c, c.sqy, nx); c.nql = gshfl(c, c.sql, nx);
-    double vx = 0, vy = 0, r2 = -3.0, tr4 = 0;
-    if (c.gl < c.d) {
-        if (c.nid == INF16) { vx = c.sqx; vy = c.sqy; r2 = -1.0; tr4 = GINF; }
-        else if (c.sid == INF16) { vx = c.nqx; vy = c.nqy; r2 = -2.0; tr4 = GINF; }
-        else {
-            double l = c.sqx * c.nqy, r = c.sqy * c.nqx, w = l - r, aw = fabs(l) + fabs(r);
-            double wl = w - 4.0e-16 * aw;
-            r2 = GINF; tr4 = GINF;
-            if (wl > 0) {
-                double ex = c.sqx - c.nqx, ey = c.sqy - c.nqy;
-                tr4 = c.sql * c.nql * (ex * ex + ey * ey) / (wl * wl) * (1.0 + 1.0e-9);
-                if (w > 1.0e-6 * aw) {
-                    double inv = 0.5 / w;
-                    vx = (c.sql * c.nqy - c.nql * c.sqy) * inv; vy = (c.nql * c.sqx - c.sql * c.nqx) * inv;
-                    r2 = (vx * vx + vy * vy) * (1.0 + 1.0e-5);
-                }
-            }
+struct StarCtl {                         // shared-memory work queue of one Delaunay pass
+    int next_pos, n_defer;
+    unsigned long long cnt[8];           // profiling counters (MVOSR_STAR_COUNTERS): tests, splices, batches, rows, runs, exact, loop iterations, refill iterations
+};
+
+// ---------------------------------------------------------------------------------------------
+// consumers of a finished star held one slot per lane (W lanes: 16 fast path, 32 fallback)
+// ---------------------------------------------------------------------------------------------
+struct FrameView {
+    const float *Z;                      // depth by feature index (graph check)
+    uint8_t *pflag;                      // by feature index: bit0 duplicate, bit1 keep
+    uint16_t *tri;                       // [T][3] feature indices, ascending inside a row
+    uint16_t *tbase; uint8_t *tcnt;      // by feature index: block of triangles owned (smallest vertex)
+    int *T; int *status;                 // triangle counter, frame status (shared)
+    uint32_t pass_mask;
+    int tri_cap;
+};
+
+__device__ __forceinline__ bool edge_consistent(float va, float za, float vb, float zb) {
+    // check_triangle (graph.py:124-129): (v_a - v_b) * (d_a - d_b) < 0 in float64 on float32-exact values --
+    // the product of two exact non-zero differences cannot underflow, so the sign rule is exact
+    return (va < vb && za > zb) || (va > vb && za < zb);
+}
+
+// graph vote (graph.py:131-145) of triangle (p,a,b) for vertex p; vertices ordered by feature index
+__device__ __forceinline__ bool graph_vote(int op, float vp, float zp, int oa, float va, float za, int ob, float vb, float zb,
+                                           uint32_t pass_mask) {
+    int i0 = op, i1 = oa, i2 = ob; float v0 = vp, v1 = va, v2 = vb, z0 = zp, z1 = za, z2 = zb;
+#define MVOSR_SWAP(A, B, C, D, E, F) { int ti = A; A = B; B = ti; float tf = C; C = D; D = tf; tf = E; E = F; F = tf; }
+    if (i0 > i1) MVOSR_SWAP(i0, i1, v0, v1, z0, z1)
+    if (i1 > i2) MVOSR_SWAP(i1, i2, v1, v2, z1, z2)
+    if (i0 > i1) MVOSR_SWAP(i0, i1, v0, v1, z0, z1)
+#undef MVOSR_SWAP
+    int a = edge_consistent(v0, z0, v1, z1), b = edge_consistent(v1, z1, v2, z2), c = edge_consistent(v0, z0, v2, z2);
+    int idx = a * 4 + b * 2 + c;
+    int k = (op == i0) ? 0 : (op == i1 ? 1 : 2);
+    return (pass_mask >> (idx * 3 + k)) & 1u;
+}
+
+// keep = (#incident triangles with p>0.6)/(#incident) > 0.5 (graph.py:33-35,131-132); 0/0 -> False
+template <int W>
+__device__ __forceinline__ void consume_vote(unsigned mask, int gl, int d, int p, int sid, int nid,
+                                             const SortedSet &ps, const FrameView &fv) {
+    const bool tri = gl < d && sid != INF16 && nid != INF16;
+    bool vote = false;
+    const int op = ps.orig[p];
+    if (tri) {
+        int oa = ps.orig[sid], ob = ps.orig[nid];
+        vote = graph_vote(op, ps.y[p], fv.Z[op], oa, ps.y[sid], fv.Z[oa], ob, ps.y[nid], fv.Z[ob], fv.pass_mask);
+    }
+    unsigned bt = __ballot_sync(mask, tri) & mask, bv = __ballot_sync(mask, vote) & mask;
+    if (gl == 0 && 2 * __popc(bv) > __popc(bt)) fv.pflag[op] |= 2;
+}
+
+// triangles (op < oa, ob) are written as one block sorted by (min,max) of the other two vertices
+template <int W>
+__device__ __forceinline__ void consume_emit(unsigned mask, int gl, int d, int p, int sid, int nid,
+                                             const SortedSet &ps, const FrameView &fv) {
+    const bool tri = gl < d && sid != INF16 && nid != INF16;
+    const int op = ps.orig[p];
+    unsigned key = 0xFFFFFFFFu;
+    if (tri) {
+        int oa = ps.orig[sid], ob = ps.orig[nid];
+        if (op < oa && op < ob) key = ((unsigned)min(oa, ob) << 16) | (unsigned)max(oa, ob);
+    }
+    const bool own = key != 0xFFFFFFFFu;
+    const int k = __popc(__ballot_sync(mask, own) & mask);
+    if (!k) return;
+    int base = 0;
+    if (gl == 0) base = atomicAdd(fv.T, k);
+    base = __shfl_sync(mask, base, 0, W);
+    if (base + k > fv.tri_cap) {
+        if (gl == 0) atomicOr(fv.status, MVOSR_ST_OVERFLOW);
+#ifdef MVOSR_DEBUG_PRINT
+        if (gl == 0) printf("emit overflow: base=%d k=%d cap=%d\n", base, k, fv.tri_cap);
+#endif
+        return;
+    }
+    int r = 0;                            // rank of this lane's key (keys of owners are distinct)
+#pragma unroll
+    for (int j = 0; j < W; ++j) { unsigned kj = __shfl_sync(mask, key, j, W); r += kj < key; }
+    if (own) { uint16_t *t = fv.tri + 3 * (base + r); t[0] = (uint16_t)op; t[1] = (uint16_t)(key >> 16); t[2] = (uint16_t)(key & 0xFFFFu); }
+    if (gl == 0) { fv.tbase[op] = (uint16_t)base; fv.tcnt[op] = (uint8_t)k; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact conflict of candidate s with star triangle (p,a,b) (a or b may be the INF slot)
+// bit0: conflict; bit1: an orientation test came out exactly zero (collinear with p and a hull neighbour)
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ int exact_conflict(const float *x, const float *y, const uint16_t *orig, int p, int a, int b, int s) {
+    int n_exact = 0;
+    const double ppx = x[p], ppy = y[p];
+    const double sx = (double)x[s] - ppx, sy = (double)y[s] - ppy;
+    int code;
+    if (b == INF16) {                    // ghost (p, a, inf): outside lies LEFT of p->a
+        double ax = (double)x[a] - ppx, ay = (double)y[a] - ppy;
+        int o = cross_sign(ax, ay, sx, sy, n_exact);
+        code = (o > 0 || (o == 0 && strictly_between(ax, ay, sx, sy))) | ((o == 0) << 1);
+    } else if (a == INF16) {             // ghost (p, inf, b): outside lies RIGHT of p->b
+        double bx = (double)x[b] - ppx, by = (double)y[b] - ppy;
+        int o = cross_sign(bx, by, sx, sy, n_exact);
+        code = (o < 0 || (o == 0 && strictly_between(bx, by, sx, sy))) | ((o == 0) << 1);
+    } else {
+        double ax = (double)x[a] - ppx, ay = (double)y[a] - ppy, bx = (double)x[b] - ppx, by = (double)y[b] - ppy;
+        code = incircle_sos(ax, ay, ax * ax + ay * ay, bx, by, bx * bx + by * by, sx, sy, sx * sx + sy * sy,
+                            orig[p], orig[a], orig[b], orig[s], n_exact);
+    }
+    return code | (n_exact << 2);          // bits 2..: predicate evaluations that needed exact arithmetic
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast path
+// ---------------------------------------------------------------------------------------------
+enum { DK_NONE = 0, DK_DISK = 1, DK_ALL = 2, DK_HALF = 3 };
+
+struct GState {
+    // group-uniform
+    int p, d;
+    float ppx, ppy;
+    int pcx, pcy;
+    // lane: slot gl, next slot, triangle gl = (p, slot gl, slot gl+1)
+    int sid, nid;
+    float qx, qy;
+    float m0, m1, m2, e0, e1, e2;
+    // lane: search region of triangle gl (lazy; valid when !dirty)
+    int kind; float vx, vy, rs; int rowlo, rowhi;
+    bool dirty;
+};
+
+// after any change of the star: fetch the next slot, recompute the cofactors of triangle gl
+__device__ __forceinline__ void g_coeffs(GState &g, unsigned mask, int gl) {
+    const int nx = gl + 1 < g.d ? gl + 1 : 0;
+    g.nid = __shfl_sync(mask, g.sid, nx, GL);
+    const float bx = __shfl_sync(mask, g.qx, nx, GL), by = __shfl_sync(mask, g.qy, nx, GL);
+    const float ax = g.qx, ay = g.qy;
+    if (gl >= g.d) { g.m0 = 1.f; g.m1 = g.m2 = 0.f; g.e0 = g.e1 = g.e2 = 0.f; }       // det = |s|^2 > 0: never in conflict
+    else if (g.nid == INF16) {           // ghost (p,a,inf): det3 = ay*sx - ax*sy  (< 0 <=> s left of p->a)
+        g.m0 = 0.f; g.m1 = ay; g.m2 = -ax; g.e0 = 0.f; g.e1 = KERR * fabsf(ay); g.e2 = KERR * fabsf(ax);
+    } else if (g.sid == INF16) {         // ghost (p,inf,b): det3 = bx*sy - by*sx  (< 0 <=> s right of p->b)
+        g.m0 = 0.f; g.m1 = -by; g.m2 = bx; g.e0 = 0.f; g.e1 = KERR * fabsf(by); g.e2 = KERR * fabsf(bx);
+    } else {
+        const float al = fmaf(ax, ax, ay * ay), bl = fmaf(bx, bx, by * by);
+        const float t0 = ax * by, t1 = ay * bx, t2 = ay * bl, t3 = al * by, t4 = al * bx, t5 = ax * bl;
+        g.m0 = t0 - t1; g.m1 = t2 - t3; g.m2 = t4 - t5;
+        g.e0 = KERR * (fabsf(t0) + fabsf(t1)); g.e1 = KERR * (fabsf(t2) + fabsf(t3)); g.e2 = KERR * (fabsf(t4) + fabsf(t5));
+    }
+}
+
+// lane: conservative search region of triangle gl, and the grid rows it touches
+__device__ __forceinline__ void g_regions(GState &g, int gl, const SortedSet &ps) {
+    int kind = DK_NONE; float vx = 0.f, vy = 0.f, rs = 0.f;
+    int rowlo = 0x7FFFFFFF, rowhi = -1;
+    if (gl < g.d) {
+        if (g.nid == INF16) { kind = DK_HALF; vx = g.qx; vy = g.qy; }                  // region: vx*y - vy*x > 0
+        else if (g.sid == INF16) { kind = DK_HALF; vx = -g.m2; vy = g.m1; }              // (-bx,-by): m1 = -by, m2 = bx
+        else if (g.m0 > 64.f * g.e0) {
+            // circumcentre (-m1,-m2)/(2 m0) with a bound on its error; the disk passes through p (the origin)
+            const float inv = 0.5f / g.m0, rho = 2.f * g.e0 * inv;
+            vx = -g.m1 * inv; vy = -g.m2 * inv;
+            const float dv = ((g.e1 + g.e2) + (fabsf(g.m1) + fabsf(g.m2)) * rho) * inv * 1.5f;
+            rs = sqrtf(fmaf(vx, vx, vy * vy)) * 1.0001f + 2.f * dv + 1.0e-3f;
+            kind = DK_DISK;
+            if (!(rs < 1.0e6f)) kind = DK_ALL;
+        } else kind = DK_ALL;                                                           // too flat to bound
+        if (kind == DK_DISK) {
+            const float a = (g.ppy + vy - rs - ps.ymin) * ps.inv_h, b = (g.ppy + vy + rs - ps.ymin) * ps.inv_h;
+            rowlo = (int)fminf(fmaxf(a, 0.f), (float)(ps.gy - 1)); rowhi = (int)fminf(fmaxf(b, 0.f), (float)(ps.gy - 1));
+            if (b < 0.f) { rowlo = 0x7FFFFFFF; rowhi = -1; }
+        } else { rowlo = 0; rowhi = ps.gy - 1; }
+    }
+    g.kind = kind; g.vx = vx; g.vy = vy; g.rs = rs; g.rowlo = rowlo; g.rowhi = rowhi;
+    g.dirty = false;
+}
+
+// lane: cell interval of grid row `row` that triangle gl's region can touch ([ca,cb], empty: ca > cb)
+__device__ __forceinline__ void g_row_interval(const GState &g, const SortedSet &ps, int row, int &ca, int &cb) {
+    const float INF = CUDART_INF_F;
+    float lo = INF, hi = -INF;
+    const float Y0 = ps.ymin + row * ps.h - g.ppy - (1.0e-3f + 1.0e-4f * ps.h), Y1 = Y0 + ps.h + 2.f * (1.0e-3f + 1.0e-4f * ps.h);
+    if (g.kind == DK_DISK) {
+        const float dy = fmaxf(fmaxf(Y0 - g.vy, g.vy - Y1), 0.f), rem = g.rs * g.rs - dy * dy;
+        if (rem > 0.f) { const float hw = sqrtf(rem) * 1.0001f + 1.0e-3f; lo = g.vx - hw; hi = g.vx + hw; }
+    } else if (g.kind == DK_ALL) { lo = -INF; hi = INF; }
+    else if (g.kind == DK_HALF) {
+        if (g.vy > 0.f) { const float t = fmaxf(g.vx * Y0, g.vx * Y1) / g.vy; hi = t + 1.0e-5f * fabsf(t) + 1.0e-3f; lo = -INF; }
+        else if (g.vy < 0.f) { const float t = fminf(g.vx * Y0 / g.vy, g.vx * Y1 / g.vy); lo = t - 1.0e-5f * fabsf(t) - 1.0e-3f; hi = INF; }
+        else if (g.vx > 0.f ? Y1 > 0.f : (g.vx < 0.f ? Y0 < 0.f : true)) { lo = -INF; hi = INF; }
+    }
+    ca = 0x7FFFFFFF; cb = -1;
+    if (lo <= hi) {
+        const float a = (lo + g.ppx - ps.xmin) * ps.inv_h, b = (hi + g.ppx - ps.xmin) * ps.inv_h;
+        if (!(b < 0.f)) {
+            ca = (int)fminf(fmaxf(a, 0.f), (float)(ps.gx - 1)); cb = (int)fminf(fmaxf(b, 0.f), (float)(ps.gx - 1));
         }
     }
-    c.vx = vx; c.vy = vy; c.r2 = r2; c.tr4 = tr4;
-    c.reach2 = c.d >= 3 ? gmax(c, tr4) : GINF;
 }
 
-// Conservative, lane-parallel: may the lane's candidate (relative sx,sy) cut the cell of p?
-__device__ __forceinline__ bool g_prefilter(const GCtx &c, double sx, double sy) {
-    bool hit = false;
-    for (int i = 0; i < c.d; ++i) {
-        double vx = gshfl(c, c.vx, i), vy = gshfl(c, c.vy, i), r2 = gshfl(c, c.r2, i);
-        if (r2 >= 0) {
-            double dx = sx - vx, dy = sy - vy;
-            hit |= (dx * dx + dy * dy < r2);
-        } else {
-            double l = vx * sy, r = vy * sx, tol = 3.4e-16 * (fabs(l) + fabs(r));
-            hit |= (r2 == -1.0) ? (l - r >= -tol) : (l - r <= tol);
-        }
-    }
-    return hit;
-}
+// All stars of the staged set, fast path; stars it gives up on are appended to defer[].
+template <bool EMIT>
+__device__ __forceinline__ void stars_fast(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, int &n_exact) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, gl = lane & (GL - 1), gshift = lane & GL;
+    const unsigned gmask = 0xFFFFu << gshift;
+    GState g;
+    g.p = -1; g.d = 0; g.ppx = g.ppy = 0.f; g.pcx = g.pcy = 0; g.sid = g.nid = INF16; g.qx = g.qy = 0.f;
+    g.m0 = 1.f; g.m1 = g.m2 = g.e0 = g.e1 = g.e2 = 0.f; g.kind = DK_NONE; g.vx = g.vy = g.rs = 0.f; g.rowlo = 0; g.rowhi = -1; g.dirty = true;
+    bool active = true, need_point = true, bail = false;
+    int phase = 0, k = 0, t = 0, ri = 0, re = 0, rdir = 1, ca2 = 1, cb2 = 0, currow = 0;
+    unsigned F = 0; int bbase = 0, bdir = 1; float cx = 0.f, cy = 0.f;
+#ifdef MVOSR_STAR_COUNTERS
+    unsigned c_test = 0, c_splice = 0, c_batch = 0, c_row = 0, c_run = 0, c_exact = 0, c_iter = 0, c_refill = 0;
+#define CNT(x) ++x
+#else
+#define CNT(x)
+#endif
 
-// Conservative, lane-parallel: can the rectangle [x0,x1]x[y0,y1] (relative to p) contain a cutting point?
-__device__ __forceinline__ bool g_rect_may_cut(const GCtx &c, double x0, double y0, double x1, double y1) {
-    bool hit = false;
-    for (int i = 0; i < c.d; ++i) {
-        double vx = gshfl(c, c.vx, i), vy = gshfl(c, c.vy, i), r2 = gshfl(c, c.r2, i);
-        if (r2 >= 0) {
-            double dx = vx < x0 ? x0 - vx : (vx > x1 ? vx - x1 : 0.0), dy = vy < y0 ? y0 - vy : (vy > y1 ? vy - y1 : 0.0);
-            hit |= (dx * dx + dy * dy < r2);
-        } else {
-            double sgn = r2 == -1.0 ? 1.0 : -1.0;
-            double c0 = sgn * (vx * y0 - vy * x0), c1 = sgn * (vx * y0 - vy * x1), c2 = sgn * (vx * y1 - vy * x0), c3 = sgn * (vx * y1 - vy * x1);
-            double tol = 1.0e-9 * (fabs(vx) + fabs(vy)) * (fabs(x0) + fabs(x1) + fabs(y0) + fabs(y1) + 1.0);
-            hit |= (fmax(fmax(c0, c1), fmax(c2, c3)) >= -tol);
-        }
-    }
-    return hit;
-}
-
-// Exact insertion of candidate s (group-uniform).  Returns 1 inserted, 0 no conflict, <0 -STAR_* error.
-__device__ __forceinline__ int g_insert(GCtx &c, int s, double sx, double sy, double sl) {
-    bool cf_lane = false;
-    if (c.gl < c.d) {
-        if (c.nid == INF16) {                // ghost (p, slot, inf): outside lies LEFT of p->slot
-            int o = cross_sign(c.sqx, c.sqy, sx, sy, c.n_exact);
-            cf_lane = o > 0 || (o == 0 && strictly_between(c.sqx, c.sqy, sx, sy));
-        } else if (c.sid == INF16) {         // ghost (p, inf, next): outside lies RIGHT of p->next
-            int o = cross_sign(c.nqx, c.nqy, sx, sy, c.n_exact);
-            cf_lane = o < 0 || (o == 0 && strictly_between(c.nqx, c.nqy, sx, sy));
-        } else {
-            cf_lane = incircle_sos(c.sqx, c.sqy, c.sql, c.nqx, c.nqy, c.nql, sx, sy, sl, c.p, c.sid, c.nid, s, c.n_exact);
-        }
-    }
-    const unsigned cf = gballot(c, cf_lane);
-    if (!cf) return 0;
-    const int d = c.d;
-    const unsigned full = (1u << d) - 1u;
-    unsigned prevm = ((cf << 1) | (cf >> (d - 1))) & full;
-    unsigned starts = cf & ~prevm;
-    if (__popc(starts) != 1) return -STAR_INCONSISTENT;
-    int i0 = __ffs(starts) - 1, len = __popc(cf);
-    unsigned rot = i0 ? (((cf >> i0) | (cf << (d - i0))) & full) : cf;
-    if (rot != ((1u << len) - 1u) || len >= d) return -STAR_INCONSISTENT;
-    const int nd = d - len + 2;
-    if (nd > GL) return -STAR_OVERFLOW;
-    // new[0] = s ; new[k] = old[(i0+len+k-1) % d], k = 1..nd-1
-    int src = (i0 + len + c.gl - 1) % d;
-    if (c.gl == 0 || c.gl >= nd) src = 0;
-    int id2 = gshfl(c, c.sid, src); double x2 = gshfl(c, c.sqx, src), y2 = gshfl(c, c.sqy, src), l2 = gshfl(c, c.sql, src);
-    if (c.gl == 0) { id2 = s; x2 = sx; y2 = sy; l2 = sl; }
-    c.sid = id2; c.sqx = x2; c.sqy = y2; c.sql = l2;
-    c.d = nd;
-    g_refresh(c);
-    return 1;
-}
-
-struct GTmpStar { int v[4]; __device__ __forceinline__ void set(int i, int x) { v[i] = x; } };
-
-// A batch of candidates, one per lane (id < 0: none).  Sorted nearest-first when `sort` is set.
-__device__ __forceinline__ int g_batch(GCtx &c, Bootstrap &bs, int id, bool sort, const double *px, const double *py) {
-    double sx = 0, sy = 0, sl = GINF;
-    if (id >= 0 && id != c.p) { sx = px[id] - c.ppx; sy = py[id] - c.ppy; sl = sx * sx + sy * sy; if (sl > c.reach2) { id = -1; sl = GINF; } }
-    else id = -1;
-    if (!gballot(c, id >= 0)) return 0;
-    if (sort) {
-        // bitonic sort of (sl, id) over the 16 lanes, ascending
-#pragma unroll
-        for (int k = 2; k <= GL; k <<= 1) {
-#pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                double osl = __shfl_xor_sync(c.gmask, sl, j, GL); int oid = __shfl_xor_sync(c.gmask, id, j, GL);
-                bool up = ((c.gl & k) == 0), lower = ((c.gl & j) == 0);
-                bool take = (lower == up) ? (osl < sl) : (osl > sl);
-                if (take) { sl = osl; id = oid; }
-            }
-        }
-        if (id >= 0) { sx = px[id] - c.ppx; sy = py[id] - c.ppy; }
-    }
-    unsigned valid = gballot(c, id >= 0);
-    if (c.d == 0) {
-        // bootstrap: sequential over the candidates until the star owns a real triangle (group-uniform)
-        while (valid && c.d == 0) {
-            int j = __ffs(valid) - 1; valid &= valid - 1;
-            int s = gshfl(c, id, j);
-            int dd = 0; GTmpStar tmp;
-            if (star_bootstrap(tmp, dd, bs, s, c.ppx, c.ppy, px, py, c.n_exact)) {
-                int q = c.gl < dd ? tmp.v[c.gl] : (int)INF16;
-                c.sid = q; c.sqx = 0; c.sqy = 0; c.sql = 0;
-                if (c.gl < dd && q != INF16) { c.sqx = px[q] - c.ppx; c.sqy = py[q] - c.ppy; c.sql = c.sqx * c.sqx + c.sqy * c.sqy; }
-                c.d = dd;
-                g_refresh(c);
-            }
-        }
-        if (c.d == 0) return 0;
-    }
-    bool mine = (valid >> c.gl) & 1u;
-    bool pf = g_prefilter(c, sx, sy);                 // contains group shuffles: every lane must execute it
-    unsigned F = gballot(c, mine && sl <= c.reach2 && pf);
-    int cnt = 0;
-    while (F) {
-        int j = __ffs(F) - 1; F &= F - 1;
-        int s = gshfl(c, id, j); double csx = gshfl(c, sx, j), csy = gshfl(c, sy, j), csl = gshfl(c, sl, j);
-        int r = g_insert(c, s, csx, csy, csl);
-        if (r < 0) return r;
-        if (r == 1 && F && (++cnt & 1) == 0) {
-            bool still = (F >> c.gl) & 1u;
-            bool pf2 = g_prefilter(c, sx, sy);
-            F &= gballot(c, still && sl <= c.reach2 && pf2);
-        }
-    }
-    return 0;
-}
-
-// Finality test after the block of half-width `half` around p's cell has been examined.
-// Returns 1 final, 0 not final, 2 the block covers the grid (final by exhaustion).
-__device__ __forceinline__ int g_final(const GCtx &c, const Grid &g, int pcx, int pcy, int half) {
-    Rect rc;
-    rc.x0 = max(0, pcx - half); rc.x1 = min(g.gx - 1, pcx + half);
-    rc.y0 = max(0, pcy - half); rc.y1 = min(g.gy - 1, pcy + half);
-    int side;
-    double m = rc.margin(g, c.ppx, c.ppy, side);
-    if (side < 0) return 2;
-    return (m > 0 && m * m >= c.reach2) ? 1 : 0;
-}
-
-// Build the star of p.  Returns STAR_OK (star in registers, c.d slots), STAR_NONE, or an error/overflow code.
-// Written as one loop around a SINGLE g_batch call site (and a single culling site): the body is large, and
-// every extra inlined copy costs instruction-cache misses on all 16 warps of the CTA.
-//   stage 1: the 3x3 cell block   = three row runs of cell_pts (lanes 0..2 describe them)
-//   stage 2: ring 2 of the 5x5    = two 5-cell row runs (lanes 0,1) + left/right cells of the middle rows (lanes 2..7)
-//   stage 3: directed search over R = cell range of all circumdisks (whole grid while open / unknown), swept in
-//            8x8-cell blocks; blocks, then cells, are culled against the disks and ghost half-planes
-__device__ __forceinline__ int g_build(GCtx &c, int p, const PointSet &ps) {
-    const Grid &g = ps.g;
-    c.p = p; c.d = 0; c.reach2 = GINF; c.ppx = ps.px[p]; c.ppy = ps.py[p];
-    c.sid = INF16; c.sqx = c.sqy = c.sql = 0; c.nid = INF16; c.nqx = c.nqy = c.nql = 0; c.vx = c.vy = 0; c.r2 = -3.0; c.tr4 = 0;
-    const int pcx = cell_coord(c.ppx, g.xmin, g.inv_h, g.gx), pcy = cell_coord(c.ppy, g.ymin, g.inv_h, g.gy);
-    Bootstrap bs; bs.qpos = bs.qneg = -1;
-    int stage = 0;                       // bumped to 1 by the first "level end" below
-    int run_beg = 0, pre = 0, total = 0, off = 0;
-    // directed-search cursor (group-uniform unless noted)
-    int rx0 = 0, rx1 = -1, ry0 = 0, ry1 = -1, bx0 = 0, by0 = 0, BW = 1, nblk = 0, b0 = 0, cbx = 0, cby = 0, q = 4, k = 0, nmax = 0;
-    unsigned am = 0;
-    int bx = 0, by = 0, n = 0, beg = 0;  // per lane
-    const int ox0 = max(0, pcx - 2), ox1 = min(g.gx - 1, pcx + 2), oy0 = max(0, pcy - 2), oy1 = min(g.gy - 1, pcy + 2);
-    for (;;) {
-        int id = -1;
-        bool sort = false;
-        if (stage <= 2) {
-            if (off >= total) {
-                // ---- level end (or start)
-                if (stage >= 1) {
-                    int f = g_final(c, g, pcx, pcy, stage);
-                    if (f) return c.d > 0 ? STAR_OK : STAR_NONE;
-                }
-                ++stage;
-                if (stage <= 2) {
-                    int len = 0; run_beg = 0;
-                    if (stage == 1) {
-                        int cy = pcy - 1 + c.gl;
-                        if (c.gl < 3 && cy >= 0 && cy < g.gy) {
-                            int x0 = max(0, pcx - 1), x1 = min(g.gx - 1, pcx + 1);
-                            run_beg = ps.cell_start[cy * g.gx + x0]; len = ps.cell_start[cy * g.gx + x1 + 1] - run_beg;
-                        }
-                    } else if (c.gl < 2) {
-                        int cy = c.gl == 0 ? pcy - 2 : pcy + 2;
-                        if (cy >= 0 && cy < g.gy) { run_beg = ps.cell_start[cy * g.gx + ox0]; len = ps.cell_start[cy * g.gx + ox1 + 1] - run_beg; }
-                    } else if (c.gl < 8) {
-                        int kk = c.gl - 2, cy = pcy - 1 + (kk >> 1), cx = (kk & 1) ? pcx + 2 : pcx - 2;
-                        if (cy >= 0 && cy < g.gy && cx >= 0 && cx < g.gx) { run_beg = ps.cell_start[cy * g.gx + cx]; len = ps.cell_start[cy * g.gx + cx + 1] - run_beg; }
-                    }
-                    pre = len;                           // inclusive prefix over the 8 run lanes
-#pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) { int t = __shfl_up_sync(c.gmask, pre, o, GL); if (c.gl >= o) pre += t; }
-                    total = gshfl(c, pre, 7); off = 0;
-                } else {
-                    // ---- enter the directed search: R from the circumdisks as they are now
-                    int a0 = g.gx, a1 = -1, c0 = g.gy, c1 = -1;
-                    if (c.d == 0) { a0 = 0; a1 = g.gx - 1; c0 = 0; c1 = g.gy - 1; }
-                    else if (c.gl < c.d) {
-                        if (c.r2 < 0 || c.r2 >= 1.0e299) { a0 = 0; a1 = g.gx - 1; c0 = 0; c1 = g.gy - 1; }
-                        else {
-                            double rr = sqrt(c.r2) * (1.0 + 1.0e-9) + 1.0e-6, cxa = c.ppx + c.vx, cya = c.ppy + c.vy;
-                            a0 = cell_coord(fmax(cxa - rr, g.xmin), g.xmin, g.inv_h, g.gx); a1 = cell_coord(fmin(cxa + rr, g.xmin + g.gx * g.h), g.xmin, g.inv_h, g.gx);
-                            c0 = cell_coord(fmax(cya - rr, g.ymin), g.ymin, g.inv_h, g.gy); c1 = cell_coord(fmin(cya + rr, g.ymin + g.gy * g.h), g.ymin, g.inv_h, g.gy);
-                        }
-                    }
-                    rx0 = gmin_i(c, a0); rx1 = gmax_i(c, a1); ry0 = gmin_i(c, c0); ry1 = gmax_i(c, c1);
-                    bx0 = rx0 >> 3; by0 = ry0 >> 3; BW = (rx1 >> 3) - bx0 + 1; nblk = BW * ((ry1 >> 3) - by0 + 1);
-                    b0 = -GL; am = 0; q = 4; k = 0; nmax = 0;
-                }
-                continue;
-            }
-            // ---- next batch of the level: lane t takes element off+gl of the concatenated runs
-            {
-                int t = off + c.gl, r = 0, base = 0;
-#pragma unroll
-                for (int kk = 0; kk < 7; ++kk) { int pk = gshfl(c, pre, kk); if (t >= pk) { r = kk + 1; base = pk; } }
-                int rb = gshfl(c, run_beg, r);
-                if (t < total) { int v = ps.cell_pts[rb + (t - base)]; if (v != INF16) id = v; }
-                off += GL; sort = true;
-            }
-        } else {
-            // ---- directed search cursor: advance until a batch of candidates is available
-            bool got = false;
+    while (__any_sync(FULL, active)) {
+        CNT(c_iter);
+        if (active && F == 0) {
+            // ================= refill: next batch / run / row / point (divergent between the two groups) =================
             for (;;) {
-                if (k < nmax) { id = k < n ? (int)ps.cell_pts[beg + k] : -1; ++k; got = true; break; }
-                int kind;                                  // 0: cells of chunk q of block (cbx,cby); 1: next 16 blocks
-                if (q < 4) kind = 0;
-                else if (am) { int l = __ffs(am) - 1; am &= am - 1; cbx = gshfl(c, bx, l); cby = gshfl(c, by, l); q = 0; kind = 0; }
-                else { b0 += GL; if (b0 >= nblk) break; kind = 1; }
-                double x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-                bool valid = false;
-                int cc = 0;
-                if (kind == 0) {
-                    int cx = (cbx << 3) + (c.gl & 7), cy = (cby << 3) + (c.gl >> 3) + 2 * q;
-                    valid = cx < g.gx && cy < g.gy && cx >= rx0 && cx <= rx1 && cy >= ry0 && cy <= ry1 &&
-                            !(cx >= ox0 && cx <= ox1 && cy >= oy0 && cy <= oy1);
-                    if (valid) {
-                        cc = cy * g.gx + cx;
-                        x0 = g.xmin + cx * g.h - c.ppx - 1.0e-6; y0 = g.ymin + cy * g.h - c.ppy - 1.0e-6;
-                        x1 = x0 + g.h + 2.0e-6; y1 = y0 + g.h + 2.0e-6;
-                    }
-                } else {
-                    int bi = b0 + c.gl;
-                    if (bi < nblk) {
-                        by = by0 + bi / BW; bx = bx0 + bi % BW; valid = true;
-                        int cxa = bx << 3, cya = by << 3, cxb = min(g.gx, cxa + 8), cyb = min(g.gy, cya + 8);
-                        x0 = g.xmin + cxa * g.h - c.ppx - 1.0e-6; y0 = g.ymin + cya * g.h - c.ppy - 1.0e-6;
-                        x1 = g.xmin + cxb * g.h - c.ppx + 1.0e-6; y1 = g.ymin + cyb * g.h - c.ppy + 1.0e-6;
-                    }
+                CNT(c_refill);
+                if (bail) {
+                    if (gl == 0) { int slot = atomicAdd(&sc->n_defer, 1); defer[slot] = (uint16_t)g.p; }
+                    bail = false; need_point = true;
                 }
-                bool cut = true;
-                if (c.d > 0) cut = g_rect_may_cut(c, x0, y0, x1, y1);       // the single culling site (group shuffles inside)
-                if (kind == 0) {
-                    n = 0; beg = 0;
-                    if (valid && cut) { n = ps.cell_n[cc]; beg = ps.cell_start[cc]; }
-                    nmax = gmax_i(c, n); k = 0; ++q;
+                if (need_point) {
+                    int pos;
+                    for (;;) {
+                        pos = 0;
+                        if (gl == 0) pos = atomicAdd(&sc->next_pos, 1);
+                        pos = __shfl_sync(gmask, pos, 0, GL);
+                        if (pos >= ps.n || ps.orig[pos] != INF16) break;
+                    }
+                    if (pos >= ps.n) { active = false; break; }
+                    g.p = pos; g.d = 0; g.ppx = ps.x[pos]; g.ppy = ps.y[pos];
+                    g.pcx = cell_of(g.ppx, ps.xmin, ps.inv_h, ps.gx); g.pcy = cell_of(g.ppy, ps.ymin, ps.inv_h, ps.gy);
+                    g.sid = g.nid = INF16; g.qx = g.qy = 0.f; g.m0 = 1.f; g.m1 = g.m2 = g.e0 = g.e1 = g.e2 = 0.f; g.dirty = true;
+                    need_point = false; phase = 0; k = 0; ri = re = 0; ca2 = 1; cb2 = 0;
+                }
+                if (ri < re) {
+                    if (phase == 1 && g.dirty && g.d > 0) {
+                        // the star changed since this row's interval was taken: clip the rest of the run to the new one
+                        g_regions(g, gl, ps);
+                        int la, lb;
+                        g_row_interval(g, ps, currow, la, lb);
+                        const int na = __reduce_min_sync(gmask, la), nb = __reduce_max_sync(gmask, lb);
+                        if (na > nb) { ri = re; ca2 = 1; cb2 = 0; continue; }
+                        if (rdir > 0) re = min(re, (int)ps.cell_start[currow * ps.gx + nb + 1]);
+                        else ri = max(ri, (int)ps.cell_start[currow * ps.gx + na]);
+                        if (cb2 >= ca2) { ca2 = max(ca2, na); cb2 = min(cb2, nb); }      // the pending range is the right-hand one
+                        if (ri >= re) continue;
+                    }
+                    // next batch of the run, nearest cell first: bit j of F <-> position bbase + j * bdir
+                    const int pos = rdir > 0 ? ri + gl : re - 1 - gl;
+                    const bool v = pos >= ri && pos < re && pos != g.p && ps.orig[pos] != INF16;
+                    cx = v ? ps.x[pos] - g.ppx : 0.f; cy = v ? ps.y[pos] - g.ppy : 0.f;
+                    bdir = rdir;
+                    if (rdir > 0) { bbase = ri; ri += GL; } else { bbase = re - 1; re -= GL; }
+                    CNT(c_batch);
+                    F = (__ballot_sync(gmask, v) >> gshift) & 0xFFFFu;
+                    if (F) break;
+                    continue;
+                }
+                int row, ca, cb, dir;
+                const int ex0 = max(g.pcx - 1, 0), ex1 = min(g.pcx + 1, ps.gx - 1);
+                if (cb2 >= ca2) { row = currow; ca = ca2; cb = cb2; dir = 1; ca2 = 1; cb2 = 0; }
+                else if (phase == 0) {
+                    if (k >= 3) { phase = 1; t = 0; continue; }
+                    row = k == 0 ? g.pcy : (k == 1 ? g.pcy - 1 : g.pcy + 1); ++k;        // own row first
+                    if (row < 0 || row >= ps.gy) continue;
+                    ca = ex0; cb = ex1; dir = 1;
                 } else {
-                    am = gballot(c, valid && cut);
+                    if (g.dirty) g_regions(g, gl, ps);
+                    int r0 = __reduce_min_sync(gmask, g.rowlo), r1 = __reduce_max_sync(gmask, g.rowhi);
+                    if (g.d == 0) { r0 = 0; r1 = ps.gy - 1; }
+                    bool found = false;
+                    row = 0;
+                    const int far = max(g.pcy - r0, r1 - g.pcy);
+                    while (r0 <= r1 && t <= 2 * far) {
+                        const int off = (t & 1) ? -((t + 1) >> 1) : (t >> 1);
+                        ++t;
+                        row = g.pcy + off;
+                        if (row >= r0 && row <= r1) { found = true; break; }
+                    }
+                    if (!found) {
+                        // ---- the sweep has left the union of the regions: the star is final
+                        if (EMIT) consume_emit<GL>(gmask, gl, g.d, g.p, g.sid, g.nid, ps, fv);
+                        else consume_vote<GL>(gmask, gl, g.d, g.p, g.sid, g.nid, ps, fv);
+                        need_point = true;
+                        continue;
+                    }
+                    CNT(c_row);
+                    int la, lb;
+                    g_row_interval(g, ps, row, la, lb);
+                    ca = __reduce_min_sync(gmask, la); cb = __reduce_max_sync(gmask, lb);
+                    if (g.d == 0) { ca = 0; cb = ps.gx - 1; }
+                    if (ca > cb) continue;
+                    // split at p's column (rows of the 3x3 block: around the examined cells): the left part is walked
+                    // right to left, the right part left to right -- nearest cells first
+                    const bool nearrow = row >= g.pcy - 1 && row <= g.pcy + 1;
+                    const int b1 = min(cb, nearrow ? ex0 - 1 : g.pcx), a2 = max(ca, nearrow ? ex1 + 1 : g.pcx + 1);
+                    if (b1 >= ca) { ca2 = a2; cb2 = cb; cb = b1; dir = -1; }
+                    else { ca = a2; dir = 1; }
+                    if (ca > cb) continue;
+                }
+                currow = row; CNT(c_run);
+                rdir = dir;
+                ri = ps.cell_start[row * ps.gx + ca]; re = ps.cell_start[row * ps.gx + cb + 1];
+            }
+        }
+        // ================= test one candidate per group against all triangles of its star (warp-convergent) =================
+        const bool doit = active && F != 0;
+        const int j = doit ? __ffs(F) - 1 : 0;
+        if (doit) { F &= F - 1; CNT(c_test); }
+        const float sx = __shfl_sync(FULL, cx, j, GL), sy = __shfl_sync(FULL, cy, j, GL);
+        const int spos = bbase + j * bdir;
+        const float sl = fmaf(sx, sx, sy * sy);
+        const float det = fmaf(g.m0, sl, fmaf(g.m1, sx, g.m2 * sy));
+        const float err = fmaf(g.e0, sl, fmaf(g.e1, fabsf(sx), g.e2 * fabsf(sy))) + 1.0e-30f;
+        const bool lane_on = doit && gl < g.d;
+        unsigned bc = __ballot_sync(FULL, lane_on && det < -err), bu = __ballot_sync(FULL, lane_on && !(fabsf(det) > err));
+        unsigned cf = (bc >> gshift) & 0xFFFFu;
+        if (bu) {
+            if ((bu >> gshift) & 0xFFFFu) {
+                // ---- the float32 filter could not decide for some triangle: exact evaluation of this candidate (group-divergent)
+                CNT(c_exact);
+                int code = 0;
+                if (lane_on) { code = exact_conflict(ps.x, ps.y, ps.orig, g.p, g.sid, g.nid, spos); n_exact += code >> 2; }
+                cf = (__ballot_sync(gmask, code & 1) >> gshift) & 0xFFFFu;
+                const unsigned zm = __ballot_sync(gmask, code & 2) & gmask;
+                if (g.d == 2 && zm) { cf = 0; bail = true; F = 0; }      // collinear bootstrap: fallback path
+            }
+        }
+        const bool first = doit && g.d == 0;
+        if (__any_sync(FULL, cf != 0 || first)) {
+            // ---- splice: remove the conflicting arc, insert s after its first slot (predicated per group)
+            bool ins = cf != 0;
+            int src = gl, nd = g.d;
+            if (ins) {
+                const int d = g.d;
+                const unsigned full = (1u << d) - 1u;
+                const unsigned prevm = ((cf << 1) | (cf >> (d - 1))) & full;
+                const unsigned starts = cf & ~prevm;
+                const int i0 = __ffs(starts) - 1, len = __popc(cf);
+                const unsigned rot = i0 > 0 ? (((cf >> i0) | (cf << (d - i0))) & full) : cf;
+                nd = d - len + 2;
+                if (__popc(starts) != 1 || rot != ((1u << len) - 1u) || len >= d || nd > GL) { ins = false; bail = true; F = 0; nd = d; }
+                else if (gl > 0 && gl < nd) { src = i0 + len + gl - 1; if (src >= d) src -= d; }
+            }
+            int sid2 = __shfl_sync(FULL, g.sid, src, GL);
+            float qx2 = __shfl_sync(FULL, g.qx, src, GL), qy2 = __shfl_sync(FULL, g.qy, src, GL);
+            if (ins) {
+                if (gl == 0) { sid2 = spos; qx2 = sx; qy2 = sy; }
+                g.sid = sid2; g.qx = qx2; g.qy = qy2; g.d = nd;
+            } else if (first) {
+                g.sid = gl == 0 ? spos : (int)INF16; g.qx = gl == 0 ? sx : 0.f; g.qy = gl == 0 ? sy : 0.f; g.d = 2;
+            }
+            if (ins || first) { g.dirty = true; CNT(c_splice); }
+            g_coeffs(g, FULL, gl);
+        }
+    }
+#ifdef MVOSR_STAR_COUNTERS
+    if (gl == 0) {
+        atomicAdd(&sc->cnt[0], (unsigned long long)c_test); atomicAdd(&sc->cnt[1], (unsigned long long)c_splice);
+        atomicAdd(&sc->cnt[2], (unsigned long long)c_batch); atomicAdd(&sc->cnt[3], (unsigned long long)c_row);
+        atomicAdd(&sc->cnt[4], (unsigned long long)c_run); atomicAdd(&sc->cnt[5], (unsigned long long)c_exact);
+        atomicAdd(&sc->cnt[7], (unsigned long long)c_refill);
+    }
+    if (lane == 0) atomicAdd(&sc->cnt[6], (unsigned long long)c_iter);
+#endif
+#undef CNT
+}
+
+// ---------------------------------------------------------------------------------------------
+// fallback: one warp, 32 slots, exact predicates, all points
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fb_reach2(int lane, int d, int sid, int nid, double ax, double ay, double al, double bx, double by, double bl) {
+    // upper bound of (2 * largest circumradius)^2; +inf when the star is open or a triangle is too flat to bound
+    double v = 0;
+    if (d < 3) v = 1.0e300;
+    else if (lane < d) {
+        if (sid == INF16 || nid == INF16) v = 1.0e300;
+        else {
+            double l = ax * by, r = ay * bx, w = (l - r) - 4.0e-16 * (fabs(l) + fabs(r));
+            double ex = ax - bx, ey = ay - by;
+            v = w > 0 ? al * bl * (ex * ex + ey * ey) / (w * w) * (1.0 + 1.0e-9) : 1.0e300;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+
+// Builds the star of p with the whole warp; on STAR_OK lane i holds slot i (sid) and slot i+1 (nid), d slots.
+struct FbResult { int rc, d, sid, nid, n_exact; };
+__device__ __noinline__ FbResult fb_build(const SortedSet &ps, int p) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const double ppx = ps.x[p], ppy = ps.y[p];
+    int n_exact = 0;
+    int d = 0, sid = INF16, nid = INF16;
+    double qx = 0, qy = 0, ql = 0, bx = 0, by = 0, bl = 0;
+    int qpos = -1, qneg = -1;            // collinear bootstrap: nearest point on either side of p on the common line
+    double reach2 = 1.0e300;
+    int rc = STAR_OK;
+    // candidates ring by ring around p's cell (nearest first keeps the intermediate stars small); ring r = the cells at
+    // Chebyshev distance r: two row runs and the two end cells of the rows between them
+    const int pcx = cell_of((float)ppx, ps.xmin, ps.inv_h, ps.gx), pcy = cell_of((float)ppy, ps.ymin, ps.inv_h, ps.gy);
+    const int rmax = max(max(pcx, ps.gx - 1 - pcx), max(pcy, ps.gy - 1 - pcy));
+    for (int r = 0; r <= rmax && rc == STAR_OK; ++r) {
+        const int ya = max(pcy - r + 1, 0), yb = min(pcy + r - 1, ps.gy - 1);
+        const int nruns = r == 0 ? 1 : 2 + 2 * max(yb - ya + 1, 0);
+        for (int q = 0; q < nruns && rc == STAR_OK; ++q) {
+            int row, c0, c1;
+            if (r == 0) { row = pcy; c0 = c1 = pcx; }
+            else if (q < 2) { row = q == 0 ? pcy - r : pcy + r; c0 = pcx - r; c1 = pcx + r; }
+            else { row = ya + ((q - 2) >> 1); c0 = c1 = (q & 1) ? pcx + r : pcx - r; }
+            if (row < 0 || row >= ps.gy) continue;
+            c0 = max(c0, 0); c1 = min(c1, ps.gx - 1);
+            if (c0 > c1) continue;
+            const int b = ps.cell_start[row * ps.gx + c0], e = ps.cell_start[row * ps.gx + c1 + 1];
+            for (int base = b; base < e && rc == STAR_OK; base += 32) {
+                const int pos = base + lane;
+                const bool v = pos < e && pos != p && ps.orig[pos] != INF16;
+                double sxl = 0, syl = 0, sll = 0;
+                if (v) { sxl = (double)ps.x[pos] - ppx; syl = (double)ps.y[pos] - ppy; sll = sxl * sxl + syl * syl; }
+                unsigned F = __ballot_sync(FULL, v && sll <= reach2);
+                while (F) {
+                    const int j = __ffs(F) - 1; F &= F - 1;
+                    const int s = base + j;
+                    const double sx = __shfl_sync(FULL, sxl, j), sy = __shfl_sync(FULL, syl, j), sl = __shfl_sync(FULL, sll, j);
+                    if (sl > reach2) continue;
+                    bool changed = false;
+                    if (d == 0) {
+                        // ---- bootstrap (warp-uniform): wait for the first point off the line through p and the first candidate
+                        if (qpos < 0) { qpos = s; continue; }
+                        const double ux = (double)ps.x[qpos] - ppx, uy = (double)ps.y[qpos] - ppy;
+                        const int o = cross_sign(ux, uy, sx, sy, n_exact);
+                        if (o == 0) {
+                            const bool same = (fabs(ux) >= fabs(uy)) ? ((sx > 0) == (ux > 0)) : ((sy > 0) == (uy > 0));
+                            if (same) { if (fabs(sx) + fabs(sy) < fabs(ux) + fabs(uy)) qpos = s; }
+                            else if (qneg < 0) qneg = s;
+                            else {
+                                const double nx = (double)ps.x[qneg] - ppx, ny = (double)ps.y[qneg] - ppy;
+                                if (fabs(sx) + fabs(sy) < fabs(nx) + fabs(ny)) qneg = s;
+                            }
+                            continue;
+                        }
+                        int ids[4], dd = 0;
+                        if (o > 0) { ids[dd++] = qpos; ids[dd++] = s; if (qneg >= 0) ids[dd++] = qneg; ids[dd++] = INF16; }
+                        else { if (qneg >= 0) ids[dd++] = qneg; ids[dd++] = s; ids[dd++] = qpos; ids[dd++] = INF16; }
+                        sid = INF16;
+                        for (int i = 0; i < dd; ++i) if (lane == i) sid = ids[i];
+                        qx = qy = ql = 0;
+                        if (lane < dd && sid != INF16) { qx = (double)ps.x[sid] - ppx; qy = (double)ps.y[sid] - ppy; ql = qx * qx + qy * qy; }
+                        d = dd; changed = true;
+                    } else {
+                        bool c = false;
+                        if (lane < d) {
+                            if (nid == INF16) {
+                                int o = cross_sign(qx, qy, sx, sy, n_exact);
+                                c = o > 0 || (o == 0 && strictly_between(qx, qy, sx, sy));
+                            } else if (sid == INF16) {
+                                int o = cross_sign(bx, by, sx, sy, n_exact);
+                                c = o < 0 || (o == 0 && strictly_between(bx, by, sx, sy));
+                            } else {
+                                c = incircle_sos(qx, qy, ql, bx, by, bl, sx, sy, sl, ps.orig[p], ps.orig[sid], ps.orig[nid], ps.orig[s], n_exact);
+                            }
+                        }
+                        const unsigned cf = __ballot_sync(FULL, c);
+                        if (!cf) continue;
+                        const unsigned full = d >= 32 ? 0xFFFFFFFFu : ((1u << d) - 1u);
+                        const unsigned prevm = ((cf << 1) | (cf >> (d - 1))) & full;
+                        const unsigned starts = cf & ~prevm;
+                        const int i0 = __ffs(starts) - 1, len = __popc(cf);
+                        const unsigned rot = i0 > 0 ? (((cf >> i0) | (cf << (d - i0))) & full) : cf;
+                        if (__popc(starts) != 1 || rot != (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) || len >= d) { rc = STAR_INCONSISTENT; break; }
+                        const int nd = d - len + 2;
+                        if (nd > 32) { rc = STAR_OVERFLOW; break; }
+                        int src = lane;
+                        if (lane > 0 && lane < nd) { src = i0 + len + lane - 1; if (src >= d) src -= d; }
+                        int sid2 = __shfl_sync(FULL, sid, src);
+                        double qx2 = __shfl_sync(FULL, qx, src), qy2 = __shfl_sync(FULL, qy, src), ql2 = __shfl_sync(FULL, ql, src);
+                        if (lane == 0) { sid2 = s; qx2 = sx; qy2 = sy; ql2 = sl; }
+                        sid = sid2; qx = qx2; qy = qy2; ql = ql2; d = nd; changed = true;
+                    }
+                    if (changed) {
+                        const int nx = lane + 1 < d ? lane + 1 : 0;
+                        nid = __shfl_sync(FULL, sid, nx); bx = __shfl_sync(FULL, qx, nx); by = __shfl_sync(FULL, qy, nx); bl = __shfl_sync(FULL, ql, nx);
+                        reach2 = fb_reach2(lane, d, sid, nid, qx, qy, ql, bx, by, bl);
+                    }
                 }
             }
-            if (!got) return c.d > 0 ? STAR_OK : STAR_NONE;
         }
-        int r = g_batch(c, bs, id, sort, ps.px, ps.py);                      // the single batch site
-        if (r < 0) return -r;
+        // final once every unexamined point (outside the block of half-width r) is farther than twice the largest circumradius
+        if (reach2 < 1.0e299) {
+            const double INFD = 1.0e300, hh = ps.h;
+            const double ml = pcx - r > 0 ? ppx - ((double)ps.xmin + (pcx - r) * hh) : INFD;
+            const double mr = pcx + r < ps.gx - 1 ? ((double)ps.xmin + (pcx + r + 1) * hh) - ppx : INFD;
+            const double mb = pcy - r > 0 ? ppy - ((double)ps.ymin + (pcy - r) * hh) : INFD;
+            const double mt = pcy + r < ps.gy - 1 ? ((double)ps.ymin + (pcy + r + 1) * hh) - ppy : INFD;
+            const double m = fmin(fmin(ml, mr), fmin(mb, mt)) - 1.0e-3 - 1.0e-4 * hh;     // slack: rounding in the cell assignment
+            if (m > 0 && m * m >= reach2) break;
+        }
     }
+    FbResult res; res.d = d; res.sid = sid; res.nid = nid; res.n_exact = n_exact;
+    res.rc = rc != STAR_OK ? rc : (d > 0 ? STAR_OK : STAR_NONE);     // d == 0: p alone, or all other points on one line through p
+    return res;
+}
+
+// All stars of the staged point set.  EMIT: triangles into fv.tri; otherwise the graph vote into fv.pflag.
+// Block-wide; sc and defer[] are shared scratch.  Returns the number of stars rebuilt by the fallback.
+template <bool EMIT>
+__device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, int &n_exact) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { sc->next_pos = 0; sc->n_defer = 0; }
+    __syncthreads();
+    stars_fast<EMIT>(ps, fv, sc, defer, n_exact);
+    __syncthreads();
+    const int nd = sc->n_defer;
+    for (int k = warp; k < nd; k += NWARP) {
+        const int p = defer[k];
+        const FbResult r = fb_build(ps, p);
+        n_exact += r.n_exact;
+        if (r.rc == STAR_OK) {
+            if (EMIT) consume_emit<32>(0xFFFFFFFFu, lane, r.d, p, r.sid, r.nid, ps, fv);
+            else consume_vote<32>(0xFFFFFFFFu, lane, r.d, p, r.sid, r.nid, ps, fv);
+        } else if (r.rc != STAR_NONE && lane == 0) {
+            atomicOr(fv.status, MVOSR_ST_OVERFLOW);
+#ifdef MVOSR_DEBUG_PRINT
+            printf("fb_build failed: rc=%d p=%d orig=%d d=%d n=%d\n", r.rc, p, (int)ps.orig[p], r.d, ps.n);
+#endif
+        }
+    }
+    __syncthreads();
+    return nd;
 }
 
 }  // namespace mvosr

@@ -38,7 +38,7 @@ __device__ __forceinline__ bool jacobi_pair(double (&a)[4][4], double (&v)[4][4]
 }
 
 // Returns the mask; X (float64, current-camera frame) and the reprojected pixel are written always.
-__device__ __forceinline__ bool triangulate_point(float cu, float cv, float ru, float rv, const Pose &pose,
+__device__ __noinline__ bool triangulate_point(float cu, float cv, float ru, float rv, const Pose &pose,
                                                   double fx, double fy, double cx, double cy, double dist,
                                                   double &X, double &Y, double &Z, double &u, double &v) {
     double x0 = ((double)cu - cx) / fx, y0 = ((double)cv - cy) / fy;

@@ -11,8 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mvoscalerecovery_b200 import synth, _native as N            # noqa: E402
 from mvoscalerecovery_b200.batch import ScaleRecovery, stats_to_numpy            # noqa: E402
 
-NAMES = {0: "load+stage1+roi", 1: "grid1", 2: "stars1_thread", 3: "stars1_warp", 6: "compact+grid2", 7: "stars2_thread",
-         8: "stars2_warp", 10: "planes", 11: "median", 12: "valid_list", 13: "ransac"}
+NAMES = {0: "load+stage1+roi", 1: "grid1|c_refill", 3: "c_test", 4: "c_splice", 5: "c_batch", 8: "c_row", 9: "c_run", 14: "c_exact", 15: "c_iter", 2: "stars1", 6: "keep+compact+grid2", 7: "stars2", 10: "planes", 11: "median", 12: "valid_list", 13: "ransac"}
 
 
 def main():

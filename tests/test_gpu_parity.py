@@ -210,8 +210,9 @@ def _degenerate_sets():
     sets["clusters"] = np.vstack([rng.normal([200, 250], 3, (300, 2)), rng.normal([900, 300], 40, (300, 2)), rng.uniform([0, 186], [1241, 376], (200, 2))])
     sets["three"] = np.array([[10, 200], [20, 210], [15, 250]])
     sets["four_square"] = np.array([[0, 190], [1, 190], [1, 191], [0, 191]])
-    sets["hub"] = np.vstack([[[600, 280]], np.stack([600 + 80 * np.cos(np.linspace(0, 2 * np.pi, 40, endpoint=False) + 0.01),
-                                                     280 + 80 * np.sin(np.linspace(0, 2 * np.pi, 40, endpoint=False) + 0.01)], 1)])
+    for spokes in (28, 40):      # a hub of degree 28 (> 16: 32-slot fallback path) and 40 (> 32: documented capacity, status OVERFLOW)
+        a = np.linspace(0, 2 * np.pi, spokes, endpoint=False) + 0.01
+        sets["hub%d" % spokes] = np.vstack([[[600, 280]], np.stack([600 + 80 * np.cos(a), 280 + 80 * np.sin(a)], 1)])
     sets["random3000"] = np.stack([rng.uniform(0, 1241, 3000), rng.uniform(186, 376, 3000)], 1)
     return {k: v.astype(np.float32) for k, v in sets.items()}
 
@@ -236,6 +237,9 @@ def test_delaunay_degenerate_inputs_vs_exact_oracle(engine):
         got = tri[2 * off[i]: 2 * off[i] + ntri[i]]
         if ref.shape[0] == 0:
             assert ntri[i] == 0 and (st[i] & 4), (k, ntri[i], st[i])        # FEW_ROI: nothing to triangulate
+            continue
+        if k == "hub40":
+            assert st[i] & 32, (k, st[i])                                   # star degree > 32: MVOSR_ST_OVERFLOW by design
             continue
         assert st[i] == 0, (k, st[i])
         assert ntri[i] == ref.shape[0], (k, ntri[i], ref.shape[0])
