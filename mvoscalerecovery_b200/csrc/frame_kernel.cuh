@@ -81,7 +81,7 @@ __host__ __device__ inline SmemPlan make_plan(int cap) {   // cap: multiple of 6
     p.t_U = p.off_T; p.t_V = p.off_T + 4 * cap;
     p.h_sx = p.off_H; p.h_sy = p.off_H + 4 * cap; p.h_sorig = p.off_H + 8 * cap;
     p.h_cell_start = p.off_H + 10 * cap;           // at most cap - 1 cells: cap uint16 entries
-    p.h_defer = p.off_H + 12 * cap;                // 2cap bytes: ends at 14cap <= 16cap
+    p.h_defer = p.off_H + 12 * cap;                // two queues of 2cap bytes each: ends at 16cap
     return p;
 }
 
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
     GridArrays ga;
     ga.sx = (float *)(smem + pl.h_sx); ga.sy = (float *)(smem + pl.h_sy); ga.sorig = (uint16_t *)(smem + pl.h_sorig);
     ga.cell_start = (uint16_t *)(smem + pl.h_cell_start); ga.scr = (uint32_t *)(smem + pl.off_scr);
-    uint16_t *defer = (uint16_t *)(smem + pl.h_defer);
+    uint16_t *defer = (uint16_t *)(smem + pl.h_defer), *defer2 = defer + cap;
     uint16_t *mult = (uint16_t *)(smem + pl.off_mult);
     double *theight = (double *)(smem + pl.off_H);           // aliases the sorted copy (dead by then)
     uint8_t *tflags = smem + pl.off_tflags;
@@ -389,10 +389,10 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             if (P.mode == MODE_DT_ONLY) {
                 for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
                 __syncthreads();
-                int nd = run_stars<true>(ctl.ps, fv, &ctl.sc, defer, n_exact);
+                int nd = run_stars<true>(ctl.ps, fv, &ctl.sc, defer, defer2, n_exact, &ctl.tphase[3]);
                 if (tid == 0) ctl.n_deferred_total += nd;
             } else {
-                int nd = run_stars<false>(ctl.ps, fv, &ctl.sc, defer, n_exact);
+                int nd = run_stars<false>(ctl.ps, fv, &ctl.sc, defer, defer2, n_exact, &ctl.tphase[3]);
                 if (tid == 0) ctl.n_deferred_total += nd;
             }
             __syncthreads();
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 // overwrites U,V, which are restored from the sorted copy afterwards)
                 for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
                 __syncthreads();
-                run_stars<true>(ctl.ps, fv, &ctl.sc, defer, n_exact);
+                run_stars<true>(ctl.ps, fv, &ctl.sc, defer, defer2, n_exact, nullptr);
                 write_canonical(n, fv, ga.scr, ctl.warp_cnt, P.dbg.tri1 + 3 * (size_t)(2 * base), P.dbg.n_tri1 ? P.dbg.n_tri1 + f : nullptr);
                 if (tid == 0) ctl.T = 0;
                 for (int i = tid; i < n; i += NT) { int o = ga.sorig[i]; if (o != INF16) { U[o] = ga.sx[i]; V[o] = ga.sy[i]; } }
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
             __syncthreads();
             TMARK(6);
-            int nd = run_stars<true>(ctl.ps, fv, &ctl.sc, defer, n_exact);
+            int nd = run_stars<true>(ctl.ps, fv, &ctl.sc, defer, defer2, n_exact, &ctl.tphase[8]);
             if (tid == 0) ctl.n_deferred_total += nd;
             __syncthreads();
             status |= ctl.status;
@@ -700,8 +700,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 s.n_deferred = ctl.n_deferred_total; s.n_exact = ctl.n_exact; s.height_level = ctl.height_level;
             }
 #ifdef MVOSR_STAR_COUNTERS
-            ctl.tphase[3] = ctl.sc.cnt[0]; ctl.tphase[4] = ctl.sc.cnt[1]; ctl.tphase[5] = ctl.sc.cnt[2]; ctl.tphase[8] = ctl.sc.cnt[3];
-            ctl.tphase[9] = ctl.sc.cnt[4]; ctl.tphase[14] = ctl.sc.cnt[5]; ctl.tphase[15] = ctl.sc.cnt[6]; ctl.tphase[1] = ctl.sc.cnt[7];
+            ctl.tphase[1] = ctl.sc.cnt[7]; ctl.tphase[4] = ctl.sc.cnt[2]; ctl.tphase[5] = ctl.sc.cnt[3]; ctl.tphase[9] = ctl.sc.cnt[4]; ctl.tphase[12] = ctl.sc.cnt[0];
+            ctl.tphase[14] = ctl.sc.cnt[5]; ctl.tphase[15] = ctl.sc.cnt[6];
 #endif
             if (P.phase_cycles) for (int k = 0; k < 16; ++k) P.phase_cycles[16 * (size_t)f + k] = ctl.tphase[k];
         }

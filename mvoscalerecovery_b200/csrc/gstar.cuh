@@ -66,8 +66,8 @@ __device__ __forceinline__ int cell_of(float v, float vmin, float inv_h, int g) 
     return c < 0 ? 0 : (c >= g ? g - 1 : c);
 }
 
-struct StarCtl {                         // shared-memory work queue of one Delaunay pass
-    int next_pos, n_defer;
+struct StarCtl {                         // shared-memory work queues of one Delaunay pass
+    int next_pos, n_defer, n_defer2;
     unsigned long long cnt[8];           // profiling counters (MVOSR_STAR_COUNTERS): tests, splices, batches, rows, runs, exact, loop iterations, refill iterations
 };
 
@@ -263,10 +263,10 @@ __device__ __forceinline__ void g_row_interval(const GState &g, const SortedSet 
     }
 }
 
-// All stars of the staged set, fast path; stars it gives up on are appended to defer[].
+// The stars of list[0..n_list) (sorted positions), one per half-warp; stars it gives up on are appended to defer[].
 template <bool EMIT>
-__device__ __forceinline__ void stars_fast(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, int &n_exact) {
-    const unsigned FULL = 0xFFFFFFFFu;
+__device__ __forceinline__ void stars_fast(const SortedSet &ps, const FrameView &fv, StarCtl *sc, const uint16_t *list, int n_list,
+                                           uint16_t *defer, int &n_exact) {
     const int lane = threadIdx.x & 31, gl = lane & (GL - 1), gshift = lane & GL;
     const unsigned gmask = 0xFFFFu << gshift;
     GState g;
@@ -276,31 +276,38 @@ __device__ __forceinline__ void stars_fast(const SortedSet &ps, const FrameView 
     int phase = 0, k = 0, t = 0, ri = 0, re = 0, rdir = 1, ca2 = 1, cb2 = 0, currow = 0;
     unsigned F = 0; int bbase = 0, bdir = 1; float cx = 0.f, cy = 0.f;
 #ifdef MVOSR_STAR_COUNTERS
-    unsigned c_test = 0, c_splice = 0, c_batch = 0, c_row = 0, c_run = 0, c_exact = 0, c_iter = 0, c_refill = 0;
+    unsigned c_test = 0, c_splice = 0, c_batch = 0, c_row = 0, c_run = 0, c_exact = 0, c_iter = 0, c_refill = 0, c_b1 = 0, c_b2 = 0, c_b3 = 0, c_star = 0; long long c_t0 = 0;
 #define CNT(x) ++x
 #else
 #define CNT(x)
 #endif
 
-    while (__any_sync(FULL, active)) {
+    while (active) {
         CNT(c_iter);
-        if (active && F == 0) {
-            // ================= refill: next batch / run / row / point (divergent between the two groups) =================
+        if (F == 0) {
+            // ================= refill: next batch / run / row / point =================
             for (;;) {
                 CNT(c_refill);
                 if (bail) {
-                    if (gl == 0) { int slot = atomicAdd(&sc->n_defer, 1); defer[slot] = (uint16_t)g.p; }
+                    if (gl == 0) { int slot = atomicAdd(&sc->n_defer2, 1); defer[slot] = (uint16_t)g.p; }
                     bail = false; need_point = true;
                 }
                 if (need_point) {
-                    int pos;
-                    for (;;) {
-                        pos = 0;
-                        if (gl == 0) pos = atomicAdd(&sc->next_pos, 1);
-                        pos = __shfl_sync(gmask, pos, 0, GL);
-                        if (pos >= ps.n || ps.orig[pos] != INF16) break;
+#ifdef MVOSR_STAR_COUNTERS
+                    if (gl == 0 && g.p >= 0) {
+                        if (c_star > 64) atomicAdd(&sc->cnt[2], 1ull);
+                        if (c_star > 256) atomicAdd(&sc->cnt[3], 1ull);
+                        if (c_star > 1024) atomicAdd(&sc->cnt[4], 1ull);
+                        atomicMax(&sc->cnt[7], (unsigned long long)c_star);
+                        atomicMax(&sc->cnt[6], (unsigned long long)(clock64() - c_t0));
                     }
-                    if (pos >= ps.n) { active = false; break; }
+                    c_star = 0; c_t0 = clock64();
+#endif
+                    int idx = 0;
+                    if (gl == 0) idx = atomicAdd(&sc->next_pos, 1);
+                    idx = __shfl_sync(gmask, idx, 0, GL);
+                    if (idx >= n_list) { active = false; break; }
+                    const int pos = list[idx];
                     g.p = pos; g.d = 0; g.ppx = ps.x[pos]; g.ppy = ps.y[pos];
                     g.pcx = cell_of(g.ppx, ps.xmin, ps.inv_h, ps.gx); g.pcy = cell_of(g.ppy, ps.ymin, ps.inv_h, ps.gy);
                     g.sid = g.nid = INF16; g.qx = g.qy = 0.f; g.m0 = 1.f; g.m1 = g.m2 = g.e0 = g.e1 = g.e2 = 0.f; g.dirty = true;
@@ -377,32 +384,29 @@ __device__ __forceinline__ void stars_fast(const SortedSet &ps, const FrameView 
                 ri = ps.cell_start[row * ps.gx + ca]; re = ps.cell_start[row * ps.gx + cb + 1];
             }
         }
-        // ================= test one candidate per group against all triangles of its star (warp-convergent) =================
-        const bool doit = active && F != 0;
-        const int j = doit ? __ffs(F) - 1 : 0;
-        if (doit) { F &= F - 1; CNT(c_test); }
-        const float sx = __shfl_sync(FULL, cx, j, GL), sy = __shfl_sync(FULL, cy, j, GL);
+        if (!active) break;
+        // ================= test one candidate against all triangles of the star =================
+        const int j = __ffs(F) - 1;
+        F &= F - 1; CNT(c_test); CNT(c_star);
+        const float sx = __shfl_sync(gmask, cx, j, GL), sy = __shfl_sync(gmask, cy, j, GL);
         const int spos = bbase + j * bdir;
         const float sl = fmaf(sx, sx, sy * sy);
         const float det = fmaf(g.m0, sl, fmaf(g.m1, sx, g.m2 * sy));
         const float err = fmaf(g.e0, sl, fmaf(g.e1, fabsf(sx), g.e2 * fabsf(sy))) + 1.0e-30f;
-        const bool lane_on = doit && gl < g.d;
-        unsigned bc = __ballot_sync(FULL, lane_on && det < -err), bu = __ballot_sync(FULL, lane_on && !(fabsf(det) > err));
-        unsigned cf = (bc >> gshift) & 0xFFFFu;
-        if (bu) {
-            if ((bu >> gshift) & 0xFFFFu) {
-                // ---- the float32 filter could not decide for some triangle: exact evaluation of this candidate (group-divergent)
-                CNT(c_exact);
-                int code = 0;
-                if (lane_on) { code = exact_conflict(ps.x, ps.y, ps.orig, g.p, g.sid, g.nid, spos); n_exact += code >> 2; }
-                cf = (__ballot_sync(gmask, code & 1) >> gshift) & 0xFFFFu;
-                const unsigned zm = __ballot_sync(gmask, code & 2) & gmask;
-                if (g.d == 2 && zm) { cf = 0; bail = true; F = 0; }      // collinear bootstrap: fallback path
-            }
+        const bool lane_on = gl < g.d;
+        unsigned cf = (__ballot_sync(gmask, lane_on && det < -err) >> gshift) & 0xFFFFu;
+        if (__ballot_sync(gmask, lane_on && !(fabsf(det) > err)) & gmask) {
+            // ---- the float32 filter could not decide for some triangle: exact evaluation of this candidate
+            CNT(c_exact);
+            int code = 0;
+            if (lane_on) { code = exact_conflict(ps.x, ps.y, ps.orig, g.p, g.sid, g.nid, spos); n_exact += code >> 2; }
+            cf = (__ballot_sync(gmask, code & 1) >> gshift) & 0xFFFFu;
+            const unsigned zm = __ballot_sync(gmask, code & 2) & gmask;
+            if (g.d == 2 && zm) { cf = 0; bail = true; F = 0; CNT(c_b1); }      // collinear bootstrap: fallback path
         }
-        const bool first = doit && g.d == 0;
-        if (__any_sync(FULL, cf != 0 || first)) {
-            // ---- splice: remove the conflicting arc, insert s after its first slot (predicated per group)
+        const bool first = g.d == 0;
+        if (cf != 0 || first) {
+            // ---- splice: remove the conflicting arc, insert s after its first slot
             bool ins = cf != 0;
             int src = gl, nd = g.d;
             if (ins) {
@@ -413,29 +417,25 @@ __device__ __forceinline__ void stars_fast(const SortedSet &ps, const FrameView 
                 const int i0 = __ffs(starts) - 1, len = __popc(cf);
                 const unsigned rot = i0 > 0 ? (((cf >> i0) | (cf << (d - i0))) & full) : cf;
                 nd = d - len + 2;
-                if (__popc(starts) != 1 || rot != ((1u << len) - 1u) || len >= d || nd > GL) { ins = false; bail = true; F = 0; nd = d; }
+                if (__popc(starts) != 1 || rot != ((1u << len) - 1u) || len >= d || nd > GL) { if (nd > GL) { CNT(c_b3); } else { CNT(c_b2); } ins = false; bail = true; F = 0; nd = d; }
                 else if (gl > 0 && gl < nd) { src = i0 + len + gl - 1; if (src >= d) src -= d; }
             }
-            int sid2 = __shfl_sync(FULL, g.sid, src, GL);
-            float qx2 = __shfl_sync(FULL, g.qx, src, GL), qy2 = __shfl_sync(FULL, g.qy, src, GL);
             if (ins) {
+                int sid2 = __shfl_sync(gmask, g.sid, src, GL);
+                float qx2 = __shfl_sync(gmask, g.qx, src, GL), qy2 = __shfl_sync(gmask, g.qy, src, GL);
                 if (gl == 0) { sid2 = spos; qx2 = sx; qy2 = sy; }
                 g.sid = sid2; g.qx = qx2; g.qy = qy2; g.d = nd;
             } else if (first) {
                 g.sid = gl == 0 ? spos : (int)INF16; g.qx = gl == 0 ? sx : 0.f; g.qy = gl == 0 ? sy : 0.f; g.d = 2;
             }
-            if (ins || first) { g.dirty = true; CNT(c_splice); }
-            g_coeffs(g, FULL, gl);
+            if (ins || first) { g.dirty = true; CNT(c_splice); g_coeffs(g, gmask, gl); }
         }
     }
 #ifdef MVOSR_STAR_COUNTERS
     if (gl == 0) {
         atomicAdd(&sc->cnt[0], (unsigned long long)c_test); atomicAdd(&sc->cnt[1], (unsigned long long)c_splice);
-        atomicAdd(&sc->cnt[2], (unsigned long long)c_batch); atomicAdd(&sc->cnt[3], (unsigned long long)c_row);
-        atomicAdd(&sc->cnt[4], (unsigned long long)c_run); atomicAdd(&sc->cnt[5], (unsigned long long)c_exact);
-        atomicAdd(&sc->cnt[7], (unsigned long long)c_refill);
+ atomicAdd(&sc->cnt[5], (unsigned long long)c_b1 + ((unsigned long long)c_b2 << 16) + ((unsigned long long)c_b3 << 32));
     }
-    if (lane == 0) atomicAdd(&sc->cnt[6], (unsigned long long)c_iter);
 #endif
 #undef CNT
 }
@@ -577,18 +577,273 @@ __device__ __noinline__ FbResult fb_build(const SortedSet &ps, int p) {
     return res;
 }
 
-// All stars of the staged point set.  EMIT: triangles into fv.tri; otherwise the graph vote into fv.pflag.
-// Block-wide; sc and defer[] are shared scratch.  Returns the number of stars rebuilt by the fallback.
+// ---------------------------------------------------------------------------------------------
+// wrap path: one warp per star, lanes = candidates (the production path)
+// ---------------------------------------------------------------------------------------------
+// Gift-wrapping around p with the candidates held in registers, two per lane: the points of the 5x5 block of grid
+// cells around p.  The nearest point q0 is a Delaunay neighbour; from edge (p,cur) the next neighbour counter-clockwise
+// is the candidate w on the left of p->cur with the smallest circumcentre parameter
+//     t(s) = (|s|^2 - s.cur) / cross(cur, s)              (coordinates relative to p)
+// -- the circle (p,cur,w) then holds no other point on the left.  Every lane evaluates t for its two candidates with a
+// forward error bound (float32), one REDUX picks the winner, a second one proves that no other candidate's interval
+// overlaps the winner's.  The winner is global once the left cap of its circle lies inside the block; otherwise (and on
+// hull edges, where no candidate lies on the left) the grid rows the cap covers are streamed 32 candidates at a time.
+// An edge with no left point anywhere is a hull edge: the walk restarts clockwise from q0 (mirrored orientation).
+// All decisions are certified by the error bounds; whenever one is not (ties, collinearities, crowded cells) the star
+// is handed to the exact path above, which decides with exact predicates.
+constexpr float WU = 5.9604644775390625e-08f;     // 2^-24, unit roundoff of float32
+constexpr int WRAP_BLOCK = 2;                     // half-width of the candidate block in cells
+
+struct WEval { float t, eps; bool cand, susp; };
+
+// candidate s (relative to p) against edge (p,cur), orientation sigma (+1 counter-clockwise walk, -1 clockwise)
+__device__ __forceinline__ WEval w_eval(bool valid, float sx, float sy, float sl, float cx, float cy, float sigma) {
+    WEval e;
+    const float p1 = cx * sy, p2 = cy * sx;
+    const float cr = sigma * (p1 - p2);
+    const float ecr = 8.f * WU * (fabsf(p1) + fabsf(p2));       // |cr - exact| <= 4u (|p1|+|p2|)
+    e.cand = valid && cr > 2.f * ecr;                             // certainly on the walk's left
+    e.susp = valid && !(fabsf(cr) > 2.f * ecr);                   // side not certain
+    const float q1 = sx * cx, q2 = sy * cy;
+    const float num = (sl - q1) - q2;
+    const float en = 8.f * WU * (sl + fabsf(q1) + fabsf(q2));     // |num - exact| <= 6u (...)
+    const float r = __fdividef(1.f, cr);
+    e.t = num * r;
+    e.eps = (en + fabsf(e.t) * ecr) * r * 1.01f + 16.f * WU * fabsf(e.t) + 1.0e-30f;
+    return e;
+}
+
+__device__ __forceinline__ unsigned w_key(float t) {             // order-preserving float -> uint
+    unsigned k = __float_as_uint(t);
+    return (k & 0x80000000u) ? ~k : (k | 0x80000000u);
+}
+
+struct WBest {                          // warp-uniform: current best of a step
+    bool have; float t, eps, x, y; int pos;
+    float vx, vy, rs;                   // its circle (p,cur,best): centre relative to p, padded radius
+};
+
+__device__ __forceinline__ void w_circle(WBest &b, float cx, float cy, float sigma) {
+    // centre = cur/2 + (sigma t / 2) * (-cy, cx)
+    b.vx = 0.5f * (cx - sigma * b.t * cy); b.vy = 0.5f * (cy + sigma * b.t * cx);
+    const float r = sqrtf(fmaf(b.vx, b.vx, b.vy * b.vy));
+    const float pad = b.eps * (fabsf(cx) + fabsf(cy)) * 0.51f + 1.0e-3f + 1.0e-4f * r;
+    b.rs = r + 2.f * pad;
+}
+
+// One batch of candidates (one per lane) against the current best of the step.  Returns false if a decision could not
+// be certified (the star goes to the exact path).
+__device__ __forceinline__ bool w_batch(WBest &b, bool valid, float sx, float sy, int pos, float cx, float cy, float sigma) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const float sl = fmaf(sx, sx, sy * sy);
+    const WEval e = w_eval(valid, sx, sy, sl, cx, cy, sigma);
+    if (__any_sync(FULL, e.susp)) return false;
+    const bool flag = e.cand && (!b.have || e.t - e.eps < b.t + b.eps);
+    const unsigned fm = __ballot_sync(FULL, flag);
+    if (!fm) return true;
+    const unsigned k = flag ? w_key(e.t) : 0xFFFFFFFFu;
+    const unsigned kmin = __reduce_min_sync(FULL, k);
+    const int wl = __ffs(__ballot_sync(FULL, k == kmin)) - 1;
+    const float wt = __shfl_sync(FULL, e.t, wl), we = __shfl_sync(FULL, e.eps, wl);
+    // the winner must beat every other flagged candidate and the previous best with disjoint intervals
+    const bool clash = flag && threadIdx.x % 32 != wl && !(e.t - e.eps > wt + we);
+    if (__any_sync(FULL, clash)) return false;
+    if (b.have && !(wt + we < b.t - b.eps)) return false;
+    b.have = true; b.t = wt; b.eps = we;
+    b.x = __shfl_sync(FULL, sx, wl); b.y = __shfl_sync(FULL, sy, wl); b.pos = __shfl_sync(FULL, pos, wl);
+    w_circle(b, cx, cy, sigma);
+    return true;
+}
+
+// Stream the grid cells that the left cap of the best's circle (the whole left half-plane while there is no best)
+// covers outside the block [bx0,bx1]x[by0,by1].  false: not certified.
+__device__ __noinline__ bool w_stream(WBest &b, const SortedSet &ps, int p, float ppx, float ppy, int pcy,
+                                      int bx0, int bx1, int by0, int by1, float cx, float cy, float sigma, int cpos) {
+    const int lane = threadIdx.x & 31;
+    const float INF = CUDART_INF_F;
+    const float hx = sigma * cx, hy = sigma * cy;                 // half-plane hx*y - hy*x > 0
+    for (int t = 0; ; ++t) {
+        // rows outwards from p's row, inside the row range of the region as it is now
+        int r0 = 0, r1 = ps.gy - 1;
+        const bool disk = b.have && b.rs < 1.0e6f;                // a larger (or non-finite) circle bounds nothing useful: half-plane only
+        if (disk) {
+            const float a = (ppy + b.vy - b.rs - ps.ymin) * ps.inv_h, c = (ppy + b.vy + b.rs - ps.ymin) * ps.inv_h;
+            if (c < 0.f) return true;
+            r0 = (int)fminf(fmaxf(a, 0.f), (float)(ps.gy - 1)); r1 = (int)fminf(fmaxf(c, 0.f), (float)(ps.gy - 1));
+        }
+        if (t > 2 * max(pcy - r0, r1 - pcy)) return true;
+        const int row = pcy + ((t & 1) ? -((t + 1) >> 1) : (t >> 1));
+        if (row < r0 || row > r1) continue;
+        const float Y0 = ps.ymin + row * ps.h - ppy - (1.0e-3f + 1.0e-4f * ps.h), Y1 = Y0 + ps.h + 2.f * (1.0e-3f + 1.0e-4f * ps.h);
+        float lo = -INF, hi = INF;
+        if (disk) {
+            const float dy = fmaxf(fmaxf(Y0 - b.vy, b.vy - Y1), 0.f), rem = b.rs * b.rs - dy * dy;
+            if (!(rem > 0.f)) continue;
+            const float hw = sqrtf(rem) * 1.0001f + 1.0e-3f;
+            lo = b.vx - hw; hi = b.vx + hw;
+        }
+        if (hy > 0.f) { const float u = fmaxf(hx * Y0, hx * Y1) / hy; hi = fminf(hi, u + 1.0e-5f * fabsf(u) + 1.0e-3f); }
+        else if (hy < 0.f) { const float u = fminf(hx * Y0 / hy, hx * Y1 / hy); lo = fmaxf(lo, u - 1.0e-5f * fabsf(u) - 1.0e-3f); }
+        else if (!(hx > 0.f ? Y1 > 0.f : (hx < 0.f ? Y0 < 0.f : true))) continue;
+        if (!(lo <= hi)) continue;
+        const float fa = (lo + ppx - ps.xmin) * ps.inv_h, fb = (hi + ppx - ps.xmin) * ps.inv_h;
+        if (fb < 0.f) continue;
+        int ca = (int)fminf(fmaxf(fa, 0.f), (float)(ps.gx - 1)), cb = (int)fminf(fmaxf(fb, 0.f), (float)(ps.gx - 1));
+        // up to two runs: the block's columns are excluded on the block's rows
+        int ca2 = 1, cb2 = 0;
+        if (row >= by0 && row <= by1) {
+            const int e1 = min(cb, bx0 - 1), a2 = max(ca, bx1 + 1);
+            if (e1 >= ca) { ca2 = a2; cb2 = cb; cb = e1; } else ca = a2;
+        }
+        for (int part = 0; part < 2; ++part) {
+            if (part == 1) { ca = ca2; cb = cb2; }
+            if (ca > cb) continue;
+            const int beg = ps.cell_start[row * ps.gx + ca], end = ps.cell_start[row * ps.gx + cb + 1];
+            for (int base = beg; base < end; base += 32) {
+                const int pos = base + lane;
+                const bool v = pos < end && pos != p && pos != cpos && ps.orig[pos] != INF16;
+                const float sx = v ? ps.x[pos] - ppx : 0.f, sy = v ? ps.y[pos] - ppy : 0.f;
+                if (!w_batch(b, v, sx, sy, pos, cx, cy, sigma)) return false;
+            }
+        }
+    }
+}
+
+// All stars of the staged set; stars that need the exact path are appended to defer[] (sc->n_defer).
 template <bool EMIT>
-__device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, int &n_exact) {
+__device__ __forceinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int p;
+        for (;;) {
+            p = 0;
+            if (lane == 0) p = atomicAdd(&sc->next_pos, 1);
+            p = __shfl_sync(FULL, p, 0);
+            if (p >= ps.n || ps.orig[p] != INF16) break;
+        }
+        if (p >= ps.n) break;
+        bool ok = true;
+        const float ppx = ps.x[p], ppy = ps.y[p];
+        const int pcx = cell_of(ppx, ps.xmin, ps.inv_h, ps.gx), pcy = cell_of(ppy, ps.ymin, ps.inv_h, ps.gy);
+        const int bx0 = max(pcx - WRAP_BLOCK, 0), bx1 = min(pcx + WRAP_BLOCK, ps.gx - 1);
+        const int by0 = max(pcy - WRAP_BLOCK, 0), by1 = min(pcy + WRAP_BLOCK, ps.gy - 1);
+        // ---- the block's candidates, two per lane: element e of the concatenated row runs goes to lane e & 31
+        int rb = 0, rn = 0;
+        if (lane <= by1 - by0) { const int row = by0 + lane; rb = ps.cell_start[row * ps.gx + bx0]; rn = ps.cell_start[row * ps.gx + bx1 + 1] - rb; }
+        int posA = -1, posB = -1, eA = lane, eB = lane + 32, M = 0;
+#pragma unroll
+        for (int r = 0; r < 2 * WRAP_BLOCK + 1; ++r) {
+            const int bb = __shfl_sync(FULL, rb, r), nn = __shfl_sync(FULL, rn, r);
+            if (posA < 0) { if (eA < nn) posA = bb + eA; else eA -= nn; }
+            if (posB < 0) { if (eB < nn) posB = bb + eB; else eB -= nn; }
+            M += nn;
+        }
+        if (M > 64) ok = false;                                   // crowded cells
+        const bool vA = posA >= 0 && posA != p && ps.orig[posA] != INF16, vB = posB >= 0 && posB != p && ps.orig[posB] != INF16;
+        const float ax = vA ? ps.x[posA] - ppx : 0.f, ay = vA ? ps.y[posA] - ppy : 0.f, al = fmaf(ax, ax, ay * ay);
+        const float bx = vB ? ps.x[posB] - ppx : 0.f, by = vB ? ps.y[posB] - ppy : 0.f, bl = fmaf(bx, bx, by * by);
+        // block bounds relative to p (sides on the grid boundary are open), shrunk by the cell-assignment slack
+        const float slack = 1.0e-3f + 1.0e-4f * ps.h;
+        const float BX0 = bx0 > 0 ? ps.xmin + bx0 * ps.h - ppx + slack : -CUDART_INF_F, BX1 = bx1 < ps.gx - 1 ? ps.xmin + (bx1 + 1) * ps.h - ppx - slack : CUDART_INF_F;
+        const float BY0 = by0 > 0 ? ps.ymin + by0 * ps.h - ppy + slack : -CUDART_INF_F, BY1 = by1 < ps.gy - 1 ? ps.ymin + (by1 + 1) * ps.h - ppy - slack : CUDART_INF_F;
+        // ---- q0 = the nearest point: certified by the distance to the block's boundary, unique up to rounding
+        int q0 = -1; float q0x = 0.f, q0y = 0.f;
+        if (ok) {
+            const unsigned kA = vA ? __float_as_uint(al) : 0xFFFFFFFFu, kB = vB ? __float_as_uint(bl) : 0xFFFFFFFFu;
+            const unsigned kmin = __reduce_min_sync(FULL, min(kA, kB));
+            const float lmin = __uint_as_float(kmin);
+            const float mg = fminf(fminf(-BX0, BX1), fminf(-BY0, BY1));
+            if (kmin == 0xFFFFFFFFu || !(lmin * 1.000001f < mg * mg)) ok = false;
+            else {
+                const float thr = lmin * 1.000002f;
+                const int cnt = __popc(__ballot_sync(FULL, vA && al <= thr)) + __popc(__ballot_sync(FULL, vB && bl <= thr));
+                if (cnt != 1) ok = false;                         // two points at (nearly) the same distance
+                const int wl = __ffs(__ballot_sync(FULL, min(kA, kB) == kmin)) - 1;
+                const bool selB = kA != kmin;
+                q0 = __shfl_sync(FULL, selB ? posB : posA, wl); q0x = __shfl_sync(FULL, selB ? bx : ax, wl); q0y = __shfl_sync(FULL, selB ? by : ay, wl);
+            }
+        }
+        // ---- the walk: lane i keeps the i-th counter-clockwise neighbour (sidC; 0 = q0) and the (i+1)-th clockwise one (sidW)
+        int sidC = INF16, sidW = INF16, nC = 1, nW = 0;
+        bool closed = false;
+        if (lane == 0) sidC = q0;
+        float sigma = 1.f, cx = q0x, cy = q0y; int cpos = q0;
+        while (ok) {
+            // block candidates
+            const WEval ea = w_eval(vA && posA != cpos, ax, ay, al, cx, cy, sigma), eb = w_eval(vB && posB != cpos, bx, by, bl, cx, cy, sigma);
+            if (__any_sync(FULL, ea.susp || eb.susp)) { ok = false; break; }
+            const unsigned kA = ea.cand ? w_key(ea.t) : 0xFFFFFFFFu, kB = eb.cand ? w_key(eb.t) : 0xFFFFFFFFu;
+            const unsigned kmin = __reduce_min_sync(FULL, min(kA, kB));
+            WBest b; b.have = kmin != 0xFFFFFFFFu; b.t = b.eps = b.x = b.y = 0.f; b.pos = -1; b.vx = b.vy = b.rs = 0.f;
+            bool inside = false;
+            if (b.have) {
+                const int wl = __ffs(__ballot_sync(FULL, min(kA, kB) == kmin)) - 1;
+                const bool selB = kA != kmin;                     // meaningful on lane wl
+                const bool wB = __shfl_sync(FULL, (int)selB, wl) != 0;
+                b.t = __shfl_sync(FULL, selB ? eb.t : ea.t, wl); b.eps = __shfl_sync(FULL, selB ? eb.eps : ea.eps, wl);
+                b.x = __shfl_sync(FULL, selB ? bx : ax, wl); b.y = __shfl_sync(FULL, selB ? by : ay, wl); b.pos = __shfl_sync(FULL, selB ? posB : posA, wl);
+                const float ub = b.t + b.eps;
+                const bool clash = (ea.cand && !(lane == wl && !wB) && !(ea.t - ea.eps > ub)) || (eb.cand && !(lane == wl && wB) && !(eb.t - eb.eps > ub));
+                if (__any_sync(FULL, clash)) { ok = false; break; }
+                w_circle(b, cx, cy, sigma);
+                if (!(fabsf(b.t) < 1.0e18f)) { ok = false; break; }
+                inside = b.vx - b.rs >= BX0 && b.vx + b.rs <= BX1 && b.vy - b.rs >= BY0 && b.vy + b.rs <= BY1;
+            }
+            if (!inside) {
+                if (!w_stream(b, ps, p, ppx, ppy, pcy, bx0, bx1, by0, by1, cx, cy, sigma, cpos)) { ok = false; break; }
+            }
+            if (!b.have) {
+                // no point on the walk's left of p->cur anywhere: hull edge
+                if (sigma > 0.f) { sigma = -1.f; cx = q0x; cy = q0y; cpos = q0; continue; }
+                break;
+            }
+            if (sigma > 0.f && b.pos == q0) { closed = true; break; }
+            if (nC + nW >= 31) { ok = false; break; }
+            if (sigma > 0.f) { if (lane == nC) sidC = b.pos; ++nC; } else { if (lane == nW) sidW = b.pos; ++nW; }
+            cx = b.x; cy = b.y; cpos = b.pos;
+        }
+        if (!ok) {
+            if (lane == 0) { const int slot = atomicAdd(&sc->n_defer, 1); defer[slot] = (uint16_t)p; }
+            continue;
+        }
+        // ---- counter-clockwise slot order: clockwise part reversed, q0, counter-clockwise part, INF when open
+        int d, sid;
+        if (closed) { d = nC; sid = sidC; }
+        else {
+            d = nW + nC + 1;
+            const int fromW = __shfl_sync(FULL, sidW, max(nW - 1 - lane, 0)), fromC = __shfl_sync(FULL, sidC, min(max(lane - nW, 0), 31));
+            sid = lane < nW ? fromW : (lane < nW + nC ? fromC : (int)INF16);
+        }
+        const int nid = __shfl_sync(FULL, sid, lane + 1 < d ? lane + 1 : 0);
+        if (EMIT) consume_emit<32>(FULL, lane, d, p, sid, nid, ps, fv);
+        else consume_vote<32>(FULL, lane, d, p, sid, nid, ps, fv);
+    }
+}
+
+// All stars of the staged point set.  EMIT: triangles into fv.tri; otherwise the graph vote into fv.pflag.
+// Block-wide; sc, defer[] and defer2[] are shared scratch.  Three levels: wrap path (all stars) -> exact half-warp path
+// (what the wrap path could not certify) -> exact full-warp path (what overflowed 16 slots or needs the collinear bootstrap).
+// Returns (#stars of level 2) + (#stars of level 3 << 16).
+template <bool EMIT>
+__device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, uint16_t *defer2,
+                                      int &n_exact, long long *t_fast) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { sc->next_pos = 0; sc->n_defer = 0; }
+    if (tid == 0) { sc->next_pos = 0; sc->n_defer = 0; sc->n_defer2 = 0; }
     __syncthreads();
-    stars_fast<EMIT>(ps, fv, sc, defer, n_exact);
+    long long tc0 = clock64();
+    stars_wrap<EMIT>(ps, fv, sc, defer);
     __syncthreads();
-    const int nd = sc->n_defer;
-    for (int k = warp; k < nd; k += NWARP) {
-        const int p = defer[k];
+    if (tid == 0 && t_fast) *t_fast += clock64() - tc0;
+    const int n1 = sc->n_defer;
+    __syncthreads();
+    if (tid == 0) sc->next_pos = 0;
+    __syncthreads();
+    if (n1) stars_fast<EMIT>(ps, fv, sc, defer, n1, defer2, n_exact);
+    __syncthreads();
+    const int n2 = sc->n_defer2;
+    for (int k = warp; k < n2; k += NWARP) {
+        const int p = defer2[k];
         const FbResult r = fb_build(ps, p);
         n_exact += r.n_exact;
         if (r.rc == STAR_OK) {
@@ -602,7 +857,7 @@ __device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, 
         }
     }
     __syncthreads();
-    return nd;
+    return n1 + (n2 << 16);
 }
 
 }  // namespace mvosr

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mvoscalerecovery_b200 import synth, _native as N            # noqa: E402
 from mvoscalerecovery_b200.batch import ScaleRecovery, stats_to_numpy            # noqa: E402
 
-NAMES = {0: "load+stage1+roi", 1: "grid1|c_refill", 3: "c_test", 4: "c_splice", 5: "c_batch", 8: "c_row", 9: "c_run", 14: "c_exact", 15: "c_iter", 2: "stars1", 6: "keep+compact+grid2", 7: "stars2", 10: "planes", 11: "median", 12: "valid_list", 13: "ransac"}
+NAMES = {0: "load+stage1+roi", 1: "grid1", 2: "stars1", 3: "stars1_wrap", 6: "keep+compact+grid2", 7: "stars2", 8: "stars2_wrap", 10: "planes", 11: "median", 12: "valid_list", 13: "ransac"}
 
 
 def main():
@@ -40,7 +40,7 @@ def main():
     res = {"frames": n_frames, "kernel_ms": ms, "fps": n_frames / ms * 1e3, "cycles_per_frame_total": tot,
            "phases": {NAMES[k]: {"cycles": float(p[:, k].mean()), "share": float(p[:, k].mean() / tot)} for k in sorted(NAMES)},
            "n_roi": float(st["n_roi"].mean()), "n_kept": float(st["n_kept"].mean()), "n_tri": float(st["n_tri"].mean()),
-           "n_deferred": float(st["n_deferred"].mean()), "hyps_used": float(st["hyps_used"].mean()), "n_exact": float(st["n_exact"].mean())}
+           "n_deferred": float((st["n_deferred"] & 0xFFFF).mean()), "n_fallback": float((st["n_deferred"] >> 16).mean()), "hyps_used": float(st["hyps_used"].mean()), "n_exact": float(st["n_exact"].mean())}
     print(json.dumps(res, indent=1))
 
 
