@@ -66,7 +66,7 @@ typedef struct mvosr_config {
     double  slew_limit;           /* 0.3 (rescale.py:169-172) */
     int32_t window_size;          /* 5: both mains pass window_size=5 (main.py:55); class default is 6 */
     double  triangulation_max_depth; /* distanceThresh=100 (visual_odometry.py:133) */
-    int32_t reserved[8];
+    int32_t reserved[8];          /* reserved[0]: grid density of the Delaunay stage x100 (mean points per cell), 0 = built-in default */
 } mvosr_config;
 
 /* ---- per-frame counters (parity probes and logging; mirrors the reference's prints) ---- */

@@ -39,6 +39,8 @@ class ScaleRecovery:
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         cfg = N.default_config()
+        if "grid_density" in config:            # tuning knob of the Delaunay stage: mean points per grid cell (reserved[0] = x100)
+            cfg.reserved[0] = int(round(100 * float(config.pop("grid_density"))))
         for k, v in config.items():
             if not hasattr(cfg, k):
                 raise TypeError("unknown config field %r" % k)

@@ -141,7 +141,7 @@ __device__ __forceinline__ void block_excl_scan(uint32_t *a, int n, int *warp_tm
 // ---------------------------------------------------------------------------------------------
 struct GridArrays { float *sx, *sy; uint16_t *sorig, *cell_start; uint32_t *scr; };
 
-__device__ __forceinline__ void build_grid(int n, const float *U, const float *V, uint8_t *pflag, GridArrays ga, int cap, Ctl *ctl) {
+__device__ __forceinline__ void build_grid(int n, const float *U, const float *V, uint8_t *pflag, GridArrays ga, int cap, Ctl *ctl, float density) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float xmn = CUDART_INF_F, xmx = -CUDART_INF_F, ymn = CUDART_INF_F, ymx = -CUDART_INF_F;
     for (int i = tid; i < n; i += NT) {
@@ -165,7 +165,7 @@ __device__ __forceinline__ void build_grid(int n, const float *U, const float *V
         if (lane == 0) {
             const int max_cells = cap - 1;
             float w = xmx - xmn, hgt = ymx - ymn, h;
-            if (w > 0.f && hgt > 0.f) h = sqrtf(GRID_DENSITY * w * hgt / (float)n);
+            if (w > 0.f && hgt > 0.f) h = sqrtf(density * w * hgt / (float)n);
             else h = fmaxf(w, hgt) * 2.f / (float)n;
             if (!(h > 0.f)) h = 1.f;
             int gx, gy; float inv_h;
@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
     fv.tbase = (uint16_t *)(smem + pl.off_tbase); fv.tcnt = smem + pl.off_tcnt;
     fv.T = &ctl.T; fv.status = &ctl.status; fv.pass_mask = P.cfg.graph_pass_mask; fv.tri_cap = 2 * cap;
     const mvosr_config &cfg = P.cfg;
+    const float density = cfg.reserved[0] > 0 ? 0.01f * (float)cfg.reserved[0] : GRID_DENSITY;     // tuning knob: mean points per grid cell x 100
 
     long long tlast = 0;
 #define TMARK(k) do { if (tid == 0) { long long tn_ = clock64(); ctl.tphase[k] += tn_ - tlast; tlast = tn_; } } while (0)
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         int n_exact = 0;
         if (!status) {
             // ---------------- Delaunay #1 -> graph vote (or triangles in DT-only mode) ----------------
-            build_grid(n, U, V, pflag, ga, cap, &ctl);
+            build_grid(n, U, V, pflag, ga, cap, &ctl, density);
             TMARK(1);
             if (P.mode == MODE_DT_ONLY) {
                 for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 for (int i = tid; i < n; i += NT) pflag[i] = 0;
                 if (tid == 0) { ctl.n_dup1 = ctl.n_dup; ctl.n_dup = 0; }
                 __syncthreads();
-                build_grid(n, U, V, pflag, ga, cap, &ctl);
+                build_grid(n, U, V, pflag, ga, cap, &ctl, density);
             } else {
                 for (int i = tid; i < n; i += NT) pflag[i] &= 1;
                 __syncthreads();

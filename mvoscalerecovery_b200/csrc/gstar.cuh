@@ -596,6 +596,10 @@ constexpr int WRAP_BLOCK = 2;                     // half-width of the candidate
 
 struct WEval { float t, eps; bool cand, susp; };
 
+// single-instruction approximations (MUFU, 2 ulp); every use below is covered by explicit padding
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // candidate s (relative to p) against edge (p,cur), orientation sigma (+1 counter-clockwise walk, -1 clockwise)
 __device__ __forceinline__ WEval w_eval(bool valid, float sx, float sy, float sl, float cx, float cy, float sigma) {
     WEval e;
@@ -607,7 +611,7 @@ __device__ __forceinline__ WEval w_eval(bool valid, float sx, float sy, float sl
     const float q1 = sx * cx, q2 = sy * cy;
     const float num = (sl - q1) - q2;
     const float en = 8.f * WU * (sl + fabsf(q1) + fabsf(q2));     // |num - exact| <= 6u (...)
-    const float r = __fdividef(1.f, cr);
+    const float r = rcp_approx(cr);
     e.t = num * r;
     e.eps = (en + fabsf(e.t) * ecr) * r * 1.01f + 16.f * WU * fabsf(e.t) + 1.0e-30f;
     return e;
@@ -626,7 +630,7 @@ struct WBest {                          // warp-uniform: current best of a step
 __device__ __forceinline__ void w_circle(WBest &b, float cx, float cy, float sigma) {
     // centre = cur/2 + (sigma t / 2) * (-cy, cx)
     b.vx = 0.5f * (cx - sigma * b.t * cy); b.vy = 0.5f * (cy + sigma * b.t * cx);
-    const float r = sqrtf(fmaf(b.vx, b.vx, b.vy * b.vy));
+    const float r = sqrt_approx(fmaf(b.vx, b.vx, b.vy * b.vy));
     const float pad = b.eps * (fabsf(cx) + fabsf(cy)) * 0.51f + 1.0e-3f + 1.0e-4f * r;
     b.rs = r + 2.f * pad;
 }
@@ -771,7 +775,9 @@ __device__ __forceinline__ void stars_wrap(const SortedSet &ps, const FrameView 
         float sigma = 1.f, cx = q0x, cy = q0y; int cpos = q0;
         while (ok) {
             // block candidates
-            const WEval ea = w_eval(vA && posA != cpos, ax, ay, al, cx, cy, sigma), eb = w_eval(vB && posB != cpos, bx, by, bl, cx, cy, sigma);
+            const WEval ea = w_eval(vA && posA != cpos, ax, ay, al, cx, cy, sigma);
+            WEval eb; eb.t = 0.f; eb.eps = 0.f; eb.cand = false; eb.susp = false;
+            if (M > 32) eb = w_eval(vB && posB != cpos, bx, by, bl, cx, cy, sigma);      // warp-uniform
             if (__any_sync(FULL, ea.susp || eb.susp)) { ok = false; break; }
             const unsigned kA = ea.cand ? w_key(ea.t) : 0xFFFFFFFFu, kB = eb.cand ? w_key(eb.t) : 0xFFFFFFFFu;
             const unsigned kmin = __reduce_min_sync(FULL, min(kA, kB));

@@ -1,0 +1,10 @@
+#!/bin/bash
+# phase profile for several grid densities
+for d in "$@"; do
+echo "== density $d"
+MVOSR_DENSITY=$d timeout 120 python scripts/phase_profile.py 592 2>&1 | python -c "
+import json,sys
+r=json.load(sys.stdin)
+print('kernel_ms %.2f fps %.0f deferred %.1f fallback %.2f' % (r['kernel_ms'], r['fps'], r['n_deferred'], r['n_fallback']))
+print(' '.join('%s=%d' % (k, int(v['cycles'])) for k,v in r['phases'].items()))"
+done

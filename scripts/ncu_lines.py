@@ -48,7 +48,7 @@ for b in blocks[1:]:
             continue
         key = [t[2] for t in tb[:12]]
         for s0 in range(0, len(texts) - len(tb) + 1):
-            if line_of[s0] is None and texts[s0:s0 + len(key)] == key and texts[s0 + len(tb) - 1] == tb[-1][2]:
+            if line_of[s0] is None and texts[s0:s0 + len(key)] == key:
                 # several template instances share prefixes: require the kernel name flavour to match for kernels
                 if "frame_kernel" in fn and (("ILb1E" in fn) != ("(bool)1" in name)):
                     break
@@ -56,6 +56,13 @@ for b in blocks[1:]:
                     line_of[s0 + k] = t[1]; func_of[s0 + k] = fn
                 used += len(tb)
                 break
+    if used == 0:
+        # the kernel's section holds all its callees: align by index when the lengths agree
+        for fn, tb in table.items():
+            if len(tb) == len(rows) and "frame_kernel" in fn and (("ILb1E" in fn) == ("(bool)1" in name)):
+                for k, t in enumerate(tb):
+                    line_of[k] = t[1]
+                used = len(tb)
     agg = collections.defaultdict(lambda: [0, 0, 0])
     tot = [0, 0, 0]
     for k, r in enumerate(rows):

@@ -1,0 +1,33 @@
+"""Sum the per-line output of ncu_lines.py over code regions of gstar.cuh / other files.  usage: ncu_regions.py <lines.txt>"""
+import re, collections, sys, os
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+out = open(sys.argv[1]).read()
+lines = open(os.path.join(root, 'mvoscalerecovery_b200/csrc/gstar.cuh')).read().splitlines()
+def find(pat):
+    for i,l in enumerate(lines):
+        if pat in l: return i+1
+    raise KeyError(pat)
+marks = {
+ 'consume': (find('struct FrameView'), find('// exact conflict of candidate')),
+ 'group path+fallback': (find('// exact conflict of candidate'), find('// wrap path: one warp per star')),
+ 'w_eval/key/circle': (find('struct WEval'), find('// One batch of candidates (one per lane)')),
+ 'w_batch': (find('// One batch of candidates (one per lane)'), find('// Stream the grid cells that the left cap')),
+ 'w_stream': (find('// Stream the grid cells that the left cap'), find('// All stars of the staged set; stars that need the exact path')),
+ 'wrap:fetch+load': (find('// All stars of the staged set; stars that need the exact path'), find('// ---- q0 = the nearest point')),
+ 'wrap:q0': (find('// ---- q0 = the nearest point'), find('// ---- the walk: lane i keeps')),
+ 'wrap:walk': (find('// ---- the walk: lane i keeps'), find('// ---- counter-clockwise slot order')),
+ 'wrap:finish': (find('// ---- counter-clockwise slot order'), find('// All stars of the staged point set.')),
+ 'run_stars': (find('// All stars of the staged point set.'), 10**6),
+}
+agg = collections.defaultdict(lambda:[0.0,0.0])
+for l in out.splitlines():
+    m = re.match(r"(\S+):(\d+)\s+samples\s+([\d.]+)%\s+winstr\s+([\d.]+)%", l)
+    if not m: continue
+    f, ln, s, w = m.group(1), int(m.group(2)), float(m.group(3)), float(m.group(4))
+    key = f
+    if f == 'gstar.cuh':
+        key = 'gstar:other'
+        for k,(a,b) in marks.items():
+            if a <= ln < b: key = k
+    agg[key][0] += s; agg[key][1] += w
+for k,v in sorted(agg.items(), key=lambda kv:-kv[1][1]): print("%-26s samples %6.2f%%  winstr %6.2f%%" % (k, v[0], v[1]))

@@ -18,7 +18,10 @@ def main():
     n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 592
     n_corr = int(sys.argv[2]) if len(sys.argv) > 2 else 2500
     b = synth.make_sequence(seed=20261017, n_frames=n_frames, n_corr=n_corr, outlier_frac=0.10)
-    eng = ScaleRecovery(absolute_reference=1.7)
+    kw = {}
+    if os.environ.get('MVOSR_DENSITY'):
+        kw['grid_density'] = float(os.environ['MVOSR_DENSITY'])
+    eng = ScaleRecovery(absolute_reference=1.7, **kw)
     dev = eng.device
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     d = [t(x) for x in (b.offsets, b.cur_u, b.cur_v, b.ref_u, b.ref_v, b.poses)]
