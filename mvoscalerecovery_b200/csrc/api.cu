@@ -33,6 +33,7 @@ struct mvosr_handle {
     int64_t launches;
     // host-API staging (grown on demand)
     void *d_stage; size_t stage_bytes;
+    void *d_ws; size_t ws_bytes;   // large-frame staging (frames beyond the shared-memory capacity)
     long long *phase_cycles;     // optional profiling sink (device), set by mvosr_set_phase_timing
 };
 
@@ -232,6 +233,7 @@ int mvosr_destroy(mvosr_handle *h) {
     cudaSetDevice(h->device);
     if (h->work_counter) cudaFree(h->work_counter);
     if (h->d_stage) cudaFree(h->d_stage);
+    if (h->d_ws) cudaFree(h->d_ws);
     delete h;
     return MVOSR_OK;
 }
@@ -252,24 +254,38 @@ int mvosr_set_phase_timing(mvosr_handle *h, int64_t *phase_cycles_device) {
 
 }  // extern "C"
 
-static int pick_cap(const mvosr_handle *h, int max_features) {
-    int cap = (max_features + 63) / 64 * 64;
-    if (cap < 256) cap = 256;
-    if (cap > h->cap_max) cap = h->cap_max;
-    return cap;
-}
+// largest capacity the 16-bit indices of the frame kernel allow (triangle blocks are addressed below 2*cap < 65536)
+static const int CAP_LIMIT = 32704;
 
 template <bool FROM_CORR>
 static int launch_frames(mvosr_handle *h, FrameParams &P, int max_features, cudaStream_t st) {
     if (P.n_frames <= 0) return MVOSR_OK;
-    P.cap = pick_cap(h, max_features);
+    int cap = (max_features + 63) / 64 * 64;
+    if (cap < 256) cap = 256;
+    if (cap > CAP_LIMIT) return MVOSR_E_CAPACITY;
+    P.cap = cap;
     P.cfg = h->cfg;
     P.work_counter = h->work_counter;
     P.phase_cycles = h->phase_cycles;
     SmemPlan pl = make_plan(P.cap);
-    CK(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
     int grid = P.n_frames < h->num_sms ? P.n_frames : h->num_sms;
-    frame_kernel<FROM_CORR><<<grid, NT, pl.total, st>>>(P);
+    size_t dyn = (size_t)pl.total;
+    P.workspace = nullptr; P.ws_stride = 0;
+    if (cap > h->cap_max) {
+        // large-frame mode: the staging lives in global memory, one slab per CTA
+        size_t stride = ((size_t)pl.total + 255) & ~(size_t)255, need = stride * (size_t)grid;
+        if (need > h->ws_bytes) {
+            CK(cudaStreamSynchronize(st));
+            if (h->d_ws) cudaFree(h->d_ws);
+            h->d_ws = nullptr; h->ws_bytes = 0;
+            if (cudaMalloc(&h->d_ws, need) != cudaSuccess) { cudaGetLastError(); return MVOSR_E_NOMEM; }
+            h->ws_bytes = need;
+        }
+        P.workspace = (unsigned char *)h->d_ws; P.ws_stride = stride;
+        dyn = 0;
+    }
+    CK(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
+    frame_kernel<FROM_CORR><<<grid, NT, dyn, st>>>(P);
     CK(cudaGetLastError());
     h->launches += 1;
     return MVOSR_OK;

@@ -53,6 +53,8 @@ struct FrameParams {
     // DT-only mode outputs
     int32_t *tri_out; int32_t *n_tri_out;
     int *work_counter;              // dynamic frame scheduler
+    unsigned char *workspace;       // large-frame mode: per-CTA staging in global memory (NULL: dynamic shared memory)
+    unsigned long long ws_stride;
     long long *phase_cycles;        // optional [F][16] per-phase SM cycles (profiling aid)
 };
 
@@ -283,8 +285,10 @@ __device__ __forceinline__ unsigned long long block_select(const double *h, cons
 // ---------------------------------------------------------------------------------------------
 template <bool FROM_CORR>
 __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ Ctl ctl;
+    // frames beyond the shared-memory capacity are staged in a per-CTA slab of global memory (L2-resident): same code
+    unsigned char *smem = P.workspace ? P.workspace + (size_t)blockIdx.x * P.ws_stride : dyn_smem;
     const SmemPlan pl = make_plan(P.cap);
     const int cap = P.cap;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

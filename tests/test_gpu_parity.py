@@ -246,3 +246,45 @@ def test_delaunay_degenerate_inputs_vs_exact_oracle(engine):
         assert np.array_equal(got, ref), "set %s differs from the exact oracle" % k
         ok, msg, _ = exact.validate_delaunay(sets[k], got, dup)
         assert ok, (k, msg)
+
+
+def test_large_frames_global_staging(engine):
+    """BASELINE configs[2] shape (dense-flow stress, ~20k features/frame): frames beyond the shared-memory capacity are
+    staged in global memory by the same kernel.  Delaunay == canonicalised Qhull; the full pipeline == the oracle."""
+    torch = _torch()
+    from mvoscalerecovery_b200 import synth
+    from mvoscalerecovery_b200.batch import stats_to_numpy
+    from oracle import pipeline as P
+    dev = engine.device
+    rng = np.random.default_rng(99)
+    n = 20000
+    pts = np.stack([rng.uniform(0, 1241, n), rng.uniform(186, 376, n)], 1).astype(np.float32)
+    off = np.array([0, n], np.int32)
+    out = engine.delaunay_frames(torch.from_numpy(off).to(dev), torch.from_numpy(np.ascontiguousarray(pts[:, 0])).to(dev),
+                                 torch.from_numpy(np.ascontiguousarray(pts[:, 1])).to(dev), n)
+    torch.cuda.synchronize()
+    assert int(out["status"].cpu().numpy()[0]) == 0
+    nt = int(out["n_tri"].cpu().numpy()[0])
+    ref = P.delaunay_canonical(pts.astype(np.float64))
+    assert nt == ref.shape[0]
+    assert np.array_equal(out["tri"].cpu().numpy()[:nt], ref)
+    # full pipeline on 2 frames of ~20k correspondences
+    seed = 5
+    b = synth.make_sequence(seed=77, n_frames=2, n_corr=22000, outlier_frac=0.1)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    s1 = engine.triangulate_frames(t(b.offsets), t(b.cur_u), t(b.cur_v), t(b.ref_u), t(b.ref_v), t(b.poses))
+    maxf = int(np.max(np.diff(b.offsets)))
+    res = engine.scale_frames(t(b.offsets), s1["x"], s1["y"], s1["z"], s1["u"], s1["v"], maxf, counts=s1["n_out"], seed=seed)
+    torch.cuda.synchronize()
+    st = stats_to_numpy(res["stats"]); raw = res["raw_scale"].cpu().numpy(); n_out = s1["n_out"].cpu().numpy()
+    for f in range(b.n_frames):
+        a = int(b.offsets[f]); m = int(n_out[f])
+        f3 = np.stack([s1[k][a:a + m].cpu().numpy() for k in "xyz"], 1).astype(np.float64)
+        f2 = np.stack([s1[k][a:a + m].cpu().numpy() for k in "uv"], 1).astype(np.float64)
+        rec = P.frame_raw_scale(f3, f2, seed, f, 0, absolute_reference=1.7)
+        assert st["n_roi"][f] > 10000
+        assert st["n_kept"][f] == int(rec["keep"].sum())
+        assert st["n_tri"][f] == rec["tri2"].shape[0]
+        assert 3 * st["n_valid"][f] == rec["n_sel"]
+        assert st["best_ic"][f] == rec["ic"] and st["hyps_used"][f] == rec["hyps_used"]
+        np.testing.assert_allclose(raw[f], rec["raw_scale"], rtol=RTOL)
