@@ -1,0 +1,56 @@
+"""Multi-GPU plumbing on CPU: frame-range sharding and the one all-gather of raw per-frame results, world_size 2,
+gloo backend (the GPU box runs the same code over NCCL)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_frame_shards_cover_and_balance():
+    from mvoscalerecovery_b200.fleet import frame_shards
+    lens = [4541, 1101, 4661, 801, 271, 2761, 1101, 1101, 4071, 1591, 1201]        # KITTI 00-10 (BASELINE configs[3])
+    total = sum(lens)
+    for w in (1, 2, 4, 8):
+        sh = frame_shards(total, w)
+        assert sh[0][0] == 0 and sh[-1][1] == total and all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+        assert max(e - s for s, e in sh) - min(e - s for s, e in sh) <= 1
+    wts = np.concatenate([np.full(n, 1000 + 100 * i) for i, n in enumerate(lens)])
+    sh = frame_shards(total, 4, wts)
+    loads = [wts[s:e].sum() for s, e in sh]
+    assert sh[0][0] == 0 and sh[-1][1] == total and max(loads) / min(loads) < 1.01
+    with pytest.raises(ValueError):
+        frame_shards(10, 0)
+
+
+def _rank_main(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mvoscalerecovery_b200.fleet import frame_shards, gather_results
+    total = 23                                  # uneven shards: 11 + 12
+    shards = frame_shards(total, world)
+    s, e = shards[rank]
+    g = torch.Generator().manual_seed(5)
+    raw_all = torch.rand(total, dtype=torch.float64, generator=g) + 0.5
+    raw_all[3] = float("nan")
+    st_all = torch.randint(0, 128, (total,), dtype=torch.uint8, generator=g)
+    nf_all = torch.randint(0, 3000, (total,), dtype=torch.int32, generator=g)
+    raw, st, nf = gather_results(raw_all[s:e].clone(), st_all[s:e].clone(), nf_all[s:e].clone(), shards)
+    ok = torch.equal(torch.nan_to_num(raw, nan=-1.0), torch.nan_to_num(raw_all, nan=-1.0)) and torch.equal(st, st_all) and torch.equal(nf, nf_all)
+    with open(os.path.join(tmp, "rank%d" % rank), "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_gather_results_world_size_2_gloo(tmp_path):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
