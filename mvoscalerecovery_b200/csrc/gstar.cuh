@@ -265,7 +265,7 @@ __device__ __forceinline__ void g_row_interval(const GState &g, const SortedSet 
 
 // The stars of list[0..n_list) (sorted positions), one per half-warp; stars it gives up on are appended to defer[].
 template <bool EMIT>
-__device__ __forceinline__ void stars_fast(const SortedSet &ps, const FrameView &fv, StarCtl *sc, const uint16_t *list, int n_list,
+__device__ __noinline__ void stars_fast(const SortedSet &ps, const FrameView &fv, StarCtl *sc, const uint16_t *list, int n_list,
                                            uint16_t *defer, int &n_exact) {
     const int lane = threadIdx.x & 31, gl = lane & (GL - 1), gshift = lane & GL;
     const unsigned gmask = 0xFFFFu << gshift;
@@ -715,18 +715,24 @@ __device__ __noinline__ bool w_stream(WBest &b, const SortedSet &ps, int p, floa
 
 // All stars of the staged set; stars that need the exact path are appended to defer[] (sc->n_defer).
 template <bool EMIT>
-__device__ __forceinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer) {
+__device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
+    const int rot = ps.cell_start[(ps.gy - 1) * ps.gx];
     for (;;) {
+        // stars are fetched in cell order starting at the LAST grid row: the hull rows (whose stars stream whole rows and
+        // cost several times the average) come first instead of forming the tail of the pass
         int p;
+        bool done = false;
         for (;;) {
-            p = 0;
-            if (lane == 0) p = atomicAdd(&sc->next_pos, 1);
-            p = __shfl_sync(FULL, p, 0);
-            if (p >= ps.n || ps.orig[p] != INF16) break;
+            int i = 0;
+            if (lane == 0) i = atomicAdd(&sc->next_pos, 1);
+            i = __shfl_sync(FULL, i, 0);
+            if (i >= ps.n) { done = true; break; }
+            p = i + rot; if (p >= ps.n) p -= ps.n;
+            if (ps.orig[p] != INF16) break;
         }
-        if (p >= ps.n) break;
+        if (done) break;
         bool ok = true;
         const float ppx = ps.x[p], ppy = ps.y[p];
         const int pcx = cell_of(ppx, ps.xmin, ps.inv_h, ps.gx), pcy = cell_of(ppy, ps.ymin, ps.inv_h, ps.gy);
@@ -797,7 +803,9 @@ __device__ __forceinline__ void stars_wrap(const SortedSet &ps, const FrameView 
                 inside = b.vx - b.rs >= BX0 && b.vx + b.rs <= BX1 && b.vy - b.rs >= BY0 && b.vy + b.rs <= BY1;
             }
             if (!inside) {
-                if (!w_stream(b, ps, p, ppx, ppy, pcy, bx0, bx1, by0, by1, cx, cy, sigma, cpos)) { ok = false; break; }
+                WBest bs = b;                                     // (a copy: keeps b itself in registers)
+                if (!w_stream(bs, ps, p, ppx, ppy, pcy, bx0, bx1, by0, by1, cx, cy, sigma, cpos)) { ok = false; break; }
+                b = bs;
             }
             if (!b.have) {
                 // no point on the walk's left of p->cur anywhere: hull edge
