@@ -114,7 +114,7 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 
 // per-warp counts already stored in cnt[0..NWARP): this warp's exclusive offset and the block total
 __device__ __forceinline__ void warp_offsets(const int *cnt, int warp, int lane, int &woff, int &tot) {
-    int c = lane < NWARP ? cnt[lane] : 0;                 // NWARP == 32
+    int c = lane < NWARP ? cnt[lane] : 0;                 // NWARP <= 32
     int inc = warp_incl_scan(c, lane);
     tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
     woff = __shfl_sync(0xFFFFFFFFu, inc - c, warp);
@@ -158,7 +158,8 @@ __device__ __forceinline__ void build_grid(int n, const float *U, const float *V
     if (lane == 0) { ctl->red[0][warp] = xmn; ctl->red[1][warp] = xmx; ctl->red[2][warp] = ymn; ctl->red[3][warp] = ymx; }
     __syncthreads();
     if (warp == 0) {
-        xmn = ctl->red[0][lane]; xmx = ctl->red[1][lane]; ymn = ctl->red[2][lane]; ymx = ctl->red[3][lane];     // NWARP == 32
+        const int wl = lane < NWARP ? lane : 0;
+        xmn = ctl->red[0][wl]; xmx = ctl->red[1][wl]; ymn = ctl->red[2][wl]; ymx = ctl->red[3][wl];
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             xmn = fminf(xmn, __shfl_xor_sync(0xFFFFFFFFu, xmn, o)); xmx = fmaxf(xmx, __shfl_xor_sync(0xFFFFFFFFu, xmx, o));
@@ -705,8 +706,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 s.n_deferred = ctl.n_deferred_total; s.n_exact = ctl.n_exact; s.height_level = ctl.height_level;
             }
 #ifdef MVOSR_STAR_COUNTERS
-            ctl.tphase[1] = ctl.sc.cnt[7]; ctl.tphase[4] = ctl.sc.cnt[2]; ctl.tphase[5] = ctl.sc.cnt[3]; ctl.tphase[9] = ctl.sc.cnt[4]; ctl.tphase[12] = ctl.sc.cnt[0];
-            ctl.tphase[14] = ctl.sc.cnt[5]; ctl.tphase[15] = ctl.sc.cnt[6];
+            ctl.tphase[4] = ctl.sc.cnt[0]; ctl.tphase[5] = ctl.sc.cnt[1]; ctl.tphase[9] = ctl.sc.cnt[2]; ctl.tphase[14] = ctl.sc.cnt[3]; ctl.tphase[15] = ctl.sc.cnt[4];
+            ctl.tphase[12] = ctl.sc.cnt[5]; ctl.tphase[11] = ctl.sc.cnt[6];
 #endif
             if (P.phase_cycles) for (int k = 0; k < 16; ++k) P.phase_cycles[16 * (size_t)f + k] = ctl.tphase[k];
         }

@@ -37,7 +37,10 @@
 
 namespace mvosr {
 
-constexpr int NT = 1024;                 // threads per CTA of the fused frame kernel
+#ifndef MVOSR_NT
+#define MVOSR_NT 1024
+#endif
+constexpr int NT = MVOSR_NT;             // threads per CTA of the fused frame kernel
 constexpr int NWARP = NT / 32;
 constexpr int GL = 16;                   // lanes per star on the fast path
 constexpr uint16_t INF16 = 0xFFFF;
@@ -275,7 +278,7 @@ __device__ __noinline__ void stars_fast(const SortedSet &ps, const FrameView &fv
     bool active = true, need_point = true, bail = false;
     int phase = 0, k = 0, t = 0, ri = 0, re = 0, rdir = 1, ca2 = 1, cb2 = 0, currow = 0;
     unsigned F = 0; int bbase = 0, bdir = 1; float cx = 0.f, cy = 0.f;
-#ifdef MVOSR_STAR_COUNTERS
+#ifdef MVOSR_GROUP_COUNTERS
     unsigned c_test = 0, c_splice = 0, c_batch = 0, c_row = 0, c_run = 0, c_exact = 0, c_iter = 0, c_refill = 0, c_b1 = 0, c_b2 = 0, c_b3 = 0, c_star = 0; long long c_t0 = 0;
 #define CNT(x) ++x
 #else
@@ -293,7 +296,7 @@ __device__ __noinline__ void stars_fast(const SortedSet &ps, const FrameView &fv
                     bail = false; need_point = true;
                 }
                 if (need_point) {
-#ifdef MVOSR_STAR_COUNTERS
+#ifdef MVOSR_GROUP_COUNTERS
                     if (gl == 0 && g.p >= 0) {
                         if (c_star > 64) atomicAdd(&sc->cnt[2], 1ull);
                         if (c_star > 256) atomicAdd(&sc->cnt[3], 1ull);
@@ -431,7 +434,7 @@ __device__ __noinline__ void stars_fast(const SortedSet &ps, const FrameView &fv
             if (ins || first) { g.dirty = true; CNT(c_splice); g_coeffs(g, gmask, gl); }
         }
     }
-#ifdef MVOSR_STAR_COUNTERS
+#ifdef MVOSR_GROUP_COUNTERS
     if (gl == 0) {
         atomicAdd(&sc->cnt[0], (unsigned long long)c_test); atomicAdd(&sc->cnt[1], (unsigned long long)c_splice);
  atomicAdd(&sc->cnt[5], (unsigned long long)c_b1 + ((unsigned long long)c_b2 << 16) + ((unsigned long long)c_b3 << 32));
@@ -719,6 +722,12 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int rot = ps.cell_start[(ps.gy - 1) * ps.gx];
+#ifdef MVOSR_STAR_COUNTERS
+    unsigned w_steps = 0, w_out = 0, w_sstars = 0, w_hull = 0, w_big = 0, w_stars = 0, w_nocand = 0;
+#define WCNT(x) ++x
+#else
+#define WCNT(x)
+#endif
     for (;;) {
         // stars are fetched in cell order starting at the LAST grid row: the hull rows (whose stars stream whole rows and
         // cost several times the average) come first instead of forming the tail of the pass
@@ -750,6 +759,8 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
             M += nn;
         }
         if (M > 64) ok = false;                                   // crowded cells
+        WCNT(w_stars); if (M > 32) { WCNT(w_big); }
+        bool streamed = false;
         const bool vA = posA >= 0 && posA != p && ps.orig[posA] != INF16, vB = posB >= 0 && posB != p && ps.orig[posB] != INF16;
         const float ax = vA ? ps.x[posA] - ppx : 0.f, ay = vA ? ps.y[posA] - ppy : 0.f, al = fmaf(ax, ax, ay * ay);
         const float bx = vB ? ps.x[posB] - ppx : 0.f, by = vB ? ps.y[posB] - ppy : 0.f, bl = fmaf(bx, bx, by * by);
@@ -802,13 +813,16 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
                 if (!(fabsf(b.t) < 1.0e18f)) { ok = false; break; }
                 inside = b.vx - b.rs >= BX0 && b.vx + b.rs <= BX1 && b.vy - b.rs >= BY0 && b.vy + b.rs <= BY1;
             }
+            WCNT(w_steps);
             if (!inside) {
+                WCNT(w_out); if (!b.have) { WCNT(w_nocand); } if (!streamed) { streamed = true; WCNT(w_sstars); }
                 WBest bs = b;                                     // (a copy: keeps b itself in registers)
                 if (!w_stream(bs, ps, p, ppx, ppy, pcy, bx0, bx1, by0, by1, cx, cy, sigma, cpos)) { ok = false; break; }
                 b = bs;
             }
             if (!b.have) {
                 // no point on the walk's left of p->cur anywhere: hull edge
+                WCNT(w_hull);
                 if (sigma > 0.f) { sigma = -1.f; cx = q0x; cy = q0y; cpos = q0; continue; }
                 break;
             }
@@ -833,6 +847,15 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
         if (EMIT) consume_emit<32>(FULL, lane, d, p, sid, nid, ps, fv);
         else consume_vote<32>(FULL, lane, d, p, sid, nid, ps, fv);
     }
+#ifdef MVOSR_STAR_COUNTERS
+    if (lane == 0) {
+        atomicAdd(&sc->cnt[0], (unsigned long long)w_steps); atomicAdd(&sc->cnt[1], (unsigned long long)w_out);
+        atomicAdd(&sc->cnt[2], (unsigned long long)w_sstars); atomicAdd(&sc->cnt[3], (unsigned long long)w_hull);
+        atomicAdd(&sc->cnt[4], (unsigned long long)w_big); atomicAdd(&sc->cnt[5], (unsigned long long)w_stars);
+        atomicAdd(&sc->cnt[6], (unsigned long long)w_nocand);
+    }
+#endif
+#undef WCNT
 }
 
 // All stars of the staged point set.  EMIT: triangles into fv.tri; otherwise the graph vote into fv.pflag.
