@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             ctl.n_degenerate = 0; ctl.height_level = CUDART_NAN;
             for (int k = 0; k < 16; ++k) ctl.tphase[k] = 0;
             for (int k = 0; k < 8; ++k) ctl.sc.cnt[k] = 0;
+            ctl.sc.n_wrap = 0;
             tlast = clock64();
         }
         __syncthreads();
@@ -706,9 +707,10 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 s.n_deferred = ctl.n_deferred_total; s.n_exact = ctl.n_exact; s.height_level = ctl.height_level;
             }
 #ifdef MVOSR_STAR_COUNTERS
-            ctl.tphase[4] = ctl.sc.cnt[0]; ctl.tphase[5] = ctl.sc.cnt[1]; ctl.tphase[9] = ctl.sc.cnt[2]; ctl.tphase[14] = ctl.sc.cnt[3]; ctl.tphase[15] = ctl.sc.cnt[4];
-            ctl.tphase[12] = ctl.sc.cnt[5]; ctl.tphase[11] = ctl.sc.cnt[6];
+            ctl.tphase[4] = ctl.sc.cnt[0]; ctl.tphase[5] = ctl.sc.cnt[1]; ctl.tphase[11] = ctl.sc.cnt[2]; ctl.tphase[12] = ctl.sc.cnt[3]; ctl.tphase[14] = ctl.sc.cnt[4];
+            ctl.tphase[15] = ctl.sc.cnt[5]; ctl.tphase[1] = ctl.sc.cnt[6]; ctl.tphase[10] = ctl.sc.cnt[7];
 #endif
+            ctl.tphase[9] = ctl.sc.n_wrap;                  // stars that left the pair path (both passes)
             if (P.phase_cycles) for (int k = 0; k < 16; ++k) P.phase_cycles[16 * (size_t)f + k] = ctl.tphase[k];
         }
     }

@@ -70,7 +70,7 @@ __device__ __forceinline__ int cell_of(float v, float vmin, float inv_h, int g) 
 }
 
 struct StarCtl {                         // shared-memory work queues of one Delaunay pass
-    int next_pos, n_defer, n_defer2;
+    int next_pos, n_defer, n_defer2, n_wrap;
     unsigned long long cnt[8];           // profiling counters (MVOSR_STAR_COUNTERS): tests, splices, batches, rows, runs, exact, loop iterations, refill iterations
 };
 
@@ -638,6 +638,19 @@ __device__ __forceinline__ void w_circle(WBest &b, float cx, float cy, float sig
     b.rs = r + 2.f * pad;
 }
 
+// Does the walk's-left cap of the padded circle (centre v, radius rs, through p = origin and cur) lie inside the box?
+// The cap's bounding box is spanned by p, cur and those axis-extreme points of the circle that lie on the left of p->cur.
+__device__ __forceinline__ bool w_cap_inside(float cx, float cy, float sigma, float vx, float vy, float rs,
+                                             float BX0, float BX1, float BY0, float BY1) {
+    const float tol = 1.0e-4f * (fabsf(cx) + fabsf(cy)) * (rs + fabsf(vx) + fabsf(vy));       // include when in doubt
+    float lox = fminf(0.f, cx), hix = fmaxf(0.f, cx), loy = fminf(0.f, cy), hiy = fmaxf(0.f, cy);
+    if (sigma * (cx * vy - cy * (vx - rs)) > -tol) lox = fminf(lox, vx - rs);
+    if (sigma * (cx * vy - cy * (vx + rs)) > -tol) hix = fmaxf(hix, vx + rs);
+    if (sigma * (cx * (vy - rs) - cy * vx) > -tol) loy = fminf(loy, vy - rs);
+    if (sigma * (cx * (vy + rs) - cy * vx) > -tol) hiy = fmaxf(hiy, vy + rs);
+    return lox >= BX0 && hix <= BX1 && loy >= BY0 && hiy <= BY1;
+}
+
 // One batch of candidates (one per lane) against the current best of the step.  Returns false if a decision could not
 // be certified (the star goes to the exact path).
 __device__ __forceinline__ bool w_batch(WBest &b, bool valid, float sx, float sy, int pos, float cx, float cy, float sigma) {
@@ -716,30 +729,26 @@ __device__ __noinline__ bool w_stream(WBest &b, const SortedSet &ps, int p, floa
     }
 }
 
-// All stars of the staged set; stars that need the exact path are appended to defer[] (sc->n_defer).
+// The stars of list[0..n_list) (sorted positions), one per warp; stars that need the exact path are appended to
+// defer[] (sc->n_defer2).
 template <bool EMIT>
-__device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer) {
+__device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv, StarCtl *sc, const uint16_t *list, int n_list, uint16_t *defer) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    const int rot = ps.cell_start[(ps.gy - 1) * ps.gx];
-#ifdef MVOSR_STAR_COUNTERS
+#ifdef MVOSR_WRAP_COUNTERS
     unsigned w_steps = 0, w_out = 0, w_sstars = 0, w_hull = 0, w_big = 0, w_stars = 0, w_nocand = 0;
 #define WCNT(x) ++x
 #else
 #define WCNT(x)
 #endif
     for (;;) {
-        // stars are fetched in cell order starting at the LAST grid row: the hull rows (whose stars stream whole rows and
-        // cost several times the average) come first instead of forming the tail of the pass
-        int p;
+        int p = 0;
         bool done = false;
-        for (;;) {
+        {
             int i = 0;
             if (lane == 0) i = atomicAdd(&sc->next_pos, 1);
             i = __shfl_sync(FULL, i, 0);
-            if (i >= ps.n) { done = true; break; }
-            p = i + rot; if (p >= ps.n) p -= ps.n;
-            if (ps.orig[p] != INF16) break;
+            if (i >= n_list) done = true; else p = list[i];
         }
         if (done) break;
         bool ok = true;
@@ -811,7 +820,7 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
                 if (__any_sync(FULL, clash)) { ok = false; break; }
                 w_circle(b, cx, cy, sigma);
                 if (!(fabsf(b.t) < 1.0e18f)) { ok = false; break; }
-                inside = b.vx - b.rs >= BX0 && b.vx + b.rs <= BX1 && b.vy - b.rs >= BY0 && b.vy + b.rs <= BY1;
+                inside = w_cap_inside(cx, cy, sigma, b.vx, b.vy, b.rs, BX0, BX1, BY0, BY1);
             }
             WCNT(w_steps);
             if (!inside) {
@@ -832,7 +841,7 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
             cx = b.x; cy = b.y; cpos = b.pos;
         }
         if (!ok) {
-            if (lane == 0) { const int slot = atomicAdd(&sc->n_defer, 1); defer[slot] = (uint16_t)p; }
+            if (lane == 0) { const int slot = atomicAdd(&sc->n_defer2, 1); defer[slot] = (uint16_t)p; }
             continue;
         }
         // ---- counter-clockwise slot order: clockwise part reversed, q0, counter-clockwise part, INF when open
@@ -847,7 +856,7 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
         if (EMIT) consume_emit<32>(FULL, lane, d, p, sid, nid, ps, fv);
         else consume_vote<32>(FULL, lane, d, p, sid, nid, ps, fv);
     }
-#ifdef MVOSR_STAR_COUNTERS
+#ifdef MVOSR_WRAP_COUNTERS
     if (lane == 0) {
         atomicAdd(&sc->cnt[0], (unsigned long long)w_steps); atomicAdd(&sc->cnt[1], (unsigned long long)w_out);
         atomicAdd(&sc->cnt[2], (unsigned long long)w_sstars); atomicAdd(&sc->cnt[3], (unsigned long long)w_hull);
@@ -858,10 +867,178 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
 #undef WCNT
 }
 
+// ---------------------------------------------------------------------------------------------
+// pair path: two stars per warp in lock step (the production path for closed stars)
+// ---------------------------------------------------------------------------------------------
+// Same gift-wrapping as stars_wrap, one star per HALF-warp with up to four block candidates per lane; the two
+// half-warps execute one instruction stream (every branch is warp-uniform, the per-star differences are predicated), so
+// a star costs half the issue slots.  Only what is cheap in this shape is kept: closed stars whose every step is
+// certified inside the 5x5 block.  Hull edges, circles leaving the block, crowded blocks and every uncertified decision
+// send the star to stars_wrap (one warp per star, streaming) and from there, if need be, to the exact paths.
+__device__ __forceinline__ unsigned gmin_u32(unsigned v, int g) {
+    const unsigned a = __reduce_min_sync(0xFFFFFFFFu, g == 0 ? v : 0xFFFFFFFFu);
+    const unsigned b = __reduce_min_sync(0xFFFFFFFFu, g == 1 ? v : 0xFFFFFFFFu);
+    return g ? b : a;
+}
+
+template <bool EMIT>
+__device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, g = lane >> 4, gl = lane & (GL - 1), gshift = lane & GL;
+    const int rot = ps.cell_start[(ps.gy - 1) * ps.gx];           // hull rows first (see stars_wrap's note on the tail)
+    const float slack = 1.0e-3f + 1.0e-4f * ps.h;
+#ifdef MVOSR_STAR_COUNTERS
+#define PR(k) do { if (gl == 0) atomicAdd(&sc->cnt[k], 1ull); } while (0)
+#else
+#define PR(k)
+#endif
+#define GBALLOT(pred) ((__ballot_sync(FULL, (pred)) >> gshift) & 0xFFFFu)
+#define GSHFL(v, src) __shfl_sync(FULL, (v), (src), GL)
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&sc->next_pos, 2);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= ps.n) break;
+        int p = i + g + rot; if (p >= ps.n) p -= ps.n; if (p >= ps.n) p -= ps.n;
+        const bool have = i + g < ps.n && ps.orig[p] != INF16;
+        bool ok = have;
+        const float ppx = ps.x[p], ppy = ps.y[p];
+        const int pcx = cell_of(ppx, ps.xmin, ps.inv_h, ps.gx), pcy = cell_of(ppy, ps.ymin, ps.inv_h, ps.gy);
+        const int bx0 = max(pcx - WRAP_BLOCK, 0), bx1 = min(pcx + WRAP_BLOCK, ps.gx - 1);
+        const int by0 = max(pcy - WRAP_BLOCK, 0), by1 = min(pcy + WRAP_BLOCK, ps.gy - 1);
+        // ---- block candidates: element e of the concatenated row runs goes to lane e & 15, slot e >> 4
+        int rb[2 * WRAP_BLOCK + 1], rn[2 * WRAP_BLOCK + 1], M = 0;
+#pragma unroll
+        for (int r = 0; r < 2 * WRAP_BLOCK + 1; ++r) {
+            const int row = by0 + r;
+            rb[r] = 0; rn[r] = 0;
+            if (row <= by1) { rb[r] = ps.cell_start[row * ps.gx + bx0]; rn[r] = ps.cell_start[row * ps.gx + bx1 + 1] - rb[r]; }
+            M += rn[r];
+        }
+        if (M > 64) { PR(0); ok = false; }
+        float sx[4], sy[4]; int sp[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int e = gl + GL * k, pos = -1;
+#pragma unroll
+            for (int r = 0; r < 2 * WRAP_BLOCK + 1; ++r) {
+                if (pos < 0) { if (e < rn[r]) pos = rb[r] + e; else e -= rn[r]; }
+            }
+            const bool v = pos >= 0 && pos != p && ps.orig[pos] != INF16;
+            sp[k] = v ? pos : (int)INF16;
+            sx[k] = v ? ps.x[pos] - ppx : 0.f; sy[k] = v ? ps.y[pos] - ppy : 0.f;
+        }
+        const float BX0 = bx0 > 0 ? ps.xmin + bx0 * ps.h - ppx + slack : -CUDART_INF_F, BX1 = bx1 < ps.gx - 1 ? ps.xmin + (bx1 + 1) * ps.h - ppx - slack : CUDART_INF_F;
+        const float BY0 = by0 > 0 ? ps.ymin + by0 * ps.h - ppy + slack : -CUDART_INF_F, BY1 = by1 < ps.gy - 1 ? ps.ymin + (by1 + 1) * ps.h - ppy - slack : CUDART_INF_F;
+        // ---- q0: the nearest point, certified and unique up to rounding
+        int q0; float cx, cy;
+        {
+            unsigned kq = 0xFFFFFFFFu; float mx = 0.f, my = 0.f; int mp = INF16;
+            float l[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                l[k] = fmaf(sx[k], sx[k], sy[k] * sy[k]);
+                const unsigned key = sp[k] != INF16 ? __float_as_uint(l[k]) : 0xFFFFFFFFu;
+                if (key < kq) { kq = key; mx = sx[k]; my = sy[k]; mp = sp[k]; }
+            }
+            const unsigned kmin = gmin_u32(kq, g);
+            const float lmin = __uint_as_float(kmin);
+            const float mg = fminf(fminf(-BX0, BX1), fminf(-BY0, BY1));
+            if (ok && (kmin == 0xFFFFFFFFu || !(lmin * 1.000001f < mg * mg))) { PR(1); ok = false; }
+            const float thr = lmin * 1.000002f;
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cnt += sp[k] != INF16 && l[k] <= thr;
+            const unsigned b1 = GBALLOT(cnt >= 1), b2 = GBALLOT(cnt >= 2);
+            if (ok && (__popc(b1) != 1 || b2)) { PR(2); ok = false; }
+            const int wl = max(__ffs(GBALLOT(kq == kmin)) - 1, 0);
+            q0 = GSHFL(mp, wl); cx = GSHFL(mx, wl); cy = GSHFL(my, wl);
+        }
+        // ---- the counter-clockwise walk; lane i of the half-warp keeps the i-th neighbour
+        int sid = gl == 0 ? q0 : (int)INF16, nC = 1, cpos = q0;
+        bool closed = false, walking = ok;
+        const bool m32 = __any_sync(FULL, ok && M > 32), m48 = __any_sync(FULL, ok && M > 48);
+        while (__any_sync(FULL, walking)) {
+            unsigned kbest = 0xFFFFFFFFu; float tb = 0.f, eb = 0.f, xb = 0.f, yb = 0.f; int pb = INF16;
+            float lb_best = CUDART_INF_F, lb_rest = CUDART_INF_F; bool susp = false;
+#define PAIR_SLOT(k) { \
+                const WEval e = w_eval(sp[k] != INF16 && sp[k] != cpos, sx[k], sy[k], fmaf(sx[k], sx[k], sy[k] * sy[k]), cx, cy, 1.f); \
+                susp |= e.susp; \
+                const unsigned key = e.cand ? w_key(e.t) : 0xFFFFFFFFu; const float lb = e.cand ? e.t - e.eps : CUDART_INF_F; \
+                if (key < kbest) { lb_rest = fminf(lb_rest, lb_best); kbest = key; tb = e.t; eb = e.eps; xb = sx[k]; yb = sy[k]; pb = sp[k]; lb_best = lb; } \
+                else lb_rest = fminf(lb_rest, lb); }
+            PAIR_SLOT(0) PAIR_SLOT(1)
+            if (m32) PAIR_SLOT(2)
+            if (m48) PAIR_SLOT(3)
+#undef PAIR_SLOT
+            const unsigned gsusp = GBALLOT(susp && walking);               // (ballots are executed by all 32 lanes)
+            if (walking && gsusp) { PR(3); ok = false; walking = false; }
+            const unsigned kmin = gmin_u32(walking ? kbest : 0xFFFFFFFFu, g);
+            if (walking && kmin == 0xFFFFFFFFu) { PR(4); ok = false; walking = false; }      // nothing on the left inside the block: hull edge or far neighbour
+            const int wl = max(__ffs(GBALLOT(walking && kbest == kmin)) - 1, 0);
+            const float wt = GSHFL(tb, wl), we = GSHFL(eb, wl), wx = GSHFL(xb, wl), wy = GSHFL(yb, wl);
+            const int wpos = GSHFL(pb, wl);
+            const float ub = wt + we;
+            const float lbo = gl == wl ? lb_rest : fminf(lb_best, lb_rest);
+            const unsigned gclash = GBALLOT(walking && !(lbo > ub));
+            if (walking && gclash) { PR(5); ok = false; walking = false; }   // another candidate's interval overlaps the winner's
+            if (walking && !(fabsf(wt) < 1.0e18f)) { PR(0); ok = false; walking = false; }
+            // the winner's circle must lie inside the block
+            const float vx = 0.5f * (cx - wt * cy), vy = 0.5f * (cy + wt * cx);
+            const float r = sqrt_approx(fmaf(vx, vx, vy * vy));
+            const float rs = r + 2.f * (we * (fabsf(cx) + fabsf(cy)) * 0.51f + 1.0e-3f + 1.0e-4f * r);
+            if (walking && !w_cap_inside(cx, cy, 1.f, vx, vy, rs, BX0, BX1, BY0, BY1)) { PR(6); ok = false; walking = false; }
+            if (walking) {
+                if (wpos == q0) { closed = true; walking = false; }
+                else if (nC >= GL) { PR(7); ok = false; walking = false; }
+                else { if (gl == nC) sid = wpos; ++nC; cx = wx; cy = wy; cpos = wpos; }
+            }
+        }
+        const bool fin = ok && closed;
+        if (have && ok && !closed) PR(2);
+        if (have && !fin && gl == 0) { const int slot = atomicAdd(&sc->n_defer, 1); defer[slot] = (uint16_t)p; }
+        // ---- consumers, both half-warps in lock step (d = 0: nothing)
+        const int d = fin ? nC : 0;
+        const int nid = GSHFL(sid, gl + 1 < d ? gl + 1 : 0);
+        const bool tri = gl < d;
+        const int op = ps.orig[p];
+        if (EMIT) {
+            unsigned key = 0xFFFFFFFFu;
+            if (tri) {
+                const int oa = ps.orig[sid], ob = ps.orig[nid];
+                if (op < oa && op < ob) key = ((unsigned)min(oa, ob) << 16) | (unsigned)max(oa, ob);
+            }
+            const bool own = key != 0xFFFFFFFFu;
+            const int k = __popc(GBALLOT(own));
+            int base = 0;
+            if (gl == 0 && k) base = atomicAdd(fv.T, k);
+            base = GSHFL(base, 0);
+            const bool over = base + k > fv.tri_cap;
+            if (over && k && gl == 0) atomicOr(fv.status, MVOSR_ST_OVERFLOW);
+            int rk = 0;
+#pragma unroll
+            for (int j = 0; j < GL; ++j) { const unsigned kj = GSHFL(key, j); rk += kj < key; }
+            if (own && !over) { uint16_t *t = fv.tri + 3 * (base + rk); t[0] = (uint16_t)op; t[1] = (uint16_t)(key >> 16); t[2] = (uint16_t)(key & 0xFFFFu); }
+            if (gl == 0 && k && !over) { fv.tbase[op] = (uint16_t)base; fv.tcnt[op] = (uint8_t)k; }
+        } else {
+            bool vote = false;
+            if (tri) {
+                const int oa = ps.orig[sid], ob = ps.orig[nid];
+                vote = graph_vote(op, ps.y[p], fv.Z[op], oa, ps.y[sid], fv.Z[oa], ob, ps.y[nid], fv.Z[ob], fv.pass_mask);
+            }
+            const unsigned bt = GBALLOT(tri), bv = GBALLOT(vote);
+            if (gl == 0 && d > 0 && 2 * __popc(bv) > __popc(bt)) fv.pflag[op] |= 2;
+        }
+    }
+#undef GBALLOT
+#undef GSHFL
+#undef PR
+}
+
 // All stars of the staged point set.  EMIT: triangles into fv.tri; otherwise the graph vote into fv.pflag.
-// Block-wide; sc, defer[] and defer2[] are shared scratch.  Three levels: wrap path (all stars) -> exact half-warp path
-// (what the wrap path could not certify) -> exact full-warp path (what overflowed 16 slots or needs the collinear bootstrap).
-// Returns (#stars of level 2) + (#stars of level 3 << 16).
+// Block-wide; sc, defer[] and defer2[] are shared scratch.  Four levels: pair path (all stars) -> wrap path (hull stars,
+// circles leaving the block) -> exact half-warp path (what float32 could not certify) -> exact full-warp path (more than
+// 16 slots, collinear bootstrap).  Returns (#stars of level 3) + (#stars of level 4 << 16); *n_wrap receives level 2's count.
 template <bool EMIT>
 __device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, uint16_t *defer2,
                                       int &n_exact, long long *t_fast) {
@@ -869,18 +1046,24 @@ __device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, 
     if (tid == 0) { sc->next_pos = 0; sc->n_defer = 0; sc->n_defer2 = 0; }
     __syncthreads();
     long long tc0 = clock64();
-    stars_wrap<EMIT>(ps, fv, sc, defer);
+    stars_pair<EMIT>(ps, fv, sc, defer);
     __syncthreads();
     if (tid == 0 && t_fast) *t_fast += clock64() - tc0;
     const int n1 = sc->n_defer;
     __syncthreads();
     if (tid == 0) sc->next_pos = 0;
     __syncthreads();
-    if (n1) stars_fast<EMIT>(ps, fv, sc, defer, n1, defer2, n_exact);
+    if (n1) stars_wrap<EMIT>(ps, fv, sc, defer, n1, defer2);
     __syncthreads();
     const int n2 = sc->n_defer2;
-    for (int k = warp; k < n2; k += NWARP) {
-        const int p = defer2[k];
+    __syncthreads();
+    if (tid == 0) { sc->next_pos = 0; sc->n_defer2 = 0; }
+    __syncthreads();
+    if (n2) stars_fast<EMIT>(ps, fv, sc, defer2, n2, defer, n_exact);       // overflow list: defer[] again (its first use is over)
+    __syncthreads();
+    const int n3 = sc->n_defer2;
+    for (int k = warp; k < n3; k += NWARP) {
+        const int p = defer[k];
         const FbResult r = fb_build(ps, p);
         n_exact += r.n_exact;
         if (r.rc == STAR_OK) {
@@ -894,7 +1077,8 @@ __device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, 
         }
     }
     __syncthreads();
-    return n1 + (n2 << 16);
+    if (tid == 0) sc->n_wrap += n1;
+    return n2 + (n3 << 16);
 }
 
 }  // namespace mvosr

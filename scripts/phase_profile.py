@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mvoscalerecovery_b200 import synth, _native as N            # noqa: E402
 from mvoscalerecovery_b200.batch import ScaleRecovery, stats_to_numpy            # noqa: E402
 
-NAMES = {0: "load+stage1+roi", 1: "grid1", 2: "stars1", 3: "stars1_wrap", 6: "keep+compact+grid2", 7: "stars2", 8: "stars2_wrap", 10: "planes", 11: "median", 12: "valid_list", 13: "ransac"}
+NAMES = {0: "load+stage1+roi", 1: "grid1", 2: "stars1", 3: "stars1_pair", 6: "keep+compact+grid2", 7: "stars2", 8: "stars2_pair", 9: "n_to_wrap_path", 10: "planes", 11: "median", 12: "valid_list", 13: "ransac"}
 
 
 def main():
