@@ -153,7 +153,7 @@ int  mvosr_scale_frames_from_correspondences(mvosr_handle *h, int32_t n_frames, 
 
 /* Stage 6 -- replaces the driver gating of src/main_offline.py:57-88 and the temporal state of
  * src/rescale.py:168-178 (slew limiter + median of the last window_size states), then
- * filter(data, 10) of script/evaluate_scale.py:25-29.  One thread per sequence; seq_offsets: [S+1]
+ * filter(data, 10) of script/evaluate_scale.py:25-29.  One CTA per sequence; seq_offsets: [S+1]
  * frame ranges.  move_flags may be NULL (all moving).  n_features may be NULL (all above the gate).
  * scale_out[f] = what main_offline appends to `scales` (scales[1:]); filter10_out may be NULL. */
 int  mvosr_filter_sequences(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets,

@@ -81,51 +81,111 @@ __global__ void __launch_bounds__(256) triangulate_kernel(int n_frames, const in
     }
 }
 
-__device__ __forceinline__ double median_small(const double *q, int n) {
-    double s[32];
-    for (int i = 0; i < n; ++i) { double v = q[i]; int j = i; while (j > 0 && s[j - 1] > v) { s[j] = s[j - 1]; --j; } s[j] = v; }
-    return (n & 1) ? s[n / 2] : (s[n / 2 - 1] + s[n / 2]) / 2.0;      // np.median: mean of the two middle values
-}
-
-// Stage 6a: driver gating (main_offline.py:57-88) + slew limiter + deque median (rescale.py:168-178).
-// The recurrence is strictly sequential per sequence: one thread per sequence.
-__global__ void filter_kernel(int n_seq, const int32_t *seq_offsets, const double *raw, const uint8_t *status,
-                              const uint8_t *move, const int32_t *n_features, mvosr_config cfg, double *out) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_seq) return;
-    double scale = 1.0;                  // self.scale = 1 (rescale.py:27)
-    double q[32]; int qn = 0;            // scale_queue
-    int win = cfg.window_size < 1 ? 1 : (cfg.window_size > 31 ? 31 : cfg.window_size);
-    double last = 0.0;                   // scales = [0] (main_offline.py:45)
-    for (int f = seq_offsets[s]; f < seq_offsets[s + 1]; ++f) {
-        double o;
-        if (move && !move[f]) o = 0.0;                                               // :64-68
-        else if (n_features && n_features[f] <= cfg.min_features) o = last;          // :73,84-86
-        else {
-            if (status[f] & MVOSR_ST_UPDATED) {
-                double r = raw[f];
-                if (r - scale > cfg.slew_limit) scale += cfg.slew_limit;
-                else if (r - scale < -cfg.slew_limit) scale -= cfg.slew_limit;
-                else scale = r;
-            }
-            q[qn++] = scale;
-            if (qn > win) { for (int i = 1; i < qn; ++i) q[i - 1] = q[i]; --qn; }
-            o = median_small(q, qn);
-        }
-        out[f] = o; last = o;
+// median of w[0..n) (n <= 32) by rank counting -- np.median semantics: mean of the two middle values for even n
+__device__ __forceinline__ double median_window(const double *w, int n) {
+    const int k0 = (n - 1) >> 1, k1 = n >> 1;
+    double a = 0, b = 0;
+    for (int i = 0; i < n; ++i) {
+        const double v = w[i];
+        int less = 0, leq = 0;
+        for (int j = 0; j < n; ++j) { less += w[j] < v; leq += w[j] <= v; }
+        if (less <= k0 && k0 < leq) a = v;
+        if (less <= k1 && k1 < leq) b = v;
     }
+    return (n & 1) ? a : (a + b) / 2.0;
 }
 
-// Stage 6b: filter(data, window=10) of script/evaluate_scale.py:25-29 -- causal running median; thread per frame.
-__global__ void filter10_kernel(int n_seq, const int32_t *seq_offsets, const double *in, double *out) {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = seq_offsets[n_seq];
-    if (f >= total) return;
-    int lo = 0, hi = n_seq;              // sequence containing f
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (seq_offsets[mid] <= f) lo = mid; else hi = mid; }
-    int s0 = seq_offsets[lo];
-    int a = f - 9 < s0 ? s0 : f - 9;
-    out[f] = median_small(in + a, f - a + 1);
+// Stage 6: driver gating (main_offline.py:57-88) + slew limiter + median of the last window_size states
+// (rescale.py:168-178), then filter(data, 10) of script/evaluate_scale.py:25-29.  One CTA per sequence, frames in chunks
+// staged in shared memory: thread 0 runs the strictly sequential recurrences (slew limiter, "repeat the last output"),
+// everything else -- the windowed medians -- is computed by all threads in parallel.
+constexpr int FCH = 1024;            // frames per chunk
+constexpr int FHIST = 32;            // history carried between chunks (window_size <= 31, filter_10 needs 9)
+__global__ void __launch_bounds__(256) filter_kernel(int n_seq, const int32_t *seq_offsets, const double *raw, const uint8_t *status,
+                              const uint8_t *move, const int32_t *n_features, mvosr_config cfg, double *out, double *out10) {
+    __shared__ double P[FHIST + FCH];       // pushed states: [0,FHIST) = tail of the earlier chunks
+    __shared__ double O[FHIST + FCH];       // outputs, same layout
+    __shared__ double R[FCH];               // raw scales, then the medians
+    __shared__ int pidx[FCH];               // number of states pushed up to and including this frame (chunk-local, + FHIST)
+    __shared__ uint8_t kind[FCH], flags[FCH];
+    __shared__ double s_scale, s_last; __shared__ int s_npush, s_nhist, s_ohist;
+    const int tid = threadIdx.x;
+    const int win = cfg.window_size < 1 ? 1 : (cfg.window_size > 31 ? 31 : cfg.window_size);
+    for (int s = blockIdx.x; s < n_seq; s += gridDim.x) {
+        const int f0 = seq_offsets[s], f1 = seq_offsets[s + 1];
+        if (tid == 0) { s_scale = 1.0; s_last = 0.0; s_nhist = 0; s_ohist = 0; }     // self.scale = 1 (rescale.py:27), scales = [0] (main_offline.py:45)
+        __syncthreads();
+        for (int c0 = f0; c0 < f1; c0 += FCH) {
+            const int n = min(FCH, f1 - c0);
+            for (int i = tid; i < n; i += blockDim.x) {
+                const int f = c0 + i;
+                R[i] = raw[f];
+                int fl = (status[f] & MVOSR_ST_UPDATED) ? 1 : 0;
+                if (move && !move[f]) fl |= 2;                                        // not moving -> 0 (:64-68)
+                else if (n_features && n_features[f] <= cfg.min_features) fl |= 4;    // too few features -> repeat (:73,84-86)
+                flags[i] = (uint8_t)fl;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double scale = s_scale; int np = FHIST;
+                for (int i = 0; i < n; ++i) {
+                    const int fl = flags[i];
+                    if (fl & 2) kind[i] = 0;
+                    else if (fl & 4) kind[i] = 1;
+                    else {
+                        if (fl & 1) {
+                            const double r = R[i];
+                            if (r - scale > cfg.slew_limit) scale += cfg.slew_limit;
+                            else if (r - scale < -cfg.slew_limit) scale -= cfg.slew_limit;
+                            else scale = r;
+                        }
+                        P[np++] = scale; kind[i] = 2;
+                    }
+                    pidx[i] = np;
+                }
+                s_scale = scale; s_npush = np;
+            }
+            __syncthreads();
+            const int nhist = s_nhist;
+            for (int i = tid; i < n; i += blockDim.x) {
+                if (kind[i] != 2) continue;
+                const int e = pidx[i];                                   // window = the last `win` pushed states
+                int b = e - win; if (b < FHIST - nhist) b = FHIST - nhist;
+                R[i] = median_window(P + b, e - b);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double last = s_last;
+                for (int i = 0; i < n; ++i) {
+                    const int k = kind[i];
+                    const double o = k == 0 ? 0.0 : (k == 1 ? last : R[i]);
+                    O[FHIST + i] = o; last = o;
+                }
+                s_last = last;
+            }
+            __syncthreads();
+            const int ohist = s_ohist;
+            for (int i = tid; i < n; i += blockDim.x) {
+                out[c0 + i] = O[FHIST + i];
+                if (out10) {                                             // causal running median over the last 10 outputs
+                    int b = FHIST + i - 9; if (b < FHIST - ohist) b = FHIST - ohist;
+                    out10[c0 + i] = median_window(O + b, FHIST + i + 1 - b);
+                }
+            }
+            __syncthreads();
+            // carry the tails into the history slots
+            const int np = s_npush, keepP = min(FHIST, nhist + (np - FHIST)), keepO = min(FHIST, ohist + n);
+            double tp = 0, to = 0;
+            if (tid < FHIST) {
+                if (tid >= FHIST - keepP) tp = P[np - FHIST + tid];
+                if (tid >= FHIST - keepO) to = O[n + tid];
+            }
+            __syncthreads();
+            if (tid < FHIST) { P[tid] = tp; O[tid] = to; }
+            if (tid == 0) { s_nhist = keepP; s_ohist = keepO; }
+            __syncthreads();
+        }
+    }
 }
 
 }  // namespace mvosr
@@ -362,21 +422,10 @@ int mvosr_filter_sequences(mvosr_handle *h, int32_t n_sequences, const int32_t *
     if (n_sequences == 0) return MVOSR_OK;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    filter_kernel<<<(n_sequences + 31) / 32, 32, 0, st>>>(n_sequences, seq_offsets, raw_scale, status, move_flags, n_features,
-                                                           h->cfg, scale_out);
+    const int grid = n_sequences < 4 * h->num_sms ? n_sequences : 4 * h->num_sms;
+    filter_kernel<<<grid, 256, 0, st>>>(n_sequences, seq_offsets, raw_scale, status, move_flags, n_features, h->cfg, scale_out, filter10_out);
     CK(cudaGetLastError());
     h->launches += 1;
-    if (filter10_out) {
-        int total = 0;
-        // the frame count is seq_offsets[n_sequences] (device memory): size the grid from a bounded copy
-        CK(cudaMemcpyAsync(&total, seq_offsets + n_sequences, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (total > 0) {
-            filter10_kernel<<<(total + 127) / 128, 128, 0, st>>>(n_sequences, seq_offsets, scale_out, filter10_out);
-            CK(cudaGetLastError());
-            h->launches += 1;
-        }
-    }
     return MVOSR_OK;
 }
 

@@ -12,11 +12,12 @@ marks = {
  'group path+fallback': (find('// exact conflict of candidate'), find('// wrap path: one warp per star')),
  'w_eval/key/circle': (find('struct WEval'), find('// One batch of candidates (one per lane)')),
  'w_batch': (find('// One batch of candidates (one per lane)'), find('// Stream the grid cells that the left cap')),
- 'w_stream': (find('// Stream the grid cells that the left cap'), find('// All stars of the staged set; stars that need the exact path')),
- 'wrap:fetch+load': (find('// All stars of the staged set; stars that need the exact path'), find('// ---- q0 = the nearest point')),
+ 'w_stream': (find('// Stream the grid cells that the left cap'), find('// The stars of list[0..n_list) (sorted positions), one per warp')),
+ 'wrap:fetch+load': (find('// The stars of list[0..n_list) (sorted positions), one per warp'), find('// ---- q0 = the nearest point')),
  'wrap:q0': (find('// ---- q0 = the nearest point'), find('// ---- the walk: lane i keeps')),
  'wrap:walk': (find('// ---- the walk: lane i keeps'), find('// ---- counter-clockwise slot order')),
- 'wrap:finish': (find('// ---- counter-clockwise slot order'), find('// All stars of the staged point set.')),
+ 'wrap:finish': (find('// ---- counter-clockwise slot order'), find('// pair path: two stars per warp in lock step')),
+ 'pair': (find('// pair path: two stars per warp in lock step'), find('// All stars of the staged point set.')),
  'run_stars': (find('// All stars of the staged point set.'), 10**6),
 }
 agg = collections.defaultdict(lambda:[0.0,0.0])
