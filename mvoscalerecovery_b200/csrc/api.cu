@@ -23,13 +23,17 @@ static thread_local char g_cuda_err[256] = "";
         }                                                                                          \
     } while (0)
 
+static const int NCOUNTERS = 16;
+
 struct mvosr_handle {
     mvosr_config cfg;
     int device;
     int num_sms;
     int smem_optin;
     int cap_max;
-    int *work_counter;           // device
+    int *work_counter;           // device: NCOUNTERS dynamic-scheduler counters (one per in-flight launch)
+    int counter_slot;            // round-robin
+    cudaStream_t s_copy, s_comp[2]; cudaEvent_t ev_copy[8]; int streams_ready;    // host-buffer pipeline
     int64_t launches;
     // host-API staging (grown on demand)
     void *d_stage; size_t stage_bytes;
@@ -281,7 +285,7 @@ int mvosr_create(const mvosr_config *cfg, int device, mvosr_handle **out) {
     int cap = 256;
     while (make_plan(cap + 64).total + (int)sizeof(Ctl) + 1024 <= h->smem_optin) cap += 64;
     h->cap_max = cap;
-    CK(cudaMalloc(&h->work_counter, sizeof(int)));
+    CK(cudaMalloc(&h->work_counter, NCOUNTERS * sizeof(int)));
     CK(cudaFuncSetAttribute(frame_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512));
     CK(cudaFuncSetAttribute(frame_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512));
     *out = h;
@@ -294,6 +298,10 @@ int mvosr_destroy(mvosr_handle *h) {
     if (h->work_counter) cudaFree(h->work_counter);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->d_ws) cudaFree(h->d_ws);
+    if (h->streams_ready) {
+        cudaStreamDestroy(h->s_copy); cudaStreamDestroy(h->s_comp[0]); cudaStreamDestroy(h->s_comp[1]);
+        for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_copy[i]);
+    }
     delete h;
     return MVOSR_OK;
 }
@@ -325,7 +333,8 @@ static int launch_frames(mvosr_handle *h, FrameParams &P, int max_features, cuda
     if (cap > CAP_LIMIT) return MVOSR_E_CAPACITY;
     P.cap = cap;
     P.cfg = h->cfg;
-    P.work_counter = h->work_counter;
+    h->counter_slot = (h->counter_slot + 1) % NCOUNTERS;      // launches in flight on different streams must not share a counter
+    P.work_counter = h->work_counter + h->counter_slot;
     P.phase_cycles = h->phase_cycles;
     SmemPlan pl = make_plan(P.cap);
     int grid = P.n_frames < h->num_sms ? P.n_frames : h->num_sms;
@@ -344,7 +353,7 @@ static int launch_frames(mvosr_handle *h, FrameParams &P, int max_features, cuda
         P.workspace = (unsigned char *)h->d_ws; P.ws_stride = stride;
         dyn = 0;
     }
-    CK(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(P.work_counter, 0, sizeof(int), st));
     frame_kernel<FROM_CORR><<<grid, NT, dyn, st>>>(P);
     CK(cudaGetLastError());
     h->launches += 1;
@@ -451,21 +460,46 @@ int mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t *
         h->stage_bytes = total;
     }
     char *d = (char *)h->d_stage;
-    cudaStream_t st = 0;
-    CK(cudaMemcpyAsync(d + o_off, offsets_host, 4 * (size_t)(n_frames + 1), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d + o_cu, cur_u_host, 4 * M, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d + o_cv, cur_v_host, 4 * M, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d + o_ru, ref_u_host, 4 * M, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d + o_rv, ref_v_host, 4 * M, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d + o_pose, poses_host, 96 * (size_t)n_frames, cudaMemcpyHostToDevice, st));
-    if (move_flags_host) CK(cudaMemcpyAsync(d + o_move, move_flags_host, (size_t)n_frames, cudaMemcpyHostToDevice, st));
+    if (!h->streams_ready) {
+        CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->s_comp[0], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->s_comp[1], cudaStreamNonBlocking));
+        for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+        h->streams_ready = 1;
+    }
+    // Pipeline: the frame range is cut into chunks; chunk k+1 is copied while chunk k is processed, and consecutive chunks
+    // run on two compute streams so that the tail of one launch overlaps the head of the next.
+    cudaStream_t sc = h->s_copy;
+    CK(cudaMemcpyAsync(d + o_off, offsets_host, 4 * (size_t)(n_frames + 1), cudaMemcpyHostToDevice, sc));
+    CK(cudaMemcpyAsync(d + o_pose, poses_host, 96 * (size_t)n_frames, cudaMemcpyHostToDevice, sc));
+    if (move_flags_host) CK(cudaMemcpyAsync(d + o_move, move_flags_host, (size_t)n_frames, cudaMemcpyHostToDevice, sc));
     int32_t seqo[2] = { 0, n_frames };
-    CK(cudaMemcpyAsync(d + o_seq, seqo, sizeof(seqo), cudaMemcpyHostToDevice, st));
-    int rc = mvosr_scale_frames_from_correspondences(h, n_frames, (const int32_t *)(d + o_off), (const float *)(d + o_cu),
-                (const float *)(d + o_cv), (const float *)(d + o_ru), (const float *)(d + o_rv), nullptr, (const double *)(d + o_pose),
-                max_features, 0, seq_id, seed, (double *)(d + o_raw), (uint8_t *)(d + o_st), (int32_t *)(d + o_nf), nullptr, st);
-    if (rc != MVOSR_OK) return rc;
-    rc = mvosr_filter_sequences(h, 1, (const int32_t *)(d + o_seq), (const double *)(d + o_raw), (const uint8_t *)(d + o_st),
+    CK(cudaMemcpyAsync(d + o_seq, seqo, sizeof(seqo), cudaMemcpyHostToDevice, sc));
+    const int n_chunks = n_frames >= 8 * h->num_sms ? 8 : (n_frames >= 2 * h->num_sms ? 2 : 1);
+    for (int c = 0; c < n_chunks; ++c) {
+        // the first chunk is small so that the GPU starts early
+        const int f0 = c == 0 ? 0 : (int)((long long)n_frames * (2 * c - 1) / (2 * n_chunks - 1));
+        const int f1 = (int)((long long)n_frames * (2 * c + 1) / (2 * n_chunks - 1));
+        const size_t a0 = (size_t)offsets_host[f0], a1 = (size_t)offsets_host[f1 > n_frames ? n_frames : f1];
+        const int fe = f1 > n_frames ? n_frames : f1;
+        if (fe <= f0) continue;
+        CK(cudaMemcpyAsync(d + o_cu + 4 * a0, cur_u_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+        CK(cudaMemcpyAsync(d + o_cv + 4 * a0, cur_v_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+        CK(cudaMemcpyAsync(d + o_ru + 4 * a0, ref_u_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+        CK(cudaMemcpyAsync(d + o_rv + 4 * a0, ref_v_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+        CK(cudaEventRecord(h->ev_copy[c], sc));
+        cudaStream_t st = h->s_comp[c & 1];
+        CK(cudaStreamWaitEvent(st, h->ev_copy[c], 0));
+        int rc = mvosr_scale_frames_from_correspondences(h, fe - f0, (const int32_t *)(d + o_off) + f0, (const float *)(d + o_cu),
+                    (const float *)(d + o_cv), (const float *)(d + o_ru), (const float *)(d + o_rv), nullptr, (const double *)(d + o_pose) + 12 * (size_t)f0,
+                    max_features, f0, seq_id, seed, (double *)(d + o_raw) + f0, (uint8_t *)(d + o_st) + f0, (int32_t *)(d + o_nf) + f0, nullptr, st);
+        if (rc != MVOSR_OK) return rc;
+    }
+    // join: the filter runs on compute stream 0 after both compute streams
+    CK(cudaEventRecord(h->ev_copy[0], h->s_comp[1]));
+    CK(cudaStreamWaitEvent(h->s_comp[0], h->ev_copy[0], 0));
+    cudaStream_t st = h->s_comp[0];
+    int rc = mvosr_filter_sequences(h, 1, (const int32_t *)(d + o_seq), (const double *)(d + o_raw), (const uint8_t *)(d + o_st),
                                 move_flags_host ? (const uint8_t *)(d + o_move) : nullptr, (const int32_t *)(d + o_nf),
                                 (double *)(d + o_out), nullptr, st);
     if (rc != MVOSR_OK) return rc;
