@@ -300,7 +300,7 @@ def run_gpu_arm(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "kernel": "frame_kernel<FROM_CORR>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                              "peak_source": peak_src,
-                             "note": "latency/ALU-bound path by construction (SURVEY 8d: 1e5 fps is 0.06 % of the HBM ceiling)"},
+                             "note": "instruction-issue-bound path by construction (SURVEY 8d: 1e5 fps is 0.06 % of the HBM ceiling); see profiles/README.md"},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "mvosr_recover_scales_host (pinned host buffers, copies inside)"},
