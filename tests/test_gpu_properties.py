@@ -1,0 +1,138 @@
+"""Size-independent properties of the CUDA path at BASELINE's sizes (where the oracle would take minutes to hours):
+determinism, shard invariance (the multi-GPU decomposition), fused == staged, Euler's formula and edge manifoldness of
+every Delaunay triangulation, and the temporal filter over a fleet of sequences against the oracle's state machine."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KITTI_LENGTHS = [4541, 1101, 4661, 801, 271, 2761, 1101, 1101, 4071, 1591, 1201]      # BASELINE configs[3]: sequences 00-10
+
+
+@pytest.fixture(scope="module")
+def workload():
+    from mvoscalerecovery_b200 import synth
+    return synth.make_sequence(seed=20261017, n_frames=1200, n_corr=2500, outlier_frac=0.10)
+
+
+def _dev(engine, b):
+    import torch
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(engine.device)
+    return dict(offsets=t(b.offsets), cur_u=t(b.cur_u), cur_v=t(b.cur_v), ref_u=t(b.ref_u), ref_v=t(b.ref_v), poses=t(b.poses))
+
+
+def _run(engine, d, maxf, lo=0, hi=None, seed=9):
+    import torch
+    hi = d["offsets"].numel() - 1 if hi is None else hi
+    r = engine.scale_frames_from_correspondences(d["offsets"][lo:hi + 1].contiguous(), d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"],
+                                                 d["poses"][lo:hi].contiguous(), max_features=maxf, frame_index0=lo, seed=seed, stats=True)
+    torch.cuda.synchronize()
+    return r["raw_scale"].cpu().numpy(), r["status"].cpu().numpy(), r["n_features"].cpu().numpy(), r["stats"]
+
+
+def test_deterministic_and_shard_invariant(engine, workload):
+    """Two runs are bit-identical; processing frame ranges separately (what fleet.frame_shards does across GPUs) gives
+    bit-identical results to one launch -- the hypothesis stream is indexed by the global frame number."""
+    b = workload
+    d = _dev(engine, b)
+    maxf = int(np.max(np.diff(b.offsets)))
+    raw, st, nf, _ = _run(engine, d, maxf)
+    raw2, st2, nf2, _ = _run(engine, d, maxf)
+    assert np.array_equal(raw, raw2, equal_nan=True) and np.array_equal(st, st2) and np.array_equal(nf, nf2)
+    from mvoscalerecovery_b200.fleet import frame_shards
+    parts = [_run(engine, d, maxf, lo, hi) for lo, hi in frame_shards(b.n_frames, 3, np.diff(b.offsets))]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), raw, equal_nan=True)
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), st)
+    assert (st & 1).mean() > 0.95
+    err = np.abs(raw[(st & 1) != 0] - b.true_scale[(st & 1) != 0]) / b.true_scale[(st & 1) != 0]
+    assert np.median(err) < 5e-3                                    # the estimator recovers the synthetic truth
+
+
+def test_fused_equals_staged_at_scale(engine, workload):
+    import torch
+    b = workload
+    d = _dev(engine, b)
+    maxf = int(np.max(np.diff(b.offsets)))
+    raw, st, nf, _ = _run(engine, d, maxf)
+    s1 = engine.triangulate_frames(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], d["poses"])
+    r = engine.scale_frames(d["offsets"], s1["x"], s1["y"], s1["z"], s1["u"], s1["v"], maxf, counts=s1["n_out"], seed=9)
+    torch.cuda.synchronize()
+    assert np.array_equal(s1["n_out"].cpu().numpy(), nf)
+    assert np.array_equal(r["raw_scale"].cpu().numpy(), raw, equal_nan=True)
+    assert np.array_equal(r["status"].cpu().numpy() & 0x3F, st & 0x3F)
+
+
+def test_delaunay_euler_and_manifold_every_frame(engine, workload):
+    """T = 2n - 2 - h (h = hull vertices, from scipy's ConvexHull) and every edge in one or two triangles, for every
+    frame's ROI point set; a sample of frames additionally through the exact validator."""
+    import torch
+    from scipy.spatial import ConvexHull
+    from oracle import exact
+    b = workload
+    d = _dev(engine, b)
+    s1 = engine.triangulate_frames(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], d["poses"])
+    torch.cuda.synchronize()
+    n_out = s1["n_out"].cpu().numpy(); U = s1["u"].cpu().numpy(); V = s1["v"].cpu().numpy()
+    frames = range(0, b.n_frames, 4)
+    pts = []
+    for f in frames:
+        a = int(b.offsets[f]); u, v = U[a:a + n_out[f]], V[a:a + n_out[f]]
+        keep = v > 185
+        pts.append(np.stack([u[keep], v[keep]], 1))
+    off = np.zeros(len(pts) + 1, np.int32); np.cumsum([p.shape[0] for p in pts], out=off[1:])
+    allp = np.concatenate(pts, 0)
+    out = engine.delaunay_frames(torch.from_numpy(off).to(engine.device), torch.from_numpy(np.ascontiguousarray(allp[:, 0])).to(engine.device),
+                                 torch.from_numpy(np.ascontiguousarray(allp[:, 1])).to(engine.device), int(np.max(np.diff(off))))
+    torch.cuda.synchronize()
+    tri = out["tri"].cpu().numpy(); ntri = out["n_tri"].cpu().numpy(); st = out["status"].cpu().numpy()
+    assert not st.any()
+    for i, p in enumerate(pts):
+        t = tri[2 * off[i]: 2 * off[i] + ntri[i]]
+        n = p.shape[0]
+        h = len(ConvexHull(p.astype(np.float64)).vertices)
+        assert ntri[i] == 2 * n - 2 - h, (i, ntri[i], n, h)
+        e = np.sort(np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [0, 2]]], 0), 1)
+        _, cnt = np.unique(e, axis=0, return_counts=True)
+        assert cnt.max() <= 2 and (cnt == 1).sum() == h              # boundary edges = hull edges
+        assert np.all(t[:, 0] < t[:, 1]) and np.all(t[:, 1] < t[:, 2])
+        assert np.all(np.lexsort((t[:, 2], t[:, 1], t[:, 0])) == np.arange(t.shape[0]))      # canonical order
+        if i % 60 == 0:
+            ok, msg, _ = exact.validate_delaunay(p, t, np.zeros(n, bool))
+            assert ok, (i, msg)
+
+
+def test_fleet_of_sequences_filter_vs_oracle(engine):
+    """BASELINE configs[3] shape: 11 sequences of KITTI 00-10 lengths through ONE filter launch == the oracle's
+    per-sequence state machine (slew limiter, median of 5, driver gating) and filter_10 on the same raw scales."""
+    import torch
+    from oracle import pipeline as P
+    rng = np.random.default_rng(3)
+    total = sum(KITTI_LENGTHS)
+    seq_off = np.concatenate([[0], np.cumsum(KITTI_LENGTHS)]).astype(np.int32)
+    truth = 0.85 + 0.3 * np.sin(np.arange(total) * 0.01) + 0.02 * rng.standard_normal(total)
+    raw = truth.copy()
+    jumps = rng.random(total) < 0.02
+    raw[jumps] += rng.choice([-0.8, 0.9], size=jumps.sum())         # exercises the +-0.3 slew limiter
+    status = np.where(rng.random(total) < 0.97, 1, 0).astype(np.uint8)      # 3 %: RANSAC did not run (state held)
+    raw[status == 0] = np.nan
+    move = (rng.random(total) > 0.01).astype(np.uint8)
+    nfeat = np.where(rng.random(total) < 0.02, 80, 2200).astype(np.int32)
+    dev = engine.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = engine.filter_sequences(t(seq_off), t(raw), t(status), t(move), t(nfeat))
+    torch.cuda.synchronize()
+    got, got10 = out["scale"].cpu().numpy(), out["filter10"].cpu().numpy()
+    for s in range(len(KITTI_LENGTHS)):
+        a, e = seq_off[s], seq_off[s + 1]
+        stt = P.TemporalState(5)
+        scales = [0.0]
+        for f in range(a, e):
+            if not move[f]:
+                scales.append(0.0)
+            elif nfeat[f] > P.MIN_FEATURES:
+                scales.append(stt.step(raw[f], bool(status[f] & 1)))
+            else:
+                scales.append(scales[-1])
+        ref = np.asarray(scales[1:])
+        assert np.array_equal(got[a:e], ref), "sequence %d" % s
+        assert np.array_equal(got10[a:e], P.filter10(ref)), "sequence %d filter_10" % s
