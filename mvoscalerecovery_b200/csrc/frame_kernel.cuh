@@ -10,12 +10,14 @@
 //   RANSAC   get_pitch_ransac / run_ransac                    estimate_road_norm.py:8-18,66-70, thirdparty/Ransac/ransac.py:3-23
 //   scale    height = h_bar/|n|, scale = ref/height           rescale.py:156-167
 //
-// Shared-memory plan for capacity `cap` ROI features, 52 bytes per feature:
+// Shared-memory plan for capacity `cap` ROI features:
 //   X,Y,Z 12cap (float32, feature order) | region T 12cap: U,V (float32 pixel coordinates, feature order) until the last
 //   grid build of the frame, then the triangle list (uint16 x 3 x 2cap) | region H 16cap: the cell-sorted copy of the
 //   points (x,y float32, orig uint16), cell_start, the deferred-star queue during the Delaunay passes, then the triangle
 //   heights (float64 x 2cap) | scr 4cap (uint32: cell counters, later scans) | tbase 2cap | tcnt cap | pflag cap |
-//   mult 2cap | tflags 2cap.
+//   mult 2cap | tflags 2cap | ring pool 12cap + ring info 4cap (the stars of Delaunay #1, kept for Delaunay #2): 68 bytes
+//   per feature.  Between the two Delaunay passes mult holds the old -> new feature index map and tflags the list of stars
+//   that must be rebuilt.
 #pragma once
 #include <stdint.h>
 #include <math_constants.h>
@@ -59,7 +61,7 @@ struct FrameParams {
 };
 
 struct SmemPlan {
-    int cap, off_X, off_Y, off_Z, off_T, off_H, off_scr, off_tbase, off_tcnt, off_pflag, off_mult, off_tflags, total;
+    int cap, off_X, off_Y, off_Z, off_T, off_H, off_scr, off_tbase, off_tcnt, off_pflag, off_mult, off_tflags, off_rpool, off_rinfo, total;
     // inside region T / H
     int t_U, t_V, h_sx, h_sy, h_sorig, h_cell_start, h_defer;
 };
@@ -79,6 +81,8 @@ __host__ __device__ inline SmemPlan make_plan(int cap) {   // cap: multiple of 6
     p.off_pflag = o; o += cap;
     p.off_mult = o; o += 2 * cap + 16;
     p.off_tflags = o; o += 2 * cap;
+    p.off_rinfo = o; o += 4 * cap;
+    p.off_rpool = o; o += 12 * cap;
     p.total = align16(o);
     p.t_U = p.off_T; p.t_V = p.off_T + 4 * cap;
     p.h_sx = p.off_H; p.h_sy = p.off_H + 4 * cap; p.h_sorig = p.off_H + 8 * cap;
@@ -89,7 +93,7 @@ __host__ __device__ inline SmemPlan make_plan(int cap) {   // cap: multiple of 6
 
 struct Ctl {                         // static shared control block
     StarCtl sc;
-    int n_roi, n_feat, status, bad, n_dup, n_dup1, n_kept, T, n_exact, n_deferred_total;
+    int n_roi, n_feat, status, bad, n_dup, n_dup1, n_kept, T, n_exact, n_deferred_total, rcount, n_todo;
     int n_loose, n_tight, n_valid, best_hyp, best_ic, hyps_used, n_degenerate;
     int warp_cnt[NWARP], warp_cnt2[NWARP];
     float red[4][NWARP];
@@ -307,6 +311,9 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
     fv.Z = Z; fv.pflag = pflag; fv.tri = (uint16_t *)(smem + pl.off_T);
     fv.tbase = (uint16_t *)(smem + pl.off_tbase); fv.tcnt = smem + pl.off_tcnt;
     fv.T = &ctl.T; fv.status = &ctl.status; fv.pass_mask = P.cfg.graph_pass_mask; fv.tri_cap = 2 * cap;
+    fv.rpool = nullptr; fv.rinfo = (uint32_t *)(smem + pl.off_rinfo); fv.rcount = &ctl.rcount; fv.rpool_cap = 6 * cap;
+    uint16_t *const rpool = (uint16_t *)(smem + pl.off_rpool);
+    uint16_t *const todo = (uint16_t *)(smem + pl.off_tflags);   // list of the stars Delaunay #2 must rebuild (tflags is free until the planes)
     const mvosr_config &cfg = P.cfg;
     const float density = cfg.reserved[0] > 0 ? 0.01f * (float)cfg.reserved[0] : GRID_DENSITY;     // tuning knob: mean points per grid cell x 100
 
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         if (f >= P.n_frames) break;
         if (tid == 0) {
             ctl.n_roi = ctl.n_feat = ctl.status = ctl.bad = ctl.n_dup = ctl.n_kept = ctl.T = 0; ctl.n_dup1 = -1;
-            ctl.n_exact = ctl.n_deferred_total = 0;
+            ctl.n_exact = ctl.n_deferred_total = 0; ctl.rcount = 0; ctl.n_todo = 0;
             ctl.n_loose = ctl.n_tight = ctl.n_valid = 0; ctl.best_hyp = -1; ctl.best_ic = 0; ctl.hyps_used = 0;
             ctl.n_degenerate = 0; ctl.height_level = CUDART_NAN;
             for (int k = 0; k < 16; ++k) ctl.tphase[k] = 0;
@@ -399,7 +406,11 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 int nd = run_stars<true>(ctl.ps, fv, &ctl.sc, defer, defer2, n_exact, &ctl.tphase[3]);
                 if (tid == 0) ctl.n_deferred_total += nd;
             } else {
+                for (int i = tid; i < n; i += NT) fv.rinfo[i] = 0;
+                __syncthreads();
+                fv.rpool = rpool;                                  // the vote pass also stores every finished star
                 int nd = run_stars<false>(ctl.ps, fv, &ctl.sc, defer, defer2, n_exact, &ctl.tphase[3]);
+                fv.rpool = nullptr;
                 if (tid == 0) ctl.n_deferred_total += nd;
             }
             __syncthreads();
@@ -448,7 +459,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                     if (k) {
                         int pos = run + woff + __popc(bal & ((1u << lane) - 1u));
                         U[pos] = a0; V[pos] = a1; X[pos] = a2; Y[pos] = a3; Z[pos] = a4;
-                    }
+                        mult[i] = (uint16_t)pos;                   // old -> new feature index
+                    } else if (i < n) mult[i] = INF16;
                     run += tot;
                     __syncthreads();
                 }
@@ -464,8 +476,67 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             // ---------------- Delaunay #2 (or #1 again) with triangle emission ----------------
             for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
             __syncthreads();
+            if (second) {
+                // A star of Delaunay #1 none of whose neighbours was dropped is a star of Delaunay #2 too (its triangles keep
+                // their empty circles and still close the fan around the point; the symbolic tie-break depends on the relative
+                // index order only, which the compaction preserves): emit its triangles from the stored ring, one thread per
+                // star, and rebuild only the others.
+                for (int o = tid; o < n1; o += NT) {
+                    const int np = mult[o];
+                    if (np == INF16) continue;
+                    const uint32_t info = fv.rinfo[o];
+                    const int d = (int)(info & 0xFFu); const uint16_t *ring = rpool + (info >> 8);
+                    bool clean = d > 0;
+                    for (int j = 0; j < d && clean; ++j) { const int q = ring[j]; if (q != INF16 && mult[q] == INF16) clean = false; }
+                    if (!clean) continue;
+                    int k = 0;
+                    for (int j = 0; j < d; ++j) {
+                        const int a = ring[j], b = ring[j + 1 < d ? j + 1 : 0];
+                        k += a != INF16 && b != INF16 && o < a && o < b;
+                    }
+                    pflag[np] |= 4;
+                    if (!k) continue;
+                    const int tb = atomicAdd(&ctl.T, k);
+                    if (tb + k > fv.tri_cap) { atomicOr(&ctl.status, MVOSR_ST_OVERFLOW); continue; }
+                    for (int j = 0; j < d; ++j) {
+                        const int a = ring[j], b = ring[j + 1 < d ? j + 1 : 0];
+                        if (!(a != INF16 && b != INF16 && o < a && o < b)) continue;
+                        const unsigned key = ((unsigned)mult[min(a, b)] << 16) | (unsigned)mult[max(a, b)];
+                        int r = 0;                                 // rank inside the block: keys of one star are distinct
+                        for (int i = 0; i < d; ++i) {
+                            const int a2 = ring[i], b2 = ring[i + 1 < d ? i + 1 : 0];
+                            if (!(a2 != INF16 && b2 != INF16 && o < a2 && o < b2)) continue;
+                            r += (((unsigned)mult[min(a2, b2)] << 16) | (unsigned)mult[max(a2, b2)]) < key;
+                        }
+                        uint16_t *t = fv.tri + 3 * (tb + r);
+                        t[0] = (uint16_t)np; t[1] = (uint16_t)(key >> 16); t[2] = (uint16_t)(key & 0xFFFFu);
+                    }
+                    fv.tbase[np] = (uint16_t)tb; fv.tcnt[np] = (uint8_t)k;
+                }
+                __syncthreads();
+                // the stars to rebuild, as sorted positions, hull rows first (see stars_pair)
+                const SortedSet &ps = ctl.ps;
+                const int rot = ps.cell_start[(ps.gy - 1) * ps.gx];
+                int run = 0;
+                for (int c0 = 0; c0 < n; c0 += NT) {
+                    const int j = c0 + tid;
+                    int i = j + rot; if (i >= n) i -= n;
+                    bool k = false;
+                    if (j < n) { const int og = ps.orig[i]; k = og != INF16 && !(pflag[og] & 4); }
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, k);
+                    if (lane == 0) ctl.warp_cnt[warp] = __popc(bal);
+                    __syncthreads();
+                    int woff, tot;
+                    warp_offsets(ctl.warp_cnt, warp, lane, woff, tot);
+                    if (k) todo[run + woff + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+                    run += tot;
+                    __syncthreads();
+                }
+                if (tid == 0) ctl.n_todo = run;
+                __syncthreads();
+            }
             TMARK(6);
-            int nd = run_stars<true>(ctl.ps, fv, &ctl.sc, defer, defer2, n_exact, &ctl.tphase[8]);
+            int nd = run_stars<true>(ctl.ps, fv, &ctl.sc, defer, defer2, n_exact, &ctl.tphase[8], second ? todo : nullptr, ctl.n_todo);
             if (tid == 0) ctl.n_deferred_total += nd;
             __syncthreads();
             status |= ctl.status;

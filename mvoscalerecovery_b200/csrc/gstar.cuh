@@ -85,6 +85,10 @@ struct FrameView {
     int *T; int *status;                 // triangle counter, frame status (shared)
     uint32_t pass_mask;
     int tri_cap;
+    // ring store (vote pass): the finished star of feature o as original feature indices, counter-clockwise, INF16 = the
+    // hull gap; rinfo[o] = (first pool entry << 8) | degree, 0 = no ring.  Stars none of whose neighbours is dropped by
+    // the graph check are stars of Delaunay #2 as well and are emitted from here instead of being rebuilt.
+    uint16_t *rpool; uint32_t *rinfo; int *rcount; int rpool_cap;
 };
 
 __device__ __forceinline__ bool edge_consistent(float va, float za, float vb, float zb) {
@@ -121,6 +125,15 @@ __device__ __forceinline__ void consume_vote(unsigned mask, int gl, int d, int p
     }
     unsigned bt = __ballot_sync(mask, tri) & mask, bv = __ballot_sync(mask, vote) & mask;
     if (gl == 0 && 2 * __popc(bv) > __popc(bt)) fv.pflag[op] |= 2;
+    if (fv.rpool && d > 0) {
+        int rb = 0;
+        if (gl == 0) rb = atomicAdd(fv.rcount, d);
+        rb = __shfl_sync(mask, rb, 0, W);
+        if (rb + d <= fv.rpool_cap) {
+            if (gl < d) fv.rpool[rb + gl] = sid != INF16 ? ps.orig[sid] : INF16;
+            if (gl == 0) fv.rinfo[op] = ((uint32_t)rb << 8) | (uint32_t)d;
+        }
+    }
 }
 
 // triangles (op < oa, ob) are written as one block sorted by (min,max) of the other two vertices
@@ -882,7 +895,8 @@ __device__ __forceinline__ unsigned gmin_u32(unsigned v, int g) {
 }
 
 template <bool EMIT>
-__device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer) {
+__device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer,
+                                        const uint16_t *todo, int n_todo) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, g = lane >> 4, gl = lane & (GL - 1), gshift = lane & GL;
     const int rot = ps.cell_start[(ps.gy - 1) * ps.gx];           // hull rows first (see stars_wrap's note on the tail)
@@ -898,9 +912,16 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
         int i = 0;
         if (lane == 0) i = atomicAdd(&sc->next_pos, 2);
         i = __shfl_sync(FULL, i, 0);
-        if (i >= ps.n) break;
-        int p = i + g + rot; if (p >= ps.n) p -= ps.n; if (p >= ps.n) p -= ps.n;
-        const bool have = i + g < ps.n && ps.orig[p] != INF16;
+        int p; bool have;
+        if (todo) {                                                // only the listed stars (sorted positions, holes excluded)
+            if (i >= n_todo) break;
+            have = i + g < n_todo;
+            p = todo[have ? i + g : i];
+        } else {
+            if (i >= ps.n) break;
+            p = i + g + rot; if (p >= ps.n) p -= ps.n; if (p >= ps.n) p -= ps.n;
+            have = i + g < ps.n && ps.orig[p] != INF16;
+        }
         bool ok = have;
         const float ppx = ps.x[p], ppy = ps.y[p];
         const int pcx = cell_of(ppx, ps.xmin, ps.inv_h, ps.gx), pcy = cell_of(ppy, ps.ymin, ps.inv_h, ps.gy);
@@ -1021,13 +1042,23 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
             if (own && !over) { uint16_t *t = fv.tri + 3 * (base + rk); t[0] = (uint16_t)op; t[1] = (uint16_t)(key >> 16); t[2] = (uint16_t)(key & 0xFFFFu); }
             if (gl == 0 && k && !over) { fv.tbase[op] = (uint16_t)base; fv.tcnt[op] = (uint8_t)k; }
         } else {
-            bool vote = false;
+            bool vote = false; int oa_ring = INF16;
             if (tri) {
                 const int oa = ps.orig[sid], ob = ps.orig[nid];
+                oa_ring = oa;
                 vote = graph_vote(op, ps.y[p], fv.Z[op], oa, ps.y[sid], fv.Z[oa], ob, ps.y[nid], fv.Z[ob], fv.pass_mask);
             }
             const unsigned bt = GBALLOT(tri), bv = GBALLOT(vote);
             if (gl == 0 && d > 0 && 2 * __popc(bv) > __popc(bt)) fv.pflag[op] |= 2;
+            if (fv.rpool) {                                                  // ring store (see FrameView)
+                int rb = 0;
+                if (gl == 0 && d > 0) rb = atomicAdd(fv.rcount, d);
+                rb = GSHFL(rb, 0);
+                if (rb + d <= fv.rpool_cap) {
+                    if (tri) fv.rpool[rb + gl] = (uint16_t)oa_ring;
+                    if (gl == 0 && d > 0) fv.rinfo[op] = ((uint32_t)rb << 8) | (uint32_t)d;
+                }
+            }
         }
     }
 #undef GBALLOT
@@ -1041,12 +1072,12 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
 // 16 slots, collinear bootstrap).  Returns (#stars of level 3) + (#stars of level 4 << 16); *n_wrap receives level 2's count.
 template <bool EMIT>
 __device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, uint16_t *defer2,
-                                      int &n_exact, long long *t_fast) {
+                                      int &n_exact, long long *t_fast, const uint16_t *todo = nullptr, int n_todo = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { sc->next_pos = 0; sc->n_defer = 0; sc->n_defer2 = 0; }
     __syncthreads();
     long long tc0 = clock64();
-    stars_pair<EMIT>(ps, fv, sc, defer);
+    stars_pair<EMIT>(ps, fv, sc, defer, todo, n_todo);
     __syncthreads();
     if (tid == 0 && t_fast) *t_fast += clock64() - tc0;
     const int n1 = sc->n_defer;
