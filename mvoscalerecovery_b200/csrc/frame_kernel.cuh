@@ -481,35 +481,52 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 // their empty circles and still close the fan around the point; the symbolic tie-break depends on the relative
                 // index order only, which the compaction preserves): emit its triangles from the stored ring, one thread per
                 // star, and rebuild only the others.
-                for (int o = tid; o < n1; o += NT) {
-                    const int np = mult[o];
-                    if (np == INF16) continue;
-                    const uint32_t info = fv.rinfo[o];
-                    const int d = (int)(info & 0xFFu); const uint16_t *ring = rpool + (info >> 8);
+                // The ring (at most RD entries; larger stars are rebuilt) is held in registers as NEW feature indices.
+                constexpr int RD = 10;
+                for (int c0 = 0; c0 < n1; c0 += NT) {
+                    const int o = c0 + tid;
+                    int np = INF16, d = 0;
+                    if (o < n1) np = mult[o];
+                    uint32_t info = 0;
+                    if (np != INF16) { info = fv.rinfo[o]; d = (int)(info & 0xFFu); if (d > RD) d = 0; }
+                    const uint16_t *ring = rpool + (info >> 8);
+                    int nb[RD];                                    // new index of ring entry j; INF16: hull gap; -1: dropped
                     bool clean = d > 0;
-                    for (int j = 0; j < d && clean; ++j) { const int q = ring[j]; if (q != INF16 && mult[q] == INF16) clean = false; }
-                    if (!clean) continue;
-                    int k = 0;
-                    for (int j = 0; j < d; ++j) {
-                        const int a = ring[j], b = ring[j + 1 < d ? j + 1 : 0];
-                        k += a != INF16 && b != INF16 && o < a && o < b;
+#pragma unroll
+                    for (int j = 0; j < RD; ++j) {
+                        nb[j] = INF16;
+                        if (j < d) { const int q = ring[j]; if (q != INF16) { const int m = mult[q]; nb[j] = m == INF16 ? -1 : m; } }
+                        clean = clean && nb[j] >= 0;
                     }
-                    pflag[np] |= 4;
+                    if (!clean) d = 0;
+                    // owned triangles (np smaller than both other vertices): key = (min << 16) | max
+                    unsigned key[RD]; int k = 0;
+#pragma unroll
+                    for (int j = 0; j < RD; ++j) {
+                        int nx = nb[0];
+#pragma unroll
+                        for (int i = 1; i < RD; ++i) if (i == j + 1 && i < d) nx = nb[i];       // nb[(j + 1) % d]
+                        const int a = nb[j];
+                        const bool own = j < d && a != INF16 && nx != INF16 && np < a && np < nx;
+                        key[j] = own ? (((unsigned)min(a, nx) << 16) | (unsigned)max(a, nx)) : 0xFFFFFFFFu;
+                        k += own;
+                    }
+                    if (clean) pflag[np] |= 4;
+                    // one atomic per warp for the triangle blocks of its stars
+                    const int inc = warp_incl_scan(k, lane), wtot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                    int tb = 0;
+                    if (lane == 31 && wtot) tb = atomicAdd(&ctl.T, wtot);
+                    tb = __shfl_sync(0xFFFFFFFFu, tb, 31) + inc - k;
                     if (!k) continue;
-                    const int tb = atomicAdd(&ctl.T, k);
                     if (tb + k > fv.tri_cap) { atomicOr(&ctl.status, MVOSR_ST_OVERFLOW); continue; }
-                    for (int j = 0; j < d; ++j) {
-                        const int a = ring[j], b = ring[j + 1 < d ? j + 1 : 0];
-                        if (!(a != INF16 && b != INF16 && o < a && o < b)) continue;
-                        const unsigned key = ((unsigned)mult[min(a, b)] << 16) | (unsigned)mult[max(a, b)];
+#pragma unroll
+                    for (int j = 0; j < RD; ++j) {
+                        if (key[j] == 0xFFFFFFFFu) continue;
                         int r = 0;                                 // rank inside the block: keys of one star are distinct
-                        for (int i = 0; i < d; ++i) {
-                            const int a2 = ring[i], b2 = ring[i + 1 < d ? i + 1 : 0];
-                            if (!(a2 != INF16 && b2 != INF16 && o < a2 && o < b2)) continue;
-                            r += (((unsigned)mult[min(a2, b2)] << 16) | (unsigned)mult[max(a2, b2)]) < key;
-                        }
+#pragma unroll
+                        for (int i = 0; i < RD; ++i) r += key[i] < key[j];
                         uint16_t *t = fv.tri + 3 * (tb + r);
-                        t[0] = (uint16_t)np; t[1] = (uint16_t)(key >> 16); t[2] = (uint16_t)(key & 0xFFFFu);
+                        t[0] = (uint16_t)np; t[1] = (uint16_t)(key[j] >> 16); t[2] = (uint16_t)(key[j] & 0xFFFFu);
                     }
                     fv.tbase[np] = (uint16_t)tb; fv.tcnt[np] = (uint8_t)k;
                 }
