@@ -174,6 +174,44 @@ int  mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t 
                         int32_t max_features, int32_t seq_id, uint64_t seed,
                         double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host);
 
+/* ---- stand-alone primitives: the same arithmetic for callers that bring their own triangles / point lists ----
+ * They back the API-surface variants of the reference that take explicit triangles or points (float64 arrays as numpy
+ * hands them): ScaleEstimator.flat_selection (src/rescale.py:75-102), Reconstruct.triangle_model (src/reconstruct.py:70-90),
+ * feature_selection_by_tri (src/scale_calculator.py:225-248), find_outliers (src/rescale.py:63-72,
+ * src/scale_calculator.py:151-167), get_pitch_ransac (src/estimate_road_norm.py:66-70), the batch scripts
+ * (src/calculate_height_pitch.py:62-204, src/triangle_batch.py:23-63) and get_path (src/main_offline.py:95-119). */
+
+/* n = P^-1 . 1 per triangle (P rows = the three vertices; the loop body of src/rescale.py:77-84).
+ * tri: [T][3] int32 indices into xyz ([N][3] float64 row-major).  Outputs, each may be NULL: normal [T][3] (not
+ * normalised), height [T] = 1/|n|, mean_y [T] = mean Y of the vertices (src/scale_calculator.py:237).  Singular -> NaN. */
+int  mvosr_triangle_planes(mvosr_handle *h, int32_t n_tri, const int32_t *tri, const double *xyz,
+                           double *normal, double *height, double *mean_y, void *stream);
+
+/* Depth-order votes per vertex (check_triangle + find_outliers, src/rescale.py:45-72): flagged[i] = number of triangles
+ * that flag vertex i ([a|b, a|b|c, c] with a,b,c the (v_i-v_j)(d_i-d_j) > 0 tests of edges 01, 02, 12), incident[i]
+ * (optional) = number of triangles vertex i belongs to.  v: pixel rows [N], d: depths [N], float64. */
+int  mvosr_triangle_votes(mvosr_handle *h, int32_t n_tri, const int32_t *tri, const double *v, const double *d,
+                          int32_t n_points, int32_t *flagged, int32_t *incident, void *stream);
+
+/* Batched 3-point plane RANSAC over explicit point lists -- get_pitch_ransac / run_ransac
+ * (src/estimate_road_norm.py:66-70, src/thirdparty/Ransac/ransac.py:3-23).  List s = rows offsets[s]..offsets[s+1] of
+ * xyz ([M][3] float64).  Hypothesis i of list s draws its three distinct positions from the Philox stream with counter
+ * (i, frame_index ? frame_index[s] : s, seq_id, 0); goal = goal_fraction * N (reference: 0.8).  Outputs: model [S][4] =
+ * the returned plane, unit 4-norm, sign b >= 0 (NaN when no hypothesis had an inlier); ic, best_hyp (-1: none),
+ * hyps_used [S] (optional). */
+int  mvosr_ransac_planes(mvosr_handle *h, int32_t n_sets, const int32_t *offsets, const double *xyz,
+                         int32_t iterations, double threshold, double goal_fraction, int32_t stop_at_goal,
+                         uint64_t seed, const int32_t *frame_index, int32_t seq_id,
+                         double *model, int32_t *ic, int32_t *best_hyp, int32_t *hyps_used, void *stream);
+
+/* get_path / motion2pose (src/main_offline.py:95-119) for S sequences: translations scaled by the per-frame scale
+ * (scales may be NULL = 1), then the running product of the relative motions.  motions: [F][12] row-major [R|t];
+ * seq_offsets: [S+1] frame ranges; poses_out: [F+S][12], sequence s occupies rows seq_offsets[s]+s ...
+ * seq_offsets[s+1]+s (its first row is the identity).  Computed as a parallel scan: equal to the reference's
+ * left-to-right product up to rounding. */
+int  mvosr_integrate_paths(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets, const double *motions,
+                           const double *scales, double *poses_out, void *stream);
+
 /* Profiling aid: when set (device pointer, [F][16] int64), the fused kernel stores per-frame SM cycles per phase:
  * 0 load+stage1+ROI, 1 grid#1, 2/3 stars#1 thread/warp path, 6 compaction+grid#2, 7/8 stars#2 thread/warp path,
  * 10 planes, 11 median, 12 valid list, 13 RANSAC. Pass NULL to disable. */

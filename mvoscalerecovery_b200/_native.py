@@ -46,6 +46,7 @@ SYMBOLS = [
     "mvosr_destroy", "mvosr_get_config", "mvosr_triangulate_frames", "mvosr_scale_frames",
     "mvosr_scale_frames_from_correspondences", "mvosr_filter_sequences", "mvosr_delaunay_frames",
     "mvosr_recover_scales_host", "mvosr_launch_count", "mvosr_set_phase_timing",
+    "mvosr_triangle_planes", "mvosr_triangle_votes", "mvosr_ransac_planes", "mvosr_integrate_paths",
 ]
 
 _lib = None
@@ -83,6 +84,11 @@ def lib():
     L.mvosr_delaunay_frames.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
     L.mvosr_recover_scales_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, u64, vp, vp, vp]
     L.mvosr_launch_count.argtypes = [vp]
+    f64 = C.c_double
+    L.mvosr_triangle_planes.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    L.mvosr_triangle_votes.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp]
+    L.mvosr_ransac_planes.argtypes = [vp, i32, vp, vp, i32, f64, f64, i32, u64, vp, i32, vp, vp, vp, vp, vp]
+    L.mvosr_integrate_paths.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mvosr_set_phase_timing.argtypes = [vp, vp]
     L.mvosr_launch_count.restype = C.c_int64
     for s in SYMBOLS:

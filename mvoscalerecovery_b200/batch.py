@@ -169,6 +169,67 @@ class ScaleRecovery:
                                                    _ptr(status), self._stream()))
         return dict(tri=tri, n_tri=ntri, status=status)
 
+    # ------------------------------------------------------------------ stand-alone primitives (caller-supplied triangles / points)
+    def triangle_planes(self, tri, xyz):
+        """n = P^-1 1 per triangle (rescale.py:77-84).  tri int32 (T,3), xyz float64 (N,3) CUDA tensors.
+        Returns dict(normal (T,3), height (T,), mean_y (T,))."""
+        dev = self.device
+        _chk(tri, torch.int32, "tri", dev)
+        _chk(xyz, torch.float64, "xyz", dev)
+        T = tri.shape[0]
+        normal = torch.empty((T, 3), dtype=torch.float64, device=dev)
+        height = torch.empty(T, dtype=torch.float64, device=dev)
+        mean_y = torch.empty(T, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_triangle_planes(self._h, T, _ptr(tri), _ptr(xyz), _ptr(normal), _ptr(height), _ptr(mean_y), self._stream()))
+        return dict(normal=normal, height=height, mean_y=mean_y)
+
+    def triangle_votes(self, tri, v, d):
+        """Depth-order votes per vertex (rescale.py:45-72): dict(flagged int32 (N,), incident int32 (N,))."""
+        dev = self.device
+        _chk(tri, torch.int32, "tri", dev)
+        _chk(v, torch.float64, "v", dev)
+        _chk(d, torch.float64, "d", dev)
+        n = v.numel()
+        flagged = torch.empty(n, dtype=torch.int32, device=dev)
+        incident = torch.empty(n, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_triangle_votes(self._h, tri.shape[0], _ptr(tri), _ptr(v), _ptr(d), n, _ptr(flagged), _ptr(incident), self._stream()))
+        return dict(flagged=flagged, incident=incident)
+
+    def ransac_planes(self, offsets, xyz, iterations: int = 100, threshold: float = 0.005, goal_fraction: float = 0.8,
+                      stop_at_goal: bool = True, seed: int = 0, frame_index=None, seq_id: int = 0):
+        """Batched get_pitch_ransac (estimate_road_norm.py:66-70) over S point lists (CSR offsets into xyz float64 (M,3)).
+        Returns dict(model (S,4), ic, best_hyp, hyps_used)."""
+        dev = self.device
+        _chk(offsets, torch.int32, "offsets", dev)
+        _chk(xyz, torch.float64, "xyz", dev)
+        S = offsets.numel() - 1
+        model = torch.empty((S, 4), dtype=torch.float64, device=dev)
+        ic = torch.zeros(S, dtype=torch.int32, device=dev)
+        best = torch.zeros(S, dtype=torch.int32, device=dev)
+        used = torch.zeros(S, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_ransac_planes(self._h, S, _ptr(offsets), _ptr(xyz), int(iterations), float(threshold), float(goal_fraction),
+                                                 int(bool(stop_at_goal)), C.c_uint64(int(seed)), _ptr(frame_index), int(seq_id),
+                                                 _ptr(model), _ptr(ic), _ptr(best), _ptr(used), self._stream()))
+        return dict(model=model, ic=ic, best_hyp=best, hyps_used=used)
+
+    def integrate_paths(self, seq_offsets, motions, scales=None):
+        """get_path / motion2pose (main_offline.py:95-119): (F,12) relative motions (+ per-frame scales) -> (F+S,12) poses,
+        sequence s in rows seq_offsets[s]+s .. seq_offsets[s+1]+s (first row = identity)."""
+        dev = self.device
+        _chk(seq_offsets, torch.int32, "seq_offsets", dev)
+        _chk(motions, torch.float64, "motions", dev)
+        if scales is not None:
+            _chk(scales, torch.float64, "scales", dev)
+        S = seq_offsets.numel() - 1
+        F = motions.shape[0]
+        poses = torch.empty((F + S, 12), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_integrate_paths(self._h, S, _ptr(seq_offsets), _ptr(motions), _ptr(scales), _ptr(poses), self._stream()))
+        return poses
+
     # ------------------------------------------------------------------ host buffers end to end
     def recover_scales_host(self, offsets: np.ndarray, cur_u, cur_v, ref_u, ref_v, poses, move_flags=None, max_features: int = 0,
                             seq_id: int = 0, seed: int = 0, out=None):

@@ -1,6 +1,9 @@
 """API surface of the reference's src/estimate_road_norm.py (plane / line models, pitch helpers).  Small host-side
-numpy helpers with the reference's signatures and conventions; the per-frame plane RANSAC itself is stage 4 of the
-CUDA frame kernel (rescale.ScaleEstimator.scale_calculation)."""
+numpy helpers with the reference's signatures and conventions.  The plane RANSAC runs on the GPU: per frame it is stage 4
+of the CUDA frame kernel (rescale.ScaleEstimator.scale_calculation), and ``get_pitch_ransac`` on an explicit point list is
+mvosr_ransac_planes (no CPU fallback).  Its draws come from the Philox position stream: key
+``ransac_seed``, one "frame" counter per call, so a process repeats its results (the reference re-seeds from OS entropy
+on every call, src/thirdparty/Ransac/ransac.py:6)."""
 import math
 import sys
 
@@ -75,10 +78,19 @@ def get_pitch_line_ransac(road_points, max_iterations, threshold):
     return run_ransac(road_points, estimate_line, lambda m, p: is_inlier_line(m, p, threshold), 2, goal, max_iterations)
 
 
+ransac_seed = 0            # Philox key of get_pitch_ransac
+ransac_calls = 0           # number of get_pitch_ransac calls so far = the stream's "frame" counter of the next call
+
+
 def get_pitch_ransac(road_points, max_iterations, threshold):
-    """3-point plane RANSAC, goal 0.8 N (:66-70).  Returns (model (4,), inlier count)."""
-    goal = road_points.shape[0] * 0.8
-    return run_ransac(road_points, estimate, lambda m, p: is_inlier(m, p, threshold), 3, goal, max_iterations)
+    """3-point plane RANSAC, goal 0.8 N, stop at the first count above the goal (:66-70).  Returns (model (4,), inlier
+    count); the model is None when no hypothesis had an inlier, as run_ransac returns it."""
+    global ransac_calls
+    import _gpu
+    frame = ransac_calls
+    ransac_calls += 1
+    m, ic, best, _ = _gpu.ransac_plane(road_points, max_iterations, threshold, seed=ransac_seed, frame=frame)
+    return (m if best >= 0 else None), ic
 
 
 def get_inliers(parameter, data, threshold):

@@ -61,11 +61,74 @@ class GraphChecker:
 
 
 class GraphGrow:
-    """Region growing over triangles (graph.py:39-107).  Constructed by the live estimator but never called by it
-    (rescale.py:33,99); kept for the constructor's sake."""
+    """Region growing over the triangle mesh (graph.py:39-107): triangles are linked across shared edges when their pitch
+    differs by less than ``threshold_angle`` degrees and their inverse height by less than 0.4 x the median inverse height;
+    the largest linked region that contains a flat (< -85 deg), low triangle is returned.
+
+    The reference grows from 100 seeds drawn with ``np.random.choice`` and keeps the largest region found.  The link test
+    is symmetric, so the region of a seed is the connected component of the seed and does not depend on the traversal;
+    here EVERY flat seed is tried, in ascending order (a superset of any random draw, and deterministic): the result is the
+    largest component, the first one on ties, listed in depth-first order from its smallest seed.  Constructed by the live
+    estimator (rescale.py:33); its call there is commented out (rescale.py:99)."""
 
     def __init__(self, threshold_angle=8):
         self.threshold_angle = threshold_angle
+        self.threshold_height = 0.2
+        self.graph = []
+        self.proposal = []
+        self.height_invs = []
+        self.angles = []
 
-    def process(self, triangle_ids, height_invs, angles):
-        raise NotImplementedError("GraphGrow.process is dead code on the reference's live path and is not provided")
+    def graph_construction(self, triangle_ids):
+        """Triangle adjacency across shared edges, each triangle linked to the EARLIER triangle on that edge (graph.py:47-71)."""
+        tri = np.asarray(triangle_ids)
+        graph = [[] for _ in range(tri.shape[0])]
+        first = {}
+        for i, (a, b, c) in enumerate(tri.tolist()):
+            for e in ((a, b), (a, c), (b, c)):
+                key = e if e[0] < e[1] else (e[1], e[0])
+                j = first.get(key)
+                if j is None:
+                    first[key] = i
+                else:
+                    graph[i].append(j)
+                    graph[j].append(i)
+        self.graph = graph
+
+    def check(self, i, j):
+        return bool(np.abs(self.angles[i] - self.angles[j]) < self.threshold_angle
+                    and np.abs(self.height_invs[i] - self.height_invs[j]) < self.threshold_height)
+
+    def expend(self, i, proposal):
+        """Depth-first growth from triangle i (graph.py:78-82), iterative (the reference recurses)."""
+        stack = [(i, iter(self.graph[i]))]
+        seen = set(proposal)
+        while stack:
+            node, it = stack[-1]
+            for j in it:
+                if j not in seen and self.check(node, j):
+                    seen.add(j)
+                    proposal.append(j)
+                    stack.append((j, iter(self.graph[j])))
+                    break
+            else:
+                stack.pop()
+
+    def process(self, triangle_ids, heights, angles):
+        self.graph_construction(triangle_ids)
+        self.height_invs = 1 / np.asarray(heights, dtype=float)
+        self.angles = np.asarray(angles, dtype=float)
+        flat = self.angles < -85
+        low = self.height_invs < np.median(self.height_invs[self.angles < -80])
+        seeds = bool2id(flat & low)
+        self.threshold_height = 0.4 * np.median(self.height_invs)
+        best, done = [], set()
+        for seed in seeds.tolist():
+            if seed in done:
+                continue
+            proposal = [seed]
+            self.expend(seed, proposal)
+            done.update(proposal)
+            if len(proposal) > len(best):
+                best = proposal
+        return best

@@ -23,15 +23,11 @@ import scale_calculator as sc
 import graph
 import param
 
-_ENGINES = {}
+import _gpu
 
 
 def _engine(absolute_reference, vanish):
-    from mvoscalerecovery_b200.batch import ScaleRecovery
-    key = (float(absolute_reference), float(vanish))
-    if key not in _ENGINES:
-        _ENGINES[key] = ScaleRecovery(absolute_reference=float(absolute_reference), vanish=float(vanish))
-    return _ENGINES[key]
+    return _gpu.engine(absolute_reference, vanish)
 
 
 class ScaleEstimator:

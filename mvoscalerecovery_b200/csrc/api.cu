@@ -9,6 +9,7 @@
 #include <new>
 
 #include "frame_kernel.cuh"
+#include "aux_kernels.cuh"
 
 using namespace mvosr;
 
@@ -507,6 +508,61 @@ int mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t *
     if (raw_scale_out_host) CK(cudaMemcpyAsync(raw_scale_out_host, d + o_raw, 8 * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
     if (status_out_host) CK(cudaMemcpyAsync(status_out_host, d + o_st, (size_t)n_frames, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return MVOSR_OK;
+}
+
+// ---- stand-alone primitives for callers that bring their own triangles / point lists / motions (aux_kernels.cuh) ----
+int mvosr_triangle_planes(mvosr_handle *h, int32_t n_tri, const int32_t *tri, const double *xyz,
+                          double *normal, double *height, double *mean_y, void *stream) {
+    if (!h || n_tri < 0 || !tri || !xyz) return MVOSR_E_INVALID;
+    if (n_tri == 0) return MVOSR_OK;
+    CK(cudaSetDevice(h->device));
+    const int grid = min((n_tri + 255) / 256, 8 * h->num_sms);
+    triangle_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_tri, tri, xyz, normal, height, mean_y);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return MVOSR_OK;
+}
+
+int mvosr_triangle_votes(mvosr_handle *h, int32_t n_tri, const int32_t *tri, const double *v, const double *d,
+                         int32_t n_points, int32_t *flagged, int32_t *incident, void *stream) {
+    if (!h || n_tri < 0 || n_points < 0 || !tri || !v || !d || !flagged) return MVOSR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(flagged, 0, sizeof(int32_t) * (size_t)n_points, st));
+    if (incident) CK(cudaMemsetAsync(incident, 0, sizeof(int32_t) * (size_t)n_points, st));
+    if (n_tri == 0) return MVOSR_OK;
+    const int grid = min((n_tri + 255) / 256, 8 * h->num_sms);
+    triangle_votes_kernel<<<grid, 256, 0, st>>>(n_tri, tri, v, d, flagged, incident);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return MVOSR_OK;
+}
+
+int mvosr_ransac_planes(mvosr_handle *h, int32_t n_sets, const int32_t *offsets, const double *xyz,
+                        int32_t iterations, double threshold, double goal_fraction, int32_t stop_at_goal,
+                        uint64_t seed, const int32_t *frame_index, int32_t seq_id,
+                        double *model, int32_t *ic, int32_t *best_hyp, int32_t *hyps_used, void *stream) {
+    if (!h || n_sets < 0 || !offsets || !xyz || !model || iterations < 0) return MVOSR_E_INVALID;
+    if (n_sets == 0) return MVOSR_OK;
+    CK(cudaSetDevice(h->device));
+    const int grid = min(n_sets, 8 * h->num_sms);
+    ransac_planes_kernel<<<grid, 32 * RW, 0, (cudaStream_t)stream>>>(n_sets, offsets, xyz, iterations, threshold, goal_fraction, stop_at_goal,
+                                                                      seed, frame_index, seq_id, model, ic, best_hyp, hyps_used);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return MVOSR_OK;
+}
+
+int mvosr_integrate_paths(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets, const double *motions,
+                          const double *scales, double *poses_out, void *stream) {
+    if (!h || n_sequences < 0 || !seq_offsets || !motions || !poses_out) return MVOSR_E_INVALID;
+    if (n_sequences == 0) return MVOSR_OK;
+    CK(cudaSetDevice(h->device));
+    const int grid = min(n_sequences, 4 * h->num_sms);
+    integrate_paths_kernel<<<grid, PT, 0, (cudaStream_t)stream>>>(n_sequences, seq_offsets, motions, scales, poses_out);
+    CK(cudaGetLastError());
+    h->launches += 1;
     return MVOSR_OK;
 }
 

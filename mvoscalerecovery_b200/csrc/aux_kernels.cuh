@@ -1,0 +1,194 @@
+// Stand-alone kernels for callers that bring their own triangles / point lists / motions (device code, sm_100a).
+//
+// Reference calls replaced (file:line into the reference tree):
+//   triangle_planes_kernel   the per-triangle body of flat_selection (src/rescale.py:77-84), Reconstruct.triangle_model
+//                            (src/reconstruct.py:70-90), feature_selection_by_tri (src/scale_calculator.py:228-238) and of
+//                            the batch scripts (src/calculate_height_pitch.py:76-93, src/triangle_batch.py:31-44)
+//   ransac_planes_kernel     get_pitch_ransac / run_ransac (src/estimate_road_norm.py:66-70,
+//                            src/thirdparty/Ransac/ransac.py:3-23) on explicit point lists
+//   integrate_paths_kernel   get_path / motion2pose (src/main_offline.py:95-119)
+//   triangle_votes_kernel    find_outliers / check_triangle (src/rescale.py:45-72, src/scale_calculator.py:105-119,151-167)
+// All of them are HBM-bound gathers / streams; the arithmetic is float64 because the callers hand float64 arrays.
+#pragma once
+#include <stdint.h>
+#include <math_constants.h>
+#include "philox.cuh"
+
+namespace mvosr {
+
+// n = P^-1 . 1 for the 3x3 matrix P whose rows are the triangle's vertices, in closed form:
+// n = (e1 x e2) / (p0 . (e1 x e2)).  One thread per triangle, grid-stride.
+__global__ void __launch_bounds__(256) triangle_planes_kernel(int n_tri, const int32_t *__restrict__ tri, const double *__restrict__ xyz,
+                                                              double *normal, double *height, double *mean_y) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tri; t += gridDim.x * blockDim.x) {
+        const int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
+        const double p0x = xyz[3 * i0], p0y = xyz[3 * i0 + 1], p0z = xyz[3 * i0 + 2];
+        const double p1y = xyz[3 * i1 + 1], p2y = xyz[3 * i2 + 1];
+        const double e1x = xyz[3 * i1] - p0x, e1y = p1y - p0y, e1z = xyz[3 * i1 + 2] - p0z;
+        const double e2x = xyz[3 * i2] - p0x, e2y = p2y - p0y, e2z = xyz[3 * i2 + 2] - p0z;
+        const double cx = e1y * e2z - e1z * e2y, cy = e1z * e2x - e1x * e2z, cz = e1x * e2y - e1y * e2x;
+        const double det = p0x * cx + p0y * cy + p0z * cz;
+        const double inv = det != 0.0 ? 1.0 / det : CUDART_NAN;
+        if (normal) { normal[3 * t] = cx * inv; normal[3 * t + 1] = cy * inv; normal[3 * t + 2] = cz * inv; }
+        if (height) height[t] = det != 0.0 ? fabs(det) / sqrt(cx * cx + cy * cy + cz * cz) : CUDART_NAN;
+        if (mean_y) mean_y[t] = (p0y + p1y + p2y) / 3.0;
+    }
+}
+
+// Depth-order votes of caller-supplied triangles: per vertex the number of triangles that flag it
+// (a = (v0-v1)(d0-d1) > 0, b = (v0-v2)(d0-d2) > 0, c = (v1-v2)(d1-d2) > 0; flags [a|b, a|b|c, c]) and the number of
+// triangles it belongs to.  v = pixel row, d = depth.
+__global__ void __launch_bounds__(256) triangle_votes_kernel(int n_tri, const int32_t *__restrict__ tri, const double *__restrict__ v,
+                                                             const double *__restrict__ d, int32_t *flagged, int32_t *incident) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tri; t += gridDim.x * blockDim.x) {
+        const int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
+        const double v0 = v[i0], v1 = v[i1], v2 = v[i2], d0 = d[i0], d1 = d[i1], d2 = d[i2];
+        const bool a = (v0 - v1) * (d0 - d1) > 0, b = (v0 - v2) * (d0 - d2) > 0, c = (v1 - v2) * (d1 - d2) > 0;
+        if (a || b) atomicAdd(flagged + i0, 1);
+        if (a || b || c) atomicAdd(flagged + i1, 1);
+        if (c) atomicAdd(flagged + i2, 1);
+        if (incident) { atomicAdd(incident + i0, 1); atomicAdd(incident + i1, 1); atomicAdd(incident + i2, 1); }
+    }
+}
+
+// Plane RANSAC over explicit point lists: one CTA per list, one warp per hypothesis, RW hypotheses per round; after each
+// round every thread replays run_ransac's sequential bookkeeping (keep the first strictly larger count, stop at the first
+// count above the goal), so the result is the one the sequential loop returns.  Model = closed-form null vector of [p 1].
+constexpr int RW = 8;                    // warps per CTA
+__global__ void __launch_bounds__(32 * RW) ransac_planes_kernel(int n_sets, const int32_t *__restrict__ offsets, const double *__restrict__ xyz,
+        int iterations, double threshold, double goal_fraction, int stop_at_goal, uint64_t seed, const int32_t *frame_index, int seq_id,
+        double *model, int32_t *ic_out, int32_t *best_hyp_out, int32_t *hyps_used_out) {
+    __shared__ int r_ic[RW];
+    __shared__ double r_m[RW][5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int s = blockIdx.x; s < n_sets; s += gridDim.x) {
+        const int base = offsets[s], n = offsets[s + 1] - base;
+        const double *P = xyz + 3 * (size_t)base;
+        const uint32_t frame = (uint32_t)(frame_index ? frame_index[s] : s);
+        const double goal = (double)n * goal_fraction;
+        int h_done = 0, best = -1, best_ic = 0, used = 0;
+        bool stop = false;
+        double b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 1;
+        while (n >= 3 && h_done < iterations && !stop) {
+            const int h = h_done + warp;
+            if (h < iterations) {
+                uint32_t i0, i1, i2;
+                sample3_positions(seed, (uint32_t)h, frame, (uint32_t)seq_id, (uint32_t)n, i0, i1, i2);
+                const double p0x = P[3 * i0], p0y = P[3 * i0 + 1], p0z = P[3 * i0 + 2];
+                const double e1x = P[3 * i1] - p0x, e1y = P[3 * i1 + 1] - p0y, e1z = P[3 * i1 + 2] - p0z;
+                const double e2x = P[3 * i2] - p0x, e2y = P[3 * i2 + 1] - p0y, e2z = P[3 * i2 + 2] - p0z;
+                // products rounded separately (no FMA contraction): the cross product of two equal edges is exactly zero
+                const double nx = __dsub_rn(__dmul_rn(e1y, e2z), __dmul_rn(e1z, e2y)), ny = __dsub_rn(__dmul_rn(e1z, e2x), __dmul_rn(e1x, e2z)),
+                             nz = __dsub_rn(__dmul_rn(e1x, e2y), __dmul_rn(e1y, e2x));
+                const double dd = -(nx * p0x + ny * p0y + nz * p0z);
+                const double n4 = sqrt(nx * nx + ny * ny + nz * nz + dd * dd);
+                // a list with multiplicity can place the same point at two positions: the 3x4 system then has a 2-D null
+                // space and the reference's SVD returns an arbitrary member of it; such hypotheses are skipped
+                const bool same = (e1x == 0 && e1y == 0 && e1z == 0) || (e2x == 0 && e2y == 0 && e2z == 0) || (e1x == e2x && e1y == e2y && e1z == e2z);
+                const bool degenerate = same || !(nx * nx + ny * ny + nz * nz > 0);
+                int ic = 0;
+                if (!degenerate) {
+                    const double thr = threshold * n4;
+                    for (int q = lane; q < n; q += 32) {
+                        const double r = nx * P[3 * q] + ny * P[3 * q + 1] + nz * P[3 * q + 2] + dd;
+                        ic += fabs(r) < thr;
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) ic += __shfl_xor_sync(0xFFFFFFFFu, ic, o);
+                }
+                if (lane == 0) { r_ic[warp] = degenerate ? -1 : ic; r_m[warp][0] = nx; r_m[warp][1] = ny; r_m[warp][2] = nz; r_m[warp][3] = dd; r_m[warp][4] = n4; }
+            }
+            __syncthreads();
+            const int hi = min(iterations, h_done + RW);
+            for (int hh = h_done; hh < hi && !stop; ++hh) {
+                const int w = hh - h_done, ic = r_ic[w];
+                used = hh + 1;
+                if (ic > best_ic) {
+                    best_ic = ic; best = hh;
+                    b0 = r_m[w][0]; b1 = r_m[w][1]; b2 = r_m[w][2]; b3 = r_m[w][3]; b4 = r_m[w][4];
+                    if ((double)ic > goal && stop_at_goal) stop = true;
+                }
+            }
+            h_done = hi;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const double sg = (b1 < 0 ? -1.0 : 1.0) / b4;
+            for (int k = 0; k < 4; ++k) model[4 * s + k] = CUDART_NAN;
+            if (best >= 0) { model[4 * s] = sg * b0; model[4 * s + 1] = sg * b1; model[4 * s + 2] = sg * b2; model[4 * s + 3] = sg * b3; }
+            if (ic_out) ic_out[s] = best_ic;
+            if (best_hyp_out) best_hyp_out[s] = best;
+            if (hyps_used_out) hyps_used_out[s] = used;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- SE(3) prefix products ------------------------------------------------------------------------
+struct Rt { double m[12]; };             // row-major [R|t]
+
+__device__ __forceinline__ Rt rt_identity() { Rt a; for (int i = 0; i < 12; ++i) a.m[i] = (i % 5 == 0) ? 1.0 : 0.0; return a; }
+
+__device__ __forceinline__ Rt rt_mul(const Rt &a, const Rt &b) {          // a * b as 4x4 with last row (0,0,0,1)
+    Rt c;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double v = a.m[4 * r] * b.m[k] + a.m[4 * r + 1] * b.m[4 + k] + a.m[4 * r + 2] * b.m[8 + k];
+            if (k == 3) v += a.m[4 * r + 3];
+            c.m[4 * r + k] = v;
+        }
+    }
+    return c;
+}
+
+__device__ __forceinline__ Rt rt_shfl_up(const Rt &a, int delta) {
+    Rt b;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) b.m[i] = __shfl_up_sync(0xFFFFFFFFu, a.m[i], delta);
+    return b;
+}
+
+// poses[0] = I, poses[i+1] = poses[i] * [R_i | s_i t_i]: one CTA per sequence.  Every thread multiplies a contiguous run of
+// motions, the run products are scanned (warp shuffles, then across warps through shared memory), and each thread replays its
+// run from its prefix.  The association order differs from the reference's left-to-right loop: results agree to rounding.
+constexpr int PT = 256;
+__global__ void __launch_bounds__(PT) integrate_paths_kernel(int n_seq, const int32_t *__restrict__ seq_offsets, const double *__restrict__ motions,
+                                                             const double *__restrict__ scales, double *poses) {
+    __shared__ Rt wtot[PT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int s = blockIdx.x; s < n_seq; s += gridDim.x) {
+        const int f0 = seq_offsets[s], n = seq_offsets[s + 1] - f0;
+        double *out = poses + 12 * (size_t)(f0 + s);
+        const int per = (n + PT - 1) / PT, b = min(n, tid * per), e = min(n, b + per);
+        auto load = [&](int i) {
+            Rt m; const double *src = motions + 12 * (size_t)(f0 + i); const double sc = scales ? scales[f0 + i] : 1.0;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) m.m[k] = (k & 3) == 3 ? sc * src[k] : src[k];
+            return m;
+        };
+        Rt run = rt_identity();
+        for (int i = b; i < e; ++i) run = rt_mul(run, load(i));
+        // inclusive scan of the run products in thread order (non-commutative: earlier * later)
+        Rt inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const Rt up = rt_shfl_up(inc, o); if (lane >= o) inc = rt_mul(up, inc); }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        Rt pre = rt_identity();                                  // product of all earlier warps
+        for (int w = 0; w < warp; ++w) pre = rt_mul(pre, wtot[w]);
+        Rt excl = rt_shfl_up(inc, 1);
+        if (lane == 0) excl = rt_identity();
+        Rt cur = rt_mul(pre, excl);                               // pose before this thread's run
+        if (tid == 0) { for (int k = 0; k < 12; ++k) out[k] = cur.m[k]; }
+        for (int i = b; i < e; ++i) {
+            cur = rt_mul(cur, load(i));
+#pragma unroll
+            for (int k = 0; k < 12; ++k) out[12 * (size_t)(i + 1) + k] = cur.m[k];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace mvosr
