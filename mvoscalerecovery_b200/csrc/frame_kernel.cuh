@@ -794,7 +794,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 s.best_hyp = ctl.best_hyp; s.best_ic = ctl.best_ic; s.hyps_used = ctl.hyps_used; s.n_degenerate = ctl.n_degenerate;
                 s.n_deferred = ctl.n_deferred_total; s.n_exact = ctl.n_exact; s.height_level = ctl.height_level;
             }
-#ifdef MVOSR_STAR_COUNTERS
+#if defined(MVOSR_STAR_COUNTERS) || defined(MVOSR_WRAP_COUNTERS)
             ctl.tphase[4] = ctl.sc.cnt[0]; ctl.tphase[5] = ctl.sc.cnt[1]; ctl.tphase[11] = ctl.sc.cnt[2]; ctl.tphase[12] = ctl.sc.cnt[3]; ctl.tphase[14] = ctl.sc.cnt[4];
             ctl.tphase[15] = ctl.sc.cnt[5]; ctl.tphase[1] = ctl.sc.cnt[6]; ctl.tphase[10] = ctl.sc.cnt[7];
 #endif

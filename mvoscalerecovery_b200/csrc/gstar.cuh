@@ -653,14 +653,31 @@ __device__ __forceinline__ void w_circle(WBest &b, float cx, float cy, float sig
 
 // Does the walk's-left cap of the padded circle (centre v, radius rs, through p = origin and cur) lie inside the box?
 // The cap's bounding box is spanned by p, cur and those axis-extreme points of the circle that lie on the left of p->cur.
+// CLIP: only the part of the cap inside the bounding box G of the point set matters (there is nothing to find outside it),
+// so the box is intersected with the box of (disk n G) -- this lets the flat triangles along the boundary of the point set
+// pass, whose circles are huge but only a thin sliver of them lies inside G.  Measured on the bench workload it keeps
+// ~40 stars per frame out of streaming but the extra instructions per step cost more than that saves (pair path +13 %,
+// wrap path +3 %), so both paths run with CLIP = false; the variant is kept for sparser inputs.
+struct WBox { float x0, x1, y0, y1; };
+template <bool CLIP>
 __device__ __forceinline__ bool w_cap_inside(float cx, float cy, float sigma, float vx, float vy, float rs,
-                                             float BX0, float BX1, float BY0, float BY1) {
+                                             float BX0, float BX1, float BY0, float BY1, const WBox &G) {
     const float tol = 1.0e-4f * (fabsf(cx) + fabsf(cy)) * (rs + fabsf(vx) + fabsf(vy));       // include when in doubt
     float lox = fminf(0.f, cx), hix = fmaxf(0.f, cx), loy = fminf(0.f, cy), hiy = fmaxf(0.f, cy);
     if (sigma * (cx * vy - cy * (vx - rs)) > -tol) lox = fminf(lox, vx - rs);
     if (sigma * (cx * vy - cy * (vx + rs)) > -tol) hix = fmaxf(hix, vx + rs);
     if (sigma * (cx * (vy - rs) - cy * vx) > -tol) loy = fminf(loy, vy - rs);
     if (sigma * (cx * (vy + rs) - cy * vx) > -tol) hiy = fmaxf(hiy, vy + rs);
+    if (CLIP) {
+        if (rs < 1.0e6f) {
+            // half-widths of the disk inside the strips G.y0..G.y1 and G.x0..G.x1 ((rs-d)(rs+d): no cancellation)
+            const float dy = fmaxf(fmaxf(G.y0 - vy, vy - G.y1), 0.f), dx = fmaxf(fmaxf(G.x0 - vx, vx - G.x1), 0.f);
+            const float hwx = sqrt_approx(fmaxf((rs - dy) * (rs + dy), 0.f)) * 1.001f + 1.0e-3f;
+            const float hwy = sqrt_approx(fmaxf((rs - dx) * (rs + dx), 0.f)) * 1.001f + 1.0e-3f;
+            lox = fmaxf(lox, vx - hwx); hix = fminf(hix, vx + hwx); loy = fmaxf(loy, vy - hwy); hiy = fminf(hiy, vy + hwy);
+        }
+        lox = fmaxf(lox, G.x0); hix = fminf(hix, G.x1); loy = fmaxf(loy, G.y0); hiy = fminf(hiy, G.y1);
+    }
     return lox >= BX0 && hix <= BX1 && loy >= BY0 && hiy <= BY1;
 }
 
@@ -690,56 +707,77 @@ __device__ __forceinline__ bool w_batch(WBest &b, bool valid, float sx, float sy
 
 // Stream the grid cells that the left cap of the best's circle (the whole left half-plane while there is no best)
 // covers outside the block [bx0,bx1]x[by0,by1].  false: not certified.
+// Dense gather, nearest rows first: lane l takes grid row pcy + (0, -1, +1, -2, +2, ...)[32 g + l] and computes the cell runs
+// of that row inside the region as it is now (32 rows at once); a warp scan turns the run lengths into one candidate
+// sequence, and the candidates are evaluated 32 at a time whatever row they come from.  A pass over a region defined by ANY
+// earlier best certifies the final best (the regions are nested and every comparison is certified with disjoint intervals,
+// hence transitive); when the best improves while much of the pass is still ahead -- always, when there was none -- the
+// gather is redone with the smaller region.
 __device__ __noinline__ bool w_stream(WBest &b, const SortedSet &ps, int p, float ppx, float ppy, int pcy,
                                       int bx0, int bx1, int by0, int by1, float cx, float cy, float sigma, int cpos) {
+    const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const float INF = CUDART_INF_F;
     const float hx = sigma * cx, hy = sigma * cy;                 // half-plane hx*y - hy*x > 0
-    for (int t = 0; ; ++t) {
-        // rows outwards from p's row, inside the row range of the region as it is now
-        int r0 = 0, r1 = ps.gy - 1;
-        const bool disk = b.have && b.rs < 1.0e6f;                // a larger (or non-finite) circle bounds nothing useful: half-plane only
-        if (disk) {
-            const float a = (ppy + b.vy - b.rs - ps.ymin) * ps.inv_h, c = (ppy + b.vy + b.rs - ps.ymin) * ps.inv_h;
-            if (c < 0.f) return true;
-            r0 = (int)fminf(fmaxf(a, 0.f), (float)(ps.gy - 1)); r1 = (int)fminf(fmaxf(c, 0.f), (float)(ps.gy - 1));
-        }
-        if (t > 2 * max(pcy - r0, r1 - pcy)) return true;
+    const float pad = 1.0e-3f + 1.0e-4f * ps.h;
+    const int tmax = 2 * max(pcy, ps.gy - 1 - pcy);               // largest row offset index
+    for (int g0 = 0; g0 <= tmax; ) {
+        const int t = g0 + lane;
         const int row = pcy + ((t & 1) ? -((t + 1) >> 1) : (t >> 1));
-        if (row < r0 || row > r1) continue;
-        const float Y0 = ps.ymin + row * ps.h - ppy - (1.0e-3f + 1.0e-4f * ps.h), Y1 = Y0 + ps.h + 2.f * (1.0e-3f + 1.0e-4f * ps.h);
+        const bool disk = b.have && b.rs < 1.0e6f;                // a larger (or non-finite) circle bounds nothing useful: half-plane only
+        bool on = row >= 0 && row < ps.gy;
+        const float Y0 = ps.ymin + row * ps.h - ppy - pad, Y1 = Y0 + ps.h + 2.f * pad;
         float lo = -INF, hi = INF;
         if (disk) {
             const float dy = fmaxf(fmaxf(Y0 - b.vy, b.vy - Y1), 0.f), rem = b.rs * b.rs - dy * dy;
-            if (!(rem > 0.f)) continue;
-            const float hw = sqrtf(rem) * 1.0001f + 1.0e-3f;
-            lo = b.vx - hw; hi = b.vx + hw;
+            if (rem > 0.f) { const float hw = sqrtf(rem) * 1.0001f + 1.0e-3f; lo = b.vx - hw; hi = b.vx + hw; }
+            else on = false;
         }
         if (hy > 0.f) { const float u = fmaxf(hx * Y0, hx * Y1) / hy; hi = fminf(hi, u + 1.0e-5f * fabsf(u) + 1.0e-3f); }
         else if (hy < 0.f) { const float u = fminf(hx * Y0 / hy, hx * Y1 / hy); lo = fmaxf(lo, u - 1.0e-5f * fabsf(u) - 1.0e-3f); }
-        else if (!(hx > 0.f ? Y1 > 0.f : (hx < 0.f ? Y0 < 0.f : true))) continue;
-        if (!(lo <= hi)) continue;
-        const float fa = (lo + ppx - ps.xmin) * ps.inv_h, fb = (hi + ppx - ps.xmin) * ps.inv_h;
-        if (fb < 0.f) continue;
-        int ca = (int)fminf(fmaxf(fa, 0.f), (float)(ps.gx - 1)), cb = (int)fminf(fmaxf(fb, 0.f), (float)(ps.gx - 1));
-        // up to two runs: the block's columns are excluded on the block's rows
-        int ca2 = 1, cb2 = 0;
-        if (row >= by0 && row <= by1) {
-            const int e1 = min(cb, bx0 - 1), a2 = max(ca, bx1 + 1);
-            if (e1 >= ca) { ca2 = a2; cb2 = cb; cb = e1; } else ca = a2;
-        }
-        for (int part = 0; part < 2; ++part) {
-            if (part == 1) { ca = ca2; cb = cb2; }
-            if (ca > cb) continue;
-            const int beg = ps.cell_start[row * ps.gx + ca], end = ps.cell_start[row * ps.gx + cb + 1];
-            for (int base = beg; base < end; base += 32) {
-                const int pos = base + lane;
-                const bool v = pos < end && pos != p && pos != cpos && ps.orig[pos] != INF16;
-                const float sx = v ? ps.x[pos] - ppx : 0.f, sy = v ? ps.y[pos] - ppy : 0.f;
-                if (!w_batch(b, v, sx, sy, pos, cx, cy, sigma)) return false;
+        else if (!(hx > 0.f ? Y1 > 0.f : (hx < 0.f ? Y0 < 0.f : true))) on = false;
+        int beg1 = 0, n1 = 0, beg2 = 0, n2 = 0;
+        if (on && lo <= hi) {
+            const float fa = (lo + ppx - ps.xmin) * ps.inv_h, fb = (hi + ppx - ps.xmin) * ps.inv_h;
+            if (!(fb < 0.f)) {
+                int ca = (int)fminf(fmaxf(fa, 0.f), (float)(ps.gx - 1)), cb = (int)fminf(fmaxf(fb, 0.f), (float)(ps.gx - 1));
+                // up to two runs: the block's columns are excluded on the block's rows
+                int ca2 = 1, cb2 = 0;
+                if (row >= by0 && row <= by1) {
+                    const int e1 = min(cb, bx0 - 1), a2 = max(ca, bx1 + 1);
+                    if (e1 >= ca) { ca2 = a2; cb2 = cb; cb = e1; } else ca = a2;
+                }
+                if (ca <= cb) { beg1 = ps.cell_start[row * ps.gx + ca]; n1 = ps.cell_start[row * ps.gx + cb + 1] - beg1; }
+                if (ca2 <= cb2) { beg2 = ps.cell_start[row * ps.gx + ca2]; n2 = ps.cell_start[row * ps.gx + cb2 + 1] - beg2; }
             }
         }
+        const int c = n1 + n2;
+        int S = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, S, o); if (lane >= o) S += u; }
+        const int total = __shfl_sync(FULL, S, 31);
+        bool redo = false;
+        for (int base = 0; base < total; base += 32) {
+            const int e = base + lane;
+            int l0 = 0, l1 = 31;                                  // smallest lane r with S[r] > e
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int mid = (l0 + l1) >> 1;
+                if (__shfl_sync(FULL, S, mid) > e) l1 = mid; else l0 = mid + 1;
+            }
+            const int r = l0 & 31;
+            const int off = e - (__shfl_sync(FULL, S, r) - __shfl_sync(FULL, c, r));
+            const int rb1 = __shfl_sync(FULL, beg1, r), rn1 = __shfl_sync(FULL, n1, r), rb2 = __shfl_sync(FULL, beg2, r);
+            const int pos = off < rn1 ? rb1 + off : rb2 + (off - rn1);
+            const bool v = e < total && pos != p && pos != cpos && pos != b.pos && ps.orig[pos] != INF16;
+            const float sx = v ? ps.x[pos] - ppx : 0.f, sy = v ? ps.y[pos] - ppy : 0.f;
+            const int prev = b.pos; const bool had = b.have;
+            if (!w_batch(b, v, sx, sy, pos, cx, cy, sigma)) return false;
+            if (b.pos != prev && total - base - 32 > (had ? 64 : 0)) { redo = true; break; }
+        }
+        if (!redo) g0 += 32;
     }
+    return true;
 }
 
 // The stars of list[0..n_list) (sorted positions), one per warp; stars that need the exact path are appended to
@@ -833,7 +871,7 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
                 if (__any_sync(FULL, clash)) { ok = false; break; }
                 w_circle(b, cx, cy, sigma);
                 if (!(fabsf(b.t) < 1.0e18f)) { ok = false; break; }
-                inside = w_cap_inside(cx, cy, sigma, b.vx, b.vy, b.rs, BX0, BX1, BY0, BY1);
+                inside = w_cap_inside<false>(cx, cy, sigma, b.vx, b.vy, b.rs, BX0, BX1, BY0, BY1, WBox());
             }
             WCNT(w_steps);
             if (!inside) {
@@ -1008,7 +1046,7 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
             const float vx = 0.5f * (cx - wt * cy), vy = 0.5f * (cy + wt * cx);
             const float r = sqrt_approx(fmaf(vx, vx, vy * vy));
             const float rs = r + 2.f * (we * (fabsf(cx) + fabsf(cy)) * 0.51f + 1.0e-3f + 1.0e-4f * r);
-            if (walking && !w_cap_inside(cx, cy, 1.f, vx, vy, rs, BX0, BX1, BY0, BY1)) { PR(6); ok = false; walking = false; }
+            if (walking && !w_cap_inside<false>(cx, cy, 1.f, vx, vy, rs, BX0, BX1, BY0, BY1, WBox())) { PR(6); ok = false; walking = false; }
             if (walking) {
                 if (wpos == q0) { closed = true; walking = false; }
                 else if (nC >= GL) { PR(7); ok = false; walking = false; }
