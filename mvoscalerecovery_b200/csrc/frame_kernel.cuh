@@ -259,30 +259,63 @@ __device__ __forceinline__ void write_canonical(int n, const FrameView &fv, uint
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long block_select(const double *h, const uint8_t *flags, int T, int k, Ctl *ctl) {
     // returns the key of rank k (0-based) among {h[t] : flags[t]&1}
-    int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     unsigned long long prefix = 0;
     for (int pass = 0; pass < 8; ++pass) {
-        int shift = 56 - 8 * pass;
+        const int shift = 56 - 8 * pass;
         for (int i = tid; i < 256; i += NT) ctl->hist[i] = 0;
         __syncthreads();
-        unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
         for (int t = tid; t < T; t += NT) {
             if (!(flags[t] & 1)) continue;
-            unsigned long long key = (unsigned long long)__double_as_longlong(h[t]);
+            const unsigned long long key = (unsigned long long)__double_as_longlong(h[t]);
             if ((key & mask) == prefix) atomicAdd(&ctl->hist[(key >> shift) & 0xFF], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            int acc = 0, b = 0;
-            for (; b < 256; ++b) { int c = (int)ctl->hist[b]; if (acc + c > k) break; acc += c; }
-            ctl->sel_k = k - acc;
-            ctl->sel_prefix = prefix | ((unsigned long long)b << shift);
+        if (tid < 32) {
+            // warp 0: lane l owns bins 8l..8l+7; the bin holding rank k is where the running count first exceeds k
+            unsigned c[8]; int sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i] = ctl->hist[8 * lane + i]; sum += (int)c[i]; }
+            const int inc = warp_incl_scan(sum, lane);
+            const unsigned before = __ballot_sync(0xFFFFFFFFu, inc <= k);      // lanes entirely below rank k (a prefix of the lanes)
+            const int owner = __popc(before);
+            if (lane == owner) {
+                int acc = inc - sum, b = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { if (acc + (int)c[i] <= k) { acc += (int)c[i]; b = i + 1; } else break; }
+                ctl->sel_k = k - acc;
+                ctl->sel_prefix = prefix | ((unsigned long long)(8 * lane + b) << shift);
+            }
         }
         __syncthreads();
         k = ctl->sel_k; prefix = ctl->sel_prefix;
         __syncthreads();
     }
     return prefix;
+}
+
+// given the key a of rank k, the key of rank k + 1: a itself if more than k + 1 values are <= a, else the smallest larger one
+__device__ __forceinline__ unsigned long long block_select_next(const double *h, const uint8_t *flags, int T, int k, unsigned long long a, Ctl *ctl) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { ctl->hist[0] = 0; ctl->sel_prefix = ~0ull; }
+    __syncthreads();
+    unsigned cnt = 0; unsigned long long mn = ~0ull;
+    for (int t = tid; t < T; t += NT) {
+        if (!(flags[t] & 1)) continue;
+        const unsigned long long key = (unsigned long long)__double_as_longlong(h[t]);
+        if (key <= a) ++cnt; else mn = key < mn ? key : mn;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        const unsigned long long m2 = __shfl_xor_sync(0xFFFFFFFFu, mn, o); mn = m2 < mn ? m2 : mn;
+    }
+    if ((tid & 31) == 0) { if (cnt) atomicAdd(&ctl->hist[0], cnt); if (mn != ~0ull) atomicMin(&ctl->sel_prefix, mn); }
+    __syncthreads();
+    const unsigned long long res = (int)ctl->hist[0] >= k + 2 ? a : ctl->sel_prefix;
+    __syncthreads();
+    return res;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -311,7 +344,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
     fv.Z = Z; fv.pflag = pflag; fv.tri = (uint16_t *)(smem + pl.off_T);
     fv.tbase = (uint16_t *)(smem + pl.off_tbase); fv.tcnt = smem + pl.off_tcnt;
     fv.T = &ctl.T; fv.status = &ctl.status; fv.pass_mask = P.cfg.graph_pass_mask; fv.tri_cap = 2 * cap;
-    fv.rpool = nullptr; fv.rinfo = (uint32_t *)(smem + pl.off_rinfo); fv.rcount = &ctl.rcount; fv.rpool_cap = 6 * cap;
+    fv.rpool = nullptr; fv.rinfo = (uint32_t *)(smem + pl.off_rinfo); fv.rcount = &ctl.rcount; fv.rpool_cap = 6 * cap; fv.oldof = nullptr;
+    uint16_t *const inv = (uint16_t *)(smem + pl.off_scr), *const oldof = inv + cap;     // new index -> sorted position / old index (scr is free between the grid build and the planes)
     uint16_t *const rpool = (uint16_t *)(smem + pl.off_rpool);
     uint16_t *const todo = (uint16_t *)(smem + pl.off_tflags);   // list of the stars Delaunay #2 must rebuild (tflags is free until the planes)
     const mvosr_config &cfg = P.cfg;
@@ -482,14 +516,18 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 // index order only, which the compaction preserves): emit its triangles from the stored ring, one thread per
                 // star, and rebuild only the others.
                 // The ring (at most RD entries; larger stars are rebuilt) is held in registers as NEW feature indices.
+                // The rings of the stars to rebuild are rewritten in place as sorted positions of the new grid (dropped
+                // neighbours marked): they seed the rebuild (stars_pair).
                 constexpr int RD = 10;
+                for (int i = tid; i < n; i += NT) { const int og = ctl.ps.orig[i]; if (og != INF16) inv[og] = (uint16_t)i; }
+                __syncthreads();
                 for (int c0 = 0; c0 < n1; c0 += NT) {
                     const int o = c0 + tid;
-                    int np = INF16, d = 0;
+                    int np = INF16, d = 0, dfull = 0;
                     if (o < n1) np = mult[o];
                     uint32_t info = 0;
-                    if (np != INF16) { info = fv.rinfo[o]; d = (int)(info & 0xFFu); if (d > RD) d = 0; }
-                    const uint16_t *ring = rpool + (info >> 8);
+                    if (np != INF16) { info = fv.rinfo[o]; dfull = d = (int)(info & 0xFFu); if (d > RD) d = 0; oldof[np] = (uint16_t)o; }
+                    uint16_t *ring = rpool + (info >> 8);
                     int nb[RD];                                    // new index of ring entry j; INF16: hull gap; -1: dropped
                     bool clean = d > 0;
 #pragma unroll
@@ -498,7 +536,13 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                         if (j < d) { const int q = ring[j]; if (q != INF16) { const int m = mult[q]; nb[j] = m == INF16 ? -1 : m; } }
                         clean = clean && nb[j] >= 0;
                     }
-                    if (!clean) d = 0;
+                    if (!clean) {
+                        d = 0;
+                        for (int j = 0; j < dfull; ++j) {
+                            const int q = ring[j];
+                            if (q != INF16) { const int m = mult[q]; ring[j] = m == INF16 ? RING_DROPPED : inv[m]; }
+                        }
+                    }
                     // owned triangles (np smaller than both other vertices): key = (min << 16) | max
                     unsigned key[RD]; int k = 0;
 #pragma unroll
@@ -553,7 +597,9 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 __syncthreads();
             }
             TMARK(6);
+            if (second) { fv.rpool = rpool; fv.oldof = oldof; }
             int nd = run_stars<true>(ctl.ps, fv, &ctl.sc, defer, defer2, n_exact, &ctl.tphase[8], second ? todo : nullptr, ctl.n_todo);
+            fv.rpool = nullptr; fv.oldof = nullptr;
             if (tid == 0) ctl.n_deferred_total += nd;
             __syncthreads();
             status |= ctl.status;
@@ -597,7 +643,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 unsigned long long ka = block_select(theight, tflags, T, (n_loose - 1) / 2, &ctl);
                 double a = __longlong_as_double((long long)ka), b = a;
                 if ((n_loose & 1) == 0) {
-                    unsigned long long kb = block_select(theight, tflags, T, n_loose / 2, &ctl);
+                    unsigned long long kb = block_select_next(theight, tflags, T, (n_loose - 1) / 2, ka, &ctl);
                     b = __longlong_as_double((long long)kb);
                 }
                 double med = (n_loose & 1) ? a : (a + b) / 2.0;

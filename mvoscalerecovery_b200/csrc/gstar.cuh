@@ -89,7 +89,11 @@ struct FrameView {
     // hull gap; rinfo[o] = (first pool entry << 8) | degree, 0 = no ring.  Stars none of whose neighbours is dropped by
     // the graph check are stars of Delaunay #2 as well and are emitted from here instead of being rebuilt.
     uint16_t *rpool; uint32_t *rinfo; int *rcount; int rpool_cap;
+    // seeds (emit pass of Delaunay #2): oldof[new feature index] = index in Delaunay #1; the rings of the stars to rebuild have
+    // been rewritten as sorted positions of the new grid, RING_DROPPED marking the neighbours the graph check removed
+    const uint16_t *oldof;
 };
+constexpr uint16_t RING_DROPPED = 0xFFFE;
 
 __device__ __forceinline__ bool edge_consistent(float va, float za, float vb, float zb) {
     // check_triangle (graph.py:124-129): (v_a - v_b) * (d_a - d_b) < 0 in float64 on float32-exact values --
@@ -989,7 +993,28 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
         }
         const float BX0 = bx0 > 0 ? ps.xmin + bx0 * ps.h - ppx + slack : -CUDART_INF_F, BX1 = bx1 < ps.gx - 1 ? ps.xmin + (bx1 + 1) * ps.h - ppx - slack : CUDART_INF_F;
         const float BY0 = by0 > 0 ? ps.ymin + by0 * ps.h - ppy + slack : -CUDART_INF_F, BY1 = by1 < ps.gy - 1 ? ps.ymin + (by1 + 1) * ps.h - ppy - slack : CUDART_INF_F;
-        // ---- q0: the nearest point, certified and unique up to rounding
+        // ---- seed (Delaunay #2 only): the neighbours of this point in Delaunay #1 that survived the graph check are still
+        // its neighbours, and two consecutive survivors with nothing dropped between them still span a triangle of the star
+        // (their circle was empty before points were removed).  Only the gaps left by dropped neighbours are walked.
+        bool seeded = false; int sid = INF16, nC = 1; unsigned gapm = 1u;
+        if (EMIT && fv.oldof) {                                    // warp-uniform
+            int e = INF16, d0 = 0;
+            if (have) {
+                const uint32_t info = fv.rinfo[fv.oldof[ps.orig[p]]];
+                d0 = (int)(info & 0xFFu);
+                if (d0 > GL) d0 = 0;
+                if (gl < d0) e = fv.rpool[(info >> 8) + gl];
+            }
+            const unsigned am = GBALLOT(gl < d0 && e < RING_DROPPED), im = GBALLOT(gl < d0 && e == INF16);
+            const int m = __popc(am);
+            seeded = m >= 1 && im == 0;
+            const int src = gl < m ? (int)__fns(am, 0, gl + 1) : 0;  // old slot of the (gl+1)-th survivor
+            const int se = GSHFL(e, src);
+            int nxt = src + 1; if (nxt >= d0) nxt = 0;
+            const unsigned gm = GBALLOT(seeded && gl < m && !((am >> nxt) & 1u));
+            if (seeded) { sid = gl < m ? se : (int)INF16; nC = m; gapm = gm; }
+        }
+        // ---- q0 (stars without a seed): the nearest point, certified and unique up to rounding
         int q0; float cx, cy;
         {
             unsigned kq = 0xFFFFFFFFu; float mx = 0.f, my = 0.f; int mp = INF16;
@@ -1003,19 +1028,24 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
             const unsigned kmin = gmin_u32(kq, g);
             const float lmin = __uint_as_float(kmin);
             const float mg = fminf(fminf(-BX0, BX1), fminf(-BY0, BY1));
-            if (ok && (kmin == 0xFFFFFFFFu || !(lmin * 1.000001f < mg * mg))) { PR(1); ok = false; }
+            if (ok && !seeded && (kmin == 0xFFFFFFFFu || !(lmin * 1.000001f < mg * mg))) { PR(1); ok = false; }
             const float thr = lmin * 1.000002f;
             int cnt = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) cnt += sp[k] != INF16 && l[k] <= thr;
             const unsigned b1 = GBALLOT(cnt >= 1), b2 = GBALLOT(cnt >= 2);
-            if (ok && (__popc(b1) != 1 || b2)) { PR(2); ok = false; }
+            if (ok && !seeded && (__popc(b1) != 1 || b2)) { PR(2); ok = false; }
             const int wl = max(__ffs(GBALLOT(kq == kmin)) - 1, 0);
             q0 = GSHFL(mp, wl); cx = GSHFL(mx, wl); cy = GSHFL(my, wl);
         }
-        // ---- the counter-clockwise walk; lane i of the half-warp keeps the i-th neighbour
-        int sid = gl == 0 ? q0 : (int)INF16, nC = 1, cpos = q0;
-        bool closed = false, walking = ok;
+        if (!seeded) sid = gl == 0 ? q0 : (int)INF16;
+        // ---- the walk.  Lane i of the half-warp keeps the i-th neighbour (counter-clockwise); bit i of gapm: the star is
+        // still open between slots i and i+1.  Each step looks for the neighbour that follows slot j (the lowest open
+        // slot): either the occupant of slot j+1 -- the gap closes -- or a new neighbour, inserted there.
+        int j = max(__ffs(gapm) - 1, 0);
+        int cpos = GSHFL(sid, j), tpos = GSHFL(sid, j + 1 < nC ? j + 1 : 0);
+        if (seeded) { cx = ps.x[cpos] - ppx; cy = ps.y[cpos] - ppy; }
+        bool closed = ok && gapm == 0u, walking = ok && gapm != 0u;
         const bool m32 = __any_sync(FULL, ok && M > 32), m48 = __any_sync(FULL, ok && M > 48);
         while (__any_sync(FULL, walking)) {
             unsigned kbest = 0xFFFFFFFFu; float tb = 0.f, eb = 0.f, xb = 0.f, yb = 0.f; int pb = INF16;
@@ -1047,10 +1077,31 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
             const float r = sqrt_approx(fmaf(vx, vx, vy * vy));
             const float rs = r + 2.f * (we * (fabsf(cx) + fabsf(cy)) * 0.51f + 1.0e-3f + 1.0e-4f * r);
             if (walking && !w_cap_inside<false>(cx, cy, 1.f, vx, vy, rs, BX0, BX1, BY0, BY1, WBox())) { PR(6); ok = false; walking = false; }
-            if (walking) {
-                if (wpos == q0) { closed = true; walking = false; }
-                else if (nC >= GL) { PR(7); ok = false; walking = false; }
-                else { if (gl == nC) sid = wpos; ++nC; cx = wx; cy = wy; cpos = wpos; }
+            if (!EMIT) {
+                // vote pass: never seeded -- the plain walk from q0 back to q0
+                if (walking) {
+                    if (wpos == q0) { closed = true; walking = false; }
+                    else if (nC >= GL) { PR(7); ok = false; walking = false; }
+                    else { if (gl == nC) sid = wpos; ++nC; cx = wx; cy = wy; cpos = wpos; }
+                }
+            } else {
+                // a winner that already sits in another slot than the expected one contradicts the seed: rebuild elsewhere
+                const unsigned dupm = GBALLOT(gl < nC && sid == wpos);
+                if (walking && wpos != tpos && (dupm || nC >= GL)) { PR(7); ok = false; walking = false; }
+                const bool ins = walking && wpos != tpos, cls = walking && wpos == tpos;
+                const int up = GSHFL(sid, max(gl - 1, 0));
+                if (ins) {
+                    if (gl == j + 1) sid = wpos; else if (gl > j + 1) sid = up;
+                    ++nC; gapm = ((gapm >> (j + 1)) << (j + 2)) | (1u << (j + 1)); ++j;
+                    cpos = wpos; cx = wx; cy = wy;
+                }
+                if (cls) {
+                    gapm &= gapm - 1u;
+                    if (!gapm) { closed = true; walking = false; } else j = __ffs(gapm) - 1;
+                }
+                const int cp2 = GSHFL(sid, j);
+                tpos = GSHFL(sid, j + 1 < nC ? j + 1 : 0);
+                if (cls && walking) { cpos = cp2; cx = ps.x[cpos] - ppx; cy = ps.y[cpos] - ppy; }
             }
         }
         const bool fin = ok && closed;
