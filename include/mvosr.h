@@ -212,6 +212,16 @@ int  mvosr_ransac_planes(mvosr_handle *h, int32_t n_sets, const int32_t *offsets
 int  mvosr_integrate_paths(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets, const double *motions,
                            const double *scales, double *poses_out, void *stream);
 
+/* Dense depth from the mesh -- Reconstruct.depth_generate (src/reconstruct.py:91-107): tri.find_simplex of every integer
+ * pixel (u, v) of a width x height image + the depth of that triangle's plane along the pixel's ray,
+ * depth = h / (n . ((u-cx)/fx, (v-cy)/fy, 1)).  tri: [T][3] int32 into uv ([N][2] float64 pixel coordinates); datas:
+ * [T][4] float64 rows (unit normal, height) as Reconstruct.triangle_model returns them (src/reconstruct.py:70-90).
+ * Outputs: depth [height][width] float64 (0 outside the triangulation), tri_id [height][width] int32 (-1 outside; on a
+ * shared edge the smaller triangle index). */
+int  mvosr_depth_from_mesh(mvosr_handle *h, int32_t width, int32_t height, double fx, double fy, double cx, double cy,
+                           int32_t n_tri, const int32_t *tri, const double *uv, const double *datas,
+                           double *depth, int32_t *tri_id, void *stream);
+
 /* Profiling aid: when set (device pointer, [F][16] int64), the fused kernel stores per-frame SM cycles per phase:
  * 0 load+stage1+ROI, 1 grid#1, 2/3 stars#1 thread/warp path, 6 compaction+grid#2, 7/8 stars#2 thread/warp path,
  * 10 planes, 11 median, 12 valid list, 13 RANSAC. Pass NULL to disable. */

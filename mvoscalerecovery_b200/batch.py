@@ -230,6 +230,19 @@ class ScaleRecovery:
             N.check(self.lib.mvosr_integrate_paths(self._h, S, _ptr(seq_offsets), _ptr(motions), _ptr(scales), _ptr(poses), self._stream()))
         return poses
 
+    def depth_from_mesh(self, width: int, height: int, fx: float, fy: float, cx: float, cy: float, tri, uv, datas):
+        """Reconstruct.depth_generate (reconstruct.py:91-107): dict(depth (H,W) float64, tri_id (H,W) int32)."""
+        dev = self.device
+        _chk(tri, torch.int32, "tri", dev)
+        _chk(uv, torch.float64, "uv", dev)
+        _chk(datas, torch.float64, "datas", dev)
+        depth = torch.empty((height, width), dtype=torch.float64, device=dev)
+        tri_id = torch.empty((height, width), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_depth_from_mesh(self._h, int(width), int(height), float(fx), float(fy), float(cx), float(cy),
+                                                   tri.shape[0], _ptr(tri), _ptr(uv), _ptr(datas), _ptr(depth), _ptr(tri_id), self._stream()))
+        return dict(depth=depth, tri_id=tri_id)
+
     # ------------------------------------------------------------------ host buffers end to end
     def recover_scales_host(self, offsets: np.ndarray, cur_u, cur_v, ref_u, ref_v, poses, move_flags=None, max_features: int = 0,
                             seq_id: int = 0, seed: int = 0, out=None):

@@ -72,3 +72,13 @@ def integrate_path(motions, scales=None):
     off = np.array([0, mot.shape[0]], np.int32)
     sc = None if scales is None else _dev(eng, np.asarray(scales, dtype=np.float64).reshape(-1), np.float64)
     return eng.integrate_paths(_dev(eng, off, np.int32), _dev(eng, mot, np.float64), sc).cpu().numpy()
+
+
+def depth_from_mesh(cam, triangle_ids, points2d, datas):
+    """Reconstruct.depth_generate (src/reconstruct.py:91-107): (depth (H,W), tri_id (H,W)) for a camera with
+    width/height/fx/fy/cx/cy attributes."""
+    eng = engine()
+    out = eng.depth_from_mesh(int(cam.width), int(cam.height), cam.fx, cam.fy, cam.cx, cam.cy,
+                              _dev(eng, np.asarray(triangle_ids).reshape(-1, 3), np.int32),
+                              _dev(eng, np.asarray(points2d).reshape(-1, 2), np.float64), _dev(eng, np.asarray(datas).reshape(-1, 4), np.float64))
+    return out["depth"].cpu().numpy(), out["tri_id"].cpu().numpy()

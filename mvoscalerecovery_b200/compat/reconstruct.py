@@ -36,3 +36,13 @@ class Reconstruct:
         flip = unit[:, 1] < 0
         unit[flip] *= -1
         return np.hstack([unit, np.where(flip, -height, height)[:, None]])
+
+    def depth_generate(self, tri, datas, img=None):
+        """Dense depth map: every pixel inside the triangulation gets the depth of its triangle's plane (reconstruct.py:91-107).
+        ``tri``: a scipy.spatial.Delaunay-like object (``.simplices``, ``.points``) or a (simplices, points2d) pair; ``datas``:
+        the rows of ``triangle_model``.  Returns the (H, W) depth map (0 outside the mesh) and stores ``self.pixel_tris``.
+        The reference's point-cloud export (open3d) and imshow are GUI code and not provided."""
+        import _gpu
+        simplices, pts = (tri.simplices, tri.points) if hasattr(tri, "simplices") else tri
+        depth, self.pixel_tris = _gpu.depth_from_mesh(self.cam, simplices, pts, datas)
+        return depth

@@ -566,4 +566,22 @@ int mvosr_integrate_paths(mvosr_handle *h, int32_t n_sequences, const int32_t *s
     return MVOSR_OK;
 }
 
+int mvosr_depth_from_mesh(mvosr_handle *h, int32_t width, int32_t height, double fx, double fy, double cx, double cy,
+                          int32_t n_tri, const int32_t *tri, const double *uv, const double *datas,
+                          double *depth, int32_t *tri_id, void *stream) {
+    if (!h || width <= 0 || height <= 0 || n_tri < 0 || !tri || !uv || !datas || !depth || !tri_id) return MVOSR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t npix = (size_t)width * (size_t)height;
+    CK(cudaMemsetAsync(tri_id, 0x7F, sizeof(int32_t) * npix, st));          // 0x7F7F7F7F: larger than any triangle index
+    if (n_tri > 0) {
+        raster_mesh_kernel<<<min((n_tri + 7) / 8, 8 * h->num_sms), 256, 0, st>>>(n_tri, tri, uv, width, height, tri_id);
+        CK(cudaGetLastError());
+    }
+    mesh_depth_kernel<<<min((int)((npix + 255) / 256), 8 * h->num_sms), 256, 0, st>>>(width, height, fx, fy, cx, cy, datas, tri_id, depth);
+    CK(cudaGetLastError());
+    h->launches += n_tri > 0 ? 2 : 1;
+    return MVOSR_OK;
+}
+
 }  // extern "C"

@@ -8,6 +8,8 @@
 //                            src/thirdparty/Ransac/ransac.py:3-23) on explicit point lists
 //   integrate_paths_kernel   get_path / motion2pose (src/main_offline.py:95-119)
 //   triangle_votes_kernel    find_outliers / check_triangle (src/rescale.py:45-72, src/scale_calculator.py:105-119,151-167)
+//   raster_mesh_kernel + mesh_depth_kernel   Reconstruct.depth_generate (src/reconstruct.py:91-107): tri.find_simplex of every
+//                            pixel + the depth of the triangle's plane along the pixel's ray
 // All of them are HBM-bound gathers / streams; the arithmetic is float64 because the callers hand float64 arrays.
 #pragma once
 #include <stdint.h>
@@ -188,6 +190,51 @@ __global__ void __launch_bounds__(PT) integrate_paths_kernel(int n_seq, const in
             for (int k = 0; k < 12; ++k) out[12 * (size_t)(i + 1) + k] = cur.m[k];
         }
         __syncthreads();
+    }
+}
+
+// ---- dense depth from the mesh ---------------------------------------------------------------------
+// Point location of all W x H integer pixels in the triangulation, done as a rasteriser: one warp per triangle walks the
+// pixels of the triangle's bounding box and claims those inside (closed edge functions in float64); a pixel on a shared edge
+// is claimed by the smaller triangle index (atomicMin), which makes the result deterministic (scipy's find_simplex returns
+// "one of" the simplices there).  tri_id must be pre-filled with a value above every triangle index (mvosr_depth_from_mesh: 0x7F7F7F7F).
+__global__ void __launch_bounds__(256) raster_mesh_kernel(int n_tri, const int32_t *__restrict__ tri, const double *__restrict__ uv,
+                                                          int width, int height, int32_t *tri_id) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < n_tri; t += gridDim.x * wpb) {
+        const int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
+        const double ax = uv[2 * i0], ay = uv[2 * i0 + 1], bx = uv[2 * i1], by = uv[2 * i1 + 1], cx = uv[2 * i2], cy = uv[2 * i2 + 1];
+        const double area = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+        if (area == 0.0) continue;
+        const double sg = area > 0 ? 1.0 : -1.0;
+        const int x0 = max((int)ceil(fmin(ax, fmin(bx, cx))), 0), x1 = min((int)floor(fmax(ax, fmax(bx, cx))), width - 1);
+        const int y0 = max((int)ceil(fmin(ay, fmin(by, cy))), 0), y1 = min((int)floor(fmax(ay, fmax(by, cy))), height - 1);
+        if (x0 > x1 || y0 > y1) continue;
+        const int w = x1 - x0 + 1, n = w * (y1 - y0 + 1);
+        for (int i = lane; i < n; i += 32) {
+            const int px = x0 + i % w, py = y0 + i / w;
+            const double X = px, Y = py;
+            const double e0 = sg * ((bx - ax) * (Y - ay) - (by - ay) * (X - ax));
+            const double e1 = sg * ((cx - bx) * (Y - by) - (cy - by) * (X - bx));
+            const double e2 = sg * ((ax - cx) * (Y - cy) - (ay - cy) * (X - cx));
+            if (e0 >= 0 && e1 >= 0 && e2 >= 0) atomicMin(tri_id + (size_t)py * width + px, t);
+        }
+    }
+}
+
+// depth = h / (n . (x_n, y_n, 1)) of the claiming triangle's plane (datas rows: unit normal, height); 0 and id -1 outside.
+__global__ void __launch_bounds__(256) mesh_depth_kernel(int width, int height, double fx, double fy, double cx, double cy,
+                                                         const double *__restrict__ datas, int32_t *tri_id, double *depth) {
+    const int n = width * height;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int t = tri_id[i];
+        double d = 0.0;
+        if (t == 0x7F7F7F7F) tri_id[i] = -1;                      // the fill pattern of mvosr_depth_from_mesh (byte memset)
+        else {
+            const double xn = ((double)(i % width) - cx) / fx, yn = ((double)(i / width) - cy) / fy;
+            d = datas[4 * t + 3] / (datas[4 * t] * xn + datas[4 * t + 1] * yn + datas[4 * t + 2]);
+        }
+        depth[i] = d;
     }
 }
 

@@ -130,3 +130,36 @@ def test_integrate_paths_vs_sequential_product(engine):
     # without scales: unit steps
     p1 = engine.integrate_paths(_t(engine, off[:2]), _t(engine, mot[:lens[0]])).cpu().numpy()
     np.testing.assert_allclose(p1, _motion2pose(mot[:lens[0]], np.ones(lens[0])), rtol=1e-9, atol=1e-6)
+
+
+def test_depth_from_mesh_vs_find_simplex(engine, ref):
+    """Reconstruct.depth_generate (reconstruct.py:91-107): per-pixel tri.find_simplex (Qhull point location) and the plane
+    depth h / (n . ray).  Pixels on a mesh edge belong to either neighbour; everywhere else the triangle index is exact."""
+    from scipy.spatial import Delaunay
+    W, H, fx, fy, cx, cy = 1241, 376, 718.856, 718.856, 607.1928, 185.2157
+    f3, f2 = ref["f3"], ref["f2"]
+    dt = Delaunay(f2)
+    tri = dt.simplices.astype(np.int32)
+    n = np.stack([np.linalg.inv(f3[t]) @ np.ones(3) for t in tri]); ln = np.linalg.norm(n, axis=1)
+    sg = np.where(n[:, 1] < 0, -1.0, 1.0)
+    datas = np.hstack([n / ln[:, None] * sg[:, None], (sg / ln)[:, None]])          # rows of triangle_model (reconstruct.py:70-90)
+    out = engine.depth_from_mesh(W, H, fx, fy, cx, cy, _t(engine, tri), _t(engine, f2), _t(engine, datas))
+    depth = out["depth"].cpu().numpy(); ids = out["tri_id"].cpu().numpy()
+    v, u = np.mgrid[0:H, 0:W]
+    pix = np.stack([u.ravel(), v.ravel()], 1).astype(np.float64)
+    want = dt.find_simplex(pix)
+    # barycentric coordinates in the reference's simplex: strictly interior pixels must agree exactly
+    T = dt.transform[np.maximum(want, 0)]
+    bc = np.einsum("nij,nj->ni", T[:, :2], pix - T[:, 2])
+    bary = np.hstack([bc, 1 - bc.sum(1, keepdims=True)])
+    interior = (want >= 0) & (bary.min(1) > 1e-7)
+    got = ids.ravel()
+    assert np.array_equal(got[interior], want[interior])
+    outside = dt.find_simplex(pix, tol=1e-7) < 0
+    assert np.all(got[outside] == -1) and np.all(depth.ravel()[outside] == 0.0)
+    assert (got != want).mean() < 2e-3                                               # only pixels on mesh edges may differ
+    ok = got >= 0
+    xn, yn = (pix[ok, 0] - cx) / fx, (pix[ok, 1] - cy) / fy
+    d = datas[got[ok]]
+    np.testing.assert_allclose(depth.ravel()[ok], d[:, 3] / (d[:, 0] * xn + d[:, 1] * yn + d[:, 2]), rtol=1e-12)
+    assert interior.sum() > 0.2 * W * H
