@@ -37,6 +37,13 @@ N_FRAMES = 4541
 N_CORR = 2500
 SEED = 20261017
 METRIC = "frames/sec scale recovery"
+KITTI_LENGTHS = (4541, 1101, 4661, 801, 271, 2761, 1101, 1101, 4071, 1591, 1201)      # sequences 00-10: 23 201 frames
+WORKLOADS = {
+    # name: (frames per GPU (None: the fleet), correspondences per frame, description)
+    "kitti00": (N_FRAMES, N_CORR, "offline sequence per GPU, KITTI-00-shaped synthetic correspondences, ~2k road features/frame (BASELINE configs[1])"),
+    "dense": (592, 25000, "dense-flow stress, ~20k road features/frame, large-frame mode (BASELINE configs[2]; 592 of the 4541 frames per GPU)"),
+    "fleet": (None, N_CORR, "fleet batch: 11 KITTI 00-10-shaped sequences, 23 201 frames sharded by frame range (BASELINE configs[3])"),
+}
 
 
 def make_workload(n_frames, n_corr, seq):
@@ -153,8 +160,9 @@ def run_reference_arm(args):
     n_frames = workers * per
     ctx = mp.get_context("fork")
     # generate the sample once in the parent so forked workers share it
-    _WORK_CACHE[(n_frames, args.features, 0)] = make_workload(n_frames, args.features, 0)
-    jobs = [(0, w * per, (w + 1) * per, n_frames, args.features) for w in range(workers)]
+    n_corr = args.features or WORKLOADS[args.workload][1]
+    _WORK_CACHE[(n_frames, n_corr, 0)] = make_workload(n_frames, n_corr, 0)
+    jobs = [(0, w * per, (w + 1) * per, n_frames, n_corr) for w in range(workers)]
     with ctx.Pool(workers) as pool:
         for _ in range(args.warmup):
             pool.map(_worker, jobs)
@@ -168,7 +176,7 @@ def run_reference_arm(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "offline sequence, KITTI-00-shaped synthetic correspondences, ~2k road features/frame",
-                       "frames_per_step": n_frames, "correspondences_per_frame": args.features},
+                       "frames_per_step": n_frames, "correspondences_per_frame": n_corr},
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": workers, "kind": "port",
                              "sample": "%d frames/step (%d per worker process), oracle/pipeline.py stages 1-5" % (n_frames, per)},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -192,18 +200,45 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_frames, n_corr = args.frames, args.features
-    batch = make_workload(n_frames, n_corr, seq=rank)             # this rank's shard: sequence `rank` of the fleet
-    shards = [(r * n_frames, (r + 1) * n_frames) for r in range(world)]
+    from mvoscalerecovery_b200 import synth
+    wl_frames, wl_corr, wl_desc = WORKLOADS[args.workload]
+    n_corr = args.features or wl_corr
+    if args.workload == "fleet":
+        # strong scaling: the concatenated fleet is cut into `world` contiguous frame ranges; a range may span sequences
+        seq_starts = np.concatenate([[0], np.cumsum(KITTI_LENGTHS)])
+        total_frames = int(seq_starts[-1])
+        shards = fleet.frame_shards(total_frames, world)
+        lo, hi = shards[rank]
+        pieces = []                                               # (sequence, first frame, end frame) of this rank's range
+        for sq, L in enumerate(KITTI_LENGTHS):
+            a, b = max(lo, int(seq_starts[sq])), min(hi, int(seq_starts[sq + 1]))
+            if a < b:
+                pieces.append((sq, a - int(seq_starts[sq]), b - int(seq_starts[sq])))
+        parts = [synth.make_sequence(seed=SEED, n_frames=KITTI_LENGTHS[sq], n_corr=n_corr, seq=sq, outlier_frac=0.10, frame_range=(a, b))
+                 for sq, a, b in pieces]
+        n_frames = hi - lo
+        seq_off_host = seq_starts.astype(np.int32)
+    else:
+        n_frames = args.frames or wl_frames
+        total_frames = world * n_frames
+        shards = [(r * n_frames, (r + 1) * n_frames) for r in range(world)]
+        pieces = [(rank, 0, n_frames)]                            # weak scaling: sequence `rank` of the fleet on this rank
+        parts = [make_workload(n_frames, n_corr, seq=rank)]
+        seq_off_host = np.arange(0, (world + 1) * n_frames, n_frames, dtype=np.int32)
+    batch = parts[0] if len(parts) == 1 else synth.CorrespondenceBatch(
+        np.concatenate([[0]] + [p.offsets[1:].astype(np.int64) + sum(int(q.offsets[-1]) for q in parts[:i]) for i, p in enumerate(parts)]).astype(np.int32),
+        *[np.concatenate([getattr(p, k) for p in parts]) for k in ("cur_u", "cur_v", "ref_u", "ref_v", "poses", "move_flags", "true_scale")])
     max_feat = int(np.max(np.diff(batch.offsets)))
     eng = ScaleRecovery(device=local_rank, absolute_reference=1.7)
+    piece_off = np.concatenate([[0], np.cumsum([b - a for _, a, b in pieces])]).astype(np.int64)      # frame offsets of the pieces in this rank's batch
 
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h = dict(offsets=pin(batch.offsets), cur_u=pin(batch.cur_u), cur_v=pin(batch.cur_v), ref_u=pin(batch.ref_u),
              ref_v=pin(batch.ref_v), poses=pin(batch.poses), move=pin(batch.move_flags))
     d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
-    seq_off = torch.arange(0, (world + 1) * n_frames, n_frames, dtype=torch.int32, device=dev)
-    move_all = torch.ones(world * n_frames, dtype=torch.uint8, device=dev)
+    seq_off = torch.from_numpy(seq_off_host).to(dev)
+    move_all = torch.ones(total_frames, dtype=torch.uint8, device=dev)
+    d_piece_off = [d["offsets"][int(piece_off[i]): int(piece_off[i + 1]) + 1] for i in range(len(pieces))]
     torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -212,8 +247,12 @@ def run_gpu_arm(args):
     def step(pair=None):
         if pair:
             pair[0].record()
-        r = eng.scale_frames_from_correspondences(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], d["poses"],
-                                                  max_features=max_feat, frame_index0=0, seq_id=rank, seed=SEED)
+        rs = []
+        for i, (sq, a, b) in enumerate(pieces):                   # one launch per sequence piece (Philox stream = (sequence, frame))
+            rs.append(eng.scale_frames_from_correspondences(d_piece_off[i], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"],
+                                                            d["poses"][int(piece_off[i]): int(piece_off[i + 1])],
+                                                            max_features=max_feat, frame_index0=a, seq_id=sq, seed=SEED))
+        r = rs[0] if len(rs) == 1 else {k: torch.cat([x[k] for x in rs]) for k in ("raw_scale", "status", "n_features")}
         if pair:
             pair[1].record()
         raw, st, nf = fleet.gather_results(r["raw_scale"], r["status"], r["n_features"], shards)
@@ -245,7 +284,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    value = world * n_frames / (ms_step * 1e-3)
+    value = total_frames / (ms_step * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call (pinned inputs, copies inside the timed region)
     res = dict(scale=np.empty(n_frames, np.float64), raw_scale=np.empty(n_frames, np.float64), status=np.empty(n_frames, np.uint8))
@@ -263,7 +302,7 @@ def run_gpu_arm(args):
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * n_frames / float(te.item())
+    e2e_val = total_frames / float(te.item())
     M = int(batch.offsets[-1])
     h2d = 4 * (n_frames + 1) + 16 * M + 96 * n_frames + n_frames + 8
     d2h = 8 * n_frames + 8 * n_frames + n_frames
@@ -279,7 +318,7 @@ def run_gpu_arm(args):
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tp):
+        if os.path.isfile(tp) and args.workload == "kitti00" and n_frames == N_FRAMES and n_corr == N_CORR:
             try:
                 traffic = float(json.load(open(tp))["frame_kernel_dram_bytes_per_launch"])
             except Exception:
@@ -289,9 +328,9 @@ def run_gpu_arm(args):
         mv = batch.move_flags.astype(bool)
         err = np.abs(scales[mv] - batch.true_scale[mv]) / batch.true_scale[mv]
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": "offline sequence per GPU, KITTI-00-shaped synthetic correspondences, ~2k road features/frame (BASELINE configs[1])",
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.workload == "fleet" else "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl_desc, "frames_total": total_frames,
                            "frames_per_gpu": n_frames, "correspondences_per_frame": n_corr, "camera": "1241x376", "camera_height_m": 1.7,
                            "outlier_frac": 0.10, "ransac_iterations": 100,
                            "l2": "inputs %.0f MB per pass > 126 MB L2" % (16.0 * M / 1e6),
@@ -316,8 +355,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=N_FRAMES)
-    ap.add_argument("--features", type=int, default=N_CORR)
+    ap.add_argument("--workload", default="kitti00", choices=sorted(WORKLOADS), help="kitti00 = BASELINE configs[1] (the bench line); dense / fleet = configs[2] / configs[3]")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (0 = the workload's own)")
+    ap.add_argument("--features", type=int, default=0, help="correspondences per frame (0 = the workload's own)")
     ap.add_argument("--cpu-sample", type=int, default=400, help="frames of the workload timed on one host core (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

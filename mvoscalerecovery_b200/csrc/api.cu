@@ -39,6 +39,7 @@ struct mvosr_handle {
     // host-API staging (grown on demand)
     void *d_stage; size_t stage_bytes;
     void *d_ws; size_t ws_bytes;   // large-frame staging (frames beyond the shared-memory capacity)
+    cudaEvent_t ev_ws; int ev_ws_ready;   // the staging is one buffer: launches that use it are chained through this event
     long long *phase_cycles;     // optional profiling sink (device), set by mvosr_set_phase_timing
 };
 
@@ -299,6 +300,7 @@ int mvosr_destroy(mvosr_handle *h) {
     if (h->work_counter) cudaFree(h->work_counter);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->d_ws) cudaFree(h->d_ws);
+    if (h->ev_ws_ready) cudaEventDestroy(h->ev_ws);
     if (h->streams_ready) {
         cudaStreamDestroy(h->s_copy); cudaStreamDestroy(h->s_comp[0]); cudaStreamDestroy(h->s_comp[1]);
         for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_copy[i]);
@@ -345,7 +347,7 @@ static int launch_frames(mvosr_handle *h, FrameParams &P, int max_features, cuda
         // large-frame mode: the staging lives in global memory, one slab per CTA
         size_t stride = ((size_t)pl.total + 255) & ~(size_t)255, need = stride * (size_t)grid;
         if (need > h->ws_bytes) {
-            CK(cudaStreamSynchronize(st));
+            CK(cudaDeviceSynchronize());                     // earlier launches on any stream may still use the old buffer
             if (h->d_ws) cudaFree(h->d_ws);
             h->d_ws = nullptr; h->ws_bytes = 0;
             if (cudaMalloc(&h->d_ws, need) != cudaSuccess) { cudaGetLastError(); return MVOSR_E_NOMEM; }
@@ -353,10 +355,14 @@ static int launch_frames(mvosr_handle *h, FrameParams &P, int max_features, cuda
         }
         P.workspace = (unsigned char *)h->d_ws; P.ws_stride = stride;
         dyn = 0;
+        // two launches in flight (e.g. the two compute streams of the host pipeline) must not share the slabs
+        if (!h->ev_ws_ready) { CK(cudaEventCreateWithFlags(&h->ev_ws, cudaEventDisableTiming)); h->ev_ws_ready = 1; }
+        else CK(cudaStreamWaitEvent(st, h->ev_ws, 0));
     }
     CK(cudaMemsetAsync(P.work_counter, 0, sizeof(int), st));
     frame_kernel<FROM_CORR><<<grid, NT, dyn, st>>>(P);
     CK(cudaGetLastError());
+    if (P.workspace) CK(cudaEventRecord(h->ev_ws, st));
     h->launches += 1;
     return MVOSR_OK;
 }

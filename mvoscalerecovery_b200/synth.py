@@ -141,8 +141,9 @@ def make_frame(seed: int, seq: int, frame: int, n_corr: int, true_scale: float,
 
 def make_sequence(seed: int, n_frames: int, n_corr: int = 2500, seq: int = 0,
                   cam: Camera = Camera(), camera_h: float = 1.7, outlier_frac: float = 0.1,
-                  n_jitter: float = 0.05, still_every: int = 0, scales=None, **kw) -> CorrespondenceBatch:
+                  n_jitter: float = 0.05, still_every: int = 0, scales=None, frame_range=None, **kw) -> CorrespondenceBatch:
     """A CSR batch of ``n_frames`` frames; frame sizes jitter by +-n_jitter around n_corr.
+    ``frame_range=(f0, f1)`` builds only frames f0..f1-1 of that sequence (same content as in the full sequence).
 
     ``still_every`` > 0 marks every k-th frame as "not moving" (move_flag 0, no
     correspondences), the case of src/main_offline.py:64-68.
@@ -154,6 +155,9 @@ def make_sequence(seed: int, n_frames: int, n_corr: int = 2500, seq: int = 0,
     if still_every:
         move[still_every - 1::still_every] = 0
         sizes[move == 0] = 0
+    f0, f1 = (0, n_frames) if frame_range is None else (int(frame_range[0]), int(frame_range[1]))
+    sizes, move, scales, first = sizes[f0:f1], move[f0:f1], scales[f0:f1], f0
+    n_frames = f1 - f0
     offsets = np.zeros(n_frames + 1, dtype=np.int64)
     np.cumsum(sizes, out=offsets[1:])
     M = int(offsets[-1])
@@ -164,7 +168,7 @@ def make_sequence(seed: int, n_frames: int, n_corr: int = 2500, seq: int = 0,
     for f in range(n_frames):
         if not move[f]:
             continue
-        c, r, R, t = make_frame(seed, seq, f, int(sizes[f]), float(scales[f]), cam, camera_h,
+        c, r, R, t = make_frame(seed, seq, first + f, int(sizes[f]), float(scales[f]), cam, camera_h,
                                 outlier_frac, **kw)
         a, b = offsets[f], offsets[f + 1]
         cu[a:b] = c[:, 0]; cv_[a:b] = c[:, 1]; ru[a:b] = r[:, 0]; rv[a:b] = r[:, 1]

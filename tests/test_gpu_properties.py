@@ -136,3 +136,80 @@ def test_fleet_of_sequences_filter_vs_oracle(engine):
         ref = np.asarray(scales[1:])
         assert np.array_equal(got[a:e], ref), "sequence %d" % s
         assert np.array_equal(got10[a:e], P.filter10(ref)), "sequence %d filter_10" % s
+
+
+def test_host_pipeline_with_large_frames(engine):
+    """mvosr_recover_scales_host on frames beyond the shared-memory capacity: the chunks of the host pipeline run on two
+    streams but share one global-memory staging buffer, so their launches must be chained; result == the device-resident
+    path (fused kernel + filter)."""
+    import torch
+    from mvoscalerecovery_b200 import synth
+    b = synth.make_sequence(seed=31, n_frames=2 * 148 + 8, n_corr=6000, outlier_frac=0.1)
+    dev = engine.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    maxf = int(np.max(np.diff(b.offsets)))
+    r = engine.scale_frames_from_correspondences(t(b.offsets), t(b.cur_u), t(b.cur_v), t(b.ref_u), t(b.ref_v), t(b.poses), max_features=maxf, seed=3)
+    seq = torch.tensor([0, b.n_frames], dtype=torch.int32, device=dev)
+    want = engine.filter_sequences(seq, r["raw_scale"], r["status"], t(b.move_flags), r["n_features"])["scale"].cpu().numpy()
+    for _ in range(2):
+        out = engine.recover_scales_host(b.offsets, b.cur_u, b.cur_v, b.ref_u, b.ref_v, b.poses, b.move_flags, max_features=maxf, seed=3)
+        assert np.array_equal(out["scale"], want)
+        assert np.array_equal(out["raw_scale"], r["raw_scale"].cpu().numpy(), equal_nan=True)
+    assert np.isfinite(want).all() and (want > 0).mean() > 0.9
+
+
+@pytest.mark.parametrize("style", ["random", "integer_pixels", "coarse_grid", "clustered", "heavy_outliers"])
+def test_second_delaunay_reuse_equals_rebuild(engine, style):
+    """Delaunay #2 is assembled from the stars of Delaunay #1 that lost no neighbour plus seeded rebuilds of the others
+    (gstar.cuh).  It must equal, triangle for triangle, a from-scratch Delaunay of the surviving points
+    (mvosr_delaunay_frames, no reuse) -- also on degenerate inputs (integer pixels: co-circular and collinear points)."""
+    import torch
+    from mvoscalerecovery_b200.batch import stats_to_numpy
+    rng = np.random.default_rng({"random": 1, "integer_pixels": 2, "coarse_grid": 3, "clustered": 4, "heavy_outliers": 5}[style])
+    F, fx, cx, cy = 24, 718.856, 607.1928, 185.2157
+    f3s, f2s = [], []
+    for f in range(F):
+        n = int(rng.integers(300, 2600))
+        u = rng.uniform(0, 1240, n); v = rng.uniform(186, 375, n)
+        if style == "integer_pixels":
+            u, v = np.round(u), np.round(v)
+        elif style == "coarse_grid":
+            u, v = 8.0 * np.round(u / 8), 186.0 + 6.0 * np.round((v - 186) / 6)
+        elif style == "clustered":
+            c = rng.uniform([100, 200], [1100, 360], (6, 2))
+            k = rng.integers(0, 6, n)
+            u = np.clip(c[k, 0] + 25 * rng.standard_normal(n), 0, 1240); v = np.clip(c[k, 1] + 12 * rng.standard_normal(n), 186, 375)
+        z = 1.7 * fx / (v - cy + 1e-3) * (1 + 0.01 * rng.standard_normal(n))
+        bad = rng.random(n) < (0.6 if style == "heavy_outliers" else 0.2)
+        z[bad] *= rng.uniform(0.4, 0.95, bad.sum())
+        f2 = np.stack([u, v], 1).astype(np.float32)
+        f3 = np.stack([(u - cx) * z / fx, (v - cy) * z / fx, z], 1).astype(np.float32)
+        f3s.append(f3); f2s.append(f2)
+    from mvoscalerecovery_b200.batch import pack_frames
+    b = pack_frames(f3s, f2s, engine.device)
+    out = engine.scale_frames(b["offsets"], b["x"], b["y"], b["z"], b["u"], b["v"], b["max_features"], seed=11, debug=True)
+    torch.cuda.synchronize()
+    st = stats_to_numpy(out["stats"]); status = out["status"].cpu().numpy()
+    dbg = {k: v.cpu().numpy() for k, v in out["debug"].items()}
+    off = b["offsets"].cpu().numpy()
+    pts, sel = [], []
+    for f in range(F):
+        if status[f] & (4 | 16 | 32) or not (status[f] & 2):
+            continue                                    # no second Delaunay for this frame
+        roi = f2s[f][f2s[f][:, 1] > 185]
+        keep = dbg["keep"][off[f]: off[f] + roi.shape[0]].astype(bool)
+        assert keep.sum() == st["n_kept"][f]
+        pts.append(roi[keep]); sel.append(f)
+    assert len(sel) >= F // 2
+    o2 = np.zeros(len(pts) + 1, np.int32)
+    np.cumsum([p.shape[0] for p in pts], out=o2[1:])
+    allp = np.concatenate(pts, 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(engine.device)
+    dt = engine.delaunay_frames(t(o2), t(allp[:, 0]), t(allp[:, 1]), int(np.max(np.diff(o2))))
+    torch.cuda.synchronize()
+    tri = dt["tri"].cpu().numpy(); ntri = dt["n_tri"].cpu().numpy()
+    for i, f in enumerate(sel):
+        got = dbg["tri2"][2 * off[f]: 2 * off[f] + st["n_tri"][f]]
+        want = tri[2 * o2[i]: 2 * o2[i] + ntri[i]]
+        assert st["n_tri"][f] == ntri[i], (style, f, st["n_tri"][f], ntri[i])
+        assert np.array_equal(got, want), (style, f)
