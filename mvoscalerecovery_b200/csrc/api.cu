@@ -133,21 +133,32 @@ __global__ void __launch_bounds__(256) filter_kernel(int n_seq, const int32_t *s
             }
             __syncthreads();
             if (tid == 0) {
+                // the slew limiter is a strict recurrence: inputs are fetched eight frames ahead so that only its own
+                // arithmetic is on the dependent path
                 double scale = s_scale; int np = FHIST;
-                for (int i = 0; i < n; ++i) {
-                    const int fl = flags[i];
-                    if (fl & 2) kind[i] = 0;
-                    else if (fl & 4) kind[i] = 1;
-                    else {
-                        if (fl & 1) {
-                            const double r = R[i];
-                            if (r - scale > cfg.slew_limit) scale += cfg.slew_limit;
-                            else if (r - scale < -cfg.slew_limit) scale -= cfg.slew_limit;
-                            else scale = r;
+                for (int i0 = 0; i0 < n; i0 += 8) {
+                    double r8[8]; int f8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { const int i = min(i0 + k, n - 1); r8[k] = R[i]; f8[k] = flags[i]; }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int i = i0 + k;
+                        if (i >= n) break;
+                        const int fl = f8[k];
+                        int kd = 2;
+                        if (fl & 2) kd = 0;
+                        else if (fl & 4) kd = 1;
+                        else {
+                            if (fl & 1) {
+                                const double r = r8[k];
+                                if (r - scale > cfg.slew_limit) scale += cfg.slew_limit;
+                                else if (r - scale < -cfg.slew_limit) scale -= cfg.slew_limit;
+                                else scale = r;
+                            }
+                            P[np++] = scale;
                         }
-                        P[np++] = scale; kind[i] = 2;
+                        kind[i] = (uint8_t)kd; pidx[i] = np;
                     }
-                    pidx[i] = np;
                 }
                 s_scale = scale; s_npush = np;
             }
@@ -162,10 +173,17 @@ __global__ void __launch_bounds__(256) filter_kernel(int n_seq, const int32_t *s
             __syncthreads();
             if (tid == 0) {
                 double last = s_last;
-                for (int i = 0; i < n; ++i) {
-                    const int k = kind[i];
-                    const double o = k == 0 ? 0.0 : (k == 1 ? last : R[i]);
-                    O[FHIST + i] = o; last = o;
+                for (int i0 = 0; i0 < n; i0 += 8) {
+                    double r8[8]; int k8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { const int i = min(i0 + k, n - 1); r8[k] = R[i]; k8[k] = kind[i]; }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int i = i0 + k;
+                        if (i >= n) break;
+                        const double o = k8[k] == 0 ? 0.0 : (k8[k] == 1 ? last : r8[k]);
+                        O[FHIST + i] = o; last = o;
+                    }
                 }
                 s_last = last;
             }

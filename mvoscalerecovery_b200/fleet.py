@@ -53,13 +53,12 @@ def gather_results(raw_scale, status, n_features, shards: List[Tuple[int, int]],
     """All-gather the per-frame raw results of every rank's shard; returns full-length
     (raw_scale f64, status u8, n_features i32) in global frame order on every rank."""
     world = len(shards)
+    if world == 1:                                            # nothing to exchange: the shard is the whole fleet
+        return raw_scale, status, n_features
     max_len = max(e - s for s, e in shards)
     mine = pack_results(raw_scale, status, n_features, max_len)
-    if world == 1:
-        full = mine.unsqueeze(0)
-    else:
-        full = torch.empty(world, max_len, 3, dtype=torch.float64, device=mine.device)
-        dist.all_gather_into_tensor(full.view(world * max_len, 3), mine, group=group)
+    full = torch.empty(world, max_len, 3, dtype=torch.float64, device=mine.device)
+    dist.all_gather_into_tensor(full.view(world * max_len, 3), mine, group=group)
     parts = [full[r, : e - s] for r, (s, e) in enumerate(shards)]
     cat = torch.cat(parts, 0) if parts else mine[:0]
     return cat[:, 0].contiguous(), cat[:, 1].to(torch.uint8).contiguous(), cat[:, 2].to(torch.int32).contiguous()
