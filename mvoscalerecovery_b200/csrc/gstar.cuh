@@ -1076,7 +1076,11 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
             const float vx = 0.5f * (cx - wt * cy), vy = 0.5f * (cy + wt * cx);
             const float r = sqrt_approx(fmaf(vx, vx, vy * vy));
             const float rs = r + 2.f * (we * (fabsf(cx) + fabsf(cy)) * 0.51f + 1.0e-3f + 1.0e-4f * r);
-            if (walking && !w_cap_inside<false>(cx, cy, 1.f, vx, vy, rs, BX0, BX1, BY0, BY1, WBox())) { PR(6); ok = false; walking = false; }
+            // (quick accept: the whole padded disk inside the block; the cap test proper only when some star needs it)
+            const bool disk_in = vx - rs >= BX0 && vx + rs <= BX1 && vy - rs >= BY0 && vy + rs <= BY1;
+            if (__any_sync(FULL, walking && !disk_in)) {
+                if (walking && !disk_in && !w_cap_inside<false>(cx, cy, 1.f, vx, vy, rs, BX0, BX1, BY0, BY1, WBox())) { PR(6); ok = false; walking = false; }
+            }
             if (!EMIT) {
                 // vote pass: never seeded -- the plain walk from q0 back to q0
                 if (walking) {
