@@ -832,9 +832,84 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
         const float slack = 1.0e-3f + 1.0e-4f * ps.h;
         const float BX0 = bx0 > 0 ? ps.xmin + bx0 * ps.h - ppx + slack : -CUDART_INF_F, BX1 = bx1 < ps.gx - 1 ? ps.xmin + (bx1 + 1) * ps.h - ppx - slack : CUDART_INF_F;
         const float BY0 = by0 > 0 ? ps.ymin + by0 * ps.h - ppy + slack : -CUDART_INF_F, BY1 = by1 < ps.gy - 1 ? ps.ymin + (by1 + 1) * ps.h - ppy - slack : CUDART_INF_F;
+        // ---- one step of the walk: the neighbour that follows cur (relative (cx,cy), position cpos) in direction sigma.
+        // Block candidates first, then streaming if the winner's cap leaves the block (or nothing lies on the left).
+        // false: a decision could not be certified.  b.have == false on return: hull edge.
+        auto step = [&](float cx, float cy, float sigma, int cpos, WBest &b) -> bool {
+            const WEval ea = w_eval(vA && posA != cpos, ax, ay, al, cx, cy, sigma);
+            WEval eb; eb.t = 0.f; eb.eps = 0.f; eb.cand = false; eb.susp = false;
+            if (M > 32) eb = w_eval(vB && posB != cpos, bx, by, bl, cx, cy, sigma);      // warp-uniform
+            if (__any_sync(FULL, ea.susp || eb.susp)) return false;
+            const unsigned kA = ea.cand ? w_key(ea.t) : 0xFFFFFFFFu, kB = eb.cand ? w_key(eb.t) : 0xFFFFFFFFu;
+            const unsigned kmin = __reduce_min_sync(FULL, min(kA, kB));
+            b.have = kmin != 0xFFFFFFFFu; b.t = b.eps = b.x = b.y = 0.f; b.pos = -1; b.vx = b.vy = b.rs = 0.f;
+            bool inside = false;
+            if (b.have) {
+                const int wl = __ffs(__ballot_sync(FULL, min(kA, kB) == kmin)) - 1;
+                const bool selB = kA != kmin;                     // meaningful on lane wl
+                const bool wB = __shfl_sync(FULL, (int)selB, wl) != 0;
+                b.t = __shfl_sync(FULL, selB ? eb.t : ea.t, wl); b.eps = __shfl_sync(FULL, selB ? eb.eps : ea.eps, wl);
+                b.x = __shfl_sync(FULL, selB ? bx : ax, wl); b.y = __shfl_sync(FULL, selB ? by : ay, wl); b.pos = __shfl_sync(FULL, selB ? posB : posA, wl);
+                const float ub = b.t + b.eps;
+                const bool clash = (ea.cand && !(lane == wl && !wB) && !(ea.t - ea.eps > ub)) || (eb.cand && !(lane == wl && wB) && !(eb.t - eb.eps > ub));
+                if (__any_sync(FULL, clash)) return false;
+                w_circle(b, cx, cy, sigma);
+                if (!(fabsf(b.t) < 1.0e18f)) return false;
+                inside = w_cap_inside<false>(cx, cy, sigma, b.vx, b.vy, b.rs, BX0, BX1, BY0, BY1, WBox());
+            }
+            WCNT(w_steps);
+            if (!inside) {
+                WCNT(w_out); if (!b.have) { WCNT(w_nocand); } if (!streamed) { streamed = true; WCNT(w_sstars); }
+                WBest bs = b;                                     // (a copy: keeps b itself in registers)
+                if (!w_stream(bs, ps, p, ppx, ppy, pcy, bx0, bx1, by0, by1, cx, cy, sigma, cpos)) return false;
+                b = bs;
+            }
+            return true;
+        };
+        // ---- the star: lane i keeps the i-th counter-clockwise neighbour (sidC) and the (i+1)-th clockwise one (sidW)
+        int sidC = INF16, sidW = INF16, nC = 1, nW = 0;
+        bool closed = false;
+        // ---- seeded rebuild (Delaunay #2): the surviving neighbours of the star in Delaunay #1 are still neighbours; only
+        // the gaps left by dropped neighbours are walked (see stars_pair).  A gap that turns out to hold a hull edge -- the
+        // star opened up -- or a winner already in the ring falls back to the plain walk below.
+        if (EMIT && fv.oldof && ok) {
+            const uint32_t info = fv.rinfo[fv.oldof[ps.orig[p]]];
+            const int d0 = (int)(info & 0xFFu);
+            const int e = lane < d0 ? (int)fv.rpool[(info >> 8) + lane] : (int)INF16;
+            const unsigned am = __ballot_sync(FULL, lane < d0 && e < RING_DROPPED), im = __ballot_sync(FULL, lane < d0 && e == INF16);
+            const int m = __popc(am);
+            if (m >= 1 && im == 0u && d0 < 31) {
+                const int src = lane < m ? (int)__fns(am, 0, lane + 1) : 0;
+                const int se = __shfl_sync(FULL, e, src);
+                int nxt = src + 1; if (nxt >= d0) nxt = 0;
+                unsigned gapm = __ballot_sync(FULL, lane < m && !((am >> nxt) & 1u));
+                int sid = lane < m ? se : (int)INF16, n = m;
+                int j = max(__ffs(gapm) - 1, 0);
+                int cpos = __shfl_sync(FULL, sid, j), tpos = __shfl_sync(FULL, sid, j + 1 < n ? j + 1 : 0);
+                float cx = ps.x[cpos] - ppx, cy = ps.y[cpos] - ppy;
+                bool fallback = false;
+                while (gapm) {
+                    WBest b;
+                    if (!step(cx, cy, 1.f, cpos, b)) { ok = false; break; }
+                    if (!b.have) { fallback = true; break; }
+                    if (b.pos == tpos) {
+                        gapm &= gapm - 1u;
+                        if (gapm) { j = __ffs(gapm) - 1; cpos = __shfl_sync(FULL, sid, j); cx = ps.x[cpos] - ppx; cy = ps.y[cpos] - ppy; }
+                    } else {
+                        if (__any_sync(FULL, lane < n && sid == b.pos) || n >= 30) { fallback = true; break; }
+                        const int up = __shfl_up_sync(FULL, sid, 1);
+                        if (lane == j + 1) sid = b.pos; else if (lane > j + 1) sid = up;
+                        ++n; gapm = ((gapm >> (j + 1)) << (j + 2)) | (1u << (j + 1)); ++j;
+                        cpos = b.pos; cx = b.x; cy = b.y;
+                    }
+                    tpos = __shfl_sync(FULL, sid, j + 1 < n ? j + 1 : 0);
+                }
+                if (ok && !fallback) { closed = true; sidC = sid; nC = n; }
+            }
+        }
         // ---- q0 = the nearest point: certified by the distance to the block's boundary, unique up to rounding
         int q0 = -1; float q0x = 0.f, q0y = 0.f;
-        if (ok) {
+        if (ok && !closed) {
             const unsigned kA = vA ? __float_as_uint(al) : 0xFFFFFFFFu, kB = vB ? __float_as_uint(bl) : 0xFFFFFFFFu;
             const unsigned kmin = __reduce_min_sync(FULL, min(kA, kB));
             const float lmin = __uint_as_float(kmin);
@@ -849,41 +924,12 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
                 q0 = __shfl_sync(FULL, selB ? posB : posA, wl); q0x = __shfl_sync(FULL, selB ? bx : ax, wl); q0y = __shfl_sync(FULL, selB ? by : ay, wl);
             }
         }
-        // ---- the walk: lane i keeps the i-th counter-clockwise neighbour (sidC; 0 = q0) and the (i+1)-th clockwise one (sidW)
-        int sidC = INF16, sidW = INF16, nC = 1, nW = 0;
-        bool closed = false;
-        if (lane == 0) sidC = q0;
+        // ---- the plain walk: counter-clockwise from q0 until it closes or meets a hull edge, then clockwise from q0
+        if (!closed) { sidC = lane == 0 ? q0 : (int)INF16; nC = 1; }
         float sigma = 1.f, cx = q0x, cy = q0y; int cpos = q0;
-        while (ok) {
-            // block candidates
-            const WEval ea = w_eval(vA && posA != cpos, ax, ay, al, cx, cy, sigma);
-            WEval eb; eb.t = 0.f; eb.eps = 0.f; eb.cand = false; eb.susp = false;
-            if (M > 32) eb = w_eval(vB && posB != cpos, bx, by, bl, cx, cy, sigma);      // warp-uniform
-            if (__any_sync(FULL, ea.susp || eb.susp)) { ok = false; break; }
-            const unsigned kA = ea.cand ? w_key(ea.t) : 0xFFFFFFFFu, kB = eb.cand ? w_key(eb.t) : 0xFFFFFFFFu;
-            const unsigned kmin = __reduce_min_sync(FULL, min(kA, kB));
-            WBest b; b.have = kmin != 0xFFFFFFFFu; b.t = b.eps = b.x = b.y = 0.f; b.pos = -1; b.vx = b.vy = b.rs = 0.f;
-            bool inside = false;
-            if (b.have) {
-                const int wl = __ffs(__ballot_sync(FULL, min(kA, kB) == kmin)) - 1;
-                const bool selB = kA != kmin;                     // meaningful on lane wl
-                const bool wB = __shfl_sync(FULL, (int)selB, wl) != 0;
-                b.t = __shfl_sync(FULL, selB ? eb.t : ea.t, wl); b.eps = __shfl_sync(FULL, selB ? eb.eps : ea.eps, wl);
-                b.x = __shfl_sync(FULL, selB ? bx : ax, wl); b.y = __shfl_sync(FULL, selB ? by : ay, wl); b.pos = __shfl_sync(FULL, selB ? posB : posA, wl);
-                const float ub = b.t + b.eps;
-                const bool clash = (ea.cand && !(lane == wl && !wB) && !(ea.t - ea.eps > ub)) || (eb.cand && !(lane == wl && wB) && !(eb.t - eb.eps > ub));
-                if (__any_sync(FULL, clash)) { ok = false; break; }
-                w_circle(b, cx, cy, sigma);
-                if (!(fabsf(b.t) < 1.0e18f)) { ok = false; break; }
-                inside = w_cap_inside<false>(cx, cy, sigma, b.vx, b.vy, b.rs, BX0, BX1, BY0, BY1, WBox());
-            }
-            WCNT(w_steps);
-            if (!inside) {
-                WCNT(w_out); if (!b.have) { WCNT(w_nocand); } if (!streamed) { streamed = true; WCNT(w_sstars); }
-                WBest bs = b;                                     // (a copy: keeps b itself in registers)
-                if (!w_stream(bs, ps, p, ppx, ppy, pcy, bx0, bx1, by0, by1, cx, cy, sigma, cpos)) { ok = false; break; }
-                b = bs;
-            }
+        while (ok && !closed) {
+            WBest b;
+            if (!step(cx, cy, sigma, cpos, b)) { ok = false; break; }
             if (!b.have) {
                 // no point on the walk's left of p->cur anywhere: hull edge
                 WCNT(w_hull);
