@@ -167,6 +167,34 @@ def main():
         g = e2.triangle2graph(tri[:50]); rg = e2.triangle2region_graph(tri[:50])
         out["sc_graph_flat"] = np.concatenate([np.asarray(x, np.int64) for x in g if len(x)]); out["sc_graph_len"] = np.array([len(x) for x in g])
         out["sc_rgraph_flat"] = np.concatenate([np.asarray(x, np.int64) for x in rg if len(x)]); out["sc_rgraph_len"] = np.array([len(x) for x in rg])
+    # ---- the evaluation scripts (script/evaluate_vo.py, script/evaluate_scale.py) on a synthetic trajectory pair
+    import importlib.util
+    mods = {}
+    for name in ("evaluate_vo", "evaluate_scale"):
+        spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(os.path.dirname(H.REF_SRC), "script", name + ".py"))
+        mods[name] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[name])
+    n = 1500
+    def traj(noise):
+        cur = np.eye(4); out_p = [cur[:3].reshape(-1).copy()]
+        r = np.random.default_rng(99)
+        for i in range(n):
+            yaw = 0.004 * np.sin(i / 60.0) + noise * 0.0004 * r.standard_normal()
+            m = np.eye(4)
+            m[:3, :3] = [[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]]
+            m[:3, 3] = [0.0, 0.0, 0.85 * (1 + noise * 0.03 * r.standard_normal())]
+            cur = cur @ m
+            out_p.append(cur[:3].reshape(-1).copy())
+        return np.array(out_p)
+    gt, res = traj(0.0), traj(1.0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        errs = np.array(mods["evaluate_vo"].calculate_sequence_error(gt, res))
+        rot, tra, _ = mods["evaluate_vo"].calculate_ave_errors(errs)
+        sgt = 0.8 + 0.3 * np.sin(np.arange(1200) / 40.0); sre = sgt[:1100] + 0.08 * rng.standard_normal(1100)
+        out.update(ev_gt=gt, ev_res=res, ev_errors=errs, ev_rot=np.asarray(rot), ev_tra=np.asarray(tra),
+                   ev_dist=np.asarray(mods["evaluate_vo"].trajectory_distances(gt)),
+                   es_gt=sgt, es_re=sre, es_patch=mods["evaluate_scale"].patch(sgt[:1100] - sre, 50, 10),
+                   es_filter=mods["evaluate_scale"].filter(sre, 10))
     path = os.path.join(ROOT, "tests", "golden", "scripts.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: np.asarray(v).shape for k, v in out.items() if not k.startswith("frame") and not k.startswith("sc_f3")})
