@@ -193,6 +193,10 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: whatever libraries print there (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
@@ -344,7 +348,8 @@ def run_gpu_arm(args):
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "mvosr_recover_scales_host (pinned host buffers, copies inside)"},
                 "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -13,9 +13,11 @@ marks = {
  'w_eval/key/circle': (find('struct WEval'), find('// One batch of candidates (one per lane)')),
  'w_batch': (find('// One batch of candidates (one per lane)'), find('// Stream the grid cells that the left cap')),
  'w_stream': (find('// Stream the grid cells that the left cap'), find('// The stars of list[0..n_list) (sorted positions), one per warp')),
- 'wrap:fetch+load': (find('// The stars of list[0..n_list) (sorted positions), one per warp'), find('// ---- q0 = the nearest point')),
- 'wrap:q0': (find('// ---- q0 = the nearest point'), find('// ---- the walk: lane i keeps')),
- 'wrap:walk': (find('// ---- the walk: lane i keeps'), find('// ---- counter-clockwise slot order')),
+ 'wrap:fetch+load': (find('// The stars of list[0..n_list) (sorted positions), one per warp'), find('// ---- one step of the walk')),
+ 'wrap:step': (find('// ---- one step of the walk'), find('// ---- the star: lane i keeps')),
+ 'wrap:seeded walk': (find('// ---- the star: lane i keeps'), find('// ---- q0 = the nearest point')),
+ 'wrap:q0': (find('// ---- q0 = the nearest point'), find('// ---- the plain walk')),
+ 'wrap:walk': (find('// ---- the plain walk'), find('// ---- counter-clockwise slot order')),
  'wrap:finish': (find('// ---- counter-clockwise slot order'), find('// pair path: two stars per warp in lock step')),
  'pair': (find('// pair path: two stars per warp in lock step'), find('// All stars of the staged point set.')),
  'run_stars': (find('// All stars of the staged point set.'), 10**6),
