@@ -1025,17 +1025,22 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
             M += rn[r];
         }
         if (M > 64) { PR(0); ok = false; }
+        // slots 2 and 3 are only populated (and later evaluated) when one of the two blocks holds more than 32 / 48 points
+        const bool m32 = __any_sync(FULL, ok && M > 32), m48 = __any_sync(FULL, ok && M > 48);
+        // element e of the concatenated runs sits at position e + (rb[r] - c[r-1]) of the row r with c[r-1] <= e < c[r] (c = running counts)
+        static_assert(WRAP_BLOCK == 2, "the decode below is written for five block rows");
+        const int c0 = rn[0], c1 = c0 + rn[1], c2 = c1 + rn[2], c3 = c2 + rn[3];
+        const int o0 = rb[0], o1 = rb[1] - c0, o2 = rb[2] - c1, o3 = rb[3] - c2, o4 = rb[4] - c3;
         float sx[4], sy[4]; int sp[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            int e = gl + GL * k, pos = -1;
-#pragma unroll
-            for (int r = 0; r < 2 * WRAP_BLOCK + 1; ++r) {
-                if (pos < 0) { if (e < rn[r]) pos = rb[r] + e; else e -= rn[r]; }
+            sp[k] = INF16; sx[k] = 0.f; sy[k] = 0.f;
+            if (k < 2 || (k == 2 ? m32 : m48)) {                   // warp-uniform
+                const int e = gl + GL * k;
+                const int pos = e + (e < c0 ? o0 : (e < c1 ? o1 : (e < c2 ? o2 : (e < c3 ? o3 : o4))));
+                const bool v = e < M && pos != p && ps.orig[pos] != INF16;
+                if (v) { sp[k] = pos; sx[k] = ps.x[pos] - ppx; sy[k] = ps.y[pos] - ppy; }
             }
-            const bool v = pos >= 0 && pos != p && ps.orig[pos] != INF16;
-            sp[k] = v ? pos : (int)INF16;
-            sx[k] = v ? ps.x[pos] - ppx : 0.f; sy[k] = v ? ps.y[pos] - ppy : 0.f;
         }
         const float BX0 = bx0 > 0 ? ps.xmin + bx0 * ps.h - ppx + slack : -CUDART_INF_F, BX1 = bx1 < ps.gx - 1 ? ps.xmin + (bx1 + 1) * ps.h - ppx - slack : CUDART_INF_F;
         const float BY0 = by0 > 0 ? ps.ymin + by0 * ps.h - ppy + slack : -CUDART_INF_F, BY1 = by1 < ps.gy - 1 ? ps.ymin + (by1 + 1) * ps.h - ppy - slack : CUDART_INF_F;
@@ -1092,20 +1097,20 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
         int cpos = GSHFL(sid, j), tpos = GSHFL(sid, j + 1 < nC ? j + 1 : 0);
         if (seeded) { cx = ps.x[cpos] - ppx; cy = ps.y[cpos] - ppy; }
         bool closed = ok && gapm == 0u, walking = ok && gapm != 0u;
-        const bool m32 = __any_sync(FULL, ok && M > 32), m48 = __any_sync(FULL, ok && M > 48);
         while (__any_sync(FULL, walking)) {
-            unsigned kbest = 0xFFFFFFFFu; float tb = 0.f, eb = 0.f, xb = 0.f, yb = 0.f; int pb = INF16;
+            float tb = CUDART_INF_F, eb = 0.f, xb = 0.f, yb = 0.f; int pb = INF16;       // tb = +inf: no candidate yet
             float lb_best = CUDART_INF_F, lb_rest = CUDART_INF_F; bool susp = false;
 #define PAIR_SLOT(k) { \
                 const WEval e = w_eval(sp[k] != INF16 && sp[k] != cpos, sx[k], sy[k], fmaf(sx[k], sx[k], sy[k] * sy[k]), cx, cy, 1.f); \
                 susp |= e.susp; \
-                const unsigned key = e.cand ? w_key(e.t) : 0xFFFFFFFFu; const float lb = e.cand ? e.t - e.eps : CUDART_INF_F; \
-                if (key < kbest) { lb_rest = fminf(lb_rest, lb_best); kbest = key; tb = e.t; eb = e.eps; xb = sx[k]; yb = sy[k]; pb = sp[k]; lb_best = lb; } \
+                const float tk = e.cand ? e.t : CUDART_INF_F, lb = e.cand ? e.t - e.eps : CUDART_INF_F; \
+                if (tk < tb) { lb_rest = fminf(lb_rest, lb_best); tb = tk; eb = e.eps; xb = sx[k]; yb = sy[k]; pb = sp[k]; lb_best = lb; } \
                 else lb_rest = fminf(lb_rest, lb); }
             PAIR_SLOT(0) PAIR_SLOT(1)
             if (m32) PAIR_SLOT(2)
             if (m48) PAIR_SLOT(3)
 #undef PAIR_SLOT
+            const unsigned kbest = tb < CUDART_INF_F ? w_key(tb) : 0xFFFFFFFFu;           // order-preserving key of the lane's best
             const unsigned gsusp = GBALLOT(susp && walking);               // (ballots are executed by all 32 lanes)
             if (walking && gsusp) { PR(3); ok = false; walking = false; }
             const unsigned kmin = gmin_u32(walking ? kbest : 0xFFFFFFFFu, g);
