@@ -52,29 +52,69 @@ def make_workload(n_frames, n_corr, seq):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Sampled through NVML every 5 ms
+    from a thread (the region is a few hundred ms: `nvidia-smi -lms` would deliver two or three lines at best); nvidia-smi
+    is the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index, uuid=None):
+        self.gpu, self.uuid = gpu_index, uuid
+        self.proc, self.nvml, self.handle = None, None, None
+        self.lines, self.sm, self.mask = [], [], 0
+        self.stop_flag = threading.Event()
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)) if not str(self.uuid).startswith("GPU-") else str(self.uuid))
+                except Exception:
+                    h = None
+            self.handle = h or pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=1)
+            reasons = sorted(name for bit, name in self.REASONS if self.mask & bit)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                    "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -95,7 +135,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
@@ -270,7 +310,11 @@ def run_gpu_arm(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
+    try:
+        uuid = torch.cuda.get_device_properties(local_rank).uuid
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
     sampler.start()
     launches0 = eng.launch_count
     e0, e1 = ev(), ev()
