@@ -212,6 +212,18 @@ int  mvosr_ransac_planes(mvosr_handle *h, int32_t n_sets, const int32_t *offsets
 int  mvosr_integrate_paths(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets, const double *motions,
                            const double *scales, double *poses_out, void *stream);
 
+/* Pose from the essential matrix -- the selection step of cv2.recoverPose(E, px_cur, px_ref, K, distanceThresh)
+ * (src/thirdparty/MonocularVO/visual_odometry.py:129-133; part of SURVEY N1): E is decomposed into its two rotations and
+ * +-t, every correspondence is triangulated under the four candidates, and the candidate with the most points in front of
+ * both cameras and nearer than triangulation_max_depth wins.  essential: [F][9] row-major, x_ref^T E x_cur = 0 in
+ * normalised coordinates (what cv2.findEssentialMat(px_cur, px_ref, K) returns).  e_mask: optional, restricts the count
+ * (the reference passes none).  Outputs: poses_out [F][12] = [R|t] with x_ref = R x_cur + t, |t| = 1 -- the input of
+ * mvosr_triangulate_frames / mvosr_scale_frames_from_correspondences; n_good [F][4] (optional): counts of (R1,t), (R2,t),
+ * (R1,-t), (R2,-t). */
+int  mvosr_recover_pose_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                               const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                               const uint8_t *e_mask, const double *essential, double *poses_out, int32_t *n_good, void *stream);
+
 /* Dense depth from the mesh -- Reconstruct.depth_generate (src/reconstruct.py:91-107): tri.find_simplex of every integer
  * pixel (u, v) of a width x height image + the depth of that triangle's plane along the pixel's ray,
  * depth = h / (n . ((u-cx)/fx, (v-cy)/fy, 1)).  tri: [T][3] int32 into uv ([N][2] float64 pixel coordinates); datas:

@@ -87,6 +87,21 @@ class ScaleRecovery:
         out["n_out"] = n_out
         return out
 
+    def recover_pose_frames(self, offsets, cur_u, cur_v, ref_u, ref_v, essential, e_mask=None):
+        """The pose selection of cv2.recoverPose (visual_odometry.py:129-133): essential (F,9) float64 -> dict(poses (F,12), n_good (F,4))."""
+        dev = self.device
+        F = offsets.numel() - 1
+        _chk(offsets, torch.int32, "offsets", dev)
+        for n, t in (("cur_u", cur_u), ("cur_v", cur_v), ("ref_u", ref_u), ("ref_v", ref_v)):
+            _chk(t, torch.float32, n, dev)
+        _chk(essential, torch.float64, "essential", dev)
+        poses = torch.empty((F, 12), dtype=torch.float64, device=dev)
+        n_good = torch.zeros((F, 4), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_recover_pose_frames(self._h, F, _ptr(offsets), _ptr(cur_u), _ptr(cur_v), _ptr(ref_u), _ptr(ref_v), _ptr(e_mask),
+                                                       _ptr(essential), _ptr(poses), _ptr(n_good), self._stream()))
+        return dict(poses=poses, n_good=n_good)
+
     # ------------------------------------------------------------------ stages 2-5
     def scale_frames(self, offsets, x, y, z, u, v, max_features: int, counts=None, frame_index0: int = 0, seq_id: int = 0,
                      seed: int = 0, stats: bool = True, debug: bool = False):

@@ -608,4 +608,17 @@ int mvosr_depth_from_mesh(mvosr_handle *h, int32_t width, int32_t height, double
     return MVOSR_OK;
 }
 
+int mvosr_recover_pose_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                              const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                              const uint8_t *e_mask, const double *essential, double *poses_out, int32_t *n_good, void *stream) {
+    if (!h || n_frames < 0 || !offsets || !cur_u || !cur_v || !ref_u || !ref_v || !essential || !poses_out) return MVOSR_E_INVALID;
+    if (n_frames == 0) return MVOSR_OK;
+    CK(cudaSetDevice(h->device));
+    const int grid = min(n_frames, 8 * h->num_sms);
+    recover_pose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_frames, offsets, cur_u, cur_v, ref_u, ref_v, e_mask, essential, h->cfg, poses_out, n_good);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return MVOSR_OK;
+}
+
 }  // extern "C"

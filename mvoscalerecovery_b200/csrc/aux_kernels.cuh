@@ -8,13 +8,17 @@
 //                            src/thirdparty/Ransac/ransac.py:3-23) on explicit point lists
 //   integrate_paths_kernel   get_path / motion2pose (src/main_offline.py:95-119)
 //   triangle_votes_kernel    find_outliers / check_triangle (src/rescale.py:45-72, src/scale_calculator.py:105-119,151-167)
+//   recover_pose_kernel      the pose selection of cv2.recoverPose(E, px_cur, px_ref, K, distanceThresh=100)
+//                            (src/thirdparty/MonocularVO/visual_odometry.py:129-133): decomposeEssentialMat + cheirality count
 //   raster_mesh_kernel + mesh_depth_kernel   Reconstruct.depth_generate (src/reconstruct.py:91-107): tri.find_simplex of every
 //                            pixel + the depth of the triangle's plane along the pixel's ray
 // All of them are HBM-bound gathers / streams; the arithmetic is float64 because the callers hand float64 arrays.
 #pragma once
 #include <stdint.h>
 #include <math_constants.h>
+#include "../../include/mvosr.h"
 #include "philox.cuh"
+#include "triangulate.cuh"
 
 namespace mvosr {
 
@@ -235,6 +239,105 @@ __global__ void __launch_bounds__(256) mesh_depth_kernel(int width, int height, 
             d = datas[4 * t + 3] / (datas[4 * t] * xn + datas[4 * t + 1] * yn + datas[4 * t + 2]);
         }
         depth[i] = d;
+    }
+}
+
+// ---- pose from the essential matrix -------------------------------------------------------------------
+// Eigenvectors of the symmetric 3x3 matrix a (cyclic Jacobi, float64), columns of v, eigenvalues in w (unsorted).
+__device__ inline void jacobi_eig3(double a[3][3], double v[3][3], double w[3]) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) v[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (off < 1.0e-300) break;
+        for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+            if (a[p][q] == 0.0) continue;
+            const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+            for (int k = 0; k < 3; ++k) { const double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - sn * akq; a[k][q] = sn * akp + c * akq; }
+            for (int k = 0; k < 3; ++k) { const double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - sn * aqk; a[q][k] = sn * apk + c * aqk; }
+            for (int k = 0; k < 3; ++k) { const double vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - sn * vkq; v[k][q] = sn * vkp + c * vkq; }
+        }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = a[i][i];
+}
+
+// decomposeEssentialMat: the two rotations U W V^T, U W^T V^T and the translation direction u3 (|t| = 1) of E = U diag(s,s,0) V^T
+// with det U = det V = +1.  V from the eigenvectors of E^T E (the two rotations do not depend on the choice inside the
+// eigenspace of the double singular value), U = E V / s on the first two columns, u3 = u1 x u2.
+__device__ inline void decompose_essential(const double *E, double R1[9], double R2[9], double t[3]) {
+    double a[3][3], v[3][3], w[3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) a[i][j] = E[0 + i] * E[0 + j] + E[3 + i] * E[3 + j] + E[6 + i] * E[6 + j];
+    jacobi_eig3(a, v, w);
+    int o0 = 0, o1 = 1, o2 = 2;                                   // eigenvalues descending: o2 = the null direction
+    if (w[o0] < w[o1]) { int x = o0; o0 = o1; o1 = x; }
+    if (w[o1] < w[o2]) { int x = o1; o1 = o2; o2 = x; }
+    if (w[o0] < w[o1]) { int x = o0; o0 = o1; o1 = x; }
+    double v1[3] = { v[0][o0], v[1][o0], v[2][o0] }, v2[3] = { v[0][o1], v[1][o1], v[2][o1] }, v3[3];
+    v3[0] = v1[1] * v2[2] - v1[2] * v2[1]; v3[1] = v1[2] * v2[0] - v1[0] * v2[2]; v3[2] = v1[0] * v2[1] - v1[1] * v2[0];   // det V = +1
+    double u1[3], u2[3], u3[3];
+    for (int i = 0; i < 3; ++i) { u1[i] = E[3 * i] * v1[0] + E[3 * i + 1] * v1[1] + E[3 * i + 2] * v1[2]; u2[i] = E[3 * i] * v2[0] + E[3 * i + 1] * v2[1] + E[3 * i + 2] * v2[2]; }
+    double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    for (int i = 0; i < 3; ++i) u1[i] /= n1;
+    const double d12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+    for (int i = 0; i < 3; ++i) u2[i] -= d12 * u1[i];
+    double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    for (int i = 0; i < 3; ++i) u2[i] /= n2;
+    u3[0] = u1[1] * u2[2] - u1[2] * u2[1]; u3[1] = u1[2] * u2[0] - u1[0] * u2[2]; u3[2] = u1[0] * u2[1] - u1[1] * u2[0];   // det U = +1
+    // U W V^T = -u2 v1^T + u1 v2^T + u3 v3^T ;  U W^T V^T = u2 v1^T - u1 v2^T + u3 v3^T   (W = [0 1 0; -1 0 0; 0 0 1])
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        const double x = u1[i] * v2[j] - u2[i] * v1[j], y = u3[i] * v3[j];
+        R1[3 * i + j] = x + y; R2[3 * i + j] = -x + y;
+    }
+    t[0] = u3[0]; t[1] = u3[1]; t[2] = u3[2];
+}
+
+// One CTA per frame: thread 0 decomposes E, all threads triangulate every correspondence under the four candidates
+// (R1,t), (R2,t), (R1,-t), (R2,-t) and count the points that pass recoverPose's mask (in front of both cameras, nearer than
+// dist); the candidate with the most points wins (first one on ties, OpenCV's order).
+__global__ void __launch_bounds__(256) recover_pose_kernel(int n_frames, const int32_t *__restrict__ offsets,
+        const float *__restrict__ cur_u, const float *__restrict__ cur_v, const float *__restrict__ ref_u, const float *__restrict__ ref_v,
+        const uint8_t *__restrict__ e_mask, const double *__restrict__ essential, mvosr_config cfg, double *poses, int32_t *n_good) {
+    __shared__ Pose cand[4];
+    __shared__ int good[4];
+    const int tid = threadIdx.x;
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        if (tid == 0) {
+            double R1[9], R2[9], t[3];
+            decompose_essential(essential + 9 * (size_t)f, R1, R2, t);
+            for (int k = 0; k < 4; ++k) {
+                for (int i = 0; i < 9; ++i) cand[k].R[i] = (k & 1) ? R2[i] : R1[i];
+                for (int i = 0; i < 3; ++i) cand[k].t[i] = (k & 2) ? -t[i] : t[i];
+                good[k] = 0;
+            }
+        }
+        __syncthreads();
+        const int base = offsets[f], n = offsets[f + 1] - base;
+        int c[4] = { 0, 0, 0, 0 };
+        for (int i = tid; i < n; i += blockDim.x) {
+            if (e_mask && !e_mask[base + i]) continue;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double X, Y, Z, u, v;
+                c[k] += triangulate_point(cur_u[base + i], cur_v[base + i], ref_u[base + i], ref_v[base + i], cand[k],
+                                          cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.triangulation_max_depth, X, Y, Z, u, v);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c[k] += __shfl_xor_sync(0xFFFFFFFFu, c[k], o);
+            if ((tid & 31) == 0 && c[k]) atomicAdd(&good[k], c[k]);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int best = 0;
+            for (int k = 1; k < 4; ++k) if (good[k] > good[best]) best = k;
+            double *P = poses + 12 * (size_t)f;
+            for (int r = 0; r < 3; ++r) { for (int cc = 0; cc < 3; ++cc) P[4 * r + cc] = cand[best].R[3 * r + cc]; P[4 * r + 3] = cand[best].t[r]; }
+            if (n_good) for (int k = 0; k < 4; ++k) n_good[4 * f + k] = good[k];
+        }
+        __syncthreads();
     }
 }
 

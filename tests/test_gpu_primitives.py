@@ -163,3 +163,24 @@ def test_depth_from_mesh_vs_find_simplex(engine, ref):
     d = datas[got[ok]]
     np.testing.assert_allclose(depth.ravel()[ok], d[:, 3] / (d[:, 0] * xn + d[:, 1] * yn + d[:, 2]), rtol=1e-12)
     assert interior.sum() > 0.2 * W * H
+
+
+def test_recover_pose_vs_opencv(engine):
+    """mvosr_recover_pose_frames against cv2.recoverPose's own R, t and mask count (tests/golden/pose.npz), on essential
+    matrices from cv2.findEssentialMat (the reference's call, visual_odometry.py:129-133) and on exact ones with arbitrary
+    scale / sign; then the fused scale recovery runs from the recovered poses."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pose.npz"))
+    d = {k: _t(engine, z[k]) for k in ("offsets", "cur_u", "cur_v", "ref_u", "ref_v")}
+    out = engine.recover_pose_frames(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], _t(engine, z["E"]))
+    poses = out["poses"].cpu().numpy().reshape(-1, 3, 4); good = out["n_good"].cpu().numpy()
+    F = poses.shape[0]
+    for f in range(F):
+        R, t = z["R"][f].reshape(3, 3), z["t"][f]
+        np.testing.assert_allclose(poses[f][:, :3], R, atol=1e-9)
+        np.testing.assert_allclose(poses[f][:, 3], t, atol=1e-9)
+        assert good[f].max() == z["n_good"][f], (f, good[f], z["n_good"][f])
+        assert abs(np.linalg.det(poses[f][:, :3]) - 1) < 1e-12 and abs(np.linalg.norm(poses[f][:, 3]) - 1) < 1e-12
+        assert np.sort(good[f])[-2] < 0.5 * good[f].max()                      # the winner is unambiguous
+    # the recovered poses drive stage 1 exactly like the poses they came from
+    a = engine.triangulate_frames(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], out["poses"])
+    assert np.array_equal(a["n_out"].cpu().numpy(), z["n_good"])
