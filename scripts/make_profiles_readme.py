@@ -97,6 +97,12 @@ Stars that leave the pair path: 350 -> 322 per frame (82 hull / far-neighbour st
 Tried and measured worse, kept out: clipping the cap test to the bounding box of the point set (pair path +13 %
 instructions for 38 fewer streaming stars); squared candidate lengths kept in registers (register pressure).
 
+## Sanitizers
+
+`compute-sanitizer --tool memcheck` and `--tool racecheck` over `scripts/sanitize_small.py` (fused and staged paths with debug
+buffers, shared-memory and large-frame staging, Delaunay-only, filter, path scan, plane RANSAC): 0 errors, 0 hazards
+(`sanitizer_r01.txt`).
+
 ## RANSAC sweep (BASELINE configs[4]; 592 frames, kernel-only frames/s, error of the RAW scale against the synthetic truth; 196 k build)
 
 """ + "\n".join(lines) + """
