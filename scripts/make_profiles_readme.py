@@ -95,7 +95,10 @@ Stars that leave the pair path: 350 -> 322 per frame (82 hull / far-neighbour st
 `scripts/star_counters.py` with `-DMVOSR_STAR_COUNTERS`); the wrap path takes 6.9 steps and 2.8 streaming calls per star
 (`-DMVOSR_WRAP_COUNTERS`).  Grid density sweep 1.1 ... 1.8 points per cell: flat between 1.4 and 1.65 (1.5 kept).
 Tried and measured worse, kept out: clipping the cap test to the bounding box of the point set (pair path +13 %
-instructions for 38 fewer streaming stars); squared candidate lengths kept in registers (register pressure).
+instructions for 38 fewer streaming stars); squared candidate lengths kept in registers (register pressure); running the
+wrap path from inside the pair pass instead of as a second phase (stars +150 k cycles); a second chance in the pair path that
+certifies steps whose cap leaves the 5x5 block against the ring of cells up to 7x7 (80 fewer wrap stars, but they are the cheap
+ones: pair path +85 k cycles for 31 k saved).
 
 ## Sanitizers
 
