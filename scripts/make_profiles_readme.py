@@ -39,7 +39,9 @@ half-warp stars) -> 91 k (warp-per-star gift wrapping, lanes = candidates) -> 11
 (registers, hull rows first) -> 136 k (two stars per warp in lock step) -> 140.6 k (temporal filter kernel) -> 166.3 k
 (**Delaunay #2 reuses the stars of Delaunay #1**) -> 188.9 k (dense nearest-first streaming, seeded rebuilds, one-pass median)
 -> 190.4 k (filter prefetch) -> 196.0 k (quick accept of the cap test, seeded wrap walk) -> {n1['value'] / 1e3:.1f} k (pair-path
-micro-optimisations: one order-preserving key per step, slots populated on demand, closed-form candidate decode).
+micro-optimisations: one order-preserving key per step, slots populated on demand, closed-form candidate decode; 203.7 k, then
+896 threads per CTA instead of 1024: 73 registers per thread, no spills).  The ncu capture and the per-phase table below are of
+the 1024-thread build (203.7 k).
 
 ## The other BASELINE configurations (`bench.py --workload ...`; measured with the 190 k build)
 
