@@ -102,6 +102,17 @@ wrap path from inside the pair pass instead of as a second phase (stars +150 k c
 certifies steps whose cap leaves the 5x5 block against the ring of cells up to 7x7 (80 fewer wrap stars, but they are the cheap
 ones: pair path +85 k cycles for 31 k saved).
 
+## Stand-alone primitives (`scripts/bench_primitives.py`, `primitives_r01.json`; median of 10 device-timed calls, L2 flushed)
+
+| kernel | workload | ms | algorithmic GB/s | of measured HBM peak |
+|---|---|---|---|---|
+""" + "\n".join("| `%s` | %s | %.3f | %.0f | %.1f %% |" % (r["kernel"], r["workload"], r["ms"], r["achieved_gbs"], 100 * r["frac_of_hbm_peak"]) for r in J('primitives_r01.json')["rows"]) + """
+
+`triangle_planes_kernel` is gather-bound (72 B of vertex gathers + 12 B of indices + 40 B out per triangle through L1/L2 for
+24 B/point of compulsory DRAM traffic); the votes are bound by their per-vertex atomics; the RANSAC with early stop reads every
+list once (first round of 8 hypotheses); the path scan and the pose selection are latency-bound at these sizes (one CTA per
+sequence / frame).
+
 ## Sanitizers
 
 `compute-sanitizer --tool memcheck` and `--tool racecheck` over `scripts/sanitize_small.py` (fused and staged paths with debug
