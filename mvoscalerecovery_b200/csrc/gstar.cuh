@@ -3,32 +3,32 @@
 // Replaces scipy.spatial.Delaunay(feature2d).simplices (Qhull 8.0.2) at reference
 // src/rescale.py:124-125,136-137, per frame.
 //
-// Method (no shared mutable mesh, no inter-thread ordering): the Delaunay star of every point p -- the
-// cyclic counter-clockwise list of its neighbours -- is built independently by Bowyer-Watson insertion
-// restricted to that one star.  A candidate s changes the star iff it lies inside the circumcircle of some
-// star triangle (p,q_i,q_i+1); the triangles in conflict form one contiguous arc (their Voronoi vertices are
-// the vertices of p's cell cut off by the bisector of p,s), which is removed and replaced by s.  Hull points
-// carry one INF slot standing for the two ghost triangles (p,q,inf),(p,inf,q); their conflict is an
-// orientation test.  Exact predicates with a symbolic tie-break (predicates.cuh) make the triangulation
-// unique, so independently built stars agree; triangle (a<b<c) is emitted by the star of a.
+// Method (no shared mutable mesh, no inter-thread ordering): the Delaunay star of every point p -- the cyclic
+// counter-clockwise list of its neighbours -- is built independently.  Exact predicates with a symbolic tie-break
+// (predicates.cuh) make the triangulation unique, so independently built stars agree; triangle (a<b<c) is emitted by the
+// star of a, into a block that a scan later orders: the canonical triangle order comes for free.  Hull points carry one INF
+// slot standing for the two ghost triangles (p,q,inf),(p,inf,q).
 //
-// Fast path (stars_fast): one half-warp of 16 lanes per star, the star in REGISTERS -- lane i holds
-// neighbour slot i and, for star triangle i, the three cofactors (m0,m1,m2) of the in-circle determinant
-// with their error weights, so that a candidate is tested against ALL triangles of the star by
-//     det = m0*|s|^2 + m1*s.x + m2*s.y,   err = e0*|s|^2 + e1*|s.x| + e2*|s.y|      (float32, 6 FMA per lane)
-// and one ballot.  |det| > err certifies the sign (forward error bound, KERR below); otherwise the group
-// re-evaluates that candidate with the exact float64/integer predicates.  Candidates come from the grid:
-// first the 3x3 block of cells around p, then a sweep over grid rows outwards from p's row in which every
-// row contributes only the cell interval covered by the union of the star's current circumdisks (ghost
-// triangles: half-planes).  That union only shrinks as the star is clipped, so one sweep suffices and a
-// star is final when the sweep has left the union.  The two half-warps of a warp run in lock step on
-// different stars: test and splice are executed warp-convergently under predication, only the refill of
-// a group's candidate batch is divergent.
+// Four levels, each handing what it cannot certify to the next (run_stars):
+//   1. stars_pair  two stars per warp in lock step (one per half-warp), lanes = the points of the 5x5 block of grid cells
+//                  around p held in registers.  Gift wrapping: from edge (p,cur) the next neighbour is the candidate on the
+//                  left with the smallest circumcentre parameter t; float32 with forward error bounds, a step is final when
+//                  the winner's interval is disjoint from every other candidate's and the left cap of its circle lies inside
+//                  the block.  Closed stars only.
+//   2. stars_wrap  one warp per star, same algorithm plus streaming: when the cap leaves the block, or nothing lies on the
+//                  left (hull edge / far neighbour), the grid rows the cap (or the half-plane) covers are gathered 32 rows at
+//                  a time, nearest first, and their points evaluated in dense batches (w_stream).
+//   3. stars_fast  exact half-warp path for whatever float32 could not certify (ties, collinearities, crowded blocks):
+//                  Bowyer-Watson restricted to one star held in registers, float32 filter + exact float64/integer
+//                  predicates, row sweep bounded by the union of circumdisks.
+//   4. fb_build    exact full-warp path, 32 slots, collinear bootstrap, ring-by-ring scan.
 //
-// Fallback (fb_build): anything the fast path does not handle -- more than 16 neighbours, a collinear
-// bootstrap, an inconsistent arc -- is queued and rebuilt by one full warp (32 slots) with exact
-// predicates only, scanning the grid ring by ring (nearest first) until every unexamined point is farther
-// than twice the largest circumradius.  Slow and simple; a handful of stars per frame at most.
+// Two passes per frame.  The vote pass (Delaunay #1, EMIT = false) feeds every finished star to the depth-order graph vote
+// (consume_vote) and stores its ring of neighbours (FrameView::rpool).  The emit pass (Delaunay #2, EMIT = true) runs over
+// the survivors of the graph check, a subset of the same points: stars that lost no neighbour are emitted straight from the
+// stored ring by the caller (frame_kernel.cuh), the others are rebuilt here SEEDED -- surviving neighbours are still
+// neighbours, consecutive survivors with nothing dropped between them still span a triangle, so only the gaps left by dropped
+// neighbours are walked (stars_pair / stars_wrap, fv.oldof != nullptr).
 #pragma once
 #include <stdint.h>
 #include <math_constants.h>

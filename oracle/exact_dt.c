@@ -2,7 +2,7 @@
  *
  * Part of oracle/: compiled by oracle/Makefile into oracle/_build/liboracle.so and loaded
  * only by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg.  The product
- * has its own, independently written device implementation (csrc/delaunay.cuh).
+ * has its own, independently written device implementation (csrc/gstar.cuh, csrc/predicates.cuh).
  *
  * What it restates: the triangle set scipy.spatial.Delaunay (Qhull 8.0.2, options
  * "Qbb Qc Qz Q12" + Qt) hands to the reference at src/rescale.py:124-125,136-137.
