@@ -390,7 +390,8 @@ def run_gpu_arm(args):
                              "note": "instruction-issue-bound path by construction (SURVEY 8d: 1e5 fps is 0.06 % of the HBM ceiling); see profiles/README.md"},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "mvosr_recover_scales_host (pinned host buffers, copies inside)"},
+                        "api": "mvosr_recover_scales_host (pinned host buffers, copies inside)" + (
+                            "; timing only for this workload: the call treats the rank's frame range as ONE sequence" if args.workload == "fleet" else "")},
                 "gpu_launches": int(launches), "clocks": clocks}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
