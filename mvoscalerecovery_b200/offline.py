@@ -25,7 +25,7 @@ def recover_sequence(seq: dict, absolute_reference: float, window_size: int = 5,
     from .batch import ScaleRecovery
     eng = engine or ScaleRecovery(absolute_reference=float(absolute_reference), window_size=int(window_size))
     dev = eng.device
-    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    t = lambda a, dt: torch.from_numpy(np.array(a, dtype=dt, order="C")).to(dev)      # (a copy: memory-mapped sections are read-only)
     off = np.asarray(seq["offsets"], np.int32)
     F = off.shape[0] - 1
     d = {k: t(seq[k], np.float32) for k in "xyzuv"}

@@ -101,3 +101,35 @@ def test_offline_driver_reproduces_reference_files(golden, tmp_path, monkeypatch
     offline.main(["x", "seq07.mvosr", ".t"])
     a = np.loadtxt("evaluate_result/07_result_scales.txt.t"); b = np.loadtxt("evaluate_result/seq07_scales.txt.t")
     assert a.shape == (F,) and np.array_equal(a, b) and np.loadtxt("evaluate_result/07_result_path.txt.t").shape == (F + 1, 12)
+
+
+@pytest.mark.gpu
+def test_gpu_path_on_the_reference_mains_own_hand_off(tmp_path, monkeypatch):
+    """BASELINE configs[0] in small: the hand-off written by the reference's unmodified src/main.py on rendered frames (AKAZE +
+    LK + findEssentialMat + recoverPose features), through the batched GPU path == the reference's estimator over the same
+    hand-off (tests/golden/make_main_golden.py): filtered scales to 1e-9, survivor / triangle / inlier counts exact."""
+    import torch
+    from mvoscalerecovery_b200 import offline
+    from mvoscalerecovery_b200.batch import ScaleRecovery, stats_to_numpy
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "main_c1.npz"))
+    seq = {k: z[k] for k in ("offsets", "move_flags", "motions", "x", "y", "z", "u", "v")}
+    ref_h = float(z["absolute_reference"])
+    res = offline.recover_sequence(seq, absolute_reference=ref_h, window_size=5, seed=int(z["seed"]))
+    np.testing.assert_allclose(res["scales"], z["scales"], rtol=1e-9, atol=1e-12)
+    called = z["called"]
+    np.testing.assert_allclose(res["raw_scale"][called], z["raw_scale"][called], rtol=1e-9)
+    eng = ScaleRecovery(absolute_reference=ref_h)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(eng.device)
+    off = seq["offsets"].astype(np.int32)
+    r = eng.scale_frames(t(off, np.int32), *[t(seq[k], np.float32) for k in "xyzuv"], int(np.max(np.diff(off))), seed=int(z["seed"]), stats=True)
+    st = stats_to_numpy(r["stats"])
+    assert np.array_equal(st["n_kept"][called], z["n_kept"][called]) and np.array_equal(st["n_tri"][called], z["n_tri"][called])
+    assert np.array_equal(st["best_ic"][called], z["best_ic"][called])
+    # the same through the packed container and the command line
+    monkeypatch.chdir(tmp_path)
+    from mvoscalerecovery_b200 import container as C
+    C.save_packed("c1.mvosr", seq)
+    import mvoscalerecovery_b200.compat.param as param
+    assert param.camera_h == ref_h
+    out = offline.main(["x", "c1.mvosr", ".t"])
+    assert out["poses"].shape == (called.shape[0] + 1, 12)

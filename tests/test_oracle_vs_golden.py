@@ -1,11 +1,15 @@
 """The oracle (oracle/pipeline.py, oracle/philox.py, oracle/exact_dt.c) pinned against outputs of the REFERENCE ITSELF
 (tests/golden/*.npz, written by tests/golden/make_golden.py through oracle/ref_harness.py) and the known answers of
 SURVEY.md section 8(c).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
 from oracle import pipeline as P
 from oracle import philox
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_philox_known_answers():
@@ -143,3 +147,16 @@ def test_exact_delaunay_oracle_degenerate_inputs_are_valid():
     assert tri.tolist() == [[0, 1, 4], [1, 2, 4]]
     tri, dup = exact.delaunay_exact(np.array([[0, 200], [1, 200], [2, 200]], np.float32))
     assert tri.shape[0] == 0
+
+
+def test_offline_loop_on_the_reference_mains_own_hand_off():
+    """BASELINE configs[0] in small: src/main.py (unmodified) ran on rendered frames and wrote its hand-off file; the oracle's
+    offline loop over that hand-off == what the reference's estimator makes of it (tests/golden/make_main_golden.py)."""
+    from mvoscalerecovery_b200 import container
+    z = np.load(os.path.join(ROOT, "tests", "golden", "main_c1.npz"))
+    lists = container.unpack_sequence({k: z[k] for k in ("offsets", "move_flags", "motions", "x", "y", "z", "u", "v")})
+    out = P.offline_loop(lists["feature3ds"], lists["feature2ds"], lists["move_flags"], int(z["seed"]),
+                         absolute_reference=float(z["absolute_reference"]), window_size=5)
+    scales = out[0] if isinstance(out, tuple) else out["scales"]
+    np.testing.assert_allclose(scales, z["scales"], rtol=1e-9, atol=1e-12)
+    assert z["called"].sum() >= 30 and np.median(np.abs(z["scales"][5:] - z["true_steps"][1:][5:len(z["scales"])]) / z["true_steps"][1:][5:len(z["scales"])]) < 0.1
