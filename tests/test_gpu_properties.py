@@ -213,3 +213,49 @@ def test_second_delaunay_reuse_equals_rebuild(engine, style):
         want = tri[2 * o2[i]: 2 * o2[i] + ntri[i]]
         assert st["n_tri"][f] == ntri[i], (style, f, st["n_tri"][f], ntri[i])
         assert np.array_equal(got, want), (style, f)
+
+
+def test_hostile_frames_are_flagged_and_do_not_disturb_their_neighbours(engine):
+    """Where the reference raises (QhullError on < 3 / collinear ROI points, src/rescale.py:124) or has no defined behaviour
+    (non-finite or absurd pixel coordinates), the frame gets a status flag and a NaN raw scale; the frames around it in the same
+    launch are bit-identical to a launch without the hostile frames."""
+    import torch
+    from mvoscalerecovery_b200 import synth, _native as N
+    from mvoscalerecovery_b200.batch import pack_frames
+    rng = np.random.default_rng(8)
+    fx, cx, cy = 718.856, 607.1928, 185.2157
+
+    def good(n, seed):
+        r = np.random.default_rng(seed)
+        u = r.uniform(0, 1240, n); v = r.uniform(186, 375, n)
+        z = 1.7 * fx / (v - cy) * (1 + 0.005 * r.standard_normal(n))
+        return np.stack([(u - cx) * z / fx, (v - cy) * z / fx, z], 1).astype(np.float32), np.stack([u, v], 1).astype(np.float32)
+
+    g0, g1, g2 = good(900, 1), good(1500, 2), good(400, 3)
+    nan2 = g0[1].copy(); nan2[::7, 0] = np.nan
+    far2 = g0[1].copy(); far2[5, 0] = 5000.0
+    inf3 = g0[0].copy(); inf3[::5] = np.inf                                 # non-finite 3-D points, valid pixels
+    line2 = np.stack([np.linspace(10, 1200, 300), np.full(300, 250.0)], 1).astype(np.float32)
+    dup2 = np.tile(np.array([[300.0, 300.0]], np.float32), (200, 1))
+    sky2 = g0[1].copy(); sky2[:, 1] = 100.0                                  # everything above the ROI row
+    f3 = [g0[0], g0[0], g0[0], g1[0], inf3, g0[0][:300], g0[0][:200], g0[0], g0[0][:2], np.zeros((0, 3), np.float32), g2[0]]
+    f2 = [g0[1], nan2, far2, g1[1], g0[1], line2, dup2, sky2, g0[1][:2], np.zeros((0, 2), np.float32), g2[1]]
+    b = pack_frames(f3, f2, engine.device)
+    out = engine.scale_frames(b["offsets"], b["x"], b["y"], b["z"], b["u"], b["v"], b["max_features"], seed=4)
+    torch.cuda.synchronize()
+    st = out["status"].cpu().numpy(); raw = out["raw_scale"].cpu().numpy()
+    assert st[0] & N.ST_UPDATED and st[3] & N.ST_UPDATED and st[10] & N.ST_UPDATED
+    assert st[1] & N.ST_BAD_INPUT and st[2] & N.ST_BAD_INPUT and np.isnan(raw[1]) and np.isnan(raw[2])
+    assert not (st[4] & N.ST_UPDATED) or np.isfinite(raw[4])                # non-finite depths: gates fail or a finite model, never a crash
+    for f in (5, 6, 7, 8, 9):
+        assert st[f] & N.ST_FEW_ROI and np.isnan(raw[f]), (f, st[f])
+    # the good frames alone, same frame indices for the hypothesis stream
+    for f, (a3, a2) in ((0, g0), (3, g1), (10, g2)):
+        bb = pack_frames([a3], [a2], engine.device)
+        o = engine.scale_frames(bb["offsets"], bb["x"], bb["y"], bb["z"], bb["u"], bb["v"], bb["max_features"], frame_index0=f, seed=4)
+        assert float(o["raw_scale"].cpu().numpy()[0]) == raw[f] and int(o["status"].cpu().numpy()[0]) == st[f]
+    # the filter holds its state over flagged frames (reference: uncaught exception -> undefined; here: hold)
+    seq = torch.tensor([0, len(f3)], dtype=torch.int32, device=engine.device)
+    nf = torch.tensor([a.shape[0] for a in f3], dtype=torch.int32, device=engine.device)
+    sc = engine.filter_sequences(seq, out["raw_scale"], out["status"], None, nf)["scale"].cpu().numpy()
+    assert np.isfinite(sc).all()
