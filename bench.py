@@ -336,15 +336,16 @@ def run_gpu_arm(args):
 
     # ---- end to end through the host-buffer C-ABI call (pinned inputs, copies inside the timed region)
     res = dict(scale=np.empty(n_frames, np.float64), raw_scale=np.empty(n_frames, np.float64), status=np.empty(n_frames, np.uint8))
+    host_kw = dict(max_features=max_feat, seq_id=pieces[0][0], seed=SEED, out=res)
+    if args.workload == "fleet":
+        host_kw["seq_offsets"] = piece_off.astype(np.int32)       # one call, every sequence piece of this rank's range a sequence
     for _ in range(2):
-        eng.recover_scales_host(h["offsets"], h["cur_u"], h["cur_v"], h["ref_u"], h["ref_v"], h["poses"], h["move"],
-                                max_features=max_feat, seq_id=rank, seed=SEED, out=res)
+        eng.recover_scales_host(h["offsets"], h["cur_u"], h["cur_v"], h["ref_u"], h["ref_v"], h["poses"], h["move"], **host_kw)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(e2e_steps):
-        eng.recover_scales_host(h["offsets"], h["cur_u"], h["cur_v"], h["ref_u"], h["ref_v"], h["poses"], h["move"],
-                                max_features=max_feat, seq_id=rank, seed=SEED, out=res)
+        eng.recover_scales_host(h["offsets"], h["cur_u"], h["cur_v"], h["ref_u"], h["ref_v"], h["poses"], h["move"], **host_kw)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -390,8 +391,7 @@ def run_gpu_arm(args):
                              "note": "instruction-issue-bound path by construction (SURVEY 8d: 1e5 fps is 0.06 % of the HBM ceiling); see profiles/README.md"},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "mvosr_recover_scales_host (pinned host buffers, copies inside)" + (
-                            "; timing only for this workload: the call treats the rank's frame range as ONE sequence" if args.workload == "fleet" else "")},
+                        "api": ("mvosr_recover_fleet_host" if args.workload == "fleet" else "mvosr_recover_scales_host") + " (pinned host buffers, copies inside)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -174,6 +174,14 @@ int  mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t 
                         int32_t max_features, int32_t seq_id, uint64_t seed,
                         double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host);
 
+/* The same for S sequences in one call (BASELINE configs[3], the fleet): seq_offsets_host [S+1] are frame ranges inside the
+ * CSR batch; sequence s uses Philox sequence id seq_id0 + s, frame counters and the temporal filter restart at every sequence. */
+int  mvosr_recover_fleet_host(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets_host, const int32_t *offsets_host,
+                        const float *cur_u_host, const float *cur_v_host, const float *ref_u_host, const float *ref_v_host,
+                        const double *poses_host, const uint8_t *move_flags_host,
+                        int32_t max_features, int32_t seq_id0, uint64_t seed,
+                        double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host);
+
 /* ---- stand-alone primitives: the same arithmetic for callers that bring their own triangles / point lists ----
  * They back the API-surface variants of the reference that take explicit triangles or points (float64 arrays as numpy
  * hands them): ScaleEstimator.flat_selection (src/rescale.py:75-102), Reconstruct.triangle_model (src/reconstruct.py:70-90),

@@ -45,7 +45,7 @@ SYMBOLS = [
     "mvosr_version", "mvosr_error_string", "mvosr_last_cuda_error", "mvosr_default_config", "mvosr_create",
     "mvosr_destroy", "mvosr_get_config", "mvosr_triangulate_frames", "mvosr_scale_frames",
     "mvosr_scale_frames_from_correspondences", "mvosr_filter_sequences", "mvosr_delaunay_frames",
-    "mvosr_recover_scales_host", "mvosr_launch_count", "mvosr_set_phase_timing",
+    "mvosr_recover_scales_host", "mvosr_recover_fleet_host", "mvosr_launch_count", "mvosr_set_phase_timing",
     "mvosr_triangle_planes", "mvosr_triangle_votes", "mvosr_ransac_planes", "mvosr_integrate_paths", "mvosr_depth_from_mesh", "mvosr_recover_pose_frames",
 ]
 
@@ -83,6 +83,7 @@ def lib():
     L.mvosr_filter_sequences.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.mvosr_delaunay_frames.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
     L.mvosr_recover_scales_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, u64, vp, vp, vp]
+    L.mvosr_recover_fleet_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, u64, vp, vp, vp]
     L.mvosr_launch_count.argtypes = [vp]
     f64 = C.c_double
     L.mvosr_triangle_planes.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]

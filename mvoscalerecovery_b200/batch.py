@@ -260,8 +260,9 @@ class ScaleRecovery:
 
     # ------------------------------------------------------------------ host buffers end to end
     def recover_scales_host(self, offsets: np.ndarray, cur_u, cur_v, ref_u, ref_v, poses, move_flags=None, max_features: int = 0,
-                            seq_id: int = 0, seed: int = 0, out=None):
-        """Host (ideally pinned) numpy/torch-CPU buffers in, filtered scales out: copies + stages 1-6 inside."""
+                            seq_id: int = 0, seed: int = 0, out=None, seq_offsets=None):
+        """Host (ideally pinned) numpy/torch-CPU buffers in, filtered scales out: copies + stages 1-6 inside.
+        ``seq_offsets`` (int32 (S+1,), host): the batch holds S sequences (mvosr_recover_fleet_host; sequence ids seq_id + s)."""
         def hp(a):
             if a is None:
                 return None
@@ -275,9 +276,15 @@ class ScaleRecovery:
             o = offsets.numpy() if isinstance(offsets, torch.Tensor) else offsets
             max_features = int(np.max(np.diff(o))) if F else 0
         with torch.cuda.device(self.device):
-            N.check(self.lib.mvosr_recover_scales_host(self._h, F, hp(offsets), hp(cur_u), hp(cur_v), hp(ref_u), hp(ref_v), hp(poses),
-                                                       hp(move_flags), int(max_features), int(seq_id), C.c_uint64(int(seed)),
-                                                       hp(out["scale"]), hp(out["raw_scale"]), hp(out["status"])))
+            if seq_offsets is None:
+                N.check(self.lib.mvosr_recover_scales_host(self._h, F, hp(offsets), hp(cur_u), hp(cur_v), hp(ref_u), hp(ref_v), hp(poses),
+                                                           hp(move_flags), int(max_features), int(seq_id), C.c_uint64(int(seed)),
+                                                           hp(out["scale"]), hp(out["raw_scale"]), hp(out["status"])))
+            else:
+                so = np.ascontiguousarray(seq_offsets.numpy() if isinstance(seq_offsets, torch.Tensor) else seq_offsets, dtype=np.int32)
+                N.check(self.lib.mvosr_recover_fleet_host(self._h, int(so.shape[0] - 1), hp(so), hp(offsets), hp(cur_u), hp(cur_v), hp(ref_u), hp(ref_v),
+                                                          hp(poses), hp(move_flags), int(max_features), int(seq_id), C.c_uint64(int(seed)),
+                                                          hp(out["scale"]), hp(out["raw_scale"]), hp(out["status"])))
         return out
 
 

@@ -463,22 +463,22 @@ int mvosr_filter_sequences(mvosr_handle *h, int32_t n_sequences, const int32_t *
     return MVOSR_OK;
 }
 
-int mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t *offsets_host,
-                       const float *cur_u_host, const float *cur_v_host, const float *ref_u_host, const float *ref_v_host,
-                       const double *poses_host, const uint8_t *move_flags_host,
-                       int32_t max_features, int32_t seq_id, uint64_t seed,
-                       double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host) {
-    if (!h || n_frames < 0 || !offsets_host || !cur_u_host || !cur_v_host || !ref_u_host || !ref_v_host || !poses_host || !scale_out_host)
-        return MVOSR_E_INVALID;
-    if (n_frames == 0) return MVOSR_OK;
+// Host-buffer pipeline shared by the two _host entry points: S sequences (frame ranges seq_off[0..S], Philox sequence ids
+// seq_id0 + s, frame counters restarting at every sequence) packed in one CSR batch.
+static int recover_host(mvosr_handle *h, int32_t n_frames, const int32_t *offsets_host,
+                        const float *cur_u_host, const float *cur_v_host, const float *ref_u_host, const float *ref_v_host,
+                        const double *poses_host, const uint8_t *move_flags_host, int32_t max_features,
+                        int32_t n_sequences, const int32_t *seq_off, int32_t seq_id0, uint64_t seed,
+                        double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host) {
     CK(cudaSetDevice(h->device));
     const size_t M = (size_t)offsets_host[n_frames];
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t o_off = 0, o_cu = o_off + al(4 * (size_t)(n_frames + 1)), o_cv = o_cu + al(4 * M), o_ru = o_cv + al(4 * M),
            o_rv = o_ru + al(4 * M), o_pose = o_rv + al(4 * M), o_move = o_pose + al(96 * (size_t)n_frames),
            o_raw = o_move + al((size_t)n_frames), o_st = o_raw + al(8 * (size_t)n_frames), o_nf = o_st + al((size_t)n_frames),
-           o_out = o_nf + al(4 * (size_t)n_frames), o_seq = o_out + al(8 * (size_t)n_frames), total = o_seq + 256;
+           o_out = o_nf + al(4 * (size_t)n_frames), o_seq = o_out + al(8 * (size_t)n_frames), total = o_seq + al(4 * (size_t)(n_sequences + 1));
     if (total > h->stage_bytes) {
+        CK(cudaDeviceSynchronize());
         if (h->d_stage) cudaFree(h->d_stage);
         h->d_stage = nullptr; h->stage_bytes = 0;
         if (cudaMalloc(&h->d_stage, total) != cudaSuccess) { cudaGetLastError(); return MVOSR_E_NOMEM; }
@@ -492,39 +492,53 @@ int mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t *
         for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
         h->streams_ready = 1;
     }
-    // Pipeline: the frame range is cut into chunks; chunk k+1 is copied while chunk k is processed, and consecutive chunks
+    // Pipeline: every sequence is cut into chunks; chunk k+1 is copied while chunk k is processed, and consecutive chunks
     // run on two compute streams so that the tail of one launch overlaps the head of the next.
     cudaStream_t sc = h->s_copy;
     CK(cudaMemcpyAsync(d + o_off, offsets_host, 4 * (size_t)(n_frames + 1), cudaMemcpyHostToDevice, sc));
     CK(cudaMemcpyAsync(d + o_pose, poses_host, 96 * (size_t)n_frames, cudaMemcpyHostToDevice, sc));
     if (move_flags_host) CK(cudaMemcpyAsync(d + o_move, move_flags_host, (size_t)n_frames, cudaMemcpyHostToDevice, sc));
-    int32_t seqo[2] = { 0, n_frames };
-    CK(cudaMemcpyAsync(d + o_seq, seqo, sizeof(seqo), cudaMemcpyHostToDevice, sc));
-    const int n_chunks = n_frames >= 8 * h->num_sms ? 8 : (n_frames >= 2 * h->num_sms ? 2 : 1);
-    for (int c = 0; c < n_chunks; ++c) {
-        // the first chunk is small so that the GPU starts early
-        const int f0 = c == 0 ? 0 : (int)((long long)n_frames * (2 * c - 1) / (2 * n_chunks - 1));
-        const int f1 = (int)((long long)n_frames * (2 * c + 1) / (2 * n_chunks - 1));
-        const size_t a0 = (size_t)offsets_host[f0], a1 = (size_t)offsets_host[f1 > n_frames ? n_frames : f1];
-        const int fe = f1 > n_frames ? n_frames : f1;
-        if (fe <= f0) continue;
-        CK(cudaMemcpyAsync(d + o_cu + 4 * a0, cur_u_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
-        CK(cudaMemcpyAsync(d + o_cv + 4 * a0, cur_v_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
-        CK(cudaMemcpyAsync(d + o_ru + 4 * a0, ref_u_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
-        CK(cudaMemcpyAsync(d + o_rv + 4 * a0, ref_v_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
-        CK(cudaEventRecord(h->ev_copy[c], sc));
-        cudaStream_t st = h->s_comp[c & 1];
-        CK(cudaStreamWaitEvent(st, h->ev_copy[c], 0));
-        int rc = mvosr_scale_frames_from_correspondences(h, fe - f0, (const int32_t *)(d + o_off) + f0, (const float *)(d + o_cu),
-                    (const float *)(d + o_cv), (const float *)(d + o_ru), (const float *)(d + o_rv), nullptr, (const double *)(d + o_pose) + 12 * (size_t)f0,
-                    max_features, f0, seq_id, seed, (double *)(d + o_raw) + f0, (uint8_t *)(d + o_st) + f0, (int32_t *)(d + o_nf) + f0, nullptr, st);
-        if (rc != MVOSR_OK) return rc;
+    CK(cudaMemcpyAsync(d + o_seq, seq_off, 4 * (size_t)(n_sequences + 1), cudaMemcpyHostToDevice, sc));
+    int launch = 0;
+    for (int s = 0; s < n_sequences; ++s) {
+        const int s0 = seq_off[s], sn = seq_off[s + 1] - s0;
+        // about 8 chunks over the whole call, the first chunk of the call small so that the GPU starts early
+        int n_chunks = (int)((long long)8 * sn / (n_frames > 0 ? n_frames : 1));
+        if (sn >= 2 * h->num_sms && n_chunks < 2) n_chunks = 2;
+        if (sn < 2 * h->num_sms || n_chunks < 1) n_chunks = 1;
+        if (n_chunks > 8) n_chunks = 8;
+        if (n_chunks > sn / h->num_sms) n_chunks = sn / h->num_sms > 0 ? sn / h->num_sms : 1;       // at least one frame per SM and chunk
+        for (int c = 0; c < n_chunks; ++c) {
+            int f0, f1;
+            if (s == 0 && n_chunks > 1) {
+                f0 = c == 0 ? 0 : (int)((long long)sn * (2 * c - 1) / (2 * n_chunks - 1));
+                f1 = (int)((long long)sn * (2 * c + 1) / (2 * n_chunks - 1));
+            } else { f0 = (int)((long long)sn * c / n_chunks); f1 = (int)((long long)sn * (c + 1) / n_chunks); }
+            if (f1 > sn) f1 = sn;
+            if (f1 <= f0) continue;
+            const size_t a0 = (size_t)offsets_host[s0 + f0], a1 = (size_t)offsets_host[s0 + f1];
+            CK(cudaMemcpyAsync(d + o_cu + 4 * a0, cur_u_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+            CK(cudaMemcpyAsync(d + o_cv + 4 * a0, cur_v_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+            CK(cudaMemcpyAsync(d + o_ru + 4 * a0, ref_u_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+            CK(cudaMemcpyAsync(d + o_rv + 4 * a0, ref_v_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+            cudaEvent_t ev = h->ev_copy[launch & 7];
+            // an event slot is reused after eight launches: by then its waiter (two compute streams, in order) has long consumed it
+            CK(cudaEventRecord(ev, sc));
+            cudaStream_t st = h->s_comp[launch & 1];
+            CK(cudaStreamWaitEvent(st, ev, 0));
+            const int g0 = s0 + f0;
+            int rc = mvosr_scale_frames_from_correspondences(h, f1 - f0, (const int32_t *)(d + o_off) + g0, (const float *)(d + o_cu),
+                        (const float *)(d + o_cv), (const float *)(d + o_ru), (const float *)(d + o_rv), nullptr, (const double *)(d + o_pose) + 12 * (size_t)g0,
+                        max_features, f0, seq_id0 + s, seed, (double *)(d + o_raw) + g0, (uint8_t *)(d + o_st) + g0, (int32_t *)(d + o_nf) + g0, nullptr, st);
+            if (rc != MVOSR_OK) return rc;
+            ++launch;
+        }
     }
     // join: the filter runs on compute stream 0 after both compute streams
     CK(cudaEventRecord(h->ev_copy[0], h->s_comp[1]));
     CK(cudaStreamWaitEvent(h->s_comp[0], h->ev_copy[0], 0));
     cudaStream_t st = h->s_comp[0];
-    int rc = mvosr_filter_sequences(h, 1, (const int32_t *)(d + o_seq), (const double *)(d + o_raw), (const uint8_t *)(d + o_st),
+    int rc = mvosr_filter_sequences(h, n_sequences, (const int32_t *)(d + o_seq), (const double *)(d + o_raw), (const uint8_t *)(d + o_st),
                                 move_flags_host ? (const uint8_t *)(d + o_move) : nullptr, (const int32_t *)(d + o_nf),
                                 (double *)(d + o_out), nullptr, st);
     if (rc != MVOSR_OK) return rc;
@@ -533,6 +547,35 @@ int mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t *
     if (status_out_host) CK(cudaMemcpyAsync(status_out_host, d + o_st, (size_t)n_frames, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return MVOSR_OK;
+}
+
+int mvosr_recover_scales_host(mvosr_handle *h, int32_t n_frames, const int32_t *offsets_host,
+                       const float *cur_u_host, const float *cur_v_host, const float *ref_u_host, const float *ref_v_host,
+                       const double *poses_host, const uint8_t *move_flags_host,
+                       int32_t max_features, int32_t seq_id, uint64_t seed,
+                       double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host) {
+    if (!h || n_frames < 0 || !offsets_host || !cur_u_host || !cur_v_host || !ref_u_host || !ref_v_host || !poses_host || !scale_out_host)
+        return MVOSR_E_INVALID;
+    if (n_frames == 0) return MVOSR_OK;
+    const int32_t seq_off[2] = { 0, n_frames };
+    return recover_host(h, n_frames, offsets_host, cur_u_host, cur_v_host, ref_u_host, ref_v_host, poses_host, move_flags_host, max_features,
+                        1, seq_off, seq_id, seed, scale_out_host, raw_scale_out_host, status_out_host);
+}
+
+int mvosr_recover_fleet_host(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets_host, const int32_t *offsets_host,
+                       const float *cur_u_host, const float *cur_v_host, const float *ref_u_host, const float *ref_v_host,
+                       const double *poses_host, const uint8_t *move_flags_host,
+                       int32_t max_features, int32_t seq_id0, uint64_t seed,
+                       double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host) {
+    if (!h || n_sequences < 0 || !seq_offsets_host || !offsets_host || !cur_u_host || !cur_v_host || !ref_u_host || !ref_v_host || !poses_host || !scale_out_host)
+        return MVOSR_E_INVALID;
+    if (n_sequences == 0) return MVOSR_OK;
+    if (seq_offsets_host[0] != 0) return MVOSR_E_INVALID;
+    for (int s = 0; s < n_sequences; ++s) if (seq_offsets_host[s + 1] < seq_offsets_host[s]) return MVOSR_E_INVALID;
+    const int32_t n_frames = seq_offsets_host[n_sequences];
+    if (n_frames == 0) return MVOSR_OK;
+    return recover_host(h, n_frames, offsets_host, cur_u_host, cur_v_host, ref_u_host, ref_v_host, poses_host, move_flags_host, max_features,
+                        n_sequences, seq_offsets_host, seq_id0, seed, scale_out_host, raw_scale_out_host, status_out_host);
 }
 
 // ---- stand-alone primitives for callers that bring their own triangles / point lists / motions (aux_kernels.cuh) ----

@@ -48,7 +48,7 @@ the 1024-thread build (203.7 k).
 | workload | GPUs | frames/s | ms/step | end to end | note | file |
 |---|---|---|---|---|---|---|
 | dense (configs[2]): 25 000 correspondences, ~20 000 ROI features per frame, 592 frames per GPU | 1 | {d1['value']:.0f} | {d1['ms_per_step']:.2f} | {d1['e2e']['value']:.0f} | large-frame mode: staging in per-CTA global-memory slabs (L2); per feature only 1.5x the cost of the shared-memory mode; CPU port: {d1['cpu_baseline']['value']:.2f} frames/s/core | `bench_r01_dense_n1.json` |
-| fleet (configs[3]): 11 KITTI 00-10-shaped sequences, 23 201 frames, frame-range shards | 1 | {f1['value']:.0f} | {f1['ms_per_step']:.2f} | {f1['e2e']['value']:.0f} | strong scaling; the end-to-end column is a timing of the host-buffer call over the rank's frame range taken as one sequence | `bench_r01_fleet_n1.json` |
+| fleet (configs[3]): 11 KITTI 00-10-shaped sequences, 23 201 frames, frame-range shards | 1 | {f1['value']:.0f} | {f1['ms_per_step']:.2f} | {f1['e2e']['value']:.0f} | strong scaling; end to end = `mvosr_recover_fleet_host` | `bench_r01_fleet_n1.json` |
 | fleet | 8 | {f8['value']:.0f} | {f8['ms_per_step']:.2f} | {f8['e2e']['value']:.0f} | {f8['value'] / f1['value']:.2f}x at 8 GPUs: 2 900 frames = 19.6 per SM per GPU (tail of the last wave) + the filter over the full vector on every rank | `bench_r01_fleet_n8.json` |
 
 ## Roofline (`roofline` block of the bench line)

@@ -259,3 +259,31 @@ def test_hostile_frames_are_flagged_and_do_not_disturb_their_neighbours(engine):
     nf = torch.tensor([a.shape[0] for a in f3], dtype=torch.int32, device=engine.device)
     sc = engine.filter_sequences(seq, out["raw_scale"], out["status"], None, nf)["scale"].cpu().numpy()
     assert np.isfinite(sc).all()
+
+
+def test_fleet_host_call_equals_device_path(engine):
+    """mvosr_recover_fleet_host: several sequences in one host-buffer call (frame counters, Philox sequence ids and the temporal
+    filter restart at every sequence) == per-sequence fused launches + one filter launch over the sequence offsets."""
+    import torch
+    from mvoscalerecovery_b200 import synth
+    lens = [310, 7, 0, 150]
+    parts = [synth.make_sequence(seed=44, n_frames=L, n_corr=700, seq=5 + s, outlier_frac=0.15, still_every=13) for s, L in enumerate(lens)]
+    so = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    off = np.concatenate([[0]] + [p.offsets[1:].astype(np.int64) + sum(int(q.offsets[-1]) for q in parts[:i]) for i, p in enumerate(parts)]).astype(np.int32)
+    cat = lambda k: np.concatenate([getattr(p, k) for p in parts])
+    cu, cv, ru, rv, poses, move = (cat(k) for k in ("cur_u", "cur_v", "ref_u", "ref_v", "poses", "move_flags"))
+    maxf = int(np.max(np.diff(off)))
+    dev = engine.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    raws, sts, nfs = [], [], []
+    for s, p in enumerate(parts):
+        if p.n_frames == 0:
+            continue
+        r = engine.scale_frames_from_correspondences(t(p.offsets), t(p.cur_u), t(p.cur_v), t(p.ref_u), t(p.ref_v), t(p.poses),
+                                                     max_features=maxf, frame_index0=0, seq_id=5 + s, seed=21)
+        raws.append(r["raw_scale"]); sts.append(r["status"]); nfs.append(r["n_features"])
+    want = engine.filter_sequences(t(so), torch.cat(raws), torch.cat(sts), t(move), torch.cat(nfs))["scale"].cpu().numpy()
+    out = engine.recover_scales_host(off, cu, cv, ru, rv, poses, move, max_features=maxf, seq_id=5, seed=21, seq_offsets=so)
+    assert np.array_equal(out["scale"], want)
+    assert np.array_equal(out["raw_scale"], torch.cat(raws).cpu().numpy(), equal_nan=True)
+    assert np.array_equal(out["status"], torch.cat(sts).cpu().numpy())
