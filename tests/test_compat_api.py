@@ -259,3 +259,27 @@ def test_get_pitch_ransac_runs_on_the_gpu_and_repeats(compat, ref):
     np.testing.assert_allclose(m, np.asarray(r["model"]) * np.sign(r["model"][1]), rtol=1e-7, atol=1e-11)
     h, pitch, inl = compat["sc"].ScaleEstimator(1.7).road_model_calculation_ransac(pts)
     assert inl.shape[1] == 3 and 0 < inl.shape[0] <= 200 and np.isfinite(h) and abs(pitch) < np.pi / 2
+
+
+def test_drop_in_directory_coexists_with_the_reference_tree():
+    """src/main.py imports thirdparty.MonocularVO.visual_odometry (its own VO front-end) AND rescale -> thirdparty.Ransac.ransac:
+    with the drop-in directory first on the path, `thirdparty` must stay a namespace package so that MonocularVO still resolves
+    to the reference tree while Ransac, rescale, ... resolve here.  Needs the reference tree (build container only)."""
+    import subprocess
+    ref_src = "/root/reference/src"
+    if not os.path.isfile(os.path.join(ref_src, "main.py")):
+        pytest.skip("reference tree not present")
+    assert not os.path.exists(os.path.join(COMPAT, "thirdparty", "__init__.py"))
+    code = (
+        "import sys, types, numpy as np\n"
+        "sys.modules['matplotlib'] = types.ModuleType('matplotlib'); sys.modules['matplotlib.pyplot'] = types.ModuleType('matplotlib.pyplot')\n"
+        "sys.path[:0] = [%r, %r]\n"
+        "import thirdparty.MonocularVO.visual_odometry as vo, thirdparty.Ransac.ransac as rr, rescale, scale_calculator, graph, estimate_road_norm, param\n"
+        "print(vo.__file__); print(rr.__file__); print(rescale.__file__); print(param.__file__)\n"
+        "est = rescale.ScaleEstimator(absolute_reference=param.camera_h, window_size=5)\n"
+        "print(est.initial_estimation(np.zeros(3)), hasattr(vo, 'VisualOdometry'))\n" % (COMPAT, ref_src))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].startswith(ref_src) and lines[1].startswith(COMPAT) and lines[2].startswith(COMPAT) and lines[3].startswith(COMPAT)
+    assert lines[4] == "0 True"
