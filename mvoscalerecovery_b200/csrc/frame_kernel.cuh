@@ -721,11 +721,13 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                         if (!(nx * nx + ny * ny + nz * nz > 0)) degenerate = true;
                         if (!degenerate) {
                             const double thr = cfg.ransac_threshold * n4;   // |m.[x 1]| < thr for the unit-4-norm model m
-                            for (int q = lane; q < n; q += 32) {
-                                int w = mult[q];
-                                if (!w) continue;
-                                double r = nx * (double)X[q] + ny * (double)Y[q] + nz * (double)Z[q] + dd;
-                                if (fabs(r) < thr) ic += w;
+                            // two points per lane and iteration, no data-dependent branch: the loads of both pipeline
+                            for (int q = lane; q < n; q += 64) {
+                                const int q2 = q + 32 < n ? q + 32 : q;
+                                const int w0 = mult[q], w1 = q + 32 < n ? mult[q2] : 0;
+                                const double r0 = nx * (double)X[q] + ny * (double)Y[q] + nz * (double)Z[q] + dd;
+                                const double r1 = nx * (double)X[q2] + ny * (double)Y[q2] + nz * (double)Z[q2] + dd;
+                                ic += (fabs(r0) < thr ? w0 : 0) + (fabs(r1) < thr ? w1 : 0);
                             }
 #pragma unroll
                             for (int o = 16; o; o >>= 1) ic += __shfl_xor_sync(0xFFFFFFFFu, ic, o);
@@ -737,17 +739,23 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                         }
                     }
                     __syncthreads();
-                    const int hi_ = min(H, h_done + NWARP);
-                    for (int hh = h_done; hh < hi_ && !stop; ++hh) {
-                        int w = hh - h_done, ic = ctl.round_ic[w];
-                        used = hh + 1;
-                        ndeg += ic < 0;
-                        if (ic > best_ic) {
-                            best_ic = ic; best = hh;
-                            b_nx = ctl.round_model[w][0]; b_ny = ctl.round_model[w][1]; b_nz = ctl.round_model[w][2];
-                            b_dd = ctl.round_model[w][3]; b_n4 = ctl.round_model[w][4];
-                            if ((double)ic > goal && cfg.ransac_stop_at_goal) stop = true;
-                        }
+                    // run_ransac's sequential bookkeeping over this round, lane = hypothesis (every warp does it redundantly):
+                    // the loop stops at the first count above the goal (it is an update: earlier counts were <= goal, or an
+                    // earlier round would have stopped); up to there the returned model is the FIRST maximum, if it beats the
+                    // best so far.
+                    const int hi_ = min(H, h_done + NWARP), cnt = hi_ - h_done;
+                    const int icl = lane < cnt ? ctl.round_ic[lane] : -2;
+                    const unsigned over = cfg.ransac_stop_at_goal ? __ballot_sync(0xFFFFFFFFu, lane < cnt && (double)icl > goal) : 0u;
+                    const int L = over ? __ffs(over) : cnt;                    // hypotheses the sequential loop evaluates in this round
+                    stop = over != 0u;
+                    used = h_done + L;
+                    ndeg += __popc(__ballot_sync(0xFFFFFFFFu, lane < L && icl == -1));
+                    const int mx = __reduce_max_sync(0xFFFFFFFFu, lane < L ? icl : -2);
+                    if (mx > best_ic) {
+                        const int w = __ffs(__ballot_sync(0xFFFFFFFFu, lane < L && icl == mx)) - 1;
+                        best_ic = mx; best = h_done + w;
+                        b_nx = ctl.round_model[w][0]; b_ny = ctl.round_model[w][1]; b_nz = ctl.round_model[w][2];
+                        b_dd = ctl.round_model[w][3]; b_n4 = ctl.round_model[w][4];
                     }
                     h_done = hi_;
                     __syncthreads();

@@ -287,3 +287,31 @@ def test_fleet_host_call_equals_device_path(engine):
     assert np.array_equal(out["scale"], want)
     assert np.array_equal(out["raw_scale"], torch.cat(raws).cpu().numpy(), equal_nan=True)
     assert np.array_equal(out["status"], torch.cat(sts).cpu().numpy())
+
+
+@pytest.mark.parametrize("iters,stop", [(100, 0), (37, 1), (300, 0), (1, 1)])
+def test_ransac_configurations_vs_oracle(iters, stop):
+    """BASELINE configs[4] (the RANSAC sweep): other hypothesis counts and "evaluate all hypotheses" (no early stop) through the
+    fused kernel == the oracle's sequential run_ransac over the same Philox stream -- chosen hypothesis, inlier count,
+    hypotheses used and raw scale, frame by frame."""
+    import torch
+    from mvoscalerecovery_b200 import synth
+    from mvoscalerecovery_b200.batch import ScaleRecovery, stats_to_numpy
+    from oracle import pipeline as P
+    eng = ScaleRecovery(absolute_reference=1.7, ransac_iterations=iters, ransac_stop_at_goal=stop)
+    b = synth.make_sequence(seed=61, n_frames=6, n_corr=900, outlier_frac=0.3)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(eng.device)
+    s1 = eng.triangulate_frames(t(b.offsets), t(b.cur_u), t(b.cur_v), t(b.ref_u), t(b.ref_v), t(b.poses))
+    maxf = int(np.max(np.diff(b.offsets)))
+    out = eng.scale_frames(t(b.offsets), s1["x"], s1["y"], s1["z"], s1["u"], s1["v"], maxf, counts=s1["n_out"], seed=17, seq_id=2)
+    torch.cuda.synchronize()
+    st = stats_to_numpy(out["stats"]); raw = out["raw_scale"].cpu().numpy(); n_out = s1["n_out"].cpu().numpy()
+    for f in range(b.n_frames):
+        a = int(b.offsets[f]); m = int(n_out[f])
+        f3 = np.stack([s1[k][a:a + m].cpu().numpy() for k in "xyz"], 1).astype(np.float64)
+        f2 = np.stack([s1[k][a:a + m].cpu().numpy() for k in "uv"], 1).astype(np.float64)
+        rec = P.feature_selection(f3, f2)
+        rr = P.ransac_plane(rec["point_selected"], 17, f, seq=2, max_iterations=iters, stop_at_goal=bool(stop))
+        assert (st["best_hyp"][f], st["best_ic"][f], st["hyps_used"][f]) == (rr["best_hyp"], rr["ic"], rr["hyps_used"]), (f, iters, stop)
+        np.testing.assert_allclose(raw[f], 1.7 / P.height_from_model(rr["model"]), rtol=1e-9)
+    eng.close()
