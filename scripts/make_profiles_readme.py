@@ -40,8 +40,7 @@ half-warp stars) -> 91 k (warp-per-star gift wrapping, lanes = candidates) -> 11
 (**Delaunay #2 reuses the stars of Delaunay #1**) -> 188.9 k (dense nearest-first streaming, seeded rebuilds, one-pass median)
 -> 190.4 k (filter prefetch) -> 196.0 k (quick accept of the cap test, seeded wrap walk) -> {n1['value'] / 1e3:.1f} k (pair-path
 micro-optimisations: one order-preserving key per step, slots populated on demand, closed-form candidate decode; 203.7 k, then
-896 threads per CTA instead of 1024: 73 registers per thread, no spills).  The ncu capture and the per-phase table below are of
-the 1024-thread build (203.7 k).
+896 threads per CTA instead of 1024: 73 registers per thread, no spills; RANSAC scoring pipelined).
 
 ## The other BASELINE configurations (`bench.py --workload ...`; measured with the 190 k build)
 
@@ -82,16 +81,16 @@ block, ~320 stars per frame); `frame_kernel.cuh` = load / grid build / ring pre-
 
 | phase | session start | now |
 |---|---|---|
-| load + stage 1 + ROI | 23 k | 23 k |
+| load + stage 1 + ROI | 23 k | 22 k |
 | grid #1 | 20 k | 20 k |
-| stars #1 (vote pass; of which pair path) | 943 k (642 k) | 832 k (571 k) |
-| keep + compaction + grid #2 (+ ring pre-pass) | 24 k | 52 k |
-| stars #2 (emit pass; of which pair path) | 838 k (570 k) | 347 k (202 k) |
-| planes | 8 k | 8 k |
-| median | 68 k | 21 k |
+| stars #1 (vote pass; of which pair path) | 943 k (642 k) | 813 k (570 k) |
+| keep + compaction + grid #2 (+ ring pre-pass) | 24 k | 54 k |
+| stars #2 (emit pass; of which pair path) | 838 k (570 k) | 342 k (199 k) |
+| planes | 8 k | 7 k |
+| median | 68 k | 20 k |
 | vertex list | 9 k | 9 k |
-| RANSAC | 39 k | 39 k |
-| total | 1.97 M | 1.35 M |
+| RANSAC | 39 k | 28 k |
+| total | 1.97 M | 1.32 M |
 
 Stars that leave the pair path: 350 -> 322 per frame (82 hull / far-neighbour steps, 229 circles leaving the 5x5 block;
 `scripts/star_counters.py` with `-DMVOSR_STAR_COUNTERS`); the wrap path takes 6.9 steps and 2.8 streaming calls per star
