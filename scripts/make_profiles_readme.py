@@ -26,10 +26,10 @@ profiler); ncu numbers are from separate profiled runs of the same command.  `sc
 | GPUs | frames/s (device-resident) | ms/step | frames/s end to end (pinned host buffers, H2D+D2H inside) | file |
 |---|---|---|---|---|
 | 1 | {n1['value']:.0f} | {n1['ms_per_step']:.2f} | {n1['e2e']['value']:.0f} | `bench_r01_final_n1.json` |
-| 8 | {n8['value']:.0f} | {n8['ms_per_step']:.2f} | {n8['e2e']['value']:.0f} | `bench_r01_final_n8.json` (an earlier build of this session: one GPU ran 190.4 k with it) |
+| 8 | {n8['value']:.0f} | {n8['ms_per_step']:.2f} | {n8['e2e']['value']:.0f} | `bench_r01_final_n8.json` |
 
-Weak scaling 8 GPUs / 1 GPU: {n8['value'] / 190435.07:.2f}x against the single-GPU line of the same build (one 4 541-frame sequence per GPU; one
-all-gather of 24 B/frame).
+Weak scaling 8 GPUs / 1 GPU: {n8['value'] / n1['value']:.2f}x (one 4 541-frame sequence per GPU; one all-gather of 24 B/frame, then the
+filter over all eight sequences on every rank); 2 GPUs: `bench_r01_final_n2.json` (408.0 k with the build before the RANSAC change).
 Reference arm (`bench.py --impl reference`, oracle port of stages 1-5 on {ref['cpu_baseline']['cores']} host cores): {ref['value']:.0f} frames/s
 (`bench_r01_reference.json`); single core: {n1['cpu_baseline']['value']:.1f} frames/s.  The unmodified reference (Python loops per triangle)
 measured 0.53-0.69 s/frame/core in the build container (SURVEY.md 3.3).
@@ -42,7 +42,7 @@ half-warp stars) -> 91 k (warp-per-star gift wrapping, lanes = candidates) -> 11
 micro-optimisations: one order-preserving key per step, slots populated on demand, closed-form candidate decode; 203.7 k, then
 896 threads per CTA instead of 1024: 73 registers per thread, no spills; RANSAC scoring pipelined).
 
-## The other BASELINE configurations (`bench.py --workload ...`; measured with the 190 k build)
+## The other BASELINE configurations (`bench.py --workload ...`; dense and the 8-GPU fleet line measured with the 190 k build)
 
 | workload | GPUs | frames/s | ms/step | end to end | note | file |
 |---|---|---|---|---|---|---|
