@@ -42,10 +42,11 @@ def frame_shards(n_frames_total: int, world_size: int, weights: Sequence[float] 
 def pack_results(raw_scale: torch.Tensor, status: torch.Tensor, n_features: torch.Tensor, pad_to: int) -> torch.Tensor:
     """(L,) f64 / u8 / i32 -> (pad_to, 3) f64 (status and counts are exactly representable)."""
     L = raw_scale.numel()
+    packed = torch.stack([raw_scale, status.to(torch.float64), n_features.to(torch.float64)], 1)
+    if L == pad_to:
+        return packed
     out = torch.zeros(pad_to, 3, dtype=torch.float64, device=raw_scale.device)
-    out[:L, 0] = raw_scale
-    out[:L, 1] = status.to(torch.float64)
-    out[:L, 2] = n_features.to(torch.float64)
+    out[:L] = packed
     return out
 
 
@@ -59,6 +60,8 @@ def gather_results(raw_scale, status, n_features, shards: List[Tuple[int, int]],
     mine = pack_results(raw_scale, status, n_features, max_len)
     full = torch.empty(world, max_len, 3, dtype=torch.float64, device=mine.device)
     dist.all_gather_into_tensor(full.view(world * max_len, 3), mine, group=group)
-    parts = [full[r, : e - s] for r, (s, e) in enumerate(shards)]
-    cat = torch.cat(parts, 0) if parts else mine[:0]
+    if all(e - s == max_len for s, e in shards):              # equal shards (weak scaling): no padding to strip
+        cat = full.view(world * max_len, 3)
+    else:
+        cat = torch.cat([full[r, : e - s] for r, (s, e) in enumerate(shards)], 0)
     return cat[:, 0].contiguous(), cat[:, 1].to(torch.uint8).contiguous(), cat[:, 2].to(torch.int32).contiguous()

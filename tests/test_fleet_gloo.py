@@ -33,16 +33,18 @@ def _rank_main(rank, world, port, tmp):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from mvoscalerecovery_b200.fleet import frame_shards, gather_results
-    total = 23                                  # uneven shards: 11 + 12
-    shards = frame_shards(total, world)
-    s, e = shards[rank]
-    g = torch.Generator().manual_seed(5)
-    raw_all = torch.rand(total, dtype=torch.float64, generator=g) + 0.5
-    raw_all[3] = float("nan")
-    st_all = torch.randint(0, 128, (total,), dtype=torch.uint8, generator=g)
-    nf_all = torch.randint(0, 3000, (total,), dtype=torch.int32, generator=g)
-    raw, st, nf = gather_results(raw_all[s:e].clone(), st_all[s:e].clone(), nf_all[s:e].clone(), shards)
-    ok = torch.equal(torch.nan_to_num(raw, nan=-1.0), torch.nan_to_num(raw_all, nan=-1.0)) and torch.equal(st, st_all) and torch.equal(nf, nf_all)
+    ok = True
+    for total in (23, 24):                      # uneven shards (11 + 12: padded) and even ones (12 + 12: the unpadded fast path)
+        shards = frame_shards(total, world)
+        s, e = shards[rank]
+        g = torch.Generator().manual_seed(5)
+        raw_all = torch.rand(total, dtype=torch.float64, generator=g) + 0.5
+        raw_all[3] = float("nan")
+        st_all = torch.randint(0, 128, (total,), dtype=torch.uint8, generator=g)
+        nf_all = torch.randint(0, 3000, (total,), dtype=torch.int32, generator=g)
+        raw, st, nf = gather_results(raw_all[s:e].clone(), st_all[s:e].clone(), nf_all[s:e].clone(), shards)
+        ok = ok and torch.equal(torch.nan_to_num(raw, nan=-1.0), torch.nan_to_num(raw_all, nan=-1.0)) and torch.equal(st, st_all) and torch.equal(nf, nf_all)
+        ok = ok and raw.is_contiguous() and st.dtype == torch.uint8 and nf.dtype == torch.int32
     with open(os.path.join(tmp, "rank%d" % rank), "w") as f:
         f.write("ok" if ok else "mismatch")
     dist.destroy_process_group()
