@@ -195,6 +195,14 @@ def main():
                    ev_dist=np.asarray(mods["evaluate_vo"].trajectory_distances(gt)),
                    es_gt=sgt, es_re=sre, es_patch=mods["evaluate_scale"].patch(sgt[:1100] - sre, 50, 10),
                    es_filter=mods["evaluate_scale"].filter(sre, 10))
+    # ---- get_path / motion2pose of src/main_offline.py:95-119 (the module reads sys.argv only inside main())
+    spec = importlib.util.spec_from_file_location("ref_main_offline", os.path.join(H.REF_SRC, "main_offline.py"))
+    mo = importlib.util.module_from_spec(spec)
+    with contextlib.redirect_stdout(io.StringIO()):
+        spec.loader.exec_module(mo)
+    gp_mot = np.tile(np.hstack([np.eye(3), [[0.0], [0.0], [1.0]]]).reshape(-1), (60, 1)) + 0.01 * rng.standard_normal((60, 12))
+    gp_sc = rng.uniform(0.0, 1.4, 60)
+    out.update(gp_motions=gp_mot.copy(), gp_scales=gp_sc, gp_poses=np.asarray(mo.get_path(gp_mot.copy(), gp_sc)))
     path = os.path.join(ROOT, "tests", "golden", "scripts.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: np.asarray(v).shape for k, v in out.items() if not k.startswith("frame") and not k.startswith("sc_f3")})
