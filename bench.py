@@ -223,6 +223,42 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def build_rank_workload(workload, rank, world, frames=0, features=0, lengths=KITTI_LENGTHS):
+    """What rank `rank` of `world` processes (host-side, no GPU): its CSR batch, the sequence pieces it consists of
+    [(sequence, first frame, end frame)], every rank's frame range in the global frame order, and the sequence offsets of
+    the whole job.  kitti00 / dense: weak scaling, sequence `rank` of the fleet on this rank.  fleet: strong scaling, the
+    concatenated sequences cut into `world` contiguous frame ranges -- a range may span sequences."""
+    from mvoscalerecovery_b200 import fleet, synth
+    wl_frames, wl_corr, wl_desc = WORKLOADS[workload]
+    n_corr = features or wl_corr
+    if workload == "fleet":
+        seq_starts = np.concatenate([[0], np.cumsum(lengths)])
+        total_frames = int(seq_starts[-1])
+        shards = fleet.frame_shards(total_frames, world)
+        lo, hi = shards[rank]
+        pieces = []
+        for sq in range(len(lengths)):
+            a, b = max(lo, int(seq_starts[sq])), min(hi, int(seq_starts[sq + 1]))
+            if a < b:
+                pieces.append((sq, a - int(seq_starts[sq]), b - int(seq_starts[sq])))
+        parts = [synth.make_sequence(seed=SEED, n_frames=lengths[sq], n_corr=n_corr, seq=sq, outlier_frac=0.10, frame_range=(a, b))
+                 for sq, a, b in pieces]
+        n_frames = hi - lo
+        seq_off_host = seq_starts.astype(np.int32)
+    else:
+        n_frames = frames or wl_frames
+        total_frames = world * n_frames
+        shards = [(r * n_frames, (r + 1) * n_frames) for r in range(world)]
+        pieces = [(rank, 0, n_frames)]
+        parts = [make_workload(n_frames, n_corr, seq=rank)]
+        seq_off_host = np.arange(0, (world + 1) * n_frames, n_frames, dtype=np.int32)
+    batch = parts[0] if len(parts) == 1 else synth.CorrespondenceBatch(
+        np.concatenate([[0]] + [p.offsets[1:].astype(np.int64) + sum(int(q.offsets[-1]) for q in parts[:i]) for i, p in enumerate(parts)]).astype(np.int32),
+        *[np.concatenate([getattr(p, k) for p in parts]) for k in ("cur_u", "cur_v", "ref_u", "ref_v", "poses", "move_flags", "true_scale")])
+    return dict(batch=batch, pieces=pieces, shards=shards, seq_off_host=seq_off_host, total_frames=total_frames, n_frames=n_frames,
+                n_corr=n_corr, desc=wl_desc)
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_gpu_arm(args):
     import torch
@@ -244,34 +280,9 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from mvoscalerecovery_b200 import synth
-    wl_frames, wl_corr, wl_desc = WORKLOADS[args.workload]
-    n_corr = args.features or wl_corr
-    if args.workload == "fleet":
-        # strong scaling: the concatenated fleet is cut into `world` contiguous frame ranges; a range may span sequences
-        seq_starts = np.concatenate([[0], np.cumsum(KITTI_LENGTHS)])
-        total_frames = int(seq_starts[-1])
-        shards = fleet.frame_shards(total_frames, world)
-        lo, hi = shards[rank]
-        pieces = []                                               # (sequence, first frame, end frame) of this rank's range
-        for sq, L in enumerate(KITTI_LENGTHS):
-            a, b = max(lo, int(seq_starts[sq])), min(hi, int(seq_starts[sq + 1]))
-            if a < b:
-                pieces.append((sq, a - int(seq_starts[sq]), b - int(seq_starts[sq])))
-        parts = [synth.make_sequence(seed=SEED, n_frames=KITTI_LENGTHS[sq], n_corr=n_corr, seq=sq, outlier_frac=0.10, frame_range=(a, b))
-                 for sq, a, b in pieces]
-        n_frames = hi - lo
-        seq_off_host = seq_starts.astype(np.int32)
-    else:
-        n_frames = args.frames or wl_frames
-        total_frames = world * n_frames
-        shards = [(r * n_frames, (r + 1) * n_frames) for r in range(world)]
-        pieces = [(rank, 0, n_frames)]                            # weak scaling: sequence `rank` of the fleet on this rank
-        parts = [make_workload(n_frames, n_corr, seq=rank)]
-        seq_off_host = np.arange(0, (world + 1) * n_frames, n_frames, dtype=np.int32)
-    batch = parts[0] if len(parts) == 1 else synth.CorrespondenceBatch(
-        np.concatenate([[0]] + [p.offsets[1:].astype(np.int64) + sum(int(q.offsets[-1]) for q in parts[:i]) for i, p in enumerate(parts)]).astype(np.int32),
-        *[np.concatenate([getattr(p, k) for p in parts]) for k in ("cur_u", "cur_v", "ref_u", "ref_v", "poses", "move_flags", "true_scale")])
+    wl = build_rank_workload(args.workload, rank, world, args.frames, args.features)
+    batch, pieces, shards, seq_off_host = wl["batch"], wl["pieces"], wl["shards"], wl["seq_off_host"]
+    total_frames, n_frames, n_corr, wl_desc = wl["total_frames"], wl["n_frames"], wl["n_corr"], wl["desc"]
     max_feat = int(np.max(np.diff(batch.offsets)))
     eng = ScaleRecovery(device=local_rank, absolute_reference=1.7)
     piece_off = np.concatenate([[0], np.cumsum([b - a for _, a, b in pieces])]).astype(np.int64)      # frame offsets of the pieces in this rank's batch
