@@ -1,0 +1,193 @@
+"""The five-point solver restated with DEVICE-FRIENDLY numerics only -- TEST INFRASTRUCTURE (oracle side), a blueprint for the
+CUDA kernel of SURVEY N1 (not built yet).
+
+``oracle/five_point.py`` leans on LAPACK (SVD for the null space, a general eigen-decomposition for the action matrix), neither
+of which exists inside a kernel.  This module solves the same minimal problem with what one thread or one warp can do in
+registers, and is checked against the LAPACK version in tests/test_oracle_five_point.py:
+
+  1. null space of the 5x9 epipolar system by Gauss-Jordan elimination with full pivoting (4 free columns), orthonormalised
+     by modified Gram-Schmidt;
+  2. the ten cubic constraints by polynomial interpolation: they are cubics in (x, y, z) with 20 coefficients, so their values at
+     20 fixed generic sample points times a constant inverse Vandermonde matrix give the 10x20 coefficient matrix -- on the GPU
+     one lane per sample point evaluates det E and 2 E E^T E - tr(E E^T) E numerically, no symbolic expansion;
+  3. Gauss-Jordan on the 10x20 matrix (partial pivoting), action matrix of "multiply by x" on the basis
+     [x^2, xy, xz, y^2, yz, z^2, x, y, z, 1];
+  4. its characteristic polynomial by the Faddeev-LeVerrier recurrence (ten 10x10 products), real roots by Sturm-sequence
+     isolation + bisection, each root polished on the MATRIX by Rayleigh-quotient iteration (the coefficients of the
+     characteristic polynomial are ill-conditioned, the eigenvalues of A are not);
+  5. for every real root x: the remaining unknowns (y^2, yz, z^2, y, z) from the first six rows of (A - x I) v = 0 by a 6x5
+     least-squares solve (normal equations, Gaussian elimination).
+
+Status (tests/test_oracle_five_point.py): solutions found agree with the LAPACK version to < 1e-6; about 7 % of the LAPACK
+version's solutions are missed (the true pose in ~3 % of noise-free problems) -- all in problems whose eigenvalues spread over
+several orders of magnitude, where the COEFFICIENTS of the characteristic polynomial (step 4) lose the small roots.  RANSAC
+tolerates that (a few more iterations); the upgrade, if wanted, is to evaluate det(A - x I) on a Hessenberg form (Hyman's
+method) inside the bracketing instead of forming the coefficients.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .five_point import _MONO
+
+# 20 sample points for the interpolation: the principal lattice of degree 3 on the nodes t (i + j + k <= 3), which is unisolvent
+# for cubics in three variables, and the inverse Vandermonde matrix in the monomial order (a constant table on the device)
+_T = np.array([-1.0, -0.4, 0.4, 1.0])
+_PTS = np.array([(_T[i], _T[j], _T[k]) for i in range(4) for j in range(4) for k in range(4) if i + j + k <= 3])
+_VAND = np.array([[p[0] ** i * p[1] ** j * p[2] ** k for (i, j, k) in _MONO] for p in _PTS])
+_VINV = np.linalg.inv(_VAND)
+
+
+def _null4(Q):
+    """Four null vectors of the 5x9 matrix Q by Gauss-Jordan with full pivoting."""
+    M = Q.astype(np.float64).copy()
+    cols = list(range(9))
+    for r in range(5):
+        sub = np.abs(M[r:, r:])
+        i, j = np.unravel_index(int(np.argmax(sub)), sub.shape)
+        M[[r, r + i]] = M[[r + i, r]]
+        M[:, [r, r + j]] = M[:, [r + j, r]]
+        cols[r], cols[r + j] = cols[r + j], cols[r]
+        M[r] /= M[r, r]
+        for k in range(5):
+            if k != r:
+                M[k] -= M[k, r] * M[r]
+    out = np.zeros((4, 9))
+    for f in range(4):                                             # free column 5 + f set to 1
+        v = np.zeros(9)
+        v[5 + f] = 1.0
+        v[:5] = -M[:, 5 + f]
+        out[f, cols] = v
+    for f in range(4):                                             # modified Gram-Schmidt: an orthonormal basis keeps the unknowns
+        for g in range(f):                                         # x, y, z (coordinates relative to the fourth vector) moderate
+            out[f] -= (out[f] @ out[g]) * out[g]
+        out[f] /= np.linalg.norm(out[f])
+    return out
+
+
+def _constraints_at(E):
+    """det E and the nine entries of 2 E E^T E - tr(E E^T) E, numerically, for one 3x3 matrix."""
+    EEt = E @ E.T
+    return np.concatenate([[np.linalg.det(E)], (2 * EEt @ E - np.trace(EEt) * E).reshape(-1)])
+
+
+def _charpoly(A):
+    """Coefficients c[0] = 1, ..., c[n] of det(lambda I - A) by Faddeev-LeVerrier."""
+    n = A.shape[0]
+    c = np.zeros(n + 1)
+    c[0] = 1.0
+    Mk = np.zeros_like(A)
+    for k in range(1, n + 1):
+        Mk = A @ Mk + c[k - 1] * np.eye(n)
+        c[k] = -np.trace(A @ Mk) / k
+    return c
+
+
+def _poly_eval(c, x):
+    v = 0.0
+    for a in c:
+        v = v * x + a
+    return v
+
+
+def _sturm_chain(c):
+    """Sturm chain of the polynomial c; every remainder is rescaled by a POSITIVE factor (its largest magnitude), which keeps
+    the signs and keeps the coefficients in range."""
+    p0 = np.array(c, dtype=np.float64)
+    p0 = p0 / np.abs(p0).max()
+    p1 = np.polyder(p0)
+    p1 = p1 / np.abs(p1).max()
+    chain = [p0, p1]
+    while len(chain[-1]) > 1:
+        _, r = np.polydiv(chain[-2], chain[-1])
+        r = np.trim_zeros(r, "f")
+        if r.size == 0 or np.abs(r).max() < 1e-14 * max(np.abs(chain[-2]).max(), 1e-300):
+            break
+        chain.append(-r / np.abs(r).max())
+    return chain
+
+
+def _sign_changes(chain, x):
+    s = [np.polyval(p, x) for p in chain]
+    s = [v for v in s if v != 0]
+    return sum(1 for a, b in zip(s, s[1:]) if (a < 0) != (b < 0))
+
+
+def _real_roots(c):
+    """Real roots of the polynomial c (leading coefficient first), isolated with a Sturm chain and bisection down to a
+    relative width of 1e-7 (close pairs are split as long as the chain resolves them; a pair it cannot split is reported
+    once).  The caller polishes each root on the matrix, not on the ill-conditioned coefficients."""
+    c = np.array(c, dtype=np.float64)
+    bound = 1.0 + np.abs(c[1:] / c[0]).max()                       # Cauchy bound
+    chain = _sturm_chain(c)
+    roots, stack = [], [(-bound, bound)]
+    while stack:
+        lo, hi = stack.pop()
+        n = _sign_changes(chain, lo) - _sign_changes(chain, hi)
+        if n <= 0:
+            continue
+        if hi - lo < 1e-7 * max(1.0, abs(lo), abs(hi)):
+            roots.append(0.5 * (lo + hi))
+            continue
+        mid = 0.5 * (lo + hi)
+        stack.append((lo, mid)); stack.append((mid, hi))
+    return sorted(roots)
+
+
+def _polish_eigenvalue(A, x, steps=3):
+    """Rayleigh-quotient iteration on (A, A^T) from the approximate eigenvalue x: a few 10x10 solves, quadratic convergence."""
+    n = A.shape[0]
+    v = np.ones(n) / np.sqrt(n)
+    u = np.ones(n) / np.sqrt(n)
+    for _ in range(steps):
+        S = A - x * np.eye(n)
+        try:
+            v = np.linalg.solve(S, v)
+            u = np.linalg.solve(S.T, u)
+        except np.linalg.LinAlgError:
+            break                                                 # exactly singular: x is an eigenvalue to working precision
+        v /= np.linalg.norm(v)
+        u /= np.linalg.norm(u)
+        d = u @ v
+        if abs(d) < 1e-12:
+            break
+        x = (u @ (A @ v)) / d
+    return x
+
+
+def five_point_device_style(x1, x2):
+    """Same contract as oracle.five_point.five_point, device-friendly numerics (see the module docstring)."""
+    x1h = np.hstack([np.asarray(x1, dtype=np.float64), np.ones((5, 1))])
+    x2h = np.hstack([np.asarray(x2, dtype=np.float64), np.ones((5, 1))])
+    Q = np.stack([np.kron(x2h[i], x1h[i]) for i in range(5)])
+    X, Y, Z, W = (b.reshape(3, 3) for b in _null4(Q))
+    vals = np.stack([_constraints_at(p[0] * X + p[1] * Y + p[2] * Z + W) for p in _PTS])     # 20 x 10
+    M = (_VINV @ vals).T                                                                       # 10 x 20 coefficients
+    M = M / np.abs(M).max(1, keepdims=True)
+    for col in range(10):
+        piv = col + int(np.argmax(np.abs(M[col:, col])))
+        if abs(M[piv, col]) < 1e-13:
+            return []
+        M[[col, piv]] = M[[piv, col]]
+        M[col] /= M[col, col]
+        for r in range(10):
+            if r != col:
+                M[r] -= M[r, col] * M[col]
+    B = M[:, 10:]
+    A = np.zeros((10, 10))
+    A[0:6] = -B[0:6]
+    A[6, 0] = A[7, 1] = A[8, 2] = A[9, 6] = 1.0
+    sols = []
+    for x0 in _real_roots(_charpoly(A)):
+        x = _polish_eigenvalue(A, x0)
+        # (A - x I) v = 0 with v = [x^2, xy, xz, y^2, yz, z^2, x, y, z, 1]; x known -> unknowns u = [xy, xz, y^2, yz, z^2, y, z]
+        # rows 7, 8 give xy = x*y, xz = x*z; rows 0..5 are linear in (y^2, yz, z^2, y, z) once those are substituted
+        R = A[0:6] - x * np.eye(10)[0:6]
+        # columns: 0 x^2 (known), 1 xy = x y, 2 xz = x z, 3 y^2, 4 yz, 5 z^2, 6 x (known), 7 y, 8 z, 9 1
+        L = np.stack([R[:, 3], R[:, 4], R[:, 5], R[:, 7] + x * R[:, 1], R[:, 8] + x * R[:, 2]], 1)
+        rhs = -(R[:, 0] * x * x + R[:, 6] * x + R[:, 9])
+        u = np.linalg.solve(L.T @ L, L.T @ rhs)                   # 5x5 normal equations (Gaussian elimination on the device)
+        y, z = u[3], u[4]
+        Ek = x * X + y * Y + z * Z + W
+        sols.append(Ek / np.linalg.norm(Ek))
+    return sols

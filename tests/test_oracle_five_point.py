@@ -58,3 +58,30 @@ def test_ransac_agrees_with_opencv_within_the_noise():
         x2 = np.stack([(ref[:, 0] - K[2]) / K[0], (ref[:, 1] - K[3]) / K[1]], 1)
         cv_mask = FP.sampson_sq(z["E"][f].reshape(3, 3) / np.linalg.norm(z["E"][f]), x1, x2) < (0.5 / K[0]) ** 2
         assert (cv_mask != mask).mean() < 0.05
+
+
+def test_device_style_solver_matches_the_lapack_one():
+    """oracle/five_point_plan.py (Gauss-Jordan null space, interpolated constraints, Faddeev-LeVerrier + Sturm, Rayleigh polish)
+    against oracle/five_point.py (SVD + eig): found solutions agree; the known limitation (module docstring) is bounded."""
+    from oracle import five_point_plan as PL
+    rng = np.random.default_rng(3)
+    matched = total = true_found = n_true = 0
+    for trial in range(80):
+        R = synth._rodrigues(*rng.uniform(-0.2, 0.2, 3))
+        t = rng.standard_normal(3); t /= np.linalg.norm(t)
+        P = np.stack([rng.uniform(-2, 2, 5), rng.uniform(-1, 1, 5), rng.uniform(4, 20, 5)], 1)
+        x1 = P[:, :2] / P[:, 2:] + 1e-3 * rng.standard_normal((5, 2)) * (trial % 2)
+        P2 = P @ R.T + t
+        x2 = P2[:, :2] / P2[:, 2:]
+        a, b = FP.five_point(x1, x2), PL.five_point_device_style(x1, x2)
+        for E in a:
+            total += 1
+            matched += min([min(np.linalg.norm(E - F), np.linalg.norm(E + F)) for F in b] or [9]) < 1e-6
+        for F in b:                                               # nothing spurious: every device-style solution is (close to) a LAPACK one
+            assert min(min(np.linalg.norm(E - F), np.linalg.norm(E + F)) for E in a) < 1e-3
+        if trial % 2 == 0:
+            n_true += 1
+            Et = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ R
+            Et /= np.linalg.norm(Et)
+            true_found += min([min(np.linalg.norm(E - Et), np.linalg.norm(E + Et)) for E in b] or [9]) < 1e-7
+    assert matched >= 0.88 * total and true_found >= 0.9 * n_true
