@@ -189,5 +189,10 @@ def five_point_device_style(x1, x2):
         u = np.linalg.solve(L.T @ L, L.T @ rhs)                   # 5x5 normal equations (Gaussian elimination on the device)
         y, z = u[3], u[4]
         Ek = x * X + y * Y + z * Z + W
-        sols.append(Ek / np.linalg.norm(Ek))
+        Ek = Ek / np.linalg.norm(Ek)
+        # accept only what IS an essential matrix (a polished value that is not an eigenvalue, or an ill-conditioned 5x5 solve,
+        # gives a matrix of the null space that violates the cubic constraints): nine multiply-adds per entry on the device
+        EEt = Ek @ Ek.T
+        if np.abs(2 * EEt @ Ek - np.trace(EEt) * Ek).max() < 1e-6 and abs(np.linalg.det(Ek)) < 1e-6:
+            sols.append(Ek)
     return sols
