@@ -232,6 +232,22 @@ int  mvosr_recover_pose_frames(mvosr_handle *h, int32_t n_frames, const int32_t 
                                const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
                                const uint8_t *e_mask, const double *essential, double *poses_out, int32_t *n_good, void *stream);
 
+/* Essential matrix by five-point RANSAC -- replaces cv2.findEssentialMat(px_cur, px_ref, cameraMatrix=K, method=cv2.RANSAC,
+ * prob=0.999, threshold=0.5) (src/thirdparty/MonocularVO/visual_odometry.py:100-102,129-130; SURVEY N1, first half).  Per
+ * frame: `hypotheses` minimal samples of five correspondences drawn from the Philox stream (key = seed, counter = (hypothesis,
+ * frame_index ? frame_index[f] : f, seq_id, 1|2), csrc/five_point.cuh), every real solution of the five-point problem scored
+ * by the Sampson distance against threshold_px / ((fx + fy) / 2) (OpenCV's normalisation of its pixel threshold); the
+ * candidate with the most inliers wins, ties to the lowest (hypothesis, candidate) pair.  The hypothesis count is fixed
+ * (OpenCV adapts it to the inlier ratio with its own RNG, which cannot be reproduced; parity is defined on this stream).
+ * Outputs: essential [F][9] row-major with unit Frobenius norm, x_ref^T E x_cur = 0 in normalised coordinates -- the input of
+ * mvosr_recover_pose_frames; e_mask_out [M] (optional) the winner's inlier mask -- the e_mask of the later stages; n_inliers
+ * [F] (optional); best_hyp [F] (optional; -1 and a zero matrix for frames with fewer than five correspondences or no
+ * solution). */
+int  mvosr_find_essential_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                                 const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                                 int32_t hypotheses, double threshold_px, uint64_t seed, const int32_t *frame_index, int32_t seq_id,
+                                 double *essential, uint8_t *e_mask_out, int32_t *n_inliers, int32_t *best_hyp, void *stream);
+
 /* Dense depth from the mesh -- Reconstruct.depth_generate (src/reconstruct.py:91-107): tri.find_simplex of every integer
  * pixel (u, v) of a width x height image + the depth of that triangle's plane along the pixel's ray,
  * depth = h / (n . ((u-cx)/fx, (v-cy)/fy, 1)).  tri: [T][3] int32 into uv ([N][2] float64 pixel coordinates); datas:

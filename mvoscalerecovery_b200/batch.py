@@ -87,6 +87,27 @@ class ScaleRecovery:
         out["n_out"] = n_out
         return out
 
+    def find_essential_frames(self, offsets, cur_u, cur_v, ref_u, ref_v, hypotheses: int = 128, threshold: float = 0.5, seed: int = 0,
+                              frame_index=None, seq_id: int = 0):
+        """Replaces cv2.findEssentialMat(px_cur, px_ref, K, RANSAC, 0.999, threshold) (visual_odometry.py:100-102,129-130) for F
+        frames: five-point RANSAC on the Philox stream.  Returns dict(essential (F,9) f64, e_mask (M,) u8, n_inliers (F,), best_hyp (F,))."""
+        dev = self.device
+        F = offsets.numel() - 1
+        _chk(offsets, torch.int32, "offsets", dev)
+        for n, t in (("cur_u", cur_u), ("cur_v", cur_v), ("ref_u", ref_u), ("ref_v", ref_v)):
+            _chk(t, torch.float32, n, dev)
+        if frame_index is not None:
+            _chk(frame_index, torch.int32, "frame_index", dev)
+        essential = torch.zeros((F, 9), dtype=torch.float64, device=dev)
+        e_mask = torch.zeros(cur_u.numel(), dtype=torch.uint8, device=dev)
+        n_inliers = torch.zeros(F, dtype=torch.int32, device=dev)
+        best_hyp = torch.full((F,), -1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_find_essential_frames(self._h, F, _ptr(offsets), _ptr(cur_u), _ptr(cur_v), _ptr(ref_u), _ptr(ref_v),
+                                                         int(hypotheses), float(threshold), int(seed), _ptr(frame_index), int(seq_id),
+                                                         _ptr(essential), _ptr(e_mask), _ptr(n_inliers), _ptr(best_hyp), self._stream()))
+        return dict(essential=essential, e_mask=e_mask, n_inliers=n_inliers, best_hyp=best_hyp)
+
     def recover_pose_frames(self, offsets, cur_u, cur_v, ref_u, ref_v, essential, e_mask=None):
         """The pose selection of cv2.recoverPose (visual_odometry.py:129-133): essential (F,9) float64 -> dict(poses (F,12), n_good (F,4))."""
         dev = self.device

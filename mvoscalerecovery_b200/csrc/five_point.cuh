@@ -1,0 +1,399 @@
+// Five-point essential matrix + RANSAC (first half): the algorithm behind
+//   cv2.findEssentialMat(px_cur, px_ref, cameraMatrix=K, method=cv2.RANSAC, prob=0.999, threshold=0.5)
+// as the reference calls it (src/thirdparty/MonocularVO/visual_odometry.py:100-102,129-130).  The algorithm lives in OpenCV
+// (calib3d five-point.cpp + ptsetreg.cpp), not in the reference tree; OpenCV draws its samples from its own RNG, so parity is
+// defined on a Philox stream of our own (below) and pinned on the pose / inlier set.
+//
+// The minimal solver is Stewenius' action-matrix form of Nister's problem, with numerics one thread can run in its own
+// registers / local memory (no LAPACK): Gauss-Jordan null space with full pivoting, the ten cubic constraints by
+// interpolation at 20 fixed nodes, Gauss-Jordan on the 10x20 coefficient matrix, the characteristic polynomial of the 10x10
+// action matrix by Faddeev-LeVerrier, Sturm isolation + bisection of its real roots, Rayleigh-quotient polish on the matrix,
+// a 6x5 least-squares back-substitution per root, and a final test that the result IS an essential matrix.
+//
+// Everything numerical is __host__ __device__ so that tests/host_sim can compile the very same functions for the host and
+// check them against the oracle without a GPU; the library itself only ever calls them from find_essential_kernel.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef __CUDACC__
+#define MVOSR_FP5_HD __host__ __device__ inline
+#else
+#define MVOSR_FP5_HD inline
+#endif
+
+namespace mvosr {
+namespace fp5 {
+
+struct Tables { double pts[20][3]; double vinv[20][20]; };
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The sample stream: five distinct positions of range(n) for hypothesis `hyp` of frame `frame` of sequence `seq`.
+//   key = (seed lo, seed hi); (r0, r1, r2, r3) = Philox4x32-10(counter = (hyp, frame, seq, 1)); r4 = word 0 of counter (.., 2)
+//   p_k = (r_k * (n - k)) >> 32, then + 1 for every earlier position (taken in ascending order) it is >= to.
+// (Counter word 3 = 0 is the plane RANSAC's stream, philox.cuh.)
+MVOSR_FP5_HD void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+MVOSR_FP5_HD void sample5(uint64_t seed, uint32_t hyp, uint32_t frame, uint32_t seq, uint32_t n, int idx[5]) {
+    uint32_t r[8];
+    philox(hyp, frame, seq, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    philox(hyp, frame, seq, 2u, (uint32_t)seed, (uint32_t)(seed >> 32), r + 4);
+    int sorted[5];
+    for (int k = 0; k < 5; ++k) {
+        int p = (int)(((uint64_t)r[k] * (uint64_t)(n - (uint32_t)k)) >> 32);
+        for (int j = 0; j < k; ++j) if (p >= sorted[j]) ++p;
+        idx[k] = p;
+        int j = k;                                                  // insert into the ascending list
+        while (j > 0 && sorted[j - 1] > p) { sorted[j] = sorted[j - 1]; --j; }
+        sorted[j] = p;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// det E and the nine entries of 2 E E^T E - tr(E E^T) E
+MVOSR_FP5_HD void constraints_at(const double E[9], double out[10]) {
+    out[0] = E[0] * (E[4] * E[8] - E[5] * E[7]) - E[1] * (E[3] * E[8] - E[5] * E[6]) + E[2] * (E[3] * E[7] - E[4] * E[6]);
+    double G[9];                                                    // E E^T
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) G[3 * r + c] = E[3 * r] * E[3 * c] + E[3 * r + 1] * E[3 * c + 1] + E[3 * r + 2] * E[3 * c + 2];
+    const double tr = G[0] + G[4] + G[8];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            out[1 + 3 * r + c] = 2.0 * (G[3 * r] * E[c] + G[3 * r + 1] * E[3 + c] + G[3 * r + 2] * E[6 + c]) - tr * E[3 * r + c];
+}
+
+// Four orthonormal null vectors of the 5x9 epipolar system (rows kron(x2h, x1h)); false when the system is rank deficient.
+MVOSR_FP5_HD bool null4(const double x1[10], const double x2[10], double basis[4][9]) {
+    double M[5][9];
+    int cols[9];
+    for (int i = 0; i < 5; ++i) {
+        const double a[3] = { x2[2 * i], x2[2 * i + 1], 1.0 }, b[3] = { x1[2 * i], x1[2 * i + 1], 1.0 };
+        for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) M[i][3 * p + q] = a[p] * b[q];
+    }
+    for (int c = 0; c < 9; ++c) cols[c] = c;
+    for (int r = 0; r < 5; ++r) {
+        int pi = r, pj = r;
+        double best = -1.0;
+        for (int i = r; i < 5; ++i)
+            for (int j = r; j < 9; ++j) { const double v = fabs(M[i][j]); if (v > best) { best = v; pi = i; pj = j; } }
+        if (!(best > 1e-300)) return false;
+        if (pi != r) for (int j = 0; j < 9; ++j) { const double t = M[r][j]; M[r][j] = M[pi][j]; M[pi][j] = t; }
+        if (pj != r) {
+            for (int i = 0; i < 5; ++i) { const double t = M[i][r]; M[i][r] = M[i][pj]; M[i][pj] = t; }
+            const int t = cols[r]; cols[r] = cols[pj]; cols[pj] = t;
+        }
+        const double piv = M[r][r];
+        for (int j = 0; j < 9; ++j) M[r][j] /= piv;
+        for (int k = 0; k < 5; ++k) {
+            if (k == r) continue;
+            const double f = M[k][r];
+            for (int j = 0; j < 9; ++j) M[k][j] -= f * M[r][j];
+        }
+    }
+    for (int f = 0; f < 4; ++f) {
+        for (int c = 0; c < 9; ++c) basis[f][c] = 0.0;
+        basis[f][cols[5 + f]] = 1.0;
+        for (int c = 0; c < 5; ++c) basis[f][cols[c]] = -M[c][5 + f];
+    }
+    for (int f = 0; f < 4; ++f) {                                   // modified Gram-Schmidt
+        for (int g = 0; g < f; ++g) {
+            double d = 0.0;
+            for (int c = 0; c < 9; ++c) d += basis[f][c] * basis[g][c];
+            for (int c = 0; c < 9; ++c) basis[f][c] -= d * basis[g][c];
+        }
+        double n2 = 0.0;
+        for (int c = 0; c < 9; ++c) n2 += basis[f][c] * basis[f][c];
+        const double nrm = sqrt(n2);
+        if (!(nrm > 0.0)) return false;
+        for (int c = 0; c < 9; ++c) basis[f][c] /= nrm;
+    }
+    return true;
+}
+
+// The 6 non-trivial rows of the action matrix of "multiply by x" on [x^2, xy, xz, y^2, yz, z^2, x, y, z, 1]
+// (rows 6..9 are the unit vectors e0, e1, e2, e6).  false when the elimination meets a vanishing pivot.
+MVOSR_FP5_HD bool action_rows(const double basis[4][9], const Tables &T, double A6[6][10]) {
+    double M[10][20];
+    {
+        double vals[20][10];
+        for (int s = 0; s < 20; ++s) {
+            double E[9];
+            for (int c = 0; c < 9; ++c) E[c] = T.pts[s][0] * basis[0][c] + T.pts[s][1] * basis[1][c] + T.pts[s][2] * basis[2][c] + basis[3][c];
+            constraints_at(E, vals[s]);
+        }
+        for (int c = 0; c < 10; ++c)
+            for (int m = 0; m < 20; ++m) {
+                double a = 0.0;
+                for (int s = 0; s < 20; ++s) a += T.vinv[m][s] * vals[s][c];
+                M[c][m] = a;
+            }
+    }
+    for (int c = 0; c < 10; ++c) {
+        double mx = 0.0;
+        for (int m = 0; m < 20; ++m) { const double v = fabs(M[c][m]); if (v > mx) mx = v; }
+        if (!(mx > 0.0) || !(mx < 1e300)) return false;
+        for (int m = 0; m < 20; ++m) M[c][m] /= mx;
+    }
+    for (int col = 0; col < 10; ++col) {
+        int piv = col;
+        double best = fabs(M[col][col]);
+        for (int r = col + 1; r < 10; ++r) { const double v = fabs(M[r][col]); if (v > best) { best = v; piv = r; } }
+        if (!(best >= 1e-13)) return false;
+        if (piv != col) for (int m = 0; m < 20; ++m) { const double t = M[col][m]; M[col][m] = M[piv][m]; M[piv][m] = t; }
+        const double p = M[col][col];
+        for (int m = 0; m < 20; ++m) M[col][m] /= p;
+        for (int r = 0; r < 10; ++r) {
+            if (r == col) continue;
+            const double f = M[r][col];
+            for (int m = 0; m < 20; ++m) M[r][m] -= f * M[col][m];
+        }
+    }
+    for (int r = 0; r < 6; ++r) for (int c = 0; c < 10; ++c) A6[r][c] = -M[r][10 + c];
+    return true;
+}
+
+// y = A x for the structured action matrix
+MVOSR_FP5_HD void action_apply_rows(const double A6[6][10], const double Min[10][10], double Pout[10][10]) {
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 10; ++c) {
+            double a = 0.0;
+            for (int k = 0; k < 10; ++k) a += A6[r][k] * Min[k][c];
+            Pout[r][c] = a;
+        }
+    for (int c = 0; c < 10; ++c) { Pout[6][c] = Min[0][c]; Pout[7][c] = Min[1][c]; Pout[8][c] = Min[2][c]; Pout[9][c] = Min[6][c]; }
+}
+
+// Coefficients c[0] = 1, ..., c[10] of det(lambda I - A): Faddeev-LeVerrier, M_k = A M_{k-1} + c_{k-1} I, c_k = -tr(A M_k) / k
+MVOSR_FP5_HD void charpoly(const double A6[6][10], double c[11]) {
+    double Mk[10][10], P[10][10];
+    for (int i = 0; i < 10; ++i) for (int j = 0; j < 10; ++j) P[i][j] = 0.0;   // A M_0 with M_0 = 0
+    c[0] = 1.0;
+    for (int k = 1; k <= 10; ++k) {
+        for (int i = 0; i < 10; ++i) for (int j = 0; j < 10; ++j) Mk[i][j] = P[i][j] + (i == j ? c[k - 1] : 0.0);
+        action_apply_rows(A6, Mk, P);
+        double tr = 0.0;
+        for (int i = 0; i < 10; ++i) tr += P[i][i];
+        c[k] = -tr / (double)k;
+    }
+}
+
+struct Sturm { double p[11][11]; int len[11]; int n; };             // polynomials, leading coefficient first
+
+MVOSR_FP5_HD double poly_eval(const double *p, int len, double x) {
+    double v = 0.0;
+    for (int i = 0; i < len; ++i) v = v * x + p[i];
+    return v;
+}
+
+MVOSR_FP5_HD double max_abs(const double *p, int len) {
+    double m = 0.0;
+    for (int i = 0; i < len; ++i) { const double v = fabs(p[i]); if (v > m) m = v; }
+    return m;
+}
+
+// Sturm chain of c (11 coefficients); every remainder is rescaled by a positive factor.  Leading remainder coefficients
+// of magnitude <= 1e-8 are dropped (what numpy.polydiv does to its remainder), a remainder below 1e-14 of its dividend ends
+// the chain.
+MVOSR_FP5_HD void sturm_chain(const double c[11], Sturm &S) {
+    const double m0 = max_abs(c, 11);
+    for (int i = 0; i < 11; ++i) S.p[0][i] = c[i] / m0;
+    S.len[0] = 11;
+    for (int i = 0; i < 10; ++i) S.p[1][i] = S.p[0][i] * (double)(10 - i);
+    const double m1 = max_abs(S.p[1], 10);
+    for (int i = 0; i < 10; ++i) S.p[1][i] /= m1;
+    S.len[1] = 10;
+    S.n = 2;
+    while (S.len[S.n - 1] > 1 && S.n < 11) {
+        const double *u = S.p[S.n - 2], *v = S.p[S.n - 1];
+        const int lu = S.len[S.n - 2], lv = S.len[S.n - 1];
+        double r[11];
+        for (int i = 0; i < lu; ++i) r[i] = u[i];
+        const double scale = 1.0 / v[0];
+        for (int k = 0; k <= lu - lv; ++k) {
+            const double d = scale * r[k];
+            for (int j = 0; j < lv; ++j) r[k + j] -= d * v[j];
+        }
+        int start = lu - lv + 1;                                    // the remainder: lv - 1 coefficients
+        while (start < lu - 1 && fabs(r[start]) <= 1e-8) ++start;
+        const int lr = lu - start;
+        const double mr = max_abs(r + start, lr);
+        if (!(mr > 0.0) || mr < 1e-14 * fmax(max_abs(u, lu), 1e-300)) break;
+        for (int i = 0; i < lr; ++i) S.p[S.n][i] = -r[start + i] / mr;
+        S.len[S.n] = lr;
+        ++S.n;
+    }
+}
+
+MVOSR_FP5_HD int sign_changes(const Sturm &S, double x) {
+    int changes = 0, have = 0;
+    bool prev_neg = false;
+    for (int i = 0; i < S.n; ++i) {
+        const double v = poly_eval(S.p[i], S.len[i], x);
+        if (v == 0.0) continue;
+        const bool neg = v < 0.0;
+        if (have && neg != prev_neg) ++changes;
+        prev_neg = neg; have = 1;
+    }
+    return changes;
+}
+
+// Real roots of c (ascending, at most 10): Sturm isolation + bisection down to a relative width of 1e-7.
+MVOSR_FP5_HD int real_roots(const double c[11], double roots[10]) {
+    double bound = 0.0;
+    for (int i = 1; i < 11; ++i) { const double v = fabs(c[i] / c[0]); if (v > bound) bound = v; }
+    bound += 1.0;
+    if (!(bound < 1e15)) return 0;
+    Sturm S;
+    sturm_chain(c, S);
+    double lo_s[96], hi_s[96];
+    int top = 0, n_roots = 0;
+    lo_s[0] = -bound; hi_s[0] = bound; top = 1;
+    for (int pops = 0; top > 0 && pops < 4000; ++pops) {
+        --top;
+        const double lo = lo_s[top], hi = hi_s[top];
+        const int n = sign_changes(S, lo) - sign_changes(S, hi);
+        if (n <= 0) continue;
+        if (hi - lo < 1e-7 * fmax(1.0, fmax(fabs(lo), fabs(hi)))) {
+            if (n_roots < 10) roots[n_roots++] = 0.5 * (lo + hi);
+            continue;
+        }
+        const double mid = 0.5 * (lo + hi);
+        if (top + 2 > 96) continue;
+        lo_s[top] = lo; hi_s[top] = mid; ++top;
+        lo_s[top] = mid; hi_s[top] = hi; ++top;
+    }
+    for (int i = 1; i < n_roots; ++i) {                             // ascending
+        const double v = roots[i];
+        int j = i;
+        while (j > 0 && roots[j - 1] > v) { roots[j] = roots[j - 1]; --j; }
+        roots[j] = v;
+    }
+    return n_roots;
+}
+
+// Solves S z = b in place (Gaussian elimination, partial pivoting); S is destroyed.  false on an exactly zero pivot.
+template <int N>
+MVOSR_FP5_HD bool solve_in_place(double S[N][N], double b[N]) {
+    for (int col = 0; col < N; ++col) {
+        int piv = col;
+        double best = fabs(S[col][col]);
+        for (int r = col + 1; r < N; ++r) { const double v = fabs(S[r][col]); if (v > best) { best = v; piv = r; } }
+        if (!(best > 0.0)) return false;
+        if (piv != col) {
+            for (int j = 0; j < N; ++j) { const double t = S[col][j]; S[col][j] = S[piv][j]; S[piv][j] = t; }
+            const double t = b[col]; b[col] = b[piv]; b[piv] = t;
+        }
+        for (int r = col + 1; r < N; ++r) {
+            const double f = S[r][col] / S[col][col];
+            if (f == 0.0) continue;
+            for (int j = col; j < N; ++j) S[r][j] -= f * S[col][j];
+            b[r] -= f * b[col];
+        }
+    }
+    for (int r = N - 1; r >= 0; --r) {
+        double a = b[r];
+        for (int j = r + 1; j < N; ++j) a -= S[r][j] * b[j];
+        b[r] = a / S[r][r];
+    }
+    return true;
+}
+
+MVOSR_FP5_HD void shifted(const double A6[6][10], double x, bool transpose, double S[10][10]) {
+    for (int i = 0; i < 10; ++i) for (int j = 0; j < 10; ++j) S[i][j] = 0.0;
+    for (int r = 0; r < 6; ++r) for (int c = 0; c < 10; ++c) { if (transpose) S[c][r] = A6[r][c]; else S[r][c] = A6[r][c]; }
+    if (transpose) { S[0][6] = 1.0; S[1][7] = 1.0; S[2][8] = 1.0; S[6][9] = 1.0; }
+    else           { S[6][0] = 1.0; S[7][1] = 1.0; S[8][2] = 1.0; S[9][6] = 1.0; }
+    for (int i = 0; i < 10; ++i) S[i][i] -= x;
+}
+
+// Rayleigh-quotient iteration on (A, A^T) from the approximate eigenvalue x
+MVOSR_FP5_HD double polish_eigenvalue(const double A6[6][10], double x) {
+    double v[10], u[10], S[10][10];
+    for (int i = 0; i < 10; ++i) v[i] = u[i] = 0.31622776601683794;     // 1 / sqrt(10)
+    for (int step = 0; step < 3; ++step) {
+        shifted(A6, x, false, S);
+        if (!solve_in_place<10>(S, v)) break;
+        shifted(A6, x, true, S);
+        if (!solve_in_place<10>(S, u)) break;
+        double nv = 0.0, nu = 0.0;
+        for (int i = 0; i < 10; ++i) { nv += v[i] * v[i]; nu += u[i] * u[i]; }
+        nv = sqrt(nv); nu = sqrt(nu);
+        for (int i = 0; i < 10; ++i) { v[i] /= nv; u[i] /= nu; }
+        double d = 0.0;
+        for (int i = 0; i < 10; ++i) d += u[i] * v[i];
+        if (fabs(d) < 1e-12) break;
+        double num = 0.0;                                           // u . (A v)
+        for (int r = 0; r < 6; ++r) {
+            double a = 0.0;
+            for (int c = 0; c < 10; ++c) a += A6[r][c] * v[c];
+            num += u[r] * a;
+        }
+        num += u[6] * v[0] + u[7] * v[1] + u[8] * v[2] + u[9] * v[6];
+        x = num / d;
+    }
+    return x;
+}
+
+// All real essential matrices through five correspondences (normalised coordinates, x2^T E x1 = 0): up to ten 3x3 matrices
+// of unit Frobenius norm, row-major, in ascending order of the eigenvalue they belong to.  Returns how many.
+MVOSR_FP5_HD int solve(const double x1[10], const double x2[10], const Tables &T, double Eout[10][9]) {
+    double basis[4][9], A6[6][10], c[11], roots[10];
+    if (!null4(x1, x2, basis)) return 0;
+    if (!action_rows(basis, T, A6)) return 0;
+    charpoly(A6, c);
+    const int nr = real_roots(c, roots);
+    int n_sol = 0;
+    for (int k = 0; k < nr; ++k) {
+        const double x = polish_eigenvalue(A6, roots[k]);
+        // (A - x I) v = 0, v = [x^2, xy, xz, y^2, yz, z^2, x, y, z, 1]: rows 0..5 are linear in (y^2, yz, z^2, y, z) once
+        // xy = x*y and xz = x*z are substituted; 6x5 least squares through the normal equations
+        double L[6][5], rhs[6];
+        for (int r = 0; r < 6; ++r) {
+            double R[10];
+            for (int j = 0; j < 10; ++j) R[j] = A6[r][j] - (j == r ? x : 0.0);
+            L[r][0] = R[3]; L[r][1] = R[4]; L[r][2] = R[5]; L[r][3] = R[7] + x * R[1]; L[r][4] = R[8] + x * R[2];
+            rhs[r] = -(R[0] * x * x + R[6] * x + R[9]);
+        }
+        double N[5][5], g[5];
+        for (int i = 0; i < 5; ++i) {
+            for (int j = 0; j < 5; ++j) { double a = 0.0; for (int r = 0; r < 6; ++r) a += L[r][i] * L[r][j]; N[i][j] = a; }
+            double a = 0.0;
+            for (int r = 0; r < 6; ++r) a += L[r][i] * rhs[r];
+            g[i] = a;
+        }
+        if (!solve_in_place<5>(N, g)) continue;
+        const double y = g[3], z = g[4];
+        double E[9], n2 = 0.0;
+        for (int i = 0; i < 9; ++i) { E[i] = x * basis[0][i] + y * basis[1][i] + z * basis[2][i] + basis[3][i]; n2 += E[i] * E[i]; }
+        const double nrm = sqrt(n2);
+        for (int i = 0; i < 9; ++i) E[i] /= nrm;
+        double cons[10];
+        constraints_at(E, cons);
+        bool ok = true;
+        for (int i = 0; i < 10; ++i) if (!(fabs(cons[i]) < 1e-6)) ok = false;
+        if (!ok) continue;
+        for (int i = 0; i < 9; ++i) Eout[n_sol][i] = E[i];
+        ++n_sol;
+    }
+    return n_sol;
+}
+
+// Is the squared Sampson distance of one correspondence (normalised coordinates) to the epipolar constraint of E below thr2?
+// Written without the division: s^2 < thr2 * (|E x1|_xy^2 + |E^T x2|_xy^2); a vanishing denominator is never an inlier.
+MVOSR_FP5_HD bool sampson_inlier(const double E[9], double ax, double ay, double bx, double by, double thr2) {
+    const double e0 = E[0] * ax + E[1] * ay + E[2], e1 = E[3] * ax + E[4] * ay + E[5], e2 = E[6] * ax + E[7] * ay + E[8];
+    const double f0 = bx * E[0] + by * E[3] + E[6], f1 = bx * E[1] + by * E[4] + E[7];
+    const double s = bx * e0 + by * e1 + e2;
+    return s * s < thr2 * (e0 * e0 + e1 * e1 + f0 * f0 + f1 * f1);
+}
+
+}  // namespace fp5
+}  // namespace mvosr

@@ -1,0 +1,117 @@
+// find_essential_kernel: five-point RANSAC per frame (first half; the numerics are in five_point.cuh).
+//   replaces  cv2.findEssentialMat(px_cur, px_ref, K, RANSAC, 0.999, threshold)   src/thirdparty/MonocularVO/visual_odometry.py:100-102,129-130
+// One CTA per frame.  A round gives every thread one hypothesis: five positions from the Philox stream, the minimal solver (up
+// to ten candidates, kept in the thread's local memory), then all threads walk the frame's correspondences together -- staged
+// tile by tile in shared memory in normalised float64 coordinates, so every lane reads the same point (a broadcast) -- and each
+// counts the Sampson inliers of its own candidates.  The winner is the candidate with the most inliers; ties go to the lowest
+// (hypothesis, candidate) pair, so the result does not depend on the CTA size.  No adaptive stopping: the hypothesis count is
+// fixed per call (OpenCV's adaptive count only ever shortens its loop).  The last pass writes the winner's inlier mask.
+#pragma once
+#include <stdint.h>
+#include "../../include/mvosr.h"
+#include "five_point.cuh"
+#include "five_point_tables.h"
+
+namespace mvosr {
+
+__constant__ fp5::Tables c_fp5_tables = MVOSR_FP5_TABLES_INIT;
+
+constexpr int FP5_THREADS = 128;         // hypotheses per round
+constexpr int FP5_TILE = 512;            // correspondences staged per tile (16 KB of shared memory)
+
+__global__ void __launch_bounds__(FP5_THREADS) find_essential_kernel(int n_frames, const int32_t *__restrict__ offsets,
+        const float *__restrict__ cur_u, const float *__restrict__ cur_v, const float *__restrict__ ref_u, const float *__restrict__ ref_v,
+        double fx, double fy, double cx, double cy, int hypotheses, double threshold_px, uint64_t seed,
+        const int32_t *__restrict__ frame_index, int seq_id,
+        double *essential, uint8_t *e_mask, int32_t *n_inliers, int32_t *best_hyp) {
+    __shared__ double s_pt[FP5_TILE][4];
+    __shared__ unsigned long long s_key[FP5_THREADS / 32];
+    __shared__ unsigned long long s_best_key;
+    __shared__ double s_best_E[9];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double thr = threshold_px / (0.5 * (fx + fy)), thr2 = thr * thr;
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const int base = offsets[f], n = offsets[f + 1] - base;
+        const uint32_t fidx = frame_index ? (uint32_t)frame_index[f] : (uint32_t)f;
+        if (tid == 0) {
+            s_best_key = 0ull;
+            for (int i = 0; i < 9; ++i) s_best_E[i] = 0.0;
+        }
+        __syncthreads();
+        if (n >= 5) {                                               // uniform over the CTA
+            for (int h0 = 0; h0 < hypotheses; h0 += FP5_THREADS) {
+                const int hyp = h0 + tid;
+                double E[10][9];
+                int cnt[10];
+                int ns = 0;
+                if (hyp < hypotheses) {
+                    int idx[5];
+                    fp5::sample5(seed, (uint32_t)hyp, fidx, (uint32_t)seq_id, (uint32_t)n, idx);
+                    double x1[10], x2[10];
+                    for (int k = 0; k < 5; ++k) {
+                        const int p = base + idx[k];
+                        x1[2 * k] = ((double)cur_u[p] - cx) / fx; x1[2 * k + 1] = ((double)cur_v[p] - cy) / fy;
+                        x2[2 * k] = ((double)ref_u[p] - cx) / fx; x2[2 * k + 1] = ((double)ref_v[p] - cy) / fy;
+                    }
+                    ns = fp5::solve(x1, x2, c_fp5_tables, E);
+                }
+                for (int k = 0; k < 10; ++k) cnt[k] = 0;
+                for (int t0 = 0; t0 < n; t0 += FP5_TILE) {
+                    const int m = min(FP5_TILE, n - t0);
+                    __syncthreads();                                // the previous tile has been consumed
+                    for (int i = tid; i < m; i += FP5_THREADS) {
+                        const int p = base + t0 + i;
+                        s_pt[i][0] = ((double)cur_u[p] - cx) / fx; s_pt[i][1] = ((double)cur_v[p] - cy) / fy;
+                        s_pt[i][2] = ((double)ref_u[p] - cx) / fx; s_pt[i][3] = ((double)ref_v[p] - cy) / fy;
+                    }
+                    __syncthreads();
+                    for (int k = 0; k < ns; ++k) {
+                        double e[9];
+                        for (int i = 0; i < 9; ++i) e[i] = E[k][i];
+                        int c = 0;
+                        for (int i = 0; i < m; ++i) c += fp5::sampson_inlier(e, s_pt[i][0], s_pt[i][1], s_pt[i][2], s_pt[i][3], thr2) ? 1 : 0;
+                        cnt[k] += c;
+                    }
+                }
+                int bk = -1, bc = 0;
+                for (int k = 0; k < ns; ++k) if (cnt[k] > bc) { bc = cnt[k]; bk = k; }
+                const unsigned long long key = bk >= 0 ? ((unsigned long long)(uint32_t)bc << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(hyp * 16 + bk)) : 0ull;
+                unsigned long long wmax = key;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, wmax, o);
+                    if (other > wmax) wmax = other;
+                }
+                if (lane == 0) s_key[warp] = wmax;
+                __syncthreads();
+                unsigned long long bmax = s_key[0];
+                for (int w = 1; w < FP5_THREADS / 32; ++w) if (s_key[w] > bmax) bmax = s_key[w];
+                const unsigned long long old = s_best_key;
+                __syncthreads();
+                if (key != 0ull && key == bmax && bmax > old) {      // keys are unique: exactly one thread
+                    s_best_key = bmax;
+                    for (int i = 0; i < 9; ++i) s_best_E[i] = E[bk][i];
+                }
+            }
+        }
+        __syncthreads();
+        const unsigned long long win = s_best_key;
+        double e[9];
+        for (int i = 0; i < 9; ++i) e[i] = s_best_E[i];
+        if (e_mask)
+            for (int i = tid; i < n; i += FP5_THREADS) {
+                const int p = base + i;
+                const double ax = ((double)cur_u[p] - cx) / fx, ay = ((double)cur_v[p] - cy) / fy;
+                const double bx = ((double)ref_u[p] - cx) / fx, by = ((double)ref_v[p] - cy) / fy;
+                e_mask[p] = (win != 0ull && fp5::sampson_inlier(e, ax, ay, bx, by, thr2)) ? 1 : 0;
+            }
+        if (tid == 0) {
+            for (int i = 0; i < 9; ++i) essential[9 * (size_t)f + i] = e[i];
+            if (n_inliers) n_inliers[f] = (int32_t)(win >> 32);
+            if (best_hyp) best_hyp[f] = win != 0ull ? (int32_t)((0xFFFFFFFFu - (uint32_t)(win & 0xFFFFFFFFull)) >> 4) : -1;
+        }
+        __syncthreads();                                            // s_best_* are reset by thread 0 for the next frame
+    }
+}
+
+}  // namespace mvosr

@@ -1,5 +1,6 @@
 """The five-point solver restated with DEVICE-FRIENDLY numerics only -- TEST INFRASTRUCTURE (oracle side), a blueprint for the
-CUDA kernel of SURVEY N1 (not built yet).
+CUDA kernel of SURVEY N1 (mvoscalerecovery_b200/csrc/five_point.cuh + five_point_kernel.cuh, written independently in C++),
+and the RANSAC around it on the shared Philox stream (``find_essential_philox``): the checker of mvosr_find_essential_frames.
 
 ``oracle/five_point.py`` leans on LAPACK (SVD for the null space, a general eigen-decomposition for the action matrix), neither
 of which exists inside a kernel.  This module solves the same minimal problem with what one thread or one warp can do in
@@ -45,6 +46,8 @@ def _null4(Q):
     for r in range(5):
         sub = np.abs(M[r:, r:])
         i, j = np.unravel_index(int(np.argmax(sub)), sub.shape)
+        if not sub[i, j] > 1e-300:
+            return None                                            # rank-deficient sample (repeated correspondences)
         M[[r, r + i]] = M[[r + i, r]]
         M[:, [r, r + j]] = M[:, [r + j, r]]
         cols[r], cols[r + j] = cols[r + j], cols[r]
@@ -119,9 +122,13 @@ def _real_roots(c):
     once).  The caller polishes each root on the matrix, not on the ill-conditioned coefficients."""
     c = np.array(c, dtype=np.float64)
     bound = 1.0 + np.abs(c[1:] / c[0]).max()                       # Cauchy bound
+    if not bound < 1e15:
+        return []
     chain = _sturm_chain(c)
     roots, stack = [], [(-bound, bound)]
-    while stack:
+    pops = 0
+    while stack and pops < 4000:
+        pops += 1
         lo, hi = stack.pop()
         n = _sign_changes(chain, lo) - _sign_changes(chain, hi)
         if n <= 0:
@@ -131,7 +138,7 @@ def _real_roots(c):
             continue
         mid = 0.5 * (lo + hi)
         stack.append((lo, mid)); stack.append((mid, hi))
-    return sorted(roots)
+    return sorted(roots[:10])
 
 
 def _polish_eigenvalue(A, x, steps=3):
@@ -160,10 +167,16 @@ def five_point_device_style(x1, x2):
     x1h = np.hstack([np.asarray(x1, dtype=np.float64), np.ones((5, 1))])
     x2h = np.hstack([np.asarray(x2, dtype=np.float64), np.ones((5, 1))])
     Q = np.stack([np.kron(x2h[i], x1h[i]) for i in range(5)])
-    X, Y, Z, W = (b.reshape(3, 3) for b in _null4(Q))
+    basis = _null4(Q)
+    if basis is None:
+        return []
+    X, Y, Z, W = (b.reshape(3, 3) for b in basis)
     vals = np.stack([_constraints_at(p[0] * X + p[1] * Y + p[2] * Z + W) for p in _PTS])     # 20 x 10
     M = (_VINV @ vals).T                                                                       # 10 x 20 coefficients
-    M = M / np.abs(M).max(1, keepdims=True)
+    mx = np.abs(M).max(1, keepdims=True)
+    if not (np.all(mx > 0) and np.all(mx < 1e300)):
+        return []
+    M = M / mx
     for col in range(10):
         piv = col + int(np.argmax(np.abs(M[col:, col])))
         if abs(M[piv, col]) < 1e-13:
@@ -186,7 +199,10 @@ def five_point_device_style(x1, x2):
         # columns: 0 x^2 (known), 1 xy = x y, 2 xz = x z, 3 y^2, 4 yz, 5 z^2, 6 x (known), 7 y, 8 z, 9 1
         L = np.stack([R[:, 3], R[:, 4], R[:, 5], R[:, 7] + x * R[:, 1], R[:, 8] + x * R[:, 2]], 1)
         rhs = -(R[:, 0] * x * x + R[:, 6] * x + R[:, 9])
-        u = np.linalg.solve(L.T @ L, L.T @ rhs)                   # 5x5 normal equations (Gaussian elimination on the device)
+        try:
+            u = np.linalg.solve(L.T @ L, L.T @ rhs)               # 5x5 normal equations (Gaussian elimination on the device)
+        except np.linalg.LinAlgError:
+            continue
         y, z = u[3], u[4]
         Ek = x * X + y * Y + z * Z + W
         Ek = Ek / np.linalg.norm(Ek)
@@ -196,3 +212,56 @@ def five_point_device_style(x1, x2):
         if np.abs(2 * EEt @ Ek - np.trace(EEt) * Ek).max() < 1e-6 and abs(np.linalg.det(Ek)) < 1e-6:
             sols.append(Ek)
     return sols
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# RANSAC on a DEFINED sample stream (OpenCV's own RNG cannot be reproduced): the checker of mvosr_find_essential_frames.
+#   key = (seed lo, seed hi); (r0..r3) = Philox4x32-10(counter = (hyp, frame, seq, 1)); r4 = word 0 of counter (hyp, frame, seq, 2)
+#   p_k = (r_k * (n - k)) >> 32, then + 1 for every earlier position (ascending) it is >= to   -> five distinct positions
+# Selection: the candidate with the most Sampson inliers over a FIXED number of hypotheses; ties go to the lowest
+# (hypothesis, candidate) pair, candidates in ascending order of their eigenvalue.
+def sample5_positions(seed, hyp, frame, seq, n):
+    from .philox import MASK, philox4x32_10
+    key = (seed & MASK, (seed >> 32) & MASK)
+    r = list(philox4x32_10((hyp, frame, seq, 1), key)) + [philox4x32_10((hyp, frame, seq, 2), key)[0]]
+    chosen = []
+    for k in range(5):
+        p = (r[k] * (n - k)) >> 32
+        for a in sorted(chosen):
+            if p >= a:
+                p += 1
+        chosen.append(p)
+    return chosen
+
+
+def sampson_inlier(E, x1, x2, thr2):
+    """s^2 < thr2 * (|E x1|_xy^2 + |E^T x2|_xy^2), the division-free form the kernel uses."""
+    x1h = np.hstack([x1, np.ones((x1.shape[0], 1))])
+    x2h = np.hstack([x2, np.ones((x2.shape[0], 1))])
+    Ex1 = x1h @ E.T
+    Etx2 = x2h @ E
+    s = np.sum(x2h * Ex1, 1)
+    return s * s < thr2 * (Ex1[:, 0] ** 2 + Ex1[:, 1] ** 2 + Etx2[:, 0] ** 2 + Etx2[:, 1] ** 2)
+
+
+def find_essential_philox(px_cur, px_ref, fx, fy, cx, cy, hypotheses=128, threshold=0.5, seed=0, frame=0, seq=0, solver=None):
+    """(E (3,3), mask (n,) bool, n_inliers, best_hyp) for one frame; px_* (n,2) pixels (float32 values).  x_ref^T E x_cur = 0 in
+    normalised coordinates, cv2.findEssentialMat(px_cur, px_ref, K)'s convention (visual_odometry.py:129-130)."""
+    solver = solver or five_point_device_style
+    px_cur = np.asarray(px_cur, dtype=np.float64)
+    px_ref = np.asarray(px_ref, dtype=np.float64)
+    x1 = np.stack([(px_cur[:, 0] - cx) / fx, (px_cur[:, 1] - cy) / fy], 1)
+    x2 = np.stack([(px_ref[:, 0] - cx) / fx, (px_ref[:, 1] - cy) / fy], 1)
+    n = x1.shape[0]
+    thr2 = (threshold / (0.5 * (fx + fy))) ** 2
+    best = (0, None, -1)
+    if n >= 5:
+        for hyp in range(hypotheses):
+            idx = sample5_positions(seed, hyp, frame, seq, n)
+            for E in solver(x1[idx], x2[idx]):
+                cnt = int(sampson_inlier(E, x1, x2, thr2).sum())
+                if cnt > best[0]:
+                    best = (cnt, E, hyp)
+    if best[1] is None:
+        return np.zeros((3, 3)), np.zeros(n, bool), 0, -1
+    return best[1], sampson_inlier(best[1], x1, x2, thr2), best[0], best[2]

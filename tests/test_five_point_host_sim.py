@@ -1,0 +1,175 @@
+"""The numerics of the five-point kernel without a GPU: csrc/five_point.cuh is __host__ __device__, tests/host_sim/fp5_host.cpp
+compiles those very functions with g++ and this file checks them against the oracle (oracle/five_point.py = LAPACK version,
+oracle/five_point_plan.py = the independent Python restatement on the shared Philox stream) and against the golden the GPU
+test uses (tests/golden/essential.npz).  The host build is test infrastructure: nothing in the product loads it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import five_point as FP
+from oracle import five_point_plan as PL
+from oracle import philox as PH
+from mvoscalerecovery_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "host_sim")
+K = (718.856, 718.856, 607.1928, 185.2157)
+vp = C.c_void_p
+
+
+def load_host_sim():
+    """Builds (g++) and loads the host compilation of csrc/five_point.cuh.  Also used by tests/test_gpu_zz_essential.py."""
+    so, src = os.path.join(SIM, "libfp5_host.so"), os.path.join(SIM, "fp5_host.cpp")
+    deps = [src] + [os.path.join(ROOT, "mvoscalerecovery_b200", "csrc", f) for f in ("five_point.cuh", "five_point_tables.h")]
+    if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    L = C.CDLL(so)
+    L.fp5_host_solve.restype = C.c_int
+    L.fp5_host_solve.argtypes = [vp, vp, vp]
+    L.fp5_host_sample5.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    L.fp5_host_philox.argtypes = [C.c_uint32] * 6 + [vp]
+    L.fp5_host_ransac_frame.argtypes = [C.c_int32, vp, vp, vp, vp] + [C.c_double] * 4 + [C.c_int32, C.c_double, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                                                       vp, vp, vp, vp]
+    return L
+
+
+@pytest.fixture(scope="module")
+def sim():
+    return load_host_sim()
+
+
+def _p(a):
+    return a.ctypes.data_as(vp)
+
+
+def _solve(L, x1, x2):
+    x1 = np.ascontiguousarray(x1, dtype=np.float64); x2 = np.ascontiguousarray(x2, dtype=np.float64)
+    out = np.zeros((10, 9))
+    n = L.fp5_host_solve(_p(x1), _p(x2), _p(out))
+    return [out[k].reshape(3, 3).copy() for k in range(n)]
+
+
+def _dist(E, S):
+    return min([min(np.linalg.norm(E - F), np.linalg.norm(E + F)) for F in S] or [9.0])
+
+
+def test_philox_kats_and_sample_stream(sim):
+    out = np.zeros(4, np.uint32)
+    for ctr, key, want in (((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),      # Random123 known answers
+                           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+                           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))):
+        sim.fp5_host_philox(*ctr, *key, _p(out))
+        assert tuple(int(v) for v in out) == want == PH.philox4x32_10(ctr, key)
+    idx = np.zeros(5, np.int32)
+    for seed, hyp, frame, seq, n in ((0, 0, 0, 0, 5), (7, 3, 11, 2, 6), (2**63 + 12345, 4095, 4540, 10, 2000), (99, 17, 5, 0, 20000), (1, 2, 3, 4, 7)):
+        sim.fp5_host_sample5(seed, hyp, frame, seq, n, _p(idx))
+        assert list(idx) == PL.sample5_positions(seed, hyp, frame, seq, n)
+        assert len(set(idx)) == 5 and 0 <= idx.min() and idx.max() < n
+    seen = set()
+    for hyp in range(400):                                         # n = 5: every draw is a permutation of range(5); all positions get used
+        sim.fp5_host_sample5(5, hyp, 0, 0, 5, _p(idx))
+        assert sorted(idx) == [0, 1, 2, 3, 4]
+        seen.add(tuple(idx))
+    assert len(seen) > 100
+
+
+def _problem(rng, noisy):
+    R = synth._rodrigues(*rng.uniform(-0.2, 0.2, 3))
+    t = rng.standard_normal(3); t /= np.linalg.norm(t)
+    P = np.stack([rng.uniform(-2, 2, 5), rng.uniform(-1, 1, 5), rng.uniform(4, 20, 5)], 1)
+    x1 = P[:, :2] / P[:, 2:] + 1e-3 * rng.standard_normal((5, 2)) * noisy
+    P2 = P @ R.T + t
+    x2 = P2[:, :2] / P2[:, 2:]
+    Et = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ R
+    return x1, x2, Et / np.linalg.norm(Et)
+
+
+def test_minimal_solver_against_lapack_and_plan(sim):
+    rng = np.random.default_rng(3)
+    lap = found = true_found = n_true = same_as_plan = 0
+    trials = 60
+    for trial in range(trials):
+        x1, x2, Et = _problem(rng, trial % 2)
+        a, h = FP.five_point(x1, x2), _solve(sim, x1, x2)
+        assert len(h) <= 10
+        for E in a:
+            lap += 1
+            found += _dist(E, h) < 1e-6
+        for F in h:                                               # nothing spurious, every solution is an essential matrix through the five points
+            assert _dist(F, a) < 1e-3
+            assert abs(np.linalg.norm(F) - 1) < 1e-12
+            s = np.linalg.svd(F, compute_uv=False)
+            assert abs(s[0] - s[1]) < 1e-5 and s[2] < 1e-5
+            x1h, x2h = np.hstack([x1, np.ones((5, 1))]), np.hstack([x2, np.ones((5, 1))])
+            assert np.abs(np.sum(x2h * (x1h @ F.T), 1)).max() < 1e-6
+        if trial % 2 == 0:
+            n_true += 1
+            true_found += _dist(Et, h) < 1e-7
+        b = PL.five_point_device_style(x1, x2)
+        same_as_plan += len(b) == len(h) and all(np.abs(F - G).max() < 1e-6 for F, G in zip(h, b))
+    assert found >= 0.9 * lap and true_found >= 0.9 * n_true
+    assert same_as_plan >= 0.85 * trials        # same algorithm, different operation order: the ill-conditioned characteristic
+                                                # polynomial loses different small roots in a few problems (module docstring of the plan)
+
+
+def test_degenerate_samples_give_no_solution_and_no_nan(sim):
+    x = np.tile(np.array([[0.1, 0.2]]), (5, 1))
+    assert _solve(sim, x, x) == []                                # one correspondence five times: rank deficient
+    z = np.zeros((5, 2))
+    assert _solve(sim, z, z) == []
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-0.5, 0.5, (5, 2))
+    for F in _solve(sim, a, a):                                   # pure rotation by identity: anything returned is finite and essential
+        assert np.isfinite(F).all()
+    bad = a.copy(); bad[2, 0] = np.nan
+    for F in _solve(sim, bad, a):
+        assert np.isfinite(F).all()
+
+
+def _ransac(L, cu, cv, ru, rv, hyps, thr, seed, frame, seq):
+    n = cu.size
+    E = np.zeros(9); mask = np.zeros(max(n, 1), np.uint8); cnt = C.c_int32(0); hyp = C.c_int32(0)
+    cu, cv, ru, rv = (np.ascontiguousarray(x, dtype=np.float32) for x in (cu, cv, ru, rv))
+    L.fp5_host_ransac_frame(n, _p(cu), _p(cv), _p(ru), _p(rv), *K, hyps, thr, seed, frame, seq, _p(E), _p(mask), C.byref(cnt), C.byref(hyp))
+    return E.reshape(3, 3), mask[:n].astype(bool), cnt.value, hyp.value
+
+
+def test_selection_rule_matches_the_oracle_exactly_given_the_same_candidates(sim):
+    """find_essential_philox with the host build as its minimal solver: sampling, scoring, tie-breaking and the mask must agree
+    bit for bit with the sequential replay of the kernel's rule."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "essential.npz"))
+    off = z["offsets"]
+    for f in (1, 4, 8, 9, 10):
+        a, e = off[f], off[f + 1]
+        cu, cv, ru, rv = (z[k][a:e] for k in ("cur_u", "cur_v", "ref_u", "ref_v"))
+        E, mask, cnt, hyp = _ransac(sim, cu, cv, ru, rv, 24, 0.5, 77, f, 1)
+        Eo, mo, co, ho = PL.find_essential_philox(np.stack([cu, cv], 1), np.stack([ru, rv], 1), *K, hypotheses=24, threshold=0.5, seed=77, frame=f, seq=1,
+                                                  solver=lambda x1, x2: _solve(sim, x1, x2))
+        assert (cnt, hyp) == (co, ho) and np.array_equal(mask, mo) and np.array_equal(E, Eo)
+        assert cnt == int(mask.sum())
+
+
+def test_host_replay_against_the_golden_of_the_python_oracle(sim):
+    """The golden of the GPU test (independent Python solver): same winner wherever both solvers found the same candidates; in
+    every frame an inlier set of the same size within a point or two, and the true matches recovered."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "essential.npz"))
+    off = z["offsets"]
+    H, thr, seed, seq = int(z["hypotheses"]), float(z["threshold"]), int(z["seed"]), int(z["seq"])
+    same = 0
+    F = len(off) - 1
+    for f in range(F):
+        a, e = off[f], off[f + 1]
+        E, mask, cnt, hyp = _ransac(sim, *(z[k][a:e] for k in ("cur_u", "cur_v", "ref_u", "ref_v")), H, thr, seed, f, seq)
+        if e - a < 8:
+            assert (cnt, hyp) == (int(z["n_inliers"][f]), int(z["best_hyp"][f]))
+            continue
+        assert abs(cnt - int(z["n_inliers"][f])) <= 2
+        truth = z["true_match"][a:e]
+        assert (mask & truth).sum() >= 0.97 * truth.sum() and (mask & ~truth).sum() <= 3
+        if hyp == int(z["best_hyp"][f]):
+            same += 1
+            assert _dist(E, [z["E"][f].reshape(3, 3)]) < 1e-6 and np.array_equal(mask, z["mask"][a:e].astype(bool))
+    assert same >= 6

@@ -1,0 +1,155 @@
+"""mvosr_find_essential_frames (five-point RANSAC on the Philox stream; SURVEY N1, first half) on the GPU, through the C ABI.
+
+What is compared, and how strictly:
+  * with itself -- hard: the mask is the Sampson test of the returned matrix, the count is the mask's, the matrix is a unit-norm
+    essential matrix, edge frames (fewer than five correspondences, a rank-deficient frame) report "no model";
+  * with the oracle's golden (tests/golden/essential.npz, written by the independent Python restatement) and with the host
+    build of the kernel's own numerics (tests/host_sim) -- the inlier count within five correspondences (of ~400), the same winner in most
+    frames and then the same matrix to 1e-6 and the same mask: the characteristic polynomial is ill-conditioned, so FMA
+    contraction on the device can lose or find a small root the host does not, which may move the
+    winner between hypotheses of equal support;
+  * with the truth -- the true matches recovered, the mismatches rejected, and the pose behind the matrix within the noise
+    (the tolerances of tests/test_oracle_five_point.py against OpenCV's own output).
+It runs last among the GPU tests on purpose (file name): it is the newest kernel."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+K = (718.856, 718.856, 607.1928, 185.2157)
+
+
+def _t(engine, a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(engine.device)
+
+
+def _norm(z, a, e):
+    x1 = np.stack([(z["cur_u"][a:e].astype(np.float64) - K[2]) / K[0], (z["cur_v"][a:e].astype(np.float64) - K[3]) / K[1]], 1)
+    x2 = np.stack([(z["ref_u"][a:e].astype(np.float64) - K[2]) / K[0], (z["ref_v"][a:e].astype(np.float64) - K[3]) / K[1]], 1)
+    return x1, x2
+
+
+def _sampson_terms(E, x1, x2):
+    x1h = np.hstack([x1, np.ones((x1.shape[0], 1))]); x2h = np.hstack([x2, np.ones((x2.shape[0], 1))])
+    Ex1 = x1h @ E.T; Etx2 = x2h @ E
+    s = np.sum(x2h * Ex1, 1)
+    return s * s, Ex1[:, 0] ** 2 + Ex1[:, 1] ** 2 + Etx2[:, 0] ** 2 + Etx2[:, 1] ** 2
+
+
+def _angle_deg(c):
+    return np.degrees(np.arccos(np.clip(c, -1, 1)))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "essential.npz"))
+
+
+@pytest.fixture(scope="module")
+def run(engine, golden):
+    z = golden
+    d = {k: _t(engine, z[k]) for k in ("offsets", "cur_u", "cur_v", "ref_u", "ref_v")}
+    out = engine.find_essential_frames(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], hypotheses=int(z["hypotheses"]),
+                                       threshold=float(z["threshold"]), seed=int(z["seed"]), seq_id=int(z["seq"]))
+    import torch
+    torch.cuda.synchronize()
+    return d, {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def test_self_consistency_and_edge_frames(golden, run):
+    z, (_, out) = golden, run
+    off = z["offsets"]
+    thr2 = (float(z["threshold"]) / (0.5 * (K[0] + K[1]))) ** 2
+    for f in range(len(off) - 1):
+        a, e = off[f], off[f + 1]
+        E = out["essential"][f].reshape(3, 3); mask = out["e_mask"][a:e].astype(bool)
+        assert out["n_inliers"][f] == mask.sum()
+        if out["best_hyp"][f] < 0:
+            assert not E.any() and not mask.any()
+            continue
+        assert 0 <= out["best_hyp"][f] < int(z["hypotheses"])
+        assert abs(np.linalg.norm(E) - 1) < 1e-12
+        s = np.linalg.svd(E, compute_uv=False)
+        assert abs(s[0] - s[1]) < 1e-5 and s[2] < 1e-5
+        num, den = _sampson_terms(E, *_norm(z, a, e))
+        clear = np.abs(num - thr2 * den) > 1e-9 * thr2 * den                          # away from the threshold the mask is determined
+        assert np.array_equal(mask[clear], (num < thr2 * den)[clear])
+    assert out["best_hyp"][8] == -1 and out["best_hyp"][10] == -1                    # four correspondences; one correspondence six times
+    assert out["best_hyp"][9] >= 0 and out["n_inliers"][9] == 5                      # exactly the minimal sample: all five fit
+
+
+def test_against_the_oracle_golden_and_the_truth(golden, run):
+    z, (_, out) = golden, run
+    off = z["offsets"]
+    same = 0
+    for f in range(8):
+        a, e = off[f], off[f + 1]
+        E = out["essential"][f].reshape(3, 3); mask = out["e_mask"][a:e].astype(bool)
+        assert abs(int(out["n_inliers"][f]) - int(z["n_inliers"][f])) <= 5, (f, out["n_inliers"][f], z["n_inliers"][f])
+        truth = z["true_match"][a:e]
+        assert (mask & truth).sum() >= 0.97 * truth.sum() and (mask & ~truth).sum() <= 4
+        if out["best_hyp"][f] == z["best_hyp"][f]:
+            same += 1
+            Eo = z["E"][f].reshape(3, 3)
+            assert min(np.abs(E - Eo).max(), np.abs(E + Eo).max()) < 1e-6
+            assert (mask != z["mask"][a:e].astype(bool)).sum() <= 1
+    assert same >= 5, same
+
+
+def test_against_the_host_build_of_the_kernel_numerics(golden, run):
+    """tests/host_sim compiles csrc/five_point.cuh for the host: same code, same stream, same selection rule."""
+    from test_five_point_host_sim import _ransac, load_host_sim
+    L = load_host_sim()
+    z, (_, out) = golden, run
+    off = z["offsets"]
+    same = 0
+    for f in range(len(off) - 1):
+        a, e = off[f], off[f + 1]
+        E, mask, cnt, hyp = _ransac(L, *(z[k][a:e] for k in ("cur_u", "cur_v", "ref_u", "ref_v")), int(z["hypotheses"]), float(z["threshold"]),
+                                    int(z["seed"]), f, int(z["seq"]))
+        assert abs(int(out["n_inliers"][f]) - cnt) <= 5
+        if out["best_hyp"][f] == hyp:
+            same += 1
+            assert np.abs(out["essential"][f].reshape(3, 3) - E).max() < 1e-6
+    assert same >= 6, same
+
+
+def test_pose_from_the_gpu_essential_matrix(engine, golden, run):
+    """find_essential -> recover_pose -> triangulation: the chain of visual_odometry.py:129-147 without OpenCV."""
+    z, (d, out) = golden, run
+    ess, emask = _t(engine, out["essential"]), _t(engine, out["e_mask"])
+    pose = engine.recover_pose_frames(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], ess, e_mask=emask)
+    poses = pose["poses"].cpu().numpy().reshape(-1, 3, 4); good = pose["n_good"].cpu().numpy()
+    for f in range(8):
+        P = z["true_poses"][f].reshape(3, 4)
+        tt = P[:, 3] / np.linalg.norm(P[:, 3])
+        assert _angle_deg((np.trace(poses[f][:, :3].T @ P[:, :3]) - 1) / 2) < 0.2
+        assert _angle_deg(float(poses[f][:, 3] @ tt)) < 1.5
+        assert good[f].max() >= 0.97 * out["n_inliers"][f]
+    tri = engine.triangulate_frames(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], pose["poses"], e_mask=emask)
+    n_out = tri["n_out"].cpu().numpy()
+    assert np.array_equal(n_out[:8], good[:8].max(1))
+
+
+def test_hypothesis_count_and_frame_index(engine, golden, run):
+    """More hypotheses never lower the support; frame_index re-addresses the stream (a shard computes what the whole does)."""
+    z, (d, out) = golden, run
+    import torch
+    more = engine.find_essential_frames(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], hypotheses=200, threshold=float(z["threshold"]),
+                                        seed=int(z["seed"]), seq_id=int(z["seq"]))
+    assert (more["n_inliers"].cpu().numpy() >= out["n_inliers"]).all()
+    off = z["offsets"]
+    a, e = int(off[3]), int(off[6])                                   # frames 3..5 as their own batch, addressed as frames 3..5
+    sub_off = _t(engine, (off[3:7] - off[3]).astype(np.int32))
+    fi = _t(engine, np.arange(3, 6, dtype=np.int32))
+    sub = engine.find_essential_frames(sub_off, d["cur_u"][a:e].contiguous(), d["cur_v"][a:e].contiguous(), d["ref_u"][a:e].contiguous(),
+                                       d["ref_v"][a:e].contiguous(), hypotheses=int(z["hypotheses"]), threshold=float(z["threshold"]),
+                                       seed=int(z["seed"]), frame_index=fi, seq_id=int(z["seq"]))
+    torch.cuda.synchronize()
+    assert np.array_equal(sub["essential"].cpu().numpy(), out["essential"][3:6])
+    assert np.array_equal(sub["e_mask"].cpu().numpy(), out["e_mask"][a:e])
+    assert np.array_equal(sub["best_hyp"].cpu().numpy(), out["best_hyp"][3:6])
