@@ -6,9 +6,9 @@
 //
 // The minimal solver is Stewenius' action-matrix form of Nister's problem, with numerics one thread can run in its own
 // registers / local memory (no LAPACK): Gauss-Jordan null space with full pivoting, the ten cubic constraints by
-// interpolation at 20 fixed nodes, Gauss-Jordan on the 10x20 coefficient matrix, the characteristic polynomial of the 10x10
-// action matrix by Faddeev-LeVerrier, Sturm isolation + bisection of its real roots, Rayleigh-quotient polish on the matrix,
-// a 6x5 least-squares back-substitution per root, and a final test that the result IS an essential matrix.
+// interpolation at 20 fixed nodes, Gauss-Jordan on the 10x20 coefficient matrix, the real eigenvalues of the 10x10 action
+// matrix by balancing + Hessenberg reduction + double-shift QR, Rayleigh-quotient polish on the matrix, a 6x5 least-squares
+// back-substitution per root, and a final test that the result IS an essential matrix.
 //
 // Everything numerical is __host__ __device__ so that tests/host_sim can compile the very same functions for the host and
 // check them against the oracle without a GPU; the library itself only ever calls them from find_essential_kernel.
@@ -160,124 +160,170 @@ MVOSR_FP5_HD bool action_rows(const double basis[4][9], const Tables &T, double 
     return true;
 }
 
-// y = A x for the structured action matrix
-MVOSR_FP5_HD void action_apply_rows(const double A6[6][10], const double Min[10][10], double Pout[10][10]) {
-    for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 10; ++c) {
-            double a = 0.0;
-            for (int k = 0; k < 10; ++k) a += A6[r][k] * Min[k][c];
-            Pout[r][c] = a;
+// Real eigenvalues of the 10x10 action matrix: balancing, reduction to Hessenberg form by stabilised elimination, and the
+// Francis double-shift QR iteration (the textbook EISPACK balanc / elmhes / hqr sequence, which is also what LAPACK's
+// general eigenvalue driver does) -- the well-conditioned route; the coefficients of the characteristic polynomial lose
+// the small roots when the eigenvalues spread over several orders of magnitude.  Every loop is bounded.
+// Returns the number of real eigenvalues (|imaginary part| <= 1e-9 max(1, |real part|), one per close pair), ascending;
+// -1 when the iteration does not converge (the hypothesis is then dropped).
+MVOSR_FP5_HD int real_eigenvalues(const double A6[6][10], double roots[10]) {
+    const int n = 10;
+    double a[10][10];
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) a[i][j] = i < 6 ? A6[i][j] : 0.0;
+    a[6][0] = 1.0; a[7][1] = 1.0; a[8][2] = 1.0; a[9][6] = 1.0;
+    // -- balancing: similarity by powers of two until row and column norms are within a factor of two
+    for (int pass = 0, again = 1; again && pass < 24; ++pass) {
+        again = 0;
+        for (int i = 0; i < n; ++i) {
+            double r = 0.0, c = 0.0;
+            for (int j = 0; j < n; ++j) if (j != i) { c += fabs(a[j][i]); r += fabs(a[i][j]); }
+            if (!(c > 0.0) || !(r > 0.0) || !(c < 1e300) || !(r < 1e300)) continue;
+            double g = r / 2.0, f = 1.0;
+            const double s = c + r;
+            for (int it = 0; c < g && it < 600; ++it) { f *= 2.0; c *= 4.0; }
+            g = r * 2.0;
+            for (int it = 0; c > g && it < 600; ++it) { f /= 2.0; c /= 4.0; }
+            if ((c + r) / f < 0.95 * s) {
+                again = 1;
+                g = 1.0 / f;
+                for (int j = 0; j < n; ++j) a[i][j] *= g;
+                for (int j = 0; j < n; ++j) a[j][i] *= f;
+            }
         }
-    for (int c = 0; c < 10; ++c) { Pout[6][c] = Min[0][c]; Pout[7][c] = Min[1][c]; Pout[8][c] = Min[2][c]; Pout[9][c] = Min[6][c]; }
-}
-
-// Coefficients c[0] = 1, ..., c[10] of det(lambda I - A): Faddeev-LeVerrier, M_k = A M_{k-1} + c_{k-1} I, c_k = -tr(A M_k) / k
-MVOSR_FP5_HD void charpoly(const double A6[6][10], double c[11]) {
-    double Mk[10][10], P[10][10];
-    for (int i = 0; i < 10; ++i) for (int j = 0; j < 10; ++j) P[i][j] = 0.0;   // A M_0 with M_0 = 0
-    c[0] = 1.0;
-    for (int k = 1; k <= 10; ++k) {
-        for (int i = 0; i < 10; ++i) for (int j = 0; j < 10; ++j) Mk[i][j] = P[i][j] + (i == j ? c[k - 1] : 0.0);
-        action_apply_rows(A6, Mk, P);
-        double tr = 0.0;
-        for (int i = 0; i < 10; ++i) tr += P[i][i];
-        c[k] = -tr / (double)k;
     }
-}
-
-struct Sturm { double p[11][11]; int len[11]; int n; };             // polynomials, leading coefficient first
-
-MVOSR_FP5_HD double poly_eval(const double *p, int len, double x) {
-    double v = 0.0;
-    for (int i = 0; i < len; ++i) v = v * x + p[i];
-    return v;
-}
-
-MVOSR_FP5_HD double max_abs(const double *p, int len) {
-    double m = 0.0;
-    for (int i = 0; i < len; ++i) { const double v = fabs(p[i]); if (v > m) m = v; }
-    return m;
-}
-
-// Sturm chain of c (11 coefficients); every remainder is rescaled by a positive factor.  Leading remainder coefficients
-// of magnitude <= 1e-8 are dropped (what numpy.polydiv does to its remainder), a remainder below 1e-14 of its dividend ends
-// the chain.
-MVOSR_FP5_HD void sturm_chain(const double c[11], Sturm &S) {
-    const double m0 = max_abs(c, 11);
-    for (int i = 0; i < 11; ++i) S.p[0][i] = c[i] / m0;
-    S.len[0] = 11;
-    for (int i = 0; i < 10; ++i) S.p[1][i] = S.p[0][i] * (double)(10 - i);
-    const double m1 = max_abs(S.p[1], 10);
-    for (int i = 0; i < 10; ++i) S.p[1][i] /= m1;
-    S.len[1] = 10;
-    S.n = 2;
-    while (S.len[S.n - 1] > 1 && S.n < 11) {
-        const double *u = S.p[S.n - 2], *v = S.p[S.n - 1];
-        const int lu = S.len[S.n - 2], lv = S.len[S.n - 1];
-        double r[11];
-        for (int i = 0; i < lu; ++i) r[i] = u[i];
-        const double scale = 1.0 / v[0];
-        for (int k = 0; k <= lu - lv; ++k) {
-            const double d = scale * r[k];
-            for (int j = 0; j < lv; ++j) r[k + j] -= d * v[j];
+    // -- Hessenberg form by elimination with pivoting
+    for (int m = 1; m < n - 1; ++m) {
+        double x = 0.0;
+        int piv = m;
+        for (int j = m; j < n; ++j) if (fabs(a[j][m - 1]) > fabs(x)) { x = a[j][m - 1]; piv = j; }
+        if (piv != m) {
+            for (int j = m - 1; j < n; ++j) { const double t = a[piv][j]; a[piv][j] = a[m][j]; a[m][j] = t; }
+            for (int j = 0; j < n; ++j) { const double t = a[j][piv]; a[j][piv] = a[j][m]; a[j][m] = t; }
         }
-        int start = lu - lv + 1;                                    // the remainder: lv - 1 coefficients
-        while (start < lu - 1 && fabs(r[start]) <= 1e-8) ++start;
-        const int lr = lu - start;
-        const double mr = max_abs(r + start, lr);
-        if (!(mr > 0.0) || mr < 1e-14 * fmax(max_abs(u, lu), 1e-300)) break;
-        for (int i = 0; i < lr; ++i) S.p[S.n][i] = -r[start + i] / mr;
-        S.len[S.n] = lr;
-        ++S.n;
+        if (x != 0.0)
+            for (int i = m + 1; i < n; ++i) {
+                double y = a[i][m - 1];
+                if (y == 0.0) continue;
+                y /= x;
+                a[i][m - 1] = 0.0;
+                for (int j = m; j < n; ++j) a[i][j] -= y * a[m][j];
+                for (int j = 0; j < n; ++j) a[j][m] += y * a[j][i];
+            }
     }
-}
-
-MVOSR_FP5_HD int sign_changes(const Sturm &S, double x) {
-    int changes = 0, have = 0;
-    bool prev_neg = false;
-    for (int i = 0; i < S.n; ++i) {
-        const double v = poly_eval(S.p[i], S.len[i], x);
-        if (v == 0.0) continue;
-        const bool neg = v < 0.0;
-        if (have && neg != prev_neg) ++changes;
-        prev_neg = neg; have = 1;
+    // -- double-shift QR on the Hessenberg matrix
+    double wr[10], wi[10];
+    double anorm = 0.0;
+    for (int i = 0; i < n; ++i) for (int j = (i > 0 ? i - 1 : 0); j < n; ++j) anorm += fabs(a[i][j]);
+    if (!(anorm < 1e300)) return -1;
+    int nn = n - 1;
+    double t = 0.0;
+    while (nn >= 0) {
+        int its = 0, l;
+        do {
+            for (l = nn; l >= 1; --l) {
+                double s = fabs(a[l - 1][l - 1]) + fabs(a[l][l]);
+                if (s == 0.0) s = anorm;
+                if (fabs(a[l][l - 1]) + s == s) { a[l][l - 1] = 0.0; break; }
+            }
+            double x = a[nn][nn];
+            if (l == nn) {                                          // one root
+                wr[nn] = x + t; wi[nn] = 0.0; --nn;
+            } else {
+                double y = a[nn - 1][nn - 1], w = a[nn][nn - 1] * a[nn - 1][nn];
+                if (l == nn - 1) {                                  // two roots
+                    const double p = 0.5 * (y - x), q = p * p + w;
+                    double z = sqrt(fabs(q));
+                    x += t;
+                    if (q >= 0.0) {
+                        z = p + (p >= 0.0 ? fabs(z) : -fabs(z));
+                        wr[nn - 1] = wr[nn] = x + z;
+                        if (z != 0.0) wr[nn] = x - w / z;
+                        wi[nn - 1] = wi[nn] = 0.0;
+                    } else {
+                        wr[nn - 1] = wr[nn] = x + p;
+                        wi[nn] = z; wi[nn - 1] = -z;
+                    }
+                    nn -= 2;
+                } else {                                            // no root yet: one more sweep
+                    if (its == 60) return -1;
+                    if (its == 10 || its == 20 || its == 40) {      // exceptional shift
+                        t += x;
+                        for (int i = 0; i <= nn; ++i) a[i][i] -= x;
+                        const double s = fabs(a[nn][nn - 1]) + fabs(a[nn - 1][nn - 2]);
+                        y = x = 0.75 * s;
+                        w = -0.4375 * s * s;
+                    }
+                    ++its;
+                    int m;
+                    double p = 0.0, q = 0.0, r = 0.0, z;
+                    for (m = nn - 2; m >= l; --m) {
+                        z = a[m][m];
+                        r = x - z;
+                        double s = y - z;
+                        p = (r * s - w) / a[m + 1][m] + a[m][m + 1];
+                        q = a[m + 1][m + 1] - z - r - s;
+                        r = a[m + 2][m + 1];
+                        s = fabs(p) + fabs(q) + fabs(r);
+                        p /= s; q /= s; r /= s;
+                        if (m == l) break;
+                        const double u = fabs(a[m][m - 1]) * (fabs(q) + fabs(r));
+                        const double v = fabs(p) * (fabs(a[m - 1][m - 1]) + fabs(z) + fabs(a[m + 1][m + 1]));
+                        if (u + v == v) break;
+                    }
+                    if (m < l) m = l;                               // only on non-finite data; keeps the indices in range
+                    for (int i = m + 2; i <= nn; ++i) {
+                        a[i][i - 2] = 0.0;
+                        if (i != m + 2) a[i][i - 3] = 0.0;
+                    }
+                    for (int k = m; k <= nn - 1; ++k) {
+                        if (k != m) {
+                            p = a[k][k - 1];
+                            q = a[k + 1][k - 1];
+                            r = k != nn - 1 ? a[k + 2][k - 1] : 0.0;
+                            x = fabs(p) + fabs(q) + fabs(r);
+                            if (x != 0.0) { p /= x; q /= x; r /= x; }
+                        }
+                        const double nrm = sqrt(p * p + q * q + r * r);
+                        const double s = p >= 0.0 ? nrm : -nrm;
+                        if (s != 0.0) {
+                            if (k == m) {
+                                if (l != m) a[k][k - 1] = -a[k][k - 1];
+                            } else {
+                                a[k][k - 1] = -s * x;
+                            }
+                            p += s;
+                            x = p / s; y = q / s; z = r / s;
+                            q /= p; r /= p;
+                            for (int j = k; j <= nn; ++j) {
+                                p = a[k][j] + q * a[k + 1][j];
+                                if (k != nn - 1) { p += r * a[k + 2][j]; a[k + 2][j] -= p * z; }
+                                a[k + 1][j] -= p * y;
+                                a[k][j] -= p * x;
+                            }
+                            const int mmin = nn < k + 3 ? nn : k + 3;
+                            for (int i = l; i <= mmin; ++i) {
+                                p = x * a[i][k] + y * a[i][k + 1];
+                                if (k != nn - 1) { p += z * a[i][k + 2]; a[i][k + 2] -= p * r; }
+                                a[i][k + 1] -= p * q;
+                                a[i][k] -= p;
+                            }
+                        }
+                    }
+                }
+            }
+        } while (l < nn - 1);
     }
-    return changes;
-}
-
-// Real roots of c (ascending, at most 10): Sturm isolation + bisection down to a relative width of 1e-7.
-MVOSR_FP5_HD int real_roots(const double c[11], double roots[10]) {
-    double bound = 0.0;
-    for (int i = 1; i < 11; ++i) { const double v = fabs(c[i] / c[0]); if (v > bound) bound = v; }
-    bound += 1.0;
-    if (!(bound < 1e15)) return 0;
-    Sturm S;
-    sturm_chain(c, S);
-    double lo_s[96], hi_s[96];
-    int top = 0, n_roots = 0;
-    lo_s[0] = -bound; hi_s[0] = bound; top = 1;
-    for (int pops = 0; top > 0 && pops < 4000; ++pops) {
-        --top;
-        const double lo = lo_s[top], hi = hi_s[top];
-        const int n = sign_changes(S, lo) - sign_changes(S, hi);
-        if (n <= 0) continue;
-        if (hi - lo < 1e-7 * fmax(1.0, fmax(fabs(lo), fabs(hi)))) {
-            if (n_roots < 10) roots[n_roots++] = 0.5 * (lo + hi);
-            continue;
-        }
-        const double mid = 0.5 * (lo + hi);
-        if (top + 2 > 96) continue;
-        lo_s[top] = lo; hi_s[top] = mid; ++top;
-        lo_s[top] = mid; hi_s[top] = hi; ++top;
-    }
-    for (int i = 1; i < n_roots; ++i) {                             // ascending
-        const double v = roots[i];
-        int j = i;
+    int n_roots = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!(fabs(wi[i]) <= 1e-9 * fmax(1.0, fabs(wr[i]))) || wi[i] < 0.0) continue;    // complex, or the second member of a close pair
+        const double v = wr[i];
+        int j = n_roots++;
         while (j > 0 && roots[j - 1] > v) { roots[j] = roots[j - 1]; --j; }
         roots[j] = v;
     }
     return n_roots;
 }
+
 
 // Solves S z = b in place (Gaussian elimination, partial pivoting); S is destroyed.  false on an exactly zero pivot.
 template <int N>
@@ -345,11 +391,10 @@ MVOSR_FP5_HD double polish_eigenvalue(const double A6[6][10], double x) {
 // All real essential matrices through five correspondences (normalised coordinates, x2^T E x1 = 0): up to ten 3x3 matrices
 // of unit Frobenius norm, row-major, in ascending order of the eigenvalue they belong to.  Returns how many.
 MVOSR_FP5_HD int solve(const double x1[10], const double x2[10], const Tables &T, double Eout[10][9]) {
-    double basis[4][9], A6[6][10], c[11], roots[10];
+    double basis[4][9], A6[6][10], roots[10];
     if (!null4(x1, x2, basis)) return 0;
     if (!action_rows(basis, T, A6)) return 0;
-    charpoly(A6, c);
-    const int nr = real_roots(c, roots);
+    const int nr = real_eigenvalues(A6, roots);
     int n_sol = 0;
     for (int k = 0; k < nr; ++k) {
         const double x = polish_eigenvalue(A6, roots[k]);

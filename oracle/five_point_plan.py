@@ -13,17 +13,16 @@ registers, and is checked against the LAPACK version in tests/test_oracle_five_p
      one lane per sample point evaluates det E and 2 E E^T E - tr(E E^T) E numerically, no symbolic expansion;
   3. Gauss-Jordan on the 10x20 matrix (partial pivoting), action matrix of "multiply by x" on the basis
      [x^2, xy, xz, y^2, yz, z^2, x, y, z, 1];
-  4. its characteristic polynomial by the Faddeev-LeVerrier recurrence (ten 10x10 products), real roots by Sturm-sequence
-     isolation + bisection, each root polished on the MATRIX by Rayleigh-quotient iteration (the coefficients of the
-     characteristic polynomial are ill-conditioned, the eigenvalues of A are not);
+  4. its real eigenvalues by balancing + Hessenberg reduction + double-shift QR (here: LAPACK's driver, which is that
+     sequence; in the kernel: its own balanc / elmhes / hqr), each polished on the matrix by Rayleigh-quotient iteration.
+     (A first version formed the characteristic polynomial by Faddeev-LeVerrier and isolated its roots with a Sturm chain:
+     the COEFFICIENTS are ill-conditioned when the eigenvalues spread over orders of magnitude, and 5-7 % of the solutions
+     were lost; the eigenvalues of A themselves are well conditioned.);
   5. for every real root x: the remaining unknowns (y^2, yz, z^2, y, z) from the first six rows of (A - x I) v = 0 by a 6x5
      least-squares solve (normal equations, Gaussian elimination).
 
-Status (tests/test_oracle_five_point.py): solutions found agree with the LAPACK version to < 1e-6; about 7 % of the LAPACK
-version's solutions are missed (the true pose in ~3 % of noise-free problems) -- all in problems whose eigenvalues spread over
-several orders of magnitude, where the COEFFICIENTS of the characteristic polynomial (step 4) lose the small roots.  RANSAC
-tolerates that (a few more iterations); the upgrade, if wanted, is to evaluate det(A - x I) on a Hessenberg form (Hyman's
-method) inside the bracketing instead of forming the coefficients.
+Status (tests/test_oracle_five_point.py, tests/test_five_point_host_sim.py): solutions agree with the LAPACK version to
+< 1e-6 and > 99 % of them are found (the rest: near-double roots that one side sees as a complex pair).
 """
 from __future__ import annotations
 
@@ -74,71 +73,13 @@ def _constraints_at(E):
     return np.concatenate([[np.linalg.det(E)], (2 * EEt @ E - np.trace(EEt) * E).reshape(-1)])
 
 
-def _charpoly(A):
-    """Coefficients c[0] = 1, ..., c[n] of det(lambda I - A) by Faddeev-LeVerrier."""
-    n = A.shape[0]
-    c = np.zeros(n + 1)
-    c[0] = 1.0
-    Mk = np.zeros_like(A)
-    for k in range(1, n + 1):
-        Mk = A @ Mk + c[k - 1] * np.eye(n)
-        c[k] = -np.trace(A @ Mk) / k
-    return c
-
-
-def _poly_eval(c, x):
-    v = 0.0
-    for a in c:
-        v = v * x + a
-    return v
-
-
-def _sturm_chain(c):
-    """Sturm chain of the polynomial c; every remainder is rescaled by a POSITIVE factor (its largest magnitude), which keeps
-    the signs and keeps the coefficients in range."""
-    p0 = np.array(c, dtype=np.float64)
-    p0 = p0 / np.abs(p0).max()
-    p1 = np.polyder(p0)
-    p1 = p1 / np.abs(p1).max()
-    chain = [p0, p1]
-    while len(chain[-1]) > 1:
-        _, r = np.polydiv(chain[-2], chain[-1])
-        r = np.trim_zeros(r, "f")
-        if r.size == 0 or np.abs(r).max() < 1e-14 * max(np.abs(chain[-2]).max(), 1e-300):
-            break
-        chain.append(-r / np.abs(r).max())
-    return chain
-
-
-def _sign_changes(chain, x):
-    s = [np.polyval(p, x) for p in chain]
-    s = [v for v in s if v != 0]
-    return sum(1 for a, b in zip(s, s[1:]) if (a < 0) != (b < 0))
-
-
-def _real_roots(c):
-    """Real roots of the polynomial c (leading coefficient first), isolated with a Sturm chain and bisection down to a
-    relative width of 1e-7 (close pairs are split as long as the chain resolves them; a pair it cannot split is reported
-    once).  The caller polishes each root on the matrix, not on the ill-conditioned coefficients."""
-    c = np.array(c, dtype=np.float64)
-    bound = 1.0 + np.abs(c[1:] / c[0]).max()                       # Cauchy bound
-    if not bound < 1e15:
-        return []
-    chain = _sturm_chain(c)
-    roots, stack = [], [(-bound, bound)]
-    pops = 0
-    while stack and pops < 4000:
-        pops += 1
-        lo, hi = stack.pop()
-        n = _sign_changes(chain, lo) - _sign_changes(chain, hi)
-        if n <= 0:
-            continue
-        if hi - lo < 1e-7 * max(1.0, abs(lo), abs(hi)):
-            roots.append(0.5 * (lo + hi))
-            continue
-        mid = 0.5 * (lo + hi)
-        stack.append((lo, mid)); stack.append((mid, hi))
-    return sorted(roots[:10])
+def _real_eigenvalues(A):
+    """Real eigenvalues of the action matrix, ascending.  LAPACK's general driver (balancing, Hessenberg reduction, double-shift
+    QR) stands in for the kernel's own balanc / elmhes / hqr sequence in csrc/five_point.cuh: same algorithm family, written
+    independently, so agreement is to rounding, not bit for bit.  A close complex pair counts once."""
+    w = np.linalg.eigvals(A)
+    keep = (np.abs(w.imag) <= 1e-9 * np.maximum(1.0, np.abs(w.real))) & (w.imag >= 0)
+    return sorted(w.real[keep])
 
 
 def _polish_eigenvalue(A, x, steps=3):
@@ -191,7 +132,9 @@ def five_point_device_style(x1, x2):
     A[0:6] = -B[0:6]
     A[6, 0] = A[7, 1] = A[8, 2] = A[9, 6] = 1.0
     sols = []
-    for x0 in _real_roots(_charpoly(A)):
+    if not np.isfinite(A).all():
+        return []
+    for x0 in _real_eigenvalues(A):
         x = _polish_eigenvalue(A, x0)
         # (A - x I) v = 0 with v = [x^2, xy, xz, y^2, yz, z^2, x, y, z, 1]; x known -> unknowns u = [xy, xz, y^2, yz, z^2, y, z]
         # rows 7, 8 give xy = x*y, xz = x*z; rows 0..5 are linear in (y^2, yz, z^2, y, z) once those are substituted

@@ -110,9 +110,9 @@ def test_minimal_solver_against_lapack_and_plan(sim):
             true_found += _dist(Et, h) < 1e-7
         b = PL.five_point_device_style(x1, x2)
         same_as_plan += len(b) == len(h) and all(np.abs(F - G).max() < 1e-6 for F, G in zip(h, b))
-    assert found >= 0.9 * lap and true_found >= 0.9 * n_true
-    assert same_as_plan >= 0.85 * trials        # same algorithm, different operation order: the ill-conditioned characteristic
-                                                # polynomial loses different small roots in a few problems (module docstring of the plan)
+    assert found >= 0.98 * lap and true_found >= 0.96 * n_true
+    assert same_as_plan >= 0.95 * trials        # same algorithm family, independent code: a near-double root may be a real pair on
+                                                # one side and a complex pair on the other
 
 
 def test_degenerate_samples_give_no_solution_and_no_nan(sim):

@@ -5,9 +5,9 @@ What is compared, and how strictly:
     essential matrix, edge frames (fewer than five correspondences, a rank-deficient frame) report "no model";
   * with the oracle's golden (tests/golden/essential.npz, written by the independent Python restatement) and with the host
     build of the kernel's own numerics (tests/host_sim) -- the inlier count within five correspondences (of ~400), the same winner in most
-    frames and then the same matrix to 1e-6 and the same mask: the characteristic polynomial is ill-conditioned, so FMA
-    contraction on the device can lose or find a small root the host does not, which may move the
-    winner between hypotheses of equal support;
+    frames and then the same matrix to 1e-6 and the same mask: FMA contraction on the device can turn a near-double real
+    root into a complex pair (or back) and flip a correspondence that sits on the threshold, which may move the winner
+    between hypotheses of equal support;
   * with the truth -- the true matches recovered, the mismatches rejected, and the pose behind the matrix within the noise
     (the tolerances of tests/test_oracle_five_point.py against OpenCV's own output).
 It runs last among the GPU tests on purpose (file name): it is the newest kernel."""
