@@ -41,6 +41,19 @@ def sim():
     return load_host_sim()
 
 
+def load_kernel_emulation():
+    """Builds (g++ -pthread) and loads tests/host_sim/fp5_kernel_emu.cpp: the SOURCE of find_essential_kernel run on the host, one
+    OS thread per CUDA thread."""
+    so, src = os.path.join(SIM, "libfp5_kernel_emu.so"), os.path.join(SIM, "fp5_kernel_emu.cpp")
+    deps = [src] + [os.path.join(ROOT, "mvoscalerecovery_b200", "csrc", f) for f in ("five_point.cuh", "five_point_kernel.cuh", "five_point_tables.h")]
+    if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-o", so, src])
+    L = C.CDLL(so)
+    L.fp5_emu_find_essential.argtypes = [C.c_int32, vp, vp, vp, vp, vp] + [C.c_double] * 4 + [C.c_int32, C.c_double, C.c_uint64, vp, C.c_int32,
+                                                                                         vp, vp, vp, vp, C.c_int32]
+    return L
+
+
 def _p(a):
     return a.ctypes.data_as(vp)
 
@@ -173,3 +186,33 @@ def test_host_replay_against_the_golden_of_the_python_oracle(sim):
             same += 1
             assert _dist(E, [z["E"][f].reshape(3, 3)]) < 1e-6 and np.array_equal(mask, z["mask"][a:e].astype(bool))
     assert same >= 6
+
+
+def test_kernel_source_on_the_host_emulation(sim):
+    """find_essential_kernel itself (five_point_kernel.cuh compiled for the host with a pthread mapping of the CUDA vocabulary):
+    tile staging, barriers, the warp-shuffle key reduction, winner hand-over between rounds, frame loop over a small grid and the
+    mask pass give, bit for bit, what the sequential replay gives -- for several grid sizes, partial rounds, frames of several
+    tiles, a frame_index map and the edge frames.  (scripts/tsan_five_point_kernel.sh runs the same build under ThreadSanitizer.)"""
+    emu = load_kernel_emulation()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "essential.npz"))
+    big = synth.make_sequence(seed=5, n_frames=2, n_corr=1300, outlier_frac=0.1)          # 3 tiles per frame
+    lens = list(np.diff(z["offsets"])) + list(np.diff(big.offsets))
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    arr = {k: np.ascontiguousarray(np.concatenate([z[k], getattr(big, k)]).astype(np.float32)) for k in ("cur_u", "cur_v", "ref_u", "ref_v")}
+    rng = np.random.default_rng(1)
+    bad = rng.permutation(arr["ref_u"].size)[: arr["ref_u"].size // 6]
+    arr["ref_u"][bad] = rng.uniform(0, 1241, bad.size).astype(np.float32)
+    F = len(off) - 1
+    fidx = np.ascontiguousarray((np.arange(F) * 3 + 1).astype(np.int32))
+    seed, seq = 2**40 + 17, 6
+    for H, grid, use_index in ((48, 4, False), (150, 1, True), (128, F, True)):
+        E = np.full((F, 9), 7.0); mask = np.full(off[-1], 9, np.uint8); cnt = np.full(F, -5, np.int32); hyp = np.full(F, -5, np.int32)
+        rc = emu.fp5_emu_find_essential(F, _p(off), *(_p(arr[k]) for k in ("cur_u", "cur_v", "ref_u", "ref_v")), *K, H, 0.5, seed,
+                                        _p(fidx) if use_index else None, seq, _p(E), _p(mask), _p(cnt), _p(hyp), grid)
+        assert rc == 0
+        for f in range(F):
+            a, e = off[f], off[f + 1]
+            Er, mr, cr, hr = _ransac(sim, *(arr[k][a:e] for k in ("cur_u", "cur_v", "ref_u", "ref_v")), H, 0.5, seed, int(fidx[f]) if use_index else f, seq)
+            assert (cr, hr) == (cnt[f], hyp[f]), (H, grid, f)
+            assert np.array_equal(Er.reshape(-1), E[f]) and np.array_equal(mr, mask[a:e].astype(bool))
+        assert cnt[-1] > 800 and cnt[-2] > 800                     # the large frames found their model
