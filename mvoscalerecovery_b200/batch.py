@@ -172,6 +172,21 @@ class ScaleRecovery:
                 self._stream()))
         return dict(raw_scale=raw, status=status, n_features=nfeat, stats=st)
 
+    def scale_frames_from_tracks(self, offsets, cur_u, cur_v, ref_u, ref_v, max_features: int, hypotheses: int = 128, threshold: float = 0.5,
+                                 frame_index0: int = 0, seq_id: int = 0, seed: int = 0, stats: bool = False):
+        """Tracked correspondences alone -> raw scales: the geometry of VisualOdometry.processFrame (visual_odometry.py:129-147:
+        findEssentialMat, recoverPose, triangulation) followed by the scale recovery of rescale.py:113-167, three kernels on one
+        stream with no host round trip.  Returns scale_frames_from_correspondences' dict + essential, e_mask, n_inliers, poses."""
+        F = offsets.numel() - 1
+        fi = None if frame_index0 == 0 else torch.arange(frame_index0, frame_index0 + F, dtype=torch.int32, device=self.device)
+        ess = self.find_essential_frames(offsets, cur_u, cur_v, ref_u, ref_v, hypotheses=hypotheses, threshold=threshold, seed=seed,
+                                         frame_index=fi, seq_id=seq_id)
+        pose = self.recover_pose_frames(offsets, cur_u, cur_v, ref_u, ref_v, ess["essential"], e_mask=ess["e_mask"])
+        out = self.scale_frames_from_correspondences(offsets, cur_u, cur_v, ref_u, ref_v, pose["poses"], max_features, e_mask=ess["e_mask"],
+                                                     frame_index0=frame_index0, seq_id=seq_id, seed=seed, stats=stats)
+        out.update(essential=ess["essential"], e_mask=ess["e_mask"], n_inliers=ess["n_inliers"], poses=pose["poses"])
+        return out
+
     # ------------------------------------------------------------------ stage 6
     def filter_sequences(self, seq_offsets, raw_scale, status, move_flags=None, n_features=None, filter10: bool = True):
         """Replaces the gating of main_offline.py:57-88 + rescale.py:168-178, then evaluate_scale.filter(...,10)."""

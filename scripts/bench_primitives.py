@@ -89,4 +89,24 @@ dd = [t(x) for x in (b.offsets, b.cur_u, b.cur_v, b.ref_u, b.ref_v)]
 d_E = t(E)
 ms = timed(lambda: eng.recover_pose_frames(*dd, d_E))
 row("recover_pose_kernel", "592 frames x 2500 correspondences (4 triangulations each)", ms, 16 * int(b.offsets[-1]) + (72 + 96 + 16) * b.n_frames, b.n_frames, "frames")
+
+# ---- essential matrix by five-point RANSAC on the same 592 frames (FP64-pipe bound, not HBM: the fraction column only says so),
+#      with OpenCV's own findEssentialMat on the host beside it (one core, a bounded sample of the same frames)
+for hyps in (128, 512):
+    ms = timed(lambda: eng.find_essential_frames(*dd, hypotheses=hyps, threshold=0.5, seed=1), reps=5)
+    row("find_essential_kernel", "592 frames x 2500 correspondences, %d hypotheses per frame" % hyps, ms, 17 * int(b.offsets[-1]) + (72 + 8) * b.n_frames,
+        b.n_frames, "frames")
+    out["rows"][-1]["hypotheses_per_s"] = hyps * b.n_frames / ms * 1e3
+try:
+    import time
+    import cv2
+    Kmat = np.array([[718.856, 0, 607.1928], [0, 718.856, 185.2157], [0, 0, 1.0]])
+    t0 = time.perf_counter()
+    for f in range(16):
+        a, e = b.offsets[f], b.offsets[f + 1]
+        cv2.findEssentialMat(np.stack([b.cur_u[a:e], b.cur_v[a:e]], 1), np.stack([b.ref_u[a:e], b.ref_v[a:e]], 1), cameraMatrix=Kmat,
+                             method=cv2.RANSAC, prob=0.999, threshold=0.5)
+    out["rows"][-1]["opencv_findEssentialMat_frames_per_s_one_core"] = 16 / (time.perf_counter() - t0)
+except Exception as ex:                                             # the bench must not die on the host-side comparison
+    out["rows"][-1]["opencv_findEssentialMat_frames_per_s_one_core"] = "unavailable: %r" % (ex,)
 print(json.dumps(out, indent=1))

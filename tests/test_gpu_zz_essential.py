@@ -154,3 +154,30 @@ def test_hypothesis_count_and_frame_index(engine, golden, run):
     assert np.array_equal(sub["essential"].cpu().numpy(), out["essential"][3:6])
     assert np.array_equal(sub["e_mask"].cpu().numpy(), out["e_mask"][a:e])
     assert np.array_equal(sub["best_hyp"].cpu().numpy(), out["best_hyp"][3:6])
+
+
+def test_tracks_to_scales_without_poses(engine):
+    """Correspondences alone -> raw scales (find_essential -> recover_pose -> fused stages 1-5), 10 % of the tracks replaced by
+    mismatches: the scale lands within 3 % of the truth (the CPU chain of the same steps -- host build of the solver,
+    oracle.extras.recover_pose, oracle.pipeline -- lands within 1 % on these frames) and close to the scale from the true poses."""
+    import torch
+    from mvoscalerecovery_b200 import synth
+    b = synth.make_sequence(seed=21, n_frames=6, n_corr=1500, outlier_frac=0.1)
+    rng = np.random.default_rng(2)
+    ru, rv = b.ref_u.copy(), b.ref_v.copy()
+    bad = rng.permutation(ru.size)[: ru.size // 10]
+    ru[bad] = rng.uniform(0, 1241, bad.size).astype(np.float32); rv[bad] = rng.uniform(0, 376, bad.size).astype(np.float32)
+    d = [_t(engine, x) for x in (b.offsets, b.cur_u, b.cur_v, ru, rv)]
+    maxf = int(np.diff(b.offsets).max())
+    out = engine.scale_frames_from_tracks(*d, max_features=maxf, hypotheses=128, threshold=0.5, seed=5)
+    ref = engine.scale_frames_from_correspondences(*d[:3], _t(engine, b.ref_u), _t(engine, b.ref_v), _t(engine, b.poses), max_features=maxf, seed=5)
+    torch.cuda.synchronize()
+    raw, raw_true = out["raw_scale"].cpu().numpy(), ref["raw_scale"].cpu().numpy()
+    n_inl = out["n_inliers"].cpu().numpy()
+    truth_bad = np.zeros(ru.size, bool); truth_bad[bad] = True
+    mask = out["e_mask"].cpu().numpy().astype(bool)
+    assert (mask & truth_bad).sum() <= 0.02 * truth_bad.sum()                      # the mismatches are rejected
+    assert (n_inl >= 0.85 * np.diff(b.offsets)).all()
+    assert (out["status"].cpu().numpy() & 1).all()                                  # every frame produced a scale
+    np.testing.assert_allclose(raw, b.true_scale, rtol=0.03)
+    np.testing.assert_allclose(raw, raw_true, rtol=0.03)
