@@ -27,3 +27,11 @@ pts = np.stack([rng.uniform(-8, 8, 500), 1.7 + 0.003 * rng.standard_normal(500),
 out = eng.ransac_planes(t(np.array([0, 500], np.int32)), t(pts), iterations=64)
 torch.cuda.synchronize()
 print("ransac ic", int(out["ic"][0]))
+# five-point RANSAC + pose + fused scale recovery from tracks alone (frames of several tiles, a frame below five correspondences)
+b = synth.make_sequence(seed=9, n_frames=4, n_corr=700, outlier_frac=0.1)
+off = np.concatenate([b.offsets, [b.offsets[-1] + 3]]).astype(np.int32)            # a fifth frame of three correspondences
+pad = lambda a: np.concatenate([a, a[:3]])
+r = eng.scale_frames_from_tracks(t(off), t(pad(b.cur_u)), t(pad(b.cur_v)), t(pad(b.ref_u)), t(pad(b.ref_v)), max_features=int(np.diff(off).max()),
+                                 hypotheses=160, seed=3)
+torch.cuda.synchronize()
+print("essential inliers", r["n_inliers"].cpu().numpy(), "scales", r["raw_scale"].cpu().numpy()[:4], "true", b.true_scale)
