@@ -237,16 +237,19 @@ int  mvosr_recover_pose_frames(mvosr_handle *h, int32_t n_frames, const int32_t 
  * frame: `hypotheses` minimal samples of five correspondences drawn from the Philox stream (key = seed, counter = (hypothesis,
  * frame_index ? frame_index[f] : f, seq_id, 1|2), csrc/five_point.cuh), every real solution of the five-point problem scored
  * by the Sampson distance against threshold_px / ((fx + fy) / 2) (OpenCV's normalisation of its pixel threshold); the
- * candidate with the most inliers wins, ties to the lowest (hypothesis, candidate) pair.  The hypothesis count is fixed
- * (OpenCV adapts it to the inlier ratio with its own RNG, which cannot be reproduced; parity is defined on this stream).
+ * candidate with the most inliers wins, ties to the lowest (hypothesis, candidate) pair.  `hypotheses` is the maximum (OpenCV's
+ * maxIters, 1000 in the reference's call); confidence (OpenCV's prob, 0.999 in the reference's call) > 0 stops a frame after the
+ * first round of 128 hypotheses at whose end  tried >= log(1 - confidence) / log(1 - w^5), w = best inlier ratio -- OpenCV's
+ * adaptive count evaluated per round; confidence = 0 runs all hypotheses.  (OpenCV draws from its own RNG, which cannot be
+ * reproduced; parity is defined on this stream.)
  * Outputs: essential [F][9] row-major with unit Frobenius norm, x_ref^T E x_cur = 0 in normalised coordinates -- the input of
  * mvosr_recover_pose_frames; e_mask_out [M] (optional) the winner's inlier mask -- the e_mask of the later stages; n_inliers
  * [F] (optional); best_hyp [F] (optional; -1 and a zero matrix for frames with fewer than five correspondences or no
- * solution). */
+ * solution); hyps_used [F] (optional): hypotheses tried. */
 int  mvosr_find_essential_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
                                  const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
-                                 int32_t hypotheses, double threshold_px, uint64_t seed, const int32_t *frame_index, int32_t seq_id,
-                                 double *essential, uint8_t *e_mask_out, int32_t *n_inliers, int32_t *best_hyp, void *stream);
+                                 int32_t hypotheses, double threshold_px, double confidence, uint64_t seed, const int32_t *frame_index, int32_t seq_id,
+                                 double *essential, uint8_t *e_mask_out, int32_t *n_inliers, int32_t *best_hyp, int32_t *hyps_used, void *stream);
 
 /* Dense depth from the mesh -- Reconstruct.depth_generate (src/reconstruct.py:91-107): tri.find_simplex of every integer
  * pixel (u, v) of a width x height image + the depth of that triangle's plane along the pixel's ray,

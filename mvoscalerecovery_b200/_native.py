@@ -92,7 +92,7 @@ def lib():
     L.mvosr_ransac_planes.argtypes = [vp, i32, vp, vp, i32, f64, f64, i32, u64, vp, i32, vp, vp, vp, vp, vp]
     L.mvosr_integrate_paths.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mvosr_recover_pose_frames.argtypes = [vp, i32] + [vp] * 10
-    L.mvosr_find_essential_frames.argtypes = [vp, i32] + [vp] * 5 + [i32, f64, u64, vp, i32] + [vp] * 5
+    L.mvosr_find_essential_frames.argtypes = [vp, i32] + [vp] * 5 + [i32, f64, f64, u64, vp, i32] + [vp] * 6
     L.mvosr_depth_from_mesh.argtypes = [vp, i32, i32, f64, f64, f64, f64, i32, vp, vp, vp, vp, vp, vp]
     L.mvosr_set_phase_timing.argtypes = [vp, vp]
     L.mvosr_launch_count.restype = C.c_int64

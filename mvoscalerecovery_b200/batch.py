@@ -87,10 +87,12 @@ class ScaleRecovery:
         out["n_out"] = n_out
         return out
 
-    def find_essential_frames(self, offsets, cur_u, cur_v, ref_u, ref_v, hypotheses: int = 128, threshold: float = 0.5, seed: int = 0,
-                              frame_index=None, seq_id: int = 0):
+    def find_essential_frames(self, offsets, cur_u, cur_v, ref_u, ref_v, hypotheses: int = 1000, threshold: float = 0.5, seed: int = 0,
+                              frame_index=None, seq_id: int = 0, confidence: float = 0.999):
         """Replaces cv2.findEssentialMat(px_cur, px_ref, K, RANSAC, 0.999, threshold) (visual_odometry.py:100-102,129-130) for F
-        frames: five-point RANSAC on the Philox stream.  Returns dict(essential (F,9) f64, e_mask (M,) u8, n_inliers (F,), best_hyp (F,))."""
+        frames: five-point RANSAC on the Philox stream; hypotheses = OpenCV's maxIters, confidence = its prob (the adaptive count,
+        checked every 128 hypotheses; 0 = run them all).  Returns dict(essential (F,9) f64, e_mask (M,) u8, n_inliers, best_hyp,
+        hyps_used (F,))."""
         dev = self.device
         F = offsets.numel() - 1
         _chk(offsets, torch.int32, "offsets", dev)
@@ -102,11 +104,12 @@ class ScaleRecovery:
         e_mask = torch.zeros(cur_u.numel(), dtype=torch.uint8, device=dev)
         n_inliers = torch.zeros(F, dtype=torch.int32, device=dev)
         best_hyp = torch.full((F,), -1, dtype=torch.int32, device=dev)
+        hyps_used = torch.zeros(F, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             N.check(self.lib.mvosr_find_essential_frames(self._h, F, _ptr(offsets), _ptr(cur_u), _ptr(cur_v), _ptr(ref_u), _ptr(ref_v),
-                                                         int(hypotheses), float(threshold), int(seed), _ptr(frame_index), int(seq_id),
-                                                         _ptr(essential), _ptr(e_mask), _ptr(n_inliers), _ptr(best_hyp), self._stream()))
-        return dict(essential=essential, e_mask=e_mask, n_inliers=n_inliers, best_hyp=best_hyp)
+                                                         int(hypotheses), float(threshold), float(confidence), int(seed), _ptr(frame_index), int(seq_id),
+                                                         _ptr(essential), _ptr(e_mask), _ptr(n_inliers), _ptr(best_hyp), _ptr(hyps_used), self._stream()))
+        return dict(essential=essential, e_mask=e_mask, n_inliers=n_inliers, best_hyp=best_hyp, hyps_used=hyps_used)
 
     def recover_pose_frames(self, offsets, cur_u, cur_v, ref_u, ref_v, essential, e_mask=None):
         """The pose selection of cv2.recoverPose (visual_odometry.py:129-133): essential (F,9) float64 -> dict(poses (F,12), n_good (F,4))."""
@@ -172,19 +175,19 @@ class ScaleRecovery:
                 self._stream()))
         return dict(raw_scale=raw, status=status, n_features=nfeat, stats=st)
 
-    def scale_frames_from_tracks(self, offsets, cur_u, cur_v, ref_u, ref_v, max_features: int, hypotheses: int = 128, threshold: float = 0.5,
-                                 frame_index0: int = 0, seq_id: int = 0, seed: int = 0, stats: bool = False):
+    def scale_frames_from_tracks(self, offsets, cur_u, cur_v, ref_u, ref_v, max_features: int, hypotheses: int = 1000, threshold: float = 0.5,
+                                 frame_index0: int = 0, seq_id: int = 0, seed: int = 0, stats: bool = False, confidence: float = 0.999):
         """Tracked correspondences alone -> raw scales: the geometry of VisualOdometry.processFrame (visual_odometry.py:129-147:
         findEssentialMat, recoverPose, triangulation) followed by the scale recovery of rescale.py:113-167, three kernels on one
         stream with no host round trip.  Returns scale_frames_from_correspondences' dict + essential, e_mask, n_inliers, poses."""
         F = offsets.numel() - 1
         fi = None if frame_index0 == 0 else torch.arange(frame_index0, frame_index0 + F, dtype=torch.int32, device=self.device)
         ess = self.find_essential_frames(offsets, cur_u, cur_v, ref_u, ref_v, hypotheses=hypotheses, threshold=threshold, seed=seed,
-                                         frame_index=fi, seq_id=seq_id)
+                                         frame_index=fi, seq_id=seq_id, confidence=confidence)
         pose = self.recover_pose_frames(offsets, cur_u, cur_v, ref_u, ref_v, ess["essential"], e_mask=ess["e_mask"])
         out = self.scale_frames_from_correspondences(offsets, cur_u, cur_v, ref_u, ref_v, pose["poses"], max_features, e_mask=ess["e_mask"],
                                                      frame_index0=frame_index0, seq_id=seq_id, seed=seed, stats=stats)
-        out.update(essential=ess["essential"], e_mask=ess["e_mask"], n_inliers=ess["n_inliers"], poses=pose["poses"])
+        out.update(essential=ess["essential"], e_mask=ess["e_mask"], n_inliers=ess["n_inliers"], hyps_used=ess["hyps_used"], poses=pose["poses"])
         return out
 
     # ------------------------------------------------------------------ stage 6

@@ -667,16 +667,16 @@ int mvosr_recover_pose_frames(mvosr_handle *h, int32_t n_frames, const int32_t *
 
 int mvosr_find_essential_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
                                 const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
-                                int32_t hypotheses, double threshold_px, uint64_t seed, const int32_t *frame_index, int32_t seq_id,
-                                double *essential, uint8_t *e_mask_out, int32_t *n_inliers, int32_t *best_hyp, void *stream) {
+                                int32_t hypotheses, double threshold_px, double confidence, uint64_t seed, const int32_t *frame_index, int32_t seq_id,
+                                double *essential, uint8_t *e_mask_out, int32_t *n_inliers, int32_t *best_hyp, int32_t *hyps_used, void *stream) {
     if (!h || n_frames < 0 || !offsets || !cur_u || !cur_v || !ref_u || !ref_v || !essential || hypotheses < 1 || hypotheses > (1 << 24) ||
-        !(threshold_px > 0.0))
+        !(threshold_px > 0.0) || !(confidence >= 0.0))
         return MVOSR_E_INVALID;
     if (n_frames == 0) return MVOSR_OK;
     CK(cudaSetDevice(h->device));
     const int grid = min(n_frames, 16 * h->num_sms);
     find_essential_kernel<<<grid, FP5_THREADS, 0, (cudaStream_t)stream>>>(n_frames, offsets, cur_u, cur_v, ref_u, ref_v,
-        h->cfg.fx, h->cfg.fy, h->cfg.cx, h->cfg.cy, hypotheses, threshold_px, seed, frame_index, seq_id, essential, e_mask_out, n_inliers, best_hyp);
+        h->cfg.fx, h->cfg.fy, h->cfg.cx, h->cfg.cy, hypotheses, threshold_px, confidence, seed, frame_index, seq_id, essential, e_mask_out, n_inliers, best_hyp, hyps_used);
     CK(cudaGetLastError());
     h->launches += 1;
     return MVOSR_OK;

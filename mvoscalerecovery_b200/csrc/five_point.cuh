@@ -440,5 +440,15 @@ MVOSR_FP5_HD bool sampson_inlier(const double E[9], double ax, double ay, double
     return s * s < thr2 * (e0 * e0 + e1 * e1 + f0 * f0 + f1 * f1);
 }
 
+// The adaptive stopping rule, checked at the end of every round: tried >= log(1 - confidence) / log(1 - w^5), w = best / n.
+// confidence <= 0 disables it; a perfect model (w = 1) or confidence >= 1 ... stops / never stops as the formula's limits say.
+MVOSR_FP5_HD bool enough_hypotheses(int tried, int best_count, int n, double confidence) {
+    if (!(confidence > 0.0) || best_count <= 0) return false;
+    if (confidence >= 1.0) return false;
+    const double w = (double)best_count / (double)n, w5 = w * w * w * w * w;
+    if (w5 >= 1.0) return true;
+    return (double)tried * log(1.0 - w5) <= log(1.0 - confidence);      // both logs negative
+}
+
 }  // namespace fp5
 }  // namespace mvosr

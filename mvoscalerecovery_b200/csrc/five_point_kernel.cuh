@@ -4,8 +4,11 @@
 // to ten candidates, kept in the thread's local memory), then all threads walk the frame's correspondences together -- staged
 // tile by tile in shared memory in normalised float64 coordinates, so every lane reads the same point (a broadcast) -- and each
 // counts the Sampson inliers of its own candidates.  The winner is the candidate with the most inliers; ties go to the lowest
-// (hypothesis, candidate) pair, so the result does not depend on the CTA size.  No adaptive stopping: the hypothesis count is
-// fixed per call (OpenCV's adaptive count only ever shortens its loop).  The last pass writes the winner's inlier mask.
+// (hypothesis, candidate) pair.  `hypotheses` is the maximum (OpenCV's maxIters); with confidence > 0 the loop stops after the
+// first round of FP5_ROUND hypotheses at whose end  hypotheses tried >= log(1 - confidence) / log(1 - w^5),  w = best inlier
+// ratio -- OpenCV's adaptive count (prob = 0.999 in the reference's call), evaluated per round instead of per sample so that
+// it is a property of the stream definition, not of the schedule.  confidence = 0: all hypotheses.  The last pass writes the
+// winner's inlier mask.
 #pragma once
 #include <stdint.h>
 #include "../../include/mvosr.h"
@@ -16,14 +19,15 @@ namespace mvosr {
 
 __constant__ fp5::Tables c_fp5_tables = MVOSR_FP5_TABLES_INIT;
 
-constexpr int FP5_THREADS = 128;         // hypotheses per round
+constexpr int FP5_ROUND = 128;           // hypotheses per round: part of the stream definition (the stopping rule is checked per round)
+constexpr int FP5_THREADS = FP5_ROUND;
 constexpr int FP5_TILE = 512;            // correspondences staged per tile (16 KB of shared memory)
 
 __global__ void __launch_bounds__(FP5_THREADS) find_essential_kernel(int n_frames, const int32_t *__restrict__ offsets,
         const float *__restrict__ cur_u, const float *__restrict__ cur_v, const float *__restrict__ ref_u, const float *__restrict__ ref_v,
-        double fx, double fy, double cx, double cy, int hypotheses, double threshold_px, uint64_t seed,
+        double fx, double fy, double cx, double cy, int hypotheses, double threshold_px, double confidence, uint64_t seed,
         const int32_t *__restrict__ frame_index, int seq_id,
-        double *essential, uint8_t *e_mask, int32_t *n_inliers, int32_t *best_hyp) {
+        double *essential, uint8_t *e_mask, int32_t *n_inliers, int32_t *best_hyp, int32_t *hyps_used) {
     __shared__ double s_pt[FP5_TILE][4];
     __shared__ unsigned long long s_key[FP5_THREADS / 32];
     __shared__ unsigned long long s_best_key;
@@ -38,6 +42,7 @@ __global__ void __launch_bounds__(FP5_THREADS) find_essential_kernel(int n_frame
             for (int i = 0; i < 9; ++i) s_best_E[i] = 0.0;
         }
         __syncthreads();
+        int used = 0;
         if (n >= 5) {                                               // uniform over the CTA
             for (int h0 = 0; h0 < hypotheses; h0 += FP5_THREADS) {
                 const int hyp = h0 + tid;
@@ -92,6 +97,8 @@ __global__ void __launch_bounds__(FP5_THREADS) find_essential_kernel(int n_frame
                     s_best_key = bmax;
                     for (int i = 0; i < 9; ++i) s_best_E[i] = E[bk][i];
                 }
+                used = min(hypotheses, h0 + FP5_THREADS);
+                if (fp5::enough_hypotheses(used, (int)((bmax > old ? bmax : old) >> 32), n, confidence)) break;   // same value in every thread
             }
         }
         __syncthreads();
@@ -109,6 +116,7 @@ __global__ void __launch_bounds__(FP5_THREADS) find_essential_kernel(int n_frame
             for (int i = 0; i < 9; ++i) essential[9 * (size_t)f + i] = e[i];
             if (n_inliers) n_inliers[f] = (int32_t)(win >> 32);
             if (best_hyp) best_hyp[f] = win != 0ull ? (int32_t)((0xFFFFFFFFu - (uint32_t)(win & 0xFFFFFFFFull)) >> 4) : -1;
+            if (hyps_used) hyps_used[f] = used;
         }
         __syncthreads();                                            // s_best_* are reset by thread 0 for the next frame
     }

@@ -161,8 +161,19 @@ def five_point_device_style(x1, x2):
 # RANSAC on a DEFINED sample stream (OpenCV's own RNG cannot be reproduced): the checker of mvosr_find_essential_frames.
 #   key = (seed lo, seed hi); (r0..r3) = Philox4x32-10(counter = (hyp, frame, seq, 1)); r4 = word 0 of counter (hyp, frame, seq, 2)
 #   p_k = (r_k * (n - k)) >> 32, then + 1 for every earlier position (ascending) it is >= to   -> five distinct positions
-# Selection: the candidate with the most Sampson inliers over a FIXED number of hypotheses; ties go to the lowest
-# (hypothesis, candidate) pair, candidates in ascending order of their eigenvalue.
+# Selection: the candidate with the most Sampson inliers; ties go to the lowest (hypothesis, candidate) pair, candidates in
+# ascending order of their eigenvalue.  `hypotheses` is the maximum (OpenCV's maxIters); confidence > 0 (OpenCV's prob) stops
+# after the first ROUND of 128 hypotheses at whose end  tried >= log(1 - confidence) / log(1 - w^5),  w = best / n.
+ROUND = 128
+
+
+def enough_hypotheses(tried, best_count, n, confidence):
+    if not confidence > 0.0 or best_count <= 0 or confidence >= 1.0:
+        return False
+    w5 = (best_count / n) ** 5
+    if w5 >= 1.0:
+        return True
+    return tried * np.log(1.0 - w5) <= np.log(1.0 - confidence)
 def sample5_positions(seed, hyp, frame, seq, n):
     from .philox import MASK, philox4x32_10
     key = (seed & MASK, (seed >> 32) & MASK)
@@ -187,8 +198,8 @@ def sampson_inlier(E, x1, x2, thr2):
     return s * s < thr2 * (Ex1[:, 0] ** 2 + Ex1[:, 1] ** 2 + Etx2[:, 0] ** 2 + Etx2[:, 1] ** 2)
 
 
-def find_essential_philox(px_cur, px_ref, fx, fy, cx, cy, hypotheses=128, threshold=0.5, seed=0, frame=0, seq=0, solver=None):
-    """(E (3,3), mask (n,) bool, n_inliers, best_hyp) for one frame; px_* (n,2) pixels (float32 values).  x_ref^T E x_cur = 0 in
+def find_essential_philox(px_cur, px_ref, fx, fy, cx, cy, hypotheses=128, threshold=0.5, seed=0, frame=0, seq=0, solver=None, confidence=0.0):
+    """(E (3,3), mask (n,) bool, n_inliers, best_hyp, hyps_used) for one frame; px_* (n,2) pixels (float32 values).  x_ref^T E x_cur = 0 in
     normalised coordinates, cv2.findEssentialMat(px_cur, px_ref, K)'s convention (visual_odometry.py:129-130)."""
     solver = solver or five_point_device_style
     px_cur = np.asarray(px_cur, dtype=np.float64)
@@ -198,13 +209,17 @@ def find_essential_philox(px_cur, px_ref, fx, fy, cx, cy, hypotheses=128, thresh
     n = x1.shape[0]
     thr2 = (threshold / (0.5 * (fx + fy))) ** 2
     best = (0, None, -1)
+    used = 0
     if n >= 5:
         for hyp in range(hypotheses):
+            if hyp > 0 and hyp % ROUND == 0 and enough_hypotheses(hyp, best[0], n, confidence):
+                break
+            used = hyp + 1
             idx = sample5_positions(seed, hyp, frame, seq, n)
             for E in solver(x1[idx], x2[idx]):
                 cnt = int(sampson_inlier(E, x1, x2, thr2).sum())
                 if cnt > best[0]:
                     best = (cnt, E, hyp)
     if best[1] is None:
-        return np.zeros((3, 3)), np.zeros(n, bool), 0, -1
-    return best[1], sampson_inlier(best[1], x1, x2, thr2), best[0], best[2]
+        return np.zeros((3, 3)), np.zeros(n, bool), 0, -1, used
+    return best[1], sampson_inlier(best[1], x1, x2, thr2), best[0], best[2], used

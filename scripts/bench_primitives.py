@@ -92,11 +92,13 @@ row("recover_pose_kernel", "592 frames x 2500 correspondences (4 triangulations 
 
 # ---- essential matrix by five-point RANSAC on the same 592 frames (FP64-pipe bound, not HBM: the fraction column only says so),
 #      with OpenCV's own findEssentialMat on the host beside it (one core, a bounded sample of the same frames)
-for hyps in (128, 512):
-    ms = timed(lambda: eng.find_essential_frames(*dd, hypotheses=hyps, threshold=0.5, seed=1), reps=5)
-    row("find_essential_kernel", "592 frames x 2500 correspondences, %d hypotheses per frame" % hyps, ms, 17 * int(b.offsets[-1]) + (72 + 8) * b.n_frames,
+for hyps, conf in ((128, 0.0), (512, 0.0), (1000, 0.999)):
+    ms = timed(lambda: eng.find_essential_frames(*dd, hypotheses=hyps, threshold=0.5, seed=1, confidence=conf), reps=5)
+    row("find_essential_kernel", "592 frames x 2500 correspondences, %s %d hypotheses per frame" % ("up to" if conf else "exactly", hyps) +
+        (" (confidence %.3f: the reference's call)" % conf if conf else ""), ms, 17 * int(b.offsets[-1]) + (72 + 8) * b.n_frames,
         b.n_frames, "frames")
-    out["rows"][-1]["hypotheses_per_s"] = hyps * b.n_frames / ms * 1e3
+    if not conf:
+        out["rows"][-1]["hypotheses_per_s"] = hyps * b.n_frames / ms * 1e3
 try:
     import time
     import cv2

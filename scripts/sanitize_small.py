@@ -32,6 +32,6 @@ b = synth.make_sequence(seed=9, n_frames=4, n_corr=700, outlier_frac=0.1)
 off = np.concatenate([b.offsets, [b.offsets[-1] + 3]]).astype(np.int32)            # a fifth frame of three correspondences
 pad = lambda a: np.concatenate([a, a[:3]])
 r = eng.scale_frames_from_tracks(t(off), t(pad(b.cur_u)), t(pad(b.cur_v)), t(pad(b.ref_u)), t(pad(b.ref_v)), max_features=int(np.diff(off).max()),
-                                 hypotheses=160, seed=3)
+                                 hypotheses=160, seed=3, confidence=0.0)
 torch.cuda.synchronize()
 print("essential inliers", r["n_inliers"].cpu().numpy(), "scales", r["raw_scale"].cpu().numpy()[:4], "true", b.true_scale)

@@ -52,7 +52,7 @@ def main():
         a, e = off[f], off[f + 1]
         cur = np.stack([d["cur_u"][a:e], d["cur_v"][a:e]], 1)
         ref = np.stack([d["ref_u"][a:e], d["ref_v"][a:e]], 1)
-        Ef, m, c, h = PL.find_essential_philox(cur, ref, *K, hypotheses=HYPOTHESES, threshold=THRESHOLD, seed=SEED, frame=f, seq=SEQ)
+        Ef, m, c, h, _ = PL.find_essential_philox(cur, ref, *K, hypotheses=HYPOTHESES, threshold=THRESHOLD, seed=SEED, frame=f, seq=SEQ)
         E[f] = Ef.reshape(-1); mask[a:e] = m; cnt[f] = c; hyp[f] = h
         print(f, e - a, c, h, int(d["true_match"][a:e].sum()))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "essential.npz"), hypotheses=HYPOTHESES, threshold=THRESHOLD, seed=SEED, seq=SEQ,

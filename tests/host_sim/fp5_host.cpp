@@ -30,13 +30,16 @@ void fp5_host_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_
 }
 
 void fp5_host_ransac_frame(int32_t n, const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
-                           double fx, double fy, double cx, double cy, int32_t hypotheses, double threshold_px, uint64_t seed,
-                           uint32_t frame, uint32_t seq, double *essential, uint8_t *e_mask, int32_t *n_inliers, int32_t *best_hyp) {
+                           double fx, double fy, double cx, double cy, int32_t hypotheses, double threshold_px, double confidence, uint64_t seed,
+                           uint32_t frame, uint32_t seq, double *essential, uint8_t *e_mask, int32_t *n_inliers, int32_t *best_hyp, int32_t *hyps_used) {
     const double thr = threshold_px / (0.5 * (fx + fy)), thr2 = thr * thr;
     unsigned long long win = 0ull;
     double best[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    int used = 0;
     if (n >= 5)
         for (int hyp = 0; hyp < hypotheses; ++hyp) {
+            if (hyp > 0 && hyp % 128 == 0 && fp5::enough_hypotheses(hyp, (int)(win >> 32), n, confidence)) break;   // the rule is checked per round of 128
+            used = hyp + 1;
             int idx[5];
             fp5::sample5(seed, (uint32_t)hyp, frame, seq, (uint32_t)n, idx);
             double x1[10], x2[10], E[10][9];
@@ -62,6 +65,7 @@ void fp5_host_ransac_frame(int32_t n, const float *cur_u, const float *cur_v, co
         e_mask[i] = (win != 0ull && fp5::sampson_inlier(best, ((double)cur_u[i] - cx) / fx, ((double)cur_v[i] - cy) / fy,
                                                         ((double)ref_u[i] - cx) / fx, ((double)ref_v[i] - cy) / fy, thr2)) ? 1 : 0;
     memcpy(essential, best, sizeof(best));
+    *hyps_used = used;
     *n_inliers = (int32_t)(win >> 32);
     *best_hyp = win != 0ull ? (int32_t)((0xFFFFFFFFu - (uint32_t)(win & 0xFFFFFFFFull)) >> 4) : -1;
 }

@@ -35,8 +35,8 @@ using std::min;
 
 namespace {
 struct Args {
-    int n_frames; const int32_t *offsets; const float *cu, *cv, *ru, *rv; double fx, fy, cx, cy; int hyps; double thr; uint64_t seed;
-    const int32_t *frame_index; int seq; double *E; uint8_t *mask; int32_t *cnt, *hyp;
+    int n_frames; const int32_t *offsets; const float *cu, *cv, *ru, *rv; double fx, fy, cx, cy; int hyps; double thr, conf; uint64_t seed;
+    const int32_t *frame_index; int seq; double *E; uint8_t *mask; int32_t *cnt, *hyp, *used;
 };
 struct ThreadArg { const Args *a; int tid, bid; };
 
@@ -44,17 +44,17 @@ void *run_thread(void *p) {
     const ThreadArg *t = (const ThreadArg *)p;
     threadIdx.x = t->tid; blockIdx.x = t->bid;
     const Args &a = *t->a;
-    mvosr::find_essential_kernel(a.n_frames, a.offsets, a.cu, a.cv, a.ru, a.rv, a.fx, a.fy, a.cx, a.cy, a.hyps, a.thr, a.seed, a.frame_index, a.seq,
-                                 a.E, a.mask, a.cnt, a.hyp);
+    mvosr::find_essential_kernel(a.n_frames, a.offsets, a.cu, a.cv, a.ru, a.rv, a.fx, a.fy, a.cx, a.cy, a.hyps, a.thr, a.conf, a.seed, a.frame_index, a.seq,
+                                 a.E, a.mask, a.cnt, a.hyp, a.used);
     return nullptr;
 }
 }  // namespace
 
 extern "C" int fp5_emu_find_essential(int32_t n_frames, const int32_t *offsets, const float *cu, const float *cv, const float *ru, const float *rv,
-                                      double fx, double fy, double cx, double cy, int32_t hyps, double thr, uint64_t seed,
-                                      const int32_t *frame_index, int32_t seq, double *E, uint8_t *mask, int32_t *cnt, int32_t *hyp, int32_t grid) {
+                                      double fx, double fy, double cx, double cy, int32_t hyps, double thr, double conf, uint64_t seed,
+                                      const int32_t *frame_index, int32_t seq, double *E, uint8_t *mask, int32_t *cnt, int32_t *hyp, int32_t *used, int32_t grid) {
     const int T = mvosr::FP5_THREADS;
-    const Args a = { n_frames, offsets, cu, cv, ru, rv, fx, fy, cx, cy, hyps, thr, seed, frame_index, seq, E, mask, cnt, hyp };
+    const Args a = { n_frames, offsets, cu, cv, ru, rv, fx, fy, cx, cy, hyps, thr, conf, seed, frame_index, seq, E, mask, cnt, hyp, used };
     blockDim.x = T; gridDim.x = grid;
     pthread_barrier_init(&g_cta_barrier, nullptr, T);
     for (int w = 0; w < T / 32; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, 32);

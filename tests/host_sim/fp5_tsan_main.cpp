@@ -1,12 +1,12 @@
 // TEST INFRASTRUCTURE: driver of the ThreadSanitizer run of the kernel emulation (scripts/tsan_five_point_kernel.sh): synthetic frames of
-// 700 / 3 / 1300 / 40 / 513 correspondences (several tiles, a tile boundary, a frame without a model), 200 hypotheses (two rounds), 2 CTAs.
+// 700 / 3 / 1300 / 40 / 513 correspondences (several tiles, a tile boundary, a frame without a model), up to 400 hypotheses with the adaptive stop, 2 CTAs.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <math.h>
 #include <vector>
 extern "C" int fp5_emu_find_essential(int32_t, const int32_t *, const float *, const float *, const float *, const float *, double, double, double, double,
-                                      int32_t, double, uint64_t, const int32_t *, int32_t, double *, uint8_t *, int32_t *, int32_t *, int32_t);
+                                      int32_t, double, double, uint64_t, const int32_t *, int32_t, double *, uint8_t *, int32_t *, int32_t *, int32_t *, int32_t);
 int main() {
     const double fx = 718.856, fy = 718.856, cx = 607.1928, cy = 185.2157;
     const int F = 5; const int lens[F] = { 700, 3, 1300, 40, 513 };
@@ -24,9 +24,9 @@ int main() {
         ru[i] = (float)(fx * X2 / Z2 + cx); rv[i] = (float)(fy * Y2 / Z2 + cy);
         if (i % 5 == 0) { ru[i] = (float)(1241 * U()); rv[i] = (float)(376 * U()); }
     }
-    std::vector<double> E(9 * F); std::vector<uint8_t> mask(M); std::vector<int32_t> cnt(F), hyp(F);
-    const int rc = fp5_emu_find_essential(F, off.data(), cu.data(), cv.data(), ru.data(), rv.data(), fx, fy, cx, cy, 200, 0.5, 99, nullptr, 0,
-                                          E.data(), mask.data(), cnt.data(), hyp.data(), 2);
-    for (int f = 0; f < F; ++f) printf("frame %d n %d inliers %d hyp %d\n", f, lens[f], cnt[f], hyp[f]);
+    std::vector<double> E(9 * F); std::vector<uint8_t> mask(M); std::vector<int32_t> cnt(F), hyp(F), used(F);
+    const int rc = fp5_emu_find_essential(F, off.data(), cu.data(), cv.data(), ru.data(), rv.data(), fx, fy, cx, cy, 400, 0.5, 0.999, 99, nullptr, 0,
+                                          E.data(), mask.data(), cnt.data(), hyp.data(), used.data(), 2);
+    for (int f = 0; f < F; ++f) printf("frame %d n %d inliers %d hyp %d used %d\n", f, lens[f], cnt[f], hyp[f], used[f]);
     return rc;
 }

@@ -31,8 +31,8 @@ def load_host_sim():
     L.fp5_host_solve.argtypes = [vp, vp, vp]
     L.fp5_host_sample5.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     L.fp5_host_philox.argtypes = [C.c_uint32] * 6 + [vp]
-    L.fp5_host_ransac_frame.argtypes = [C.c_int32, vp, vp, vp, vp] + [C.c_double] * 4 + [C.c_int32, C.c_double, C.c_uint64, C.c_uint32, C.c_uint32,
-                                                                                       vp, vp, vp, vp]
+    L.fp5_host_ransac_frame.argtypes = [C.c_int32, vp, vp, vp, vp] + [C.c_double] * 4 + [C.c_int32, C.c_double, C.c_double, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                                                       vp, vp, vp, vp, vp]
     return L
 
 
@@ -49,8 +49,8 @@ def load_kernel_emulation():
     if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-o", so, src])
     L = C.CDLL(so)
-    L.fp5_emu_find_essential.argtypes = [C.c_int32, vp, vp, vp, vp, vp] + [C.c_double] * 4 + [C.c_int32, C.c_double, C.c_uint64, vp, C.c_int32,
-                                                                                         vp, vp, vp, vp, C.c_int32]
+    L.fp5_emu_find_essential.argtypes = [C.c_int32, vp, vp, vp, vp, vp] + [C.c_double] * 4 + [C.c_int32, C.c_double, C.c_double, C.c_uint64, vp, C.c_int32,
+                                                                                         vp, vp, vp, vp, vp, C.c_int32]
     return L
 
 
@@ -142,12 +142,14 @@ def test_degenerate_samples_give_no_solution_and_no_nan(sim):
         assert np.isfinite(F).all()
 
 
-def _ransac(L, cu, cv, ru, rv, hyps, thr, seed, frame, seq):
+def _ransac(L, cu, cv, ru, rv, hyps, thr, seed, frame, seq, confidence=0.0, with_used=False):
     n = cu.size
-    E = np.zeros(9); mask = np.zeros(max(n, 1), np.uint8); cnt = C.c_int32(0); hyp = C.c_int32(0)
+    E = np.zeros(9); mask = np.zeros(max(n, 1), np.uint8); cnt = C.c_int32(0); hyp = C.c_int32(0); used = C.c_int32(0)
     cu, cv, ru, rv = (np.ascontiguousarray(x, dtype=np.float32) for x in (cu, cv, ru, rv))
-    L.fp5_host_ransac_frame(n, _p(cu), _p(cv), _p(ru), _p(rv), *K, hyps, thr, seed, frame, seq, _p(E), _p(mask), C.byref(cnt), C.byref(hyp))
-    return E.reshape(3, 3), mask[:n].astype(bool), cnt.value, hyp.value
+    L.fp5_host_ransac_frame(n, _p(cu), _p(cv), _p(ru), _p(rv), *K, hyps, thr, confidence, seed, frame, seq, _p(E), _p(mask), C.byref(cnt), C.byref(hyp),
+                            C.byref(used))
+    out = (E.reshape(3, 3), mask[:n].astype(bool), cnt.value, hyp.value)
+    return out + (used.value,) if with_used else out
 
 
 def test_selection_rule_matches_the_oracle_exactly_given_the_same_candidates(sim):
@@ -159,7 +161,7 @@ def test_selection_rule_matches_the_oracle_exactly_given_the_same_candidates(sim
         a, e = off[f], off[f + 1]
         cu, cv, ru, rv = (z[k][a:e] for k in ("cur_u", "cur_v", "ref_u", "ref_v"))
         E, mask, cnt, hyp = _ransac(sim, cu, cv, ru, rv, 24, 0.5, 77, f, 1)
-        Eo, mo, co, ho = PL.find_essential_philox(np.stack([cu, cv], 1), np.stack([ru, rv], 1), *K, hypotheses=24, threshold=0.5, seed=77, frame=f, seq=1,
+        Eo, mo, co, ho, _ = PL.find_essential_philox(np.stack([cu, cv], 1), np.stack([ru, rv], 1), *K, hypotheses=24, threshold=0.5, seed=77, frame=f, seq=1,
                                                   solver=lambda x1, x2: _solve(sim, x1, x2))
         assert (cnt, hyp) == (co, ho) and np.array_equal(mask, mo) and np.array_equal(E, Eo)
         assert cnt == int(mask.sum())
@@ -205,14 +207,41 @@ def test_kernel_source_on_the_host_emulation(sim):
     F = len(off) - 1
     fidx = np.ascontiguousarray((np.arange(F) * 3 + 1).astype(np.int32))
     seed, seq = 2**40 + 17, 6
-    for H, grid, use_index in ((48, 4, False), (150, 1, True), (128, F, True)):
+    for H, grid, use_index, conf in ((48, 4, False, 0.0), (150, 1, True, 0.0), (128, F, True, 0.999), (400, 3, False, 0.999), (300, 2, True, 0.5)):
         E = np.full((F, 9), 7.0); mask = np.full(off[-1], 9, np.uint8); cnt = np.full(F, -5, np.int32); hyp = np.full(F, -5, np.int32)
-        rc = emu.fp5_emu_find_essential(F, _p(off), *(_p(arr[k]) for k in ("cur_u", "cur_v", "ref_u", "ref_v")), *K, H, 0.5, seed,
-                                        _p(fidx) if use_index else None, seq, _p(E), _p(mask), _p(cnt), _p(hyp), grid)
+        used = np.full(F, -5, np.int32)
+        rc = emu.fp5_emu_find_essential(F, _p(off), *(_p(arr[k]) for k in ("cur_u", "cur_v", "ref_u", "ref_v")), *K, H, 0.5, conf, seed,
+                                        _p(fidx) if use_index else None, seq, _p(E), _p(mask), _p(cnt), _p(hyp), _p(used), grid)
         assert rc == 0
         for f in range(F):
             a, e = off[f], off[f + 1]
-            Er, mr, cr, hr = _ransac(sim, *(arr[k][a:e] for k in ("cur_u", "cur_v", "ref_u", "ref_v")), H, 0.5, seed, int(fidx[f]) if use_index else f, seq)
-            assert (cr, hr) == (cnt[f], hyp[f]), (H, grid, f)
+            Er, mr, cr, hr, ur = _ransac(sim, *(arr[k][a:e] for k in ("cur_u", "cur_v", "ref_u", "ref_v")), H, 0.5, seed,
+                                         int(fidx[f]) if use_index else f, seq, confidence=conf, with_used=True)
+            assert (cr, hr, ur) == (cnt[f], hyp[f], used[f]), (H, grid, f)
             assert np.array_equal(Er.reshape(-1), E[f]) and np.array_equal(mr, mask[a:e].astype(bool))
         assert cnt[-1] > 800 and cnt[-2] > 800                     # the large frames found their model
+        if H == 400:                                               # ~80 % inliers: the adaptive rule stops after the first round
+            assert (used[:8] == 128).all() and used[8] == 0 and used[9] == 128 and used[10] == 400
+
+
+def test_adaptive_stopping_rule_against_the_oracle(sim):
+    """OpenCV's adaptive hypothesis count (prob = 0.999), evaluated per round of 128: the replay of the kernel's rule and the
+    oracle's stop at the same hypothesis, on frames from 90 % down to 35 % inliers, and the count is the formula's."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pose.npz"))
+    a, e = z["offsets"][2], z["offsets"][3]
+    rng = np.random.default_rng(11)
+    for frac_bad, want_rounds in ((0.0, 1), (0.45, 2), (0.65, None)):
+        cu, cv, ru, rv = (z[k][a:e].copy() for k in ("cur_u", "cur_v", "ref_u", "ref_v"))
+        bad = rng.permutation(e - a)[: int(frac_bad * (e - a))]
+        ru[bad] = rng.uniform(0, 1241, bad.size).astype(np.float32); rv[bad] = rng.uniform(0, 376, bad.size).astype(np.float32)
+        E, mask, cnt, hyp, used = _ransac(sim, cu, cv, ru, rv, 1000, 0.5, 31, 2, 0, confidence=0.999, with_used=True)
+        Eo, mo, co, ho, uo = PL.find_essential_philox(np.stack([cu, cv], 1), np.stack([ru, rv], 1), *K, hypotheses=1000, threshold=0.5, seed=31, frame=2,
+                                                      seq=0, solver=lambda x1, x2: _solve(sim, x1, x2), confidence=0.999)
+        assert (cnt, hyp, used) == (co, ho, uo) and np.array_equal(E, Eo) and np.array_equal(mask, mo)
+        with np.errstate(divide="ignore"):
+            need = np.log(1 - 0.999) / np.log(1 - (cnt / (e - a)) ** 5)
+        assert used % 128 == 0 or used == 1000
+        assert used == 1000 or (used >= need and used - 128 < max(need, 128) + 128)
+        if want_rounds:
+            assert used == 128 * want_rounds, (frac_bad, used, cnt, need)
+        assert cnt >= 0.9 * (1 - frac_bad) * (e - a)

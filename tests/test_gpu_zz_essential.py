@@ -141,8 +141,18 @@ def test_hypothesis_count_and_frame_index(engine, golden, run):
     z, (d, out) = golden, run
     import torch
     more = engine.find_essential_frames(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], hypotheses=200, threshold=float(z["threshold"]),
-                                        seed=int(z["seed"]), seq_id=int(z["seq"]))
+                                        seed=int(z["seed"]), seq_id=int(z["seq"]), confidence=0.0)
     assert (more["n_inliers"].cpu().numpy() >= out["n_inliers"]).all()
+    n = np.diff(z["offsets"])
+    assert np.array_equal(more["hyps_used"].cpu().numpy(), np.where(n >= 5, 200, 0))
+    assert np.array_equal(out["hyps_used"], np.where(n >= 5, int(z["hypotheses"]), 0))
+    # OpenCV's adaptive count (prob = 0.999, maxIters = 1000: the reference's call), checked per round of 128: ~80 % inliers stop
+    # after the first round, the frame without a model runs to the end; the first round is the same stream as above
+    ada = engine.find_essential_frames(d["offsets"], d["cur_u"], d["cur_v"], d["ref_u"], d["ref_v"], hypotheses=1000, threshold=float(z["threshold"]),
+                                       seed=int(z["seed"]), seq_id=int(z["seq"]), confidence=0.999)
+    used = ada["hyps_used"].cpu().numpy()
+    assert (used[:8] == 128).all() and used[8] == 0 and used[9] == 128 and used[10] == 1000
+    assert (ada["n_inliers"].cpu().numpy() >= out["n_inliers"]).all() and (ada["n_inliers"].cpu().numpy() <= more["n_inliers"].cpu().numpy()).all()
     off = z["offsets"]
     a, e = int(off[3]), int(off[6])                                   # frames 3..5 as their own batch, addressed as frames 3..5
     sub_off = _t(engine, (off[3:7] - off[3]).astype(np.int32))
