@@ -79,6 +79,7 @@ MVOSR_FP5_HD bool null4(const double x1[10], const double x2[10], double basis[4
         for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) M[i][3 * p + q] = a[p] * b[q];
     }
     for (int c = 0; c < 9; ++c) cols[c] = c;
+    #pragma unroll 1
     for (int r = 0; r < 5; ++r) {
         int pi = r, pj = r;
         double best = -1.0;
@@ -124,24 +125,29 @@ MVOSR_FP5_HD bool action_rows(const double basis[4][9], const Tables &T, double 
     double M[10][20];
     {
         double vals[20][10];
+        #pragma unroll 1
         for (int s = 0; s < 20; ++s) {
             double E[9];
             for (int c = 0; c < 9; ++c) E[c] = T.pts[s][0] * basis[0][c] + T.pts[s][1] * basis[1][c] + T.pts[s][2] * basis[2][c] + basis[3][c];
             constraints_at(E, vals[s]);
         }
+        #pragma unroll 1
         for (int c = 0; c < 10; ++c)
+#pragma unroll 1
             for (int m = 0; m < 20; ++m) {
                 double a = 0.0;
                 for (int s = 0; s < 20; ++s) a += T.vinv[m][s] * vals[s][c];
                 M[c][m] = a;
             }
     }
+    #pragma unroll 1
     for (int c = 0; c < 10; ++c) {
         double mx = 0.0;
         for (int m = 0; m < 20; ++m) { const double v = fabs(M[c][m]); if (v > mx) mx = v; }
         if (!(mx > 0.0) || !(mx < 1e300)) return false;
         for (int m = 0; m < 20; ++m) M[c][m] /= mx;
     }
+    #pragma unroll 1
     for (int col = 0; col < 10; ++col) {
         int piv = col;
         double best = fabs(M[col][col]);
@@ -150,6 +156,7 @@ MVOSR_FP5_HD bool action_rows(const double basis[4][9], const Tables &T, double 
         if (piv != col) for (int m = 0; m < 20; ++m) { const double t = M[col][m]; M[col][m] = M[piv][m]; M[piv][m] = t; }
         const double p = M[col][col];
         for (int m = 0; m < 20; ++m) M[col][m] /= p;
+        #pragma unroll 1
         for (int r = 0; r < 10; ++r) {
             if (r == col) continue;
             const double f = M[r][col];
@@ -174,6 +181,7 @@ MVOSR_FP5_HD int real_eigenvalues(const double A6[6][10], double roots[10]) {
     // -- balancing: similarity by powers of two until row and column norms are within a factor of two
     for (int pass = 0, again = 1; again && pass < 24; ++pass) {
         again = 0;
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) {
             double r = 0.0, c = 0.0;
             for (int j = 0; j < n; ++j) if (j != i) { c += fabs(a[j][i]); r += fabs(a[i][j]); }
@@ -192,6 +200,7 @@ MVOSR_FP5_HD int real_eigenvalues(const double A6[6][10], double roots[10]) {
         }
     }
     // -- Hessenberg form by elimination with pivoting
+    #pragma unroll 1
     for (int m = 1; m < n - 1; ++m) {
         double x = 0.0;
         int piv = m;
@@ -201,6 +210,7 @@ MVOSR_FP5_HD int real_eigenvalues(const double A6[6][10], double roots[10]) {
             for (int j = 0; j < n; ++j) { const double t = a[j][piv]; a[j][piv] = a[j][m]; a[j][m] = t; }
         }
         if (x != 0.0)
+            #pragma unroll 1
             for (int i = m + 1; i < n; ++i) {
                 double y = a[i][m - 1];
                 if (y == 0.0) continue;
@@ -328,6 +338,7 @@ MVOSR_FP5_HD int real_eigenvalues(const double A6[6][10], double roots[10]) {
 // Solves S z = b in place (Gaussian elimination, partial pivoting); S is destroyed.  false on an exactly zero pivot.
 template <int N>
 MVOSR_FP5_HD bool solve_in_place(double S[N][N], double b[N]) {
+    #pragma unroll 1
     for (int col = 0; col < N; ++col) {
         int piv = col;
         double best = fabs(S[col][col]);
@@ -337,6 +348,7 @@ MVOSR_FP5_HD bool solve_in_place(double S[N][N], double b[N]) {
             for (int j = 0; j < N; ++j) { const double t = S[col][j]; S[col][j] = S[piv][j]; S[piv][j] = t; }
             const double t = b[col]; b[col] = b[piv]; b[piv] = t;
         }
+        #pragma unroll 1
         for (int r = col + 1; r < N; ++r) {
             const double f = S[r][col] / S[col][col];
             if (f == 0.0) continue;
@@ -344,6 +356,7 @@ MVOSR_FP5_HD bool solve_in_place(double S[N][N], double b[N]) {
             b[r] -= f * b[col];
         }
     }
+    #pragma unroll 1
     for (int r = N - 1; r >= 0; --r) {
         double a = b[r];
         for (int j = r + 1; j < N; ++j) a -= S[r][j] * b[j];
@@ -364,6 +377,7 @@ MVOSR_FP5_HD void shifted(const double A6[6][10], double x, bool transpose, doub
 MVOSR_FP5_HD double polish_eigenvalue(const double A6[6][10], double x) {
     double v[10], u[10], S[10][10];
     for (int i = 0; i < 10; ++i) v[i] = u[i] = 0.31622776601683794;     // 1 / sqrt(10)
+    #pragma unroll 1
     for (int step = 0; step < 3; ++step) {
         shifted(A6, x, false, S);
         if (!solve_in_place<10>(S, v)) break;
@@ -396,6 +410,7 @@ MVOSR_FP5_HD int solve(const double x1[10], const double x2[10], const Tables &T
     if (!action_rows(basis, T, A6)) return 0;
     const int nr = real_eigenvalues(A6, roots);
     int n_sol = 0;
+    #pragma unroll 1
     for (int k = 0; k < nr; ++k) {
         const double x = polish_eigenvalue(A6, roots[k]);
         // (A - x I) v = 0, v = [x^2, xy, xz, y^2, yz, z^2, x, y, z, 1]: rows 0..5 are linear in (y^2, yz, z^2, y, z) once

@@ -23,7 +23,7 @@ constexpr int FP5_ROUND = 128;           // hypotheses per round: part of the st
 constexpr int FP5_THREADS = FP5_ROUND;
 constexpr int FP5_TILE = 512;            // correspondences staged per tile (16 KB of shared memory)
 
-__global__ void __launch_bounds__(FP5_THREADS) find_essential_kernel(int n_frames, const int32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(FP5_THREADS, 4) find_essential_kernel(int n_frames, const int32_t *__restrict__ offsets,
         const float *__restrict__ cur_u, const float *__restrict__ cur_v, const float *__restrict__ ref_u, const float *__restrict__ ref_v,
         double fx, double fy, double cx, double cy, int hypotheses, double threshold_px, double confidence, uint64_t seed,
         const int32_t *__restrict__ frame_index, int seq_id,

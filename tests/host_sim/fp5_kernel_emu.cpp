@@ -26,7 +26,7 @@ static inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long v,
 }
 using std::min;
 #define __global__
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __restrict__
 #define __shared__ static
 #define __constant__ static const
