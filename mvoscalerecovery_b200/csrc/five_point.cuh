@@ -7,8 +7,8 @@
 // The minimal solver is Stewenius' action-matrix form of Nister's problem, with numerics one thread can run in its own
 // registers / local memory (no LAPACK): Gauss-Jordan null space with full pivoting, the ten cubic constraints by
 // interpolation at 20 fixed nodes, Gauss-Jordan on the 10x20 coefficient matrix, the real eigenvalues of the 10x10 action
-// matrix by balancing + Hessenberg reduction + double-shift QR, Rayleigh-quotient polish on the matrix, a 6x5 least-squares
-// back-substitution per root, and a final test that the result IS an essential matrix.
+// matrix by balancing + Hessenberg reduction + double-shift QR (accurate as they come: a Rayleigh-quotient polish changed
+// nothing measurable and was dropped), a 6x5 least-squares back-substitution per root, and a final test that the result IS an essential matrix.
 //
 // Everything numerical is __host__ __device__ so that tests/host_sim can compile the very same functions for the host and
 // check them against the oracle without a GPU; the library itself only ever calls them from find_essential_kernel.
@@ -365,43 +365,6 @@ MVOSR_FP5_HD bool solve_in_place(double S[N][N], double b[N]) {
     return true;
 }
 
-MVOSR_FP5_HD void shifted(const double A6[6][10], double x, bool transpose, double S[10][10]) {
-    for (int i = 0; i < 10; ++i) for (int j = 0; j < 10; ++j) S[i][j] = 0.0;
-    for (int r = 0; r < 6; ++r) for (int c = 0; c < 10; ++c) { if (transpose) S[c][r] = A6[r][c]; else S[r][c] = A6[r][c]; }
-    if (transpose) { S[0][6] = 1.0; S[1][7] = 1.0; S[2][8] = 1.0; S[6][9] = 1.0; }
-    else           { S[6][0] = 1.0; S[7][1] = 1.0; S[8][2] = 1.0; S[9][6] = 1.0; }
-    for (int i = 0; i < 10; ++i) S[i][i] -= x;
-}
-
-// Rayleigh-quotient iteration on (A, A^T) from the approximate eigenvalue x
-MVOSR_FP5_HD double polish_eigenvalue(const double A6[6][10], double x) {
-    double v[10], u[10], S[10][10];
-    for (int i = 0; i < 10; ++i) v[i] = u[i] = 0.31622776601683794;     // 1 / sqrt(10)
-    #pragma unroll 1
-    for (int step = 0; step < 3; ++step) {
-        shifted(A6, x, false, S);
-        if (!solve_in_place<10>(S, v)) break;
-        shifted(A6, x, true, S);
-        if (!solve_in_place<10>(S, u)) break;
-        double nv = 0.0, nu = 0.0;
-        for (int i = 0; i < 10; ++i) { nv += v[i] * v[i]; nu += u[i] * u[i]; }
-        nv = sqrt(nv); nu = sqrt(nu);
-        for (int i = 0; i < 10; ++i) { v[i] /= nv; u[i] /= nu; }
-        double d = 0.0;
-        for (int i = 0; i < 10; ++i) d += u[i] * v[i];
-        if (fabs(d) < 1e-12) break;
-        double num = 0.0;                                           // u . (A v)
-        for (int r = 0; r < 6; ++r) {
-            double a = 0.0;
-            for (int c = 0; c < 10; ++c) a += A6[r][c] * v[c];
-            num += u[r] * a;
-        }
-        num += u[6] * v[0] + u[7] * v[1] + u[8] * v[2] + u[9] * v[6];
-        x = num / d;
-    }
-    return x;
-}
-
 // All real essential matrices through five correspondences (normalised coordinates, x2^T E x1 = 0): up to ten 3x3 matrices
 // of unit Frobenius norm, row-major, in ascending order of the eigenvalue they belong to.  Returns how many.
 MVOSR_FP5_HD int solve(const double x1[10], const double x2[10], const Tables &T, double Eout[10][9]) {
@@ -412,7 +375,7 @@ MVOSR_FP5_HD int solve(const double x1[10], const double x2[10], const Tables &T
     int n_sol = 0;
     #pragma unroll 1
     for (int k = 0; k < nr; ++k) {
-        const double x = polish_eigenvalue(A6, roots[k]);
+        const double x = roots[k];
         // (A - x I) v = 0, v = [x^2, xy, xz, y^2, yz, z^2, x, y, z, 1]: rows 0..5 are linear in (y^2, yz, z^2, y, z) once
         // xy = x*y and xz = x*z are substituted; 6x5 least squares through the normal equations
         double L[6][5], rhs[6];

@@ -14,7 +14,8 @@ registers, and is checked against the LAPACK version in tests/test_oracle_five_p
   3. Gauss-Jordan on the 10x20 matrix (partial pivoting), action matrix of "multiply by x" on the basis
      [x^2, xy, xz, y^2, yz, z^2, x, y, z, 1];
   4. its real eigenvalues by balancing + Hessenberg reduction + double-shift QR (here: LAPACK's driver, which is that
-     sequence; in the kernel: its own balanc / elmhes / hqr), each polished on the matrix by Rayleigh-quotient iteration.
+     sequence; in the kernel: its own balanc / elmhes / hqr); no polishing -- a Rayleigh-quotient iteration on the matrix
+     changed nothing measurable once the eigenvalues came from QR and was dropped on both sides.
      (A first version formed the characteristic polynomial by Faddeev-LeVerrier and isolated its roots with a Sturm chain:
      the COEFFICIENTS are ill-conditioned when the eigenvalues spread over orders of magnitude, and 5-7 % of the solutions
      were lost; the eigenvalues of A themselves are well conditioned.);
@@ -82,27 +83,6 @@ def _real_eigenvalues(A):
     return sorted(w.real[keep])
 
 
-def _polish_eigenvalue(A, x, steps=3):
-    """Rayleigh-quotient iteration on (A, A^T) from the approximate eigenvalue x: a few 10x10 solves, quadratic convergence."""
-    n = A.shape[0]
-    v = np.ones(n) / np.sqrt(n)
-    u = np.ones(n) / np.sqrt(n)
-    for _ in range(steps):
-        S = A - x * np.eye(n)
-        try:
-            v = np.linalg.solve(S, v)
-            u = np.linalg.solve(S.T, u)
-        except np.linalg.LinAlgError:
-            break                                                 # exactly singular: x is an eigenvalue to working precision
-        v /= np.linalg.norm(v)
-        u /= np.linalg.norm(u)
-        d = u @ v
-        if abs(d) < 1e-12:
-            break
-        x = (u @ (A @ v)) / d
-    return x
-
-
 def five_point_device_style(x1, x2):
     """Same contract as oracle.five_point.five_point, device-friendly numerics (see the module docstring)."""
     x1h = np.hstack([np.asarray(x1, dtype=np.float64), np.ones((5, 1))])
@@ -134,8 +114,7 @@ def five_point_device_style(x1, x2):
     sols = []
     if not np.isfinite(A).all():
         return []
-    for x0 in _real_eigenvalues(A):
-        x = _polish_eigenvalue(A, x0)
+    for x in _real_eigenvalues(A):
         # (A - x I) v = 0 with v = [x^2, xy, xz, y^2, yz, z^2, x, y, z, 1]; x known -> unknowns u = [xy, xz, y^2, yz, z^2, y, z]
         # rows 7, 8 give xy = x*y, xz = x*z; rows 0..5 are linear in (y^2, yz, z^2, y, z) once those are substituted
         R = A[0:6] - x * np.eye(10)[0:6]
@@ -149,7 +128,7 @@ def five_point_device_style(x1, x2):
         y, z = u[3], u[4]
         Ek = x * X + y * Y + z * Z + W
         Ek = Ek / np.linalg.norm(Ek)
-        # accept only what IS an essential matrix (a polished value that is not an eigenvalue, or an ill-conditioned 5x5 solve,
+        # accept only what IS an essential matrix (an inaccurate eigenvalue of a near-multiple root, or an ill-conditioned 5x5 solve,
         # gives a matrix of the null space that violates the cubic constraints): nine multiply-adds per entry on the device
         EEt = Ek @ Ek.T
         if np.abs(2 * EEt @ Ek - np.trace(EEt) * Ek).max() < 1e-6 and abs(np.linalg.det(Ek)) < 1e-6:

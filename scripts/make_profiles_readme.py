@@ -129,9 +129,9 @@ the error.
 ## Not measured this round: `find_essential_kernel` (five-point RANSAC)
 
 Written after the round's GPU minutes were spent; no number in this file covers it.  Evidence so far is CPU-side only:
-the solver's `__host__ __device__` numerics against LAPACK (2 794 of 2 810 solutions, none spurious), the kernel SOURCE under a
+the solver's `__host__ __device__` numerics against LAPACK (2 797 of 2 810 solutions, none spurious), the kernel SOURCE under a
 pthread emulation bit-exact against a sequential replay and race-free under ThreadSanitizer (`sanitizer_r01.txt`, last section),
-`ptxas`: 128 registers, 5.0 KB stack, 350 B spills, 11 k instructions.  `scripts/gpu_round2_first.sh` is the GPU call it owes
+`ptxas`: 128 registers, 5.3 KB stack, 0.8 KB spills, ~10 k instructions.  `scripts/gpu_round2_first.sh` is the GPU call it owes
 (parity, compute-sanitizer, `scripts/bench_primitives.py` rows with OpenCV's `findEssentialMat` on the host beside them, one ncu
 capture).  OpenCV's `findEssentialMat` in the build container: ~830 frames/s on one sequence of 400- or 2 500-correspondence frames.
 """
