@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE: driver of the ThreadSanitizer run of the kernel emulation (scripts/tsan_five_point_kernel.sh): synthetic frames of
-// 700 / 3 / 1300 / 40 / 513 correspondences (several tiles, a tile boundary, a frame without a model), up to 400 hypotheses with the adaptive stop, 2 CTAs.
+// 700 / 3 / 1300 / 40 / 513 correspondences (several tiles, a tile boundary, a frame without a model), 300 hypotheses (three rounds, the last partial), 2 CTAs.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -25,7 +25,7 @@ int main() {
         if (i % 5 == 0) { ru[i] = (float)(1241 * U()); rv[i] = (float)(376 * U()); }
     }
     std::vector<double> E(9 * F); std::vector<uint8_t> mask(M); std::vector<int32_t> cnt(F), hyp(F), used(F);
-    const int rc = fp5_emu_find_essential(F, off.data(), cu.data(), cv.data(), ru.data(), rv.data(), fx, fy, cx, cy, 400, 0.5, 0.999, 99, nullptr, 0,
+    const int rc = fp5_emu_find_essential(F, off.data(), cu.data(), cv.data(), ru.data(), rv.data(), fx, fy, cx, cy, 300, 0.5, 0.0, 99, nullptr, 0,
                                           E.data(), mask.data(), cnt.data(), hyp.data(), used.data(), 2);
     for (int f = 0; f < F; ++f) printf("frame %d n %d inliers %d hyp %d used %d\n", f, lens[f], cnt[f], hyp[f], used[f]);
     return rc;
