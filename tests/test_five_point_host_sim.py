@@ -245,3 +245,28 @@ def test_adaptive_stopping_rule_against_the_oracle(sim):
         if want_rounds:
             assert used == 128 * want_rounds, (frac_bad, used, cnt, need)
         assert cnt >= 0.9 * (1 - frac_bad) * (e - a)
+
+
+def test_kernel_emulation_on_tile_and_chunk_boundaries(sim):
+    """Frames of 5 ... 1 500 correspondences (around the 128-candidate chunk and the 512-point tile sizes), a third of the tracks
+    mismatched, several (hypotheses, confidence, grid) combinations: the kernel source == the sequential replay, bit for bit."""
+    emu = load_kernel_emulation()
+    rng = np.random.default_rng(123)
+    sizes = [5, 6, 7, 9, 33, 127, 128, 129, 511, 512, 513, 1024, 1025, 1500, 40, 300]
+    parts = []
+    for i, n in enumerate(sizes):
+        b = synth.make_sequence(seed=100 + i, n_frames=1, n_corr=max(n, 8), n_jitter=0.0, outlier_frac=0.2)
+        parts.append([getattr(b, k)[:n].copy() for k in ("cur_u", "cur_v", "ref_u", "ref_v")])
+        bad = rng.permutation(n)[: n // 3]
+        parts[-1][2][bad] = rng.uniform(0, 1241, bad.size).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    arr = [np.ascontiguousarray(np.concatenate([p[j] for p in parts])) for j in range(4)]
+    F = len(sizes)
+    for H, conf, grid in ((260, 0.0, 5), (700, 0.999, 16), (1, 0.0, 2), (129, 0.9, 1)):
+        E = np.zeros((F, 9)); mask = np.zeros(off[-1], np.uint8); cnt = np.zeros(F, np.int32); hyp = np.zeros(F, np.int32); used = np.zeros(F, np.int32)
+        assert emu.fp5_emu_find_essential(F, _p(off), *(_p(a) for a in arr), *K, H, 0.5, conf, 77, None, 2, _p(E), _p(mask), _p(cnt), _p(hyp), _p(used), grid) == 0
+        for f in range(F):
+            a, e = off[f], off[f + 1]
+            Er, mr, cr, hr, ur = _ransac(sim, *(x[a:e] for x in arr), H, 0.5, 77, f, 2, confidence=conf, with_used=True)
+            assert (cr, hr, ur) == (cnt[f], hyp[f], used[f]), (H, conf, grid, sizes[f])
+            assert np.array_equal(Er.reshape(-1), E[f]) and np.array_equal(mr, mask[a:e].astype(bool))
