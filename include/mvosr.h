@@ -232,6 +232,13 @@ int  mvosr_recover_pose_frames(mvosr_handle *h, int32_t n_frames, const int32_t 
                                const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
                                const uint8_t *e_mask, const double *essential, double *poses_out, int32_t *n_good, void *stream);
 
+/* recoverPose's per-correspondence mask under a given pose: mask_out [M] = 1 where the correspondence triangulates in front of
+ * both cameras and nearer than triangulation_max_depth (and e_mask, when given, is set) -- `mask_bool & mask_e_bool` of
+ * src/thirdparty/MonocularVO/visual_odometry.py:134-136; exactly the correspondences mvosr_triangulate_frames keeps, in order. */
+int  mvosr_pose_mask_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                            const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                            const uint8_t *e_mask, const double *poses, uint8_t *mask_out, void *stream);
+
 /* Essential matrix by five-point RANSAC -- replaces cv2.findEssentialMat(px_cur, px_ref, cameraMatrix=K, method=cv2.RANSAC,
  * prob=0.999, threshold=0.5) (src/thirdparty/MonocularVO/visual_odometry.py:100-102,129-130; SURVEY N1, first half).  Per
  * frame: `hypotheses` minimal samples of five correspondences drawn from the Philox stream (key = seed, counter = (hypothesis,

@@ -175,6 +175,21 @@ class ScaleRecovery:
                 self._stream()))
         return dict(raw_scale=raw, status=status, n_features=nfeat, stats=st)
 
+    def pose_mask_frames(self, offsets, cur_u, cur_v, ref_u, ref_v, poses, e_mask=None):
+        """recoverPose's per-correspondence mask under the given poses, ANDed with e_mask (visual_odometry.py:134-136): (M,) uint8,
+        set exactly for the correspondences triangulate_frames keeps."""
+        dev = self.device
+        F = offsets.numel() - 1
+        _chk(offsets, torch.int32, "offsets", dev)
+        for n, t in (("cur_u", cur_u), ("cur_v", cur_v), ("ref_u", ref_u), ("ref_v", ref_v)):
+            _chk(t, torch.float32, n, dev)
+        _chk(poses, torch.float64, "poses", dev)
+        mask = torch.zeros(cur_u.numel(), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_pose_mask_frames(self._h, F, _ptr(offsets), _ptr(cur_u), _ptr(cur_v), _ptr(ref_u), _ptr(ref_v), _ptr(e_mask),
+                                                    _ptr(poses), _ptr(mask), self._stream()))
+        return mask
+
     def scale_frames_from_tracks(self, offsets, cur_u, cur_v, ref_u, ref_v, max_features: int, hypotheses: int = 1000, threshold: float = 0.5,
                                  frame_index0: int = 0, seq_id: int = 0, seed: int = 0, stats: bool = False, confidence: float = 0.999):
         """Tracked correspondences alone -> raw scales: the geometry of VisualOdometry.processFrame (visual_odometry.py:129-147:
@@ -184,7 +199,7 @@ class ScaleRecovery:
         fi = None if frame_index0 == 0 else torch.arange(frame_index0, frame_index0 + F, dtype=torch.int32, device=self.device)
         ess = self.find_essential_frames(offsets, cur_u, cur_v, ref_u, ref_v, hypotheses=hypotheses, threshold=threshold, seed=seed,
                                          frame_index=fi, seq_id=seq_id, confidence=confidence)
-        pose = self.recover_pose_frames(offsets, cur_u, cur_v, ref_u, ref_v, ess["essential"], e_mask=ess["e_mask"])
+        pose = self.recover_pose_frames(offsets, cur_u, cur_v, ref_u, ref_v, ess["essential"])     # over all tracks, as the reference calls it
         out = self.scale_frames_from_correspondences(offsets, cur_u, cur_v, ref_u, ref_v, pose["poses"], max_features, e_mask=ess["e_mask"],
                                                      frame_index0=frame_index0, seq_id=seq_id, seed=seed, stats=stats)
         out.update(essential=ess["essential"], e_mask=ess["e_mask"], n_inliers=ess["n_inliers"], hyps_used=ess["hyps_used"], poses=pose["poses"])

@@ -665,6 +665,18 @@ int mvosr_recover_pose_frames(mvosr_handle *h, int32_t n_frames, const int32_t *
     return MVOSR_OK;
 }
 
+int mvosr_pose_mask_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                           const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                           const uint8_t *e_mask, const double *poses, uint8_t *mask_out, void *stream) {
+    if (!h || n_frames < 0 || !offsets || !cur_u || !cur_v || !ref_u || !ref_v || !poses || !mask_out) return MVOSR_E_INVALID;
+    if (n_frames == 0) return MVOSR_OK;
+    CK(cudaSetDevice(h->device));
+    pose_mask_kernel<<<min(n_frames, 8 * h->num_sms), 256, 0, (cudaStream_t)stream>>>(n_frames, offsets, cur_u, cur_v, ref_u, ref_v, e_mask, poses, h->cfg, mask_out);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return MVOSR_OK;
+}
+
 int mvosr_find_essential_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
                                 const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
                                 int32_t hypotheses, double threshold_px, double confidence, uint64_t seed, const int32_t *frame_index, int32_t seq_id,

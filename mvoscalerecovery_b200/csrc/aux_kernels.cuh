@@ -10,6 +10,7 @@
 //   triangle_votes_kernel    find_outliers / check_triangle (src/rescale.py:45-72, src/scale_calculator.py:105-119,151-167)
 //   recover_pose_kernel      the pose selection of cv2.recoverPose(E, px_cur, px_ref, K, distanceThresh=100)
 //                            (src/thirdparty/MonocularVO/visual_odometry.py:129-133): decomposeEssentialMat + cheirality count
+//   pose_mask_kernel         recoverPose's per-correspondence mask under the chosen pose (visual_odometry.py:134-136)
 //   raster_mesh_kernel + mesh_depth_kernel   Reconstruct.depth_generate (src/reconstruct.py:91-107): tri.find_simplex of every
 //                            pixel + the depth of the triangle's plane along the pixel's ray
 // All of them are HBM-bound gathers / streams; the arithmetic is float64 because the callers hand float64 arrays.
@@ -338,6 +339,27 @@ __global__ void __launch_bounds__(256) recover_pose_kernel(int n_frames, const i
             if (n_good) for (int k = 0; k < 4; ++k) n_good[4 * f + k] = good[k];
         }
         __syncthreads();
+    }
+}
+
+// recoverPose's per-correspondence mask under a GIVEN pose (in front of both cameras, nearer than dist), optionally ANDed with
+// the essential-matrix inlier mask: mask_bool & mask_e_bool of src/thirdparty/MonocularVO/visual_odometry.py:134-136.  The
+// test is triangulate_point itself, so the mask marks exactly the correspondences triangulate_kernel keeps (in their order).
+__global__ void __launch_bounds__(256) pose_mask_kernel(int n_frames, const int32_t *__restrict__ offsets,
+        const float *__restrict__ cur_u, const float *__restrict__ cur_v, const float *__restrict__ ref_u, const float *__restrict__ ref_v,
+        const uint8_t *__restrict__ e_mask, const double *__restrict__ poses, mvosr_config cfg, uint8_t *mask_out) {
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const int base = offsets[f], n = offsets[f + 1] - base;
+        Pose pose;
+        for (int i = 0; i < 9; ++i) pose.R[i] = poses[12 * (size_t)f + (i / 3) * 4 + (i % 3)];
+        pose.t[0] = poses[12 * (size_t)f + 3]; pose.t[1] = poses[12 * (size_t)f + 7]; pose.t[2] = poses[12 * (size_t)f + 11];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            double X, Y, Z, u, v;
+            bool ok = triangulate_point(cur_u[base + i], cur_v[base + i], ref_u[base + i], ref_v[base + i], pose,
+                                        cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.triangulation_max_depth, X, Y, Z, u, v);
+            if (e_mask) ok = ok && e_mask[base + i] != 0;
+            mask_out[base + i] = ok ? 1 : 0;
+        }
     }
 }
 

@@ -191,3 +191,33 @@ def test_tracks_to_scales_without_poses(engine):
     assert (out["status"].cpu().numpy() & 1).all()                                  # every frame produced a scale
     np.testing.assert_allclose(raw, b.true_scale, rtol=0.03)
     np.testing.assert_allclose(raw, raw_true, rtol=0.03)
+
+
+def test_process_tracks_drop_in(engine, golden):
+    """compat.vo_geometry.process_tracks = lines 129-147 of visual_odometry.py for one frame, numpy in / numpy out: the attributes
+    the reference's main loop reads (motion_R, motion_t, feature3d, px_*_selected) are consistent with each other, with the
+    batch entry points, and with the truth."""
+    from mvoscalerecovery_b200.compat import vo_geometry
+    z = golden
+    Kmat = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1.0]])
+    off = z["offsets"]
+    for f in (1, 6):
+        a, e = off[f], off[f + 1]
+        cur = np.stack([z["cur_u"][a:e], z["cur_v"][a:e]], 1); ref = np.stack([z["ref_u"][a:e], z["ref_v"][a:e]], 1)
+        g = vo_geometry.process_tracks(cur, ref, Kmat, threshold=0.5, prob=0.999, max_iters=1000, seed=int(z["seed"]), frame=f, seq=int(z["seq"]))
+        P = z["true_poses"][f].reshape(3, 4)
+        tt = P[:, 3] / np.linalg.norm(P[:, 3])
+        assert _angle_deg((np.trace(g["R"].T @ P[:, :3]) - 1) / 2) < 0.2 and _angle_deg(float(g["t"][:, 0] @ tt)) < 1.5
+        assert abs(np.linalg.det(g["R"]) - 1) < 1e-9 and abs(np.linalg.norm(g["t"]) - 1) < 1e-9
+        m = g["mask"]
+        assert g["feature3d"].shape == (m.sum(), 3) and np.array_equal(g["px_cur_selected"], cur[m]) and np.array_equal(g["px_ref_selected"], ref[m])
+        assert g["hyps_used"] == 128 and abs(g["n_inliers"] - int(z["n_inliers"][f])) <= 5
+        truth = z["true_match"][a:e]
+        assert (m & ~truth).sum() <= 4 and (m & truth).sum() >= 0.95 * truth.sum()
+        X = g["feature3d"]
+        assert (X[:, 2] > 0).all() and (X[:, 2] < 100).all()
+        # the triangulated points reproject onto the current-image tracks (fx on both axes, main.py:102-104, fx == fy here)
+        uv = np.stack([X[:, 0] * K[0] / X[:, 2] + K[2], X[:, 1] * K[1] / X[:, 2] + K[3]], 1)
+        assert np.median(np.abs(uv - cur[m])) < 0.5
+    with pytest.raises(RuntimeError):
+        vo_geometry.process_tracks(cur[:4], ref[:4], Kmat)
