@@ -35,3 +35,6 @@ r = eng.scale_frames_from_tracks(t(off), t(pad(b.cur_u)), t(pad(b.cur_v)), t(pad
                                  hypotheses=160, seed=3, confidence=0.0)
 torch.cuda.synchronize()
 print("essential inliers", r["n_inliers"].cpu().numpy(), "scales", r["raw_scale"].cpu().numpy()[:4], "true", b.true_scale)
+m = eng.pose_mask_frames(t(off), t(pad(b.cur_u)), t(pad(b.cur_v)), t(pad(b.ref_u)), t(pad(b.ref_v)), r["poses"], e_mask=r["e_mask"])
+torch.cuda.synchronize()
+print("pose mask", int(m.sum()), "of", m.numel())
