@@ -99,6 +99,11 @@ for hyps, conf in ((128, 0.0), (512, 0.0), (1000, 0.999)):
         b.n_frames, "frames")
     if not conf:
         out["rows"][-1]["hypotheses_per_s"] = hyps * b.n_frames / ms * 1e3
+# ---- the whole chain from tracks alone: essential matrix -> pose -> fused stages 1-5 (the reference's call: maxIters 1000, prob 0.999)
+maxf = int(np.diff(b.offsets).max())
+ms = timed(lambda: eng.scale_frames_from_tracks(*dd, max_features=maxf, seed=1), reps=5)
+row("find_essential_kernel + recover_pose_kernel + frame_kernel", "592 frames x 2500 correspondences, tracks -> raw scales", ms,
+    16 * int(b.offsets[-1]) + 64 * b.n_frames, b.n_frames, "frames")
 try:
     import time
     import cv2
