@@ -1,7 +1,9 @@
-"""Five-point essential matrix + RANSAC on the CPU -- TEST INFRASTRUCTURE (oracle side), groundwork for SURVEY N1.
+"""Five-point essential matrix + RANSAC on the CPU with LAPACK -- TEST INFRASTRUCTURE (oracle side) for SURVEY N1.
 
-Part of ``oracle/``: imported only by ``tests/``.  No product code uses it (the product consumes the essential matrix the
-front-end hands over: mvosr_recover_pose_frames).
+Part of ``oracle/``: imported only by ``tests/``.  No product code uses it: the product's own five-point RANSAC is the CUDA
+kernel behind mvosr_find_essential_frames (csrc/five_point.cuh, five_point_kernel.cuh); this module is the independent
+LAPACK-based statement its minimal solver is checked against (tests/test_five_point_host_sim.py), and
+oracle/five_point_plan.py is the restatement on the shared Philox stream that checks the RANSAC around it.
 
 What it restates: ``cv2.findEssentialMat(px_cur, px_ref, cameraMatrix=K, method=cv2.RANSAC, prob=0.999, threshold=0.5)`` as
 the reference calls it (src/thirdparty/MonocularVO/visual_odometry.py:129-130).  The algorithm lives in OpenCV (4.13 in this
