@@ -270,3 +270,26 @@ def test_kernel_emulation_on_tile_and_chunk_boundaries(sim):
             Er, mr, cr, hr, ur = _ransac(sim, *(x[a:e] for x in arr), H, 0.5, 77, f, 2, confidence=conf, with_used=True)
             assert (cr, hr, ur) == (cnt[f], hyp[f], used[f]), (H, conf, grid, sizes[f])
             assert np.array_equal(Er.reshape(-1), E[f]) and np.array_equal(mr, mask[a:e].astype(bool))
+
+
+def test_kernel_numerics_agree_with_opencv_own_output(sim):
+    """The reference's call -- cv2.findEssentialMat(px_cur, px_ref, K, RANSAC, 0.999, 0.5) -- stored with its recoverPose result in
+    tests/golden/pose.npz (frames 0, 2, 4, 6), against the replay of the kernel's rule on the host build of its numerics with the
+    same maxIters / prob / threshold: pose within the noise of the data, and (almost) the same inlier set under OpenCV's own E."""
+    from oracle import extras as X
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pose.npz"))
+    off = z["offsets"]
+    ang = lambda c: np.degrees(np.arccos(np.clip(c, -1, 1)))
+    for f in (0, 2, 4, 6):
+        a, e = off[f], off[f + 1]
+        cu, cv, ru, rv = (z[k][a:e] for k in ("cur_u", "cur_v", "ref_u", "ref_v"))
+        E, mask, cnt, hyp, used = _ransac(sim, cu, cv, ru, rv, 1000, 0.5, 1, f, 0, confidence=0.999, with_used=True)
+        assert used == 128 and mask.mean() > 0.9
+        cur = np.stack([cu, cv], 1).astype(np.float64); ref = np.stack([ru, rv], 1).astype(np.float64)
+        R, t, _, counts = X.recover_pose(E, cur, ref, *K)
+        Rcv, tcv = z["R"][f].reshape(3, 3), z["t"][f]
+        assert ang((np.trace(R.T @ Rcv) - 1) / 2) < 0.2 and ang(float(np.ravel(t) @ tcv)) < 1.5
+        x1 = np.stack([(cur[:, 0] - K[2]) / K[0], (cur[:, 1] - K[3]) / K[1]], 1)
+        x2 = np.stack([(ref[:, 0] - K[2]) / K[0], (ref[:, 1] - K[3]) / K[1]], 1)
+        cv_mask = PL.sampson_inlier(z["E"][f].reshape(3, 3) / np.linalg.norm(z["E"][f]), x1, x2, (0.5 / K[0]) ** 2)
+        assert (cv_mask != mask).mean() < 0.05
