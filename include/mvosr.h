@@ -232,6 +232,18 @@ int  mvosr_recover_pose_frames(mvosr_handle *h, int32_t n_frames, const int32_t 
                                const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
                                const uint8_t *e_mask, const double *essential, double *poses_out, int32_t *n_good, void *stream);
 
+/* Feature bucketing of the VO front-end -- bucket(features, bucket_size=30, density=2) of src/detector.py:65-95 (and
+ * FeatureDetector.bucket, :18-47): features binned into bucket_size x bucket_size pixel cells, each cell keeps at
+ * most `density` of them, survivors listed cell by cell (rows of cells top to bottom, cells left to right).  The reference
+ * shuffles each cell with numpy's global RNG; here a cell keeps its `density` smallest (r_i, i), r_i = word 0 of
+ * Philox4x32-10(counter = (i, frame_index ? frame_index[f] : f, seq_id, 3), key = seed), in that order.  u, v: [M] float32 pixel
+ * coordinates (non-negative, below 1024 x 1023 cells), CSR by offsets; frames hold at most 4096 features.  Outputs: out_index
+ * [M] = positions (within the frame) of the survivors, compacted at the frame's base offset; n_out [F]; status [F] (optional):
+ * 0 ok, 1 coordinate out of range / not finite, 2 more than 4096 features (such frames keep nothing). */
+int  mvosr_bucket_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets, const float *u, const float *v,
+                         int32_t bucket_size, int32_t density, uint64_t seed, const int32_t *frame_index, int32_t seq_id,
+                         int32_t *out_index, int32_t *n_out, uint8_t *status, void *stream);
+
 /* recoverPose's per-correspondence mask under a given pose: mask_out [M] = 1 where the correspondence triangulates in front of
  * both cameras and nearer than triangulation_max_depth (and e_mask, when given, is set) -- `mask_bool & mask_e_bool` of
  * src/thirdparty/MonocularVO/visual_odometry.py:134-136; exactly the correspondences mvosr_triangulate_frames keeps, in order. */

@@ -47,7 +47,7 @@ SYMBOLS = [
     "mvosr_scale_frames_from_correspondences", "mvosr_filter_sequences", "mvosr_delaunay_frames",
     "mvosr_recover_scales_host", "mvosr_recover_fleet_host", "mvosr_launch_count", "mvosr_set_phase_timing",
     "mvosr_triangle_planes", "mvosr_triangle_votes", "mvosr_ransac_planes", "mvosr_integrate_paths", "mvosr_depth_from_mesh", "mvosr_recover_pose_frames",
-    "mvosr_find_essential_frames", "mvosr_pose_mask_frames",
+    "mvosr_find_essential_frames", "mvosr_pose_mask_frames", "mvosr_bucket_frames",
 ]
 
 _lib = None
@@ -92,6 +92,7 @@ def lib():
     L.mvosr_ransac_planes.argtypes = [vp, i32, vp, vp, i32, f64, f64, i32, u64, vp, i32, vp, vp, vp, vp, vp]
     L.mvosr_integrate_paths.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mvosr_recover_pose_frames.argtypes = [vp, i32] + [vp] * 10
+    L.mvosr_bucket_frames.argtypes = [vp, i32, vp, vp, vp, i32, i32, u64, vp, i32, vp, vp, vp, vp]
     L.mvosr_pose_mask_frames.argtypes = [vp, i32] + [vp] * 9
     L.mvosr_find_essential_frames.argtypes = [vp, i32] + [vp] * 5 + [i32, f64, f64, u64, vp, i32] + [vp] * 6
     L.mvosr_depth_from_mesh.argtypes = [vp, i32, i32, f64, f64, f64, f64, i32, vp, vp, vp, vp, vp, vp]

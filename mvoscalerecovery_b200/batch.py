@@ -175,6 +175,24 @@ class ScaleRecovery:
                 self._stream()))
         return dict(raw_scale=raw, status=status, n_features=nfeat, stats=st)
 
+    def bucket_frames(self, offsets, u, v, bucket_size: int = 30, density: int = 2, seed: int = 0, frame_index=None, seq_id: int = 0):
+        """bucket(features, bucket_size, density) of detector.py:65-95 for F frames: dict(index (M,) int32 = survivors' positions inside
+        their frame, compacted at the frame's base offset, n_out (F,), status (F,))."""
+        dev = self.device
+        F = offsets.numel() - 1
+        _chk(offsets, torch.int32, "offsets", dev)
+        _chk(u, torch.float32, "u", dev)
+        _chk(v, torch.float32, "v", dev)
+        if frame_index is not None:
+            _chk(frame_index, torch.int32, "frame_index", dev)
+        index = torch.full((u.numel(),), -1, dtype=torch.int32, device=dev)
+        n_out = torch.zeros(F, dtype=torch.int32, device=dev)
+        status = torch.zeros(F, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_bucket_frames(self._h, F, _ptr(offsets), _ptr(u), _ptr(v), int(bucket_size), int(density), int(seed),
+                                                 _ptr(frame_index), int(seq_id), _ptr(index), _ptr(n_out), _ptr(status), self._stream()))
+        return dict(index=index, n_out=n_out, status=status)
+
     def pose_mask_frames(self, offsets, cur_u, cur_v, ref_u, ref_v, poses, e_mask=None):
         """recoverPose's per-correspondence mask under the given poses, ANDed with e_mask (visual_odometry.py:134-136): (M,) uint8,
         set exactly for the correspondences triangulate_frames keeps."""

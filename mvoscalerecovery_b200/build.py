@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmvosr.so")
 SOURCES = ["api.cu"]
 HEADERS = ["frame_kernel.cuh", "gstar.cuh", "predicates.cuh", "philox.cuh", "triangulate.cuh", "aux_kernels.cuh",
-           "five_point.cuh", "five_point_kernel.cuh", "five_point_tables.h",
+           "five_point.cuh", "five_point_kernel.cuh", "five_point_tables.h", "bucket_kernel.cuh",
            os.path.join("..", "..", "include", "mvosr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -11,6 +11,7 @@
 #include "frame_kernel.cuh"
 #include "aux_kernels.cuh"
 #include "five_point_kernel.cuh"
+#include "bucket_kernel.cuh"
 
 using namespace mvosr;
 
@@ -660,6 +661,19 @@ int mvosr_recover_pose_frames(mvosr_handle *h, int32_t n_frames, const int32_t *
     CK(cudaSetDevice(h->device));
     const int grid = min(n_frames, 8 * h->num_sms);
     recover_pose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_frames, offsets, cur_u, cur_v, ref_u, ref_v, e_mask, essential, h->cfg, poses_out, n_good);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return MVOSR_OK;
+}
+
+int mvosr_bucket_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets, const float *u, const float *v,
+                        int32_t bucket_size, int32_t density, uint64_t seed, const int32_t *frame_index, int32_t seq_id,
+                        int32_t *out_index, int32_t *n_out, uint8_t *status, void *stream) {
+    if (!h || n_frames < 0 || !offsets || !u || !v || !out_index || !n_out || bucket_size < 1 || density < 1) return MVOSR_E_INVALID;
+    if (n_frames == 0) return MVOSR_OK;
+    CK(cudaSetDevice(h->device));
+    bucket_kernel<<<min(n_frames, 8 * h->num_sms), BUCKET_THREADS, 0, (cudaStream_t)stream>>>(n_frames, offsets, u, v, bucket_size, density, seed,
+                                                                                            frame_index, seq_id, out_index, n_out, status);
     CK(cudaGetLastError());
     h->launches += 1;
     return MVOSR_OK;

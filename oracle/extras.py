@@ -88,3 +88,20 @@ def depth_from_mesh(width, height, fx, fy, cx, cy, delaunay, datas):
     depth = d[:, 3] / (d[:, 0] * ((u.ravel() - cx) / fx) + d[:, 1] * ((v.ravel() - cy) / fy) + d[:, 2])
     depth[ids < 0] = 0.0
     return depth.reshape(height, width), ids.reshape(height, width)
+
+
+def bucket_philox(features, bucket_size=30, density=2, seed=0, frame=0, seq=0):
+    """bucket(features, bucket_size, density) of src/detector.py:65-95 with the shuffle replaced by a DEFINED order: positions of
+    the surviving features, cell by cell (rows of cells top to bottom, cells left to right), inside a cell the `density`
+    smallest (r_i, i), r_i = word 0 of Philox4x32-10(counter = (i, frame, seq, 3), key = seed).  The reference shuffles with
+    numpy's global RNG: which members of a cell survive cannot be reproduced, the cells, their order and the counts can."""
+    from .philox import MASK, philox4x32_10
+    f = np.asarray(features, dtype=np.float32).reshape(-1, 2)
+    key = (seed & MASK, (seed >> 32) & MASK)
+    cells = {}
+    for i, (u, v) in enumerate(f):
+        cells.setdefault((int(v) // bucket_size, int(u) // bucket_size), []).append((philox4x32_10((i, frame, seq, 3), key)[0], i))
+    out = []
+    for c in sorted(cells):
+        out += [i for _, i in sorted(cells[c])[:density]]
+    return np.array(out, dtype=np.int32)

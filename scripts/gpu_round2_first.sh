@@ -3,7 +3,7 @@
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_round2_first.sh'
 # It was written and CPU-verified (host build + pthread emulation + ThreadSanitizer) after the round's GPU minutes had run out.
 mkdir -p gpurun_out
-echo "== parity (new kernel)"; timeout 600 python -m pytest tests/test_gpu_zz_essential.py -q -m gpu 2>&1 | tail -15
+echo "== parity (new kernel)"; timeout 600 python -m pytest tests/test_gpu_zz_essential.py tests/test_gpu_zzz_bucket.py -q -m gpu 2>&1 | tail -15
 echo "== whole GPU suite"; timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -5
 echo "== compute-sanitizer memcheck / racecheck (small)"
 for tool in memcheck racecheck; do

@@ -38,3 +38,6 @@ print("essential inliers", r["n_inliers"].cpu().numpy(), "scales", r["raw_scale"
 m = eng.pose_mask_frames(t(off), t(pad(b.cur_u)), t(pad(b.cur_v)), t(pad(b.ref_u)), t(pad(b.ref_v)), r["poses"], e_mask=r["e_mask"])
 torch.cuda.synchronize()
 print("pose mask", int(m.sum()), "of", m.numel())
+bk = eng.bucket_frames(t(off), t(pad(b.cur_u)), t(pad(b.cur_v)), seed=3)
+torch.cuda.synchronize()
+print("bucketing kept", bk["n_out"].cpu().numpy())

@@ -8,3 +8,7 @@ cd "$(dirname "$0")/../tests/host_sim"
 g++ -O1 -g -std=c++17 -fsanitize=thread -pthread -Wno-unknown-pragmas -o /tmp/fp5_tsan fp5_kernel_emu.cpp fp5_tsan_main.cpp
 /tmp/fp5_tsan 2>/tmp/fp5_tsan.err
 echo "ThreadSanitizer warnings: $(grep -c 'WARNING: ThreadSanitizer' /tmp/fp5_tsan.err || true)"
+# the same for bucket_kernel (bitonic sort in shared memory, survivors compacted in order)
+g++ -O1 -g -std=c++17 -fsanitize=thread -pthread -Wno-unknown-pragmas -o /tmp/bucket_tsan bucket_kernel_emu.cpp bucket_tsan_main.cpp
+/tmp/bucket_tsan 2>/tmp/bucket_tsan.err
+echo "ThreadSanitizer warnings (bucket_kernel): $(grep -c 'WARNING: ThreadSanitizer' /tmp/bucket_tsan.err || true)"
