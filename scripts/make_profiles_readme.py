@@ -126,9 +126,9 @@ buffers, shared-memory and large-frame staging, Delaunay-only, filter, path scan
 hypothesis above 0.8 N usually ends the loop; evaluating all hypotheses costs ~10 us per frame per 1 000 hypotheses and halves
 the error.
 
-## Not measured this round: `find_essential_kernel` (five-point RANSAC, SURVEY N1)
+## Not measured this round: `find_essential_kernel` (five-point RANSAC), `pose_mask_kernel`, `bucket_kernel` (SURVEY N1)
 
-Written after the round's GPU minutes were spent; no number in this file covers it.  Evidence so far is CPU-side only:
+Written after the round's GPU minutes were spent; no number in this file covers them.  Evidence so far is CPU-side only:
 the solver's `__host__ __device__` numerics against LAPACK (2 797 of 2 810 solutions, none spurious), the kernel SOURCE under a
 pthread emulation bit-exact against a sequential replay and race-free under ThreadSanitizer (`sanitizer_r01.txt`, last section),
 `ptxas`: 128 registers, 5.3 KB stack, 0.8 KB spills, ~10 k instructions.  `scripts/gpu_round2_first.sh` is the GPU call it owes
