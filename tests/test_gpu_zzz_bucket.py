@@ -27,3 +27,20 @@ def test_bucket_frames_on_the_gpu(engine, golden):
     out = engine.bucket_frames(t(off), t(u), t(v), seed=5)
     torch.cuda.synchronize()
     _check_against_oracle(off, u, v, 30, 2, 5, None, 0, out["index"].cpu().numpy(), out["n_out"].cpu().numpy(), out["status"].cpu().numpy())
+
+
+def test_compat_bucket_returns_what_the_reference_returns(engine, golden):
+    """compat.bucketing.bucket: the reference's signature and return type; same cells in the same order with the same number of
+    survivors as the reference's own output (tests/golden/bucket.npz), every survivor a member of its cell."""
+    from mvoscalerecovery_b200.compat import bucketing
+    from test_bucket import _cells
+    for k in (0, 2, 4):
+        f, kept = golden["f%d" % k], golden["kept%d" % k]
+        bs, dens = (int(x) for x in golden["par%d" % k])
+        got = bucketing.bucket(f, bs, dens, seed=1, frame=k)
+        assert got.dtype == np.float32 and got.shape == kept.shape
+        assert _cells(got, bs) == _cells(kept, bs)
+        members = {tuple(p) for p in f.tolist()}
+        assert all(tuple(p) in members for p in got.tolist())
+    with pytest.raises(ValueError):
+        bucketing.bucket(np.array([[1.0, -3.0], [2.0, 2.0]]))
