@@ -1,4 +1,4 @@
-"""Dry run of tests/test_gpu_zz_essential.py WITHOUT a GPU -- a check of the test code and its tolerances, not of the device.
+"""Dry run of tests/test_gpu_zz_essential.py and tests/test_gpu_zzz_bucket.py WITHOUT a GPU -- a check of the test code and its tolerances, not of the device.
 The seven GPU tests are called with a stand-in engine: find_essential_frames = the kernel SOURCE under the pthread emulation
 (tests/host_sim/fp5_kernel_emu.cpp), the other entry points = the oracle (oracle.extras.recover_pose, oracle.pipeline).  Written
 because the five-point kernel was finished after the round's GPU minutes were spent: a bug in an assertion or an index of the
@@ -98,3 +98,27 @@ G.test_hypothesis_count_and_frame_index(eng, z, run)
 G.test_tracks_to_scales_without_poses(eng)
 G.test_process_tracks_drop_in(eng, z)
 print("all 7 tests of tests/test_gpu_zz_essential.py pass against the CPU stand-ins")
+
+# ---- the GPU tests of the bucketing kernel (tests/test_gpu_zzz_bucket.py) against the emulation of bucket_kernel's source
+import test_bucket as TB                                             # noqa: E402
+import test_gpu_zzz_bucket as GB                                     # noqa: E402
+from mvoscalerecovery_b200.compat import _gpu as compat_gpu          # noqa: E402
+
+bemu = TB.load_bucket_emulation()
+
+
+def bucket_frames(self, offsets, u, v, bucket_size=30, density=2, seed=0, frame_index=None, seq_id=0):
+    off = np.ascontiguousarray(offsets.numpy()); F = len(off) - 1
+    uu, vv = np.ascontiguousarray(u.numpy()), np.ascontiguousarray(v.numpy())
+    fi = None if frame_index is None else np.ascontiguousarray(frame_index.numpy())
+    index = np.full(uu.size, -1, np.int32); n_out = np.zeros(F, np.int32); status = np.zeros(F, np.uint8)
+    bemu.bucket_emu(F, TB._p(off), TB._p(uu), TB._p(vv), bucket_size, density, seed, TB._p(fi), seq_id, TB._p(index), TB._p(n_out), TB._p(status), 2)
+    return dict(index=f(index), n_out=f(n_out), status=f(status))
+
+
+StandInEngine.bucket_frames = bucket_frames
+compat_gpu.engine = lambda *a, **k: eng
+gb = np.load(os.path.join(ROOT, "tests", "golden", "bucket.npz"))
+GB.test_bucket_frames_on_the_gpu(eng, gb)
+GB.test_compat_bucket_returns_what_the_reference_returns(eng, gb)
+print("both tests of tests/test_gpu_zzz_bucket.py pass against the CPU stand-in")
