@@ -264,7 +264,8 @@ int  mvosr_pose_mask_frames(mvosr_handle *h, int32_t n_frames, const int32_t *of
  * Outputs: essential [F][9] row-major with unit Frobenius norm, x_ref^T E x_cur = 0 in normalised coordinates -- the input of
  * mvosr_recover_pose_frames; e_mask_out [M] (optional) the winner's inlier mask -- the e_mask of the later stages; n_inliers
  * [F] (optional); best_hyp [F] (optional; -1 and a zero matrix for frames with fewer than five correspondences or no
- * solution); hyps_used [F] (optional): hypotheses tried. */
+ * solution -- e.g. a frame without motion, whose epipolar system is rank deficient; the reference gates such frames before its
+ * estimator); hyps_used [F] (optional): hypotheses tried.  Non-finite correspondences are never inliers. */
 int  mvosr_find_essential_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
                                  const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
                                  int32_t hypotheses, double threshold_px, double confidence, uint64_t seed, const int32_t *frame_index, int32_t seq_id,

@@ -293,3 +293,28 @@ def test_kernel_numerics_agree_with_opencv_own_output(sim):
         x2 = np.stack([(ref[:, 0] - K[2]) / K[0], (ref[:, 1] - K[3]) / K[1]], 1)
         cv_mask = PL.sampson_inlier(z["E"][f].reshape(3, 3) / np.linalg.norm(z["E"][f]), x1, x2, (0.5 / K[0]) ** 2)
         assert (cv_mask != mask).mean() < 0.05
+
+
+def test_hostile_frames_neither_hang_nor_leak_into_the_result(sim):
+    """NaN / inf pixels, a frame without motion (ref == cur: the epipolar system is rank deficient), absurd magnitudes, all current
+    points identical -- through the kernel source under the emulation: finite output, non-finite correspondences are never
+    inliers, degenerate frames report "no model" after exhausting their hypotheses."""
+    emu = load_kernel_emulation()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "essential.npz"))
+    a, e = z["offsets"][0], z["offsets"][1]
+    base = [z[k][a:e].copy() for k in ("cur_u", "cur_v", "ref_u", "ref_v")]
+    f1 = [x.copy() for x in base]; f1[0][::7] = np.nan; f1[3][5::11] = np.inf
+    f2 = [x.copy() for x in base]; f2[2][:] = f2[0]; f2[3][:] = f2[1]
+    f3 = [np.full(50, 1e30, np.float32) for _ in range(4)]
+    f4 = [x[:8].copy() for x in base]; f4[0][:] = f4[0][0]; f4[1][:] = f4[1][0]
+    frames = [f1, f2, f3, f4]
+    off = np.concatenate([[0], np.cumsum([len(f[0]) for f in frames])]).astype(np.int32)
+    arr = [np.ascontiguousarray(np.concatenate([f[j] for f in frames]).astype(np.float32)) for j in range(4)]
+    F = len(frames)
+    E = np.zeros((F, 9)); mask = np.zeros(off[-1], np.uint8); cnt = np.zeros(F, np.int32); hyp = np.zeros(F, np.int32); used = np.zeros(F, np.int32)
+    assert emu.fp5_emu_find_essential(F, _p(off), *(_p(x) for x in arr), *K, 256, 0.5, 0.999, 3, None, 0, _p(E), _p(mask), _p(cnt), _p(hyp), _p(used), 2) == 0
+    assert np.isfinite(E).all()
+    bad = ~np.isfinite(arr[0][off[0]:off[1]]) | ~np.isfinite(arr[3][off[0]:off[1]])
+    m0 = mask[off[0]:off[1]].astype(bool)
+    assert not (m0 & bad).any() and (m0 & ~bad).sum() >= 0.9 * (z["true_match"][a:e] & ~bad).sum() and hyp[0] >= 0 and used[0] == 128
+    assert list(hyp[1:]) == [-1, -1, -1] and list(cnt[1:]) == [0, 0, 0] and list(used[1:]) == [256, 256, 256] and not mask[off[1]:].any()
