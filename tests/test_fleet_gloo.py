@@ -56,3 +56,37 @@ def test_gather_results_world_size_2_gloo(tmp_path):
     mp.spawn(_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
+def _essential_rank_main(rank, world, port, tmp):
+    """Five-point RANSAC sharded by frame range: every rank estimates its frames addressed by their GLOBAL index (frame_index of
+    mvosr_find_essential_frames; here the host build of the kernel's numerics stands in for the device), one gather, and the
+    result equals the unsharded run -- the sample stream is a function of (seed, sequence, frame), not of the shard."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mvoscalerecovery_b200.fleet import frame_shards, gather_results
+    import test_five_point_host_sim as T
+    L = T.load_host_sim()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "essential.npz"))
+    off = z["offsets"]
+    F = len(off) - 1
+    run = lambda f: T._ransac(L, *(z[k][off[f]:off[f + 1]] for k in ("cur_u", "cur_v", "ref_u", "ref_v")), 150, 0.5, 9, f, 2, confidence=0.999, with_used=True)
+    shards = frame_shards(F, world)
+    s, e = shards[rank]
+    mine = [run(f) for f in range(s, e)]
+    cnt, used, hyp = gather_results(torch.tensor([float(m[2]) for m in mine], dtype=torch.float64), torch.tensor([m[4] for m in mine], dtype=torch.uint8),
+                                    torch.tensor([m[3] for m in mine], dtype=torch.int32), shards)
+    whole = [run(f) for f in range(F)]
+    ok = [int(c) for c in cnt] == [w[2] for w in whole] and hyp.tolist() == [w[3] for w in whole] and used.tolist() == [w[4] for w in whole]
+    with open(os.path.join(tmp, "ess_rank%d" % rank), "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_sharded_essential_estimation_world_size_2_gloo(tmp_path):
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_essential_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "ess_rank%d" % r)).read() == "ok"
