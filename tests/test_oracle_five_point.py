@@ -61,8 +61,8 @@ def test_ransac_agrees_with_opencv_within_the_noise():
 
 
 def test_device_style_solver_matches_the_lapack_one():
-    """oracle/five_point_plan.py (Gauss-Jordan null space, interpolated constraints, Faddeev-LeVerrier + Sturm, Rayleigh polish)
-    against oracle/five_point.py (SVD + eig): found solutions agree; the known limitation (module docstring) is bounded."""
+    """oracle/five_point_plan.py (Gauss-Jordan null space, interpolated constraints, eigenvalues by QR, 6x5 back-substitution)
+    against oracle/five_point.py (SVD + symbolic expansion + eigenvectors): found solutions agree and (almost) all are found."""
     from oracle import five_point_plan as PL
     rng = np.random.default_rng(3)
     matched = total = true_found = n_true = 0
@@ -84,4 +84,4 @@ def test_device_style_solver_matches_the_lapack_one():
             Et = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ R
             Et /= np.linalg.norm(Et)
             true_found += min([min(np.linalg.norm(E - Et), np.linalg.norm(E + Et)) for E in b] or [9]) < 1e-7
-    assert matched >= 0.88 * total and true_found >= 0.9 * n_true
+    assert matched >= 0.98 * total and true_found >= 0.97 * n_true
