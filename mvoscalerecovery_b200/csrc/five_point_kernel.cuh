@@ -22,9 +22,12 @@ __constant__ fp5::Tables c_fp5_tables = MVOSR_FP5_TABLES_INIT;
 
 constexpr int FP5_ROUND = 128;           // hypotheses per round: part of the stream definition (the stopping rule is checked per round)
 constexpr int FP5_THREADS = FP5_ROUND;
+#ifndef MVOSR_FP5_MIN_BLOCKS
+#define MVOSR_FP5_MIN_BLOCKS 4       // CTAs per SM the register allocation aims at (128 registers); sweep with MVOSR_NVCC_EXTRA=-DMVOSR_FP5_MIN_BLOCKS=2|3
+#endif
 constexpr int FP5_TILE = 512;            // correspondences staged per tile (16 KB of shared memory)
 
-__global__ void __launch_bounds__(FP5_THREADS, 4) find_essential_kernel(int n_frames, const int32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(FP5_THREADS, MVOSR_FP5_MIN_BLOCKS) find_essential_kernel(int n_frames, const int32_t *__restrict__ offsets,
         const float *__restrict__ cur_u, const float *__restrict__ cur_v, const float *__restrict__ ref_u, const float *__restrict__ ref_v,
         double fx, double fy, double cx, double cy, int hypotheses, double threshold_px, double confidence, uint64_t seed,
         const int32_t *__restrict__ frame_index, int seq_id,
