@@ -76,3 +76,31 @@ def test_missing_library_raises(monkeypatch):
     monkeypatch.setattr(N, "LIB_PATH", os.path.join(ROOT, "does_not_exist.so"))
     with pytest.raises(N.NativeLibraryError, match="no CPU fallback"):
         N.lib()
+
+
+def test_binding_argument_counts_match_the_header():
+    """Every prototype of include/mvosr.h against the ctypes argtypes of the binding: same number of parameters, and pointers /
+    integers / doubles in the same places (a mismatch here is a crash on the GPU box, not an exception)."""
+    from mvoscalerecovery_b200 import _native as N
+    lib = N.lib()
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    checked = 0
+    for m in re.finditer(r"\b(mvosr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        assert len(plist) == len(fn.argtypes), (name, len(plist), len(fn.argtypes))
+        for p, t in zip(plist, fn.argtypes):
+            is_ptr = "*" in p
+            if is_ptr:
+                assert t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) is not None, (name, p, t)
+            elif p.startswith("double"):
+                assert t is C.c_double, (name, p, t)
+            elif p.startswith("uint64_t"):
+                assert t is C.c_uint64, (name, p, t)
+            elif p.startswith(("int32_t", "int ")):
+                assert t in (C.c_int32, C.c_int), (name, p, t)
+        checked += 1
+    assert checked >= 18
