@@ -1,7 +1,8 @@
 """Deterministic harness around the UNMODIFIED reference -- TEST INFRASTRUCTURE.
 
-Only usable in the build container (``/root/reference`` does not exist on the GPU
-box).  It imports the reference's own modules from ``/root/reference/src`` under
+It imports the reference's own modules from ``/root/reference/src`` (build container) or
+from the staged copy ``oracle/_ref/src`` that ``make -C oracle ref`` makes of the same files
+(git-ignored; it travels to the GPU box, where bench.py's CPU legs time it) under
 the external shims of SURVEY.md section 8(c) and records, per frame, every
 intermediate the parity tests compare.  Nothing here restates the algorithm:
 values are read out of the reference's own stack frames with ``sys.setprofile``.
@@ -27,7 +28,8 @@ import types
 
 import numpy as np
 
-REF_SRC = os.environ.get("MVOSR_REFERENCE_SRC", "/root/reference/src")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "src")     # `make -C oracle ref`: the same files, staged
+REF_SRC = os.environ.get("MVOSR_REFERENCE_SRC") or ("/root/reference/src" if os.path.isfile("/root/reference/src/rescale.py") else _STAGED)
 
 _loaded = None
 
@@ -128,7 +130,13 @@ def run_frame(ns, estimator, feature3d, feature2d, frame, seq=0):
     fs = probe.out.get("flat_selection", {})
     fe = probe.out.get("feature_selection", {})
     sr = probe.out.get("scale_calculation_ransac", {})
+    # the returned model's inlier set over the vertex list, by the reference's own is_inlier (estimate_road_norm.py:17-18;
+    # threshold 0.005 as get_pitch_ransac is called, rescale.py:155) -- "RANSAC inlier index sets" of the north star
+    inlier = np.zeros(0, dtype=bool)
+    if "m" in sr and sr["m"] is not None and "point_selected" in fe:
+        inlier = np.array([bool(ns.ern.is_inlier(sr["m"], p, 0.005)) for p in np.asarray(fe["point_selected"])], dtype=bool)
     rec = {
+        "inlier": inlier,
         "roi": np.asarray(fe.get("lower_feature_ids")),
         "tri1": ns.dt_log[0].simplices,
         "coplanar1": np.asarray(ns.dt_log[0].coplanar),

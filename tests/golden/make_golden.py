@@ -92,6 +92,7 @@ def pack_sequence(name, b, store_stage1_frames=()):
         out["f%d_data_id" % f] = r["data_id"].astype(np.int16 if r["data_id"].size == 0 or r["data_id"].max() < 32768 else np.int32)
         out["f%d_hyp_log" % f] = r["hyp_log"].astype(np.int32)
         out["f%d_model" % f] = r["model"]
+        out["f%d_inlier" % f] = np.packbits(r["inlier"])          # is_inlier(model, data[j]) over the vertex list (N_sel bits)
         out["f%d_scalars" % f] = np.array([r["height_level"], r["best_ic"], r["raw_scale"], r["height"], float(r["updated"]),
                                            r["state_before"], r["state_after"], r["scale_out"], float(r["second_dt"])])
     path = os.path.join(OUT, name + ".npz")
