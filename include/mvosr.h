@@ -10,7 +10,9 @@
  * enqueued on the given stream and the call returns without synchronising (the _host entry
  * points synchronise before returning because they copy results to host memory).
  *
- * Threading: a handle may be used by one host thread at a time.
+ * Threading: a handle must not be used from two host threads concurrently (its workspace, scheduler counters and streams are
+ * unguarded); different handles are independent.  Every call except mvosr_create makes the handle's device current for the
+ * calling thread (cudaSetDevice) and leaves it so.
  * Errors: every function returns MVOSR_OK (0) or a negative MVOSR_E_* code; per-frame
  * conditions are reported in the status byte of each frame, never as a call failure.
  *
@@ -27,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MVOSR_VERSION 100
+#define MVOSR_VERSION 200
 
 /* ---- return codes ---- */
 #define MVOSR_OK                 0
@@ -103,6 +105,14 @@ typedef struct mvosr_debug_buffers {
     int32_t *data_id;       /* [6*M] the vertex list handed to RANSAC (rescale.py:101), 3*n_valid entries */
 } mvosr_debug_buffers;
 
+/* ---- one frame's result as a single 16-byte record: what a rank contributes to the fleet's all-gather (fleet.py) ---- */
+typedef struct mvosr_frame_record {
+    double  raw_scale;      /* absolute_reference / height, NaN unless status has MVOSR_ST_UPDATED */
+    int32_t n_features;     /* post-mask feature count (the n > min_features gate of main_offline.py:73) */
+    uint8_t status;         /* MVOSR_ST_* */
+    uint8_t pad[3];
+} mvosr_frame_record;
+
 typedef struct mvosr_handle mvosr_handle;
 
 int  mvosr_version(void);
@@ -150,6 +160,25 @@ int  mvosr_scale_frames_from_correspondences(mvosr_handle *h, int32_t n_frames, 
                         int32_t max_features, int32_t frame_index0, int32_t seq_id, uint64_t seed,
                         double *raw_scale, uint8_t *status, int32_t *n_features, mvosr_frame_stats *stats,
                         void *stream);
+
+/* Stages 1-5 over a SHARD of a fleet (BASELINE configs[3]): one contiguous frame range of the concatenated sequences, which
+ * may span sequence boundaries, in ONE launch.  Replaces the frame loop of src/main_offline.py:57-88 for that range.
+ * frame_seq[f] / frame_index[f] (device int32 [F], either may be NULL = seq_id / frame_index0 + f) give the Philox stream of
+ * every frame, so a frame draws the same hypotheses wherever the shard boundaries fall; order (device int32 [F], optional) is
+ * the processing order of the persistent CTAs -- e.g. frames sorted by decreasing size, which shortens the tail of the last
+ * wave; records[f] receives (raw_scale, n_features, status) of frame f (not of work item f). */
+int  mvosr_scale_shard_from_correspondences(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                        const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                        const uint8_t *e_mask, const double *poses, int32_t max_features,
+                        const int32_t *frame_seq, const int32_t *frame_index, int32_t frame_index0, int32_t seq_id,
+                        const int32_t *order, uint64_t seed, mvosr_frame_record *records, void *stream);
+
+/* Stage 6 over gathered records: as mvosr_filter_sequences, reading frame f of the global frame order from
+ * records[slot ? slot[f] : f] -- slot maps a global frame to its place in the all-gathered buffer (rank-major, every rank's
+ * block padded to the longest shard), so the gather output is consumed in place with no unpacking pass. */
+int  mvosr_filter_records(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets,
+                          const mvosr_frame_record *records, const int32_t *slot, const uint8_t *move_flags,
+                          double *scale_out, double *filter10_out, void *stream);
 
 /* Stage 6 -- replaces the driver gating of src/main_offline.py:57-88 and the temporal state of
  * src/rescale.py:168-178 (slew limiter + median of the last window_size states), then

@@ -35,6 +35,15 @@ class FrameStats(C.Structure):
         ("height_level", C.c_double), ("model", C.c_double * 4), ("height", C.c_double)]
 
 
+class FrameRecord(C.Structure):
+    """mvosr_frame_record: one frame's (raw_scale, n_features, status) in 16 bytes -- a rank's contribution to the fleet gather."""
+    _fields_ = [("raw_scale", C.c_double), ("n_features", C.c_int32), ("status", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+RECORD_BYTES = C.sizeof(FrameRecord)
+assert RECORD_BYTES == 16
+
+
 class DebugBuffers(C.Structure):
     _fields_ = [("tri1", C.c_void_p), ("n_tri1", C.c_void_p), ("keep", C.c_void_p), ("tri2", C.c_void_p),
                 ("tri_flags", C.c_void_p), ("tri_height", C.c_void_p), ("inlier", C.c_void_p), ("data_id", C.c_void_p)]
@@ -48,6 +57,7 @@ SYMBOLS = [
     "mvosr_recover_scales_host", "mvosr_recover_fleet_host", "mvosr_launch_count", "mvosr_set_phase_timing",
     "mvosr_triangle_planes", "mvosr_triangle_votes", "mvosr_ransac_planes", "mvosr_integrate_paths", "mvosr_depth_from_mesh", "mvosr_recover_pose_frames",
     "mvosr_find_essential_frames", "mvosr_pose_mask_frames", "mvosr_bucket_frames",
+    "mvosr_scale_shard_from_correspondences", "mvosr_filter_records",
 ]
 
 _lib = None
@@ -82,6 +92,8 @@ def lib():
     L.mvosr_scale_frames_from_correspondences.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, u64,
                                                           vp, vp, vp, vp, vp]
     L.mvosr_filter_sequences.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.mvosr_scale_shard_from_correspondences.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp, u64, vp, vp]
+    L.mvosr_filter_records.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.mvosr_delaunay_frames.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
     L.mvosr_recover_scales_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, u64, vp, vp, vp]
     L.mvosr_recover_fleet_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, u64, vp, vp, vp]

@@ -23,9 +23,31 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _chk(t: torch.Tensor, dtype, name: str, device):
-    if t.dtype != dtype or not t.is_contiguous() or t.device != device:
-        raise ValueError("%s must be a contiguous %s tensor on %s (got %s, %s)" % (name, dtype, device, t.dtype, t.device))
+def _chk(t: torch.Tensor, dtype, name: str, device, numel: Optional[int] = None):
+    if not isinstance(t, torch.Tensor) or t.dtype != dtype or not t.is_contiguous() or t.device != device:
+        raise ValueError("%s must be a contiguous %s tensor on %s (got %s, %s)" % (name, dtype, device, getattr(t, "dtype", type(t)), getattr(t, "device", None)))
+    if numel is not None and t.numel() < numel:
+        raise ValueError("%s holds %d elements, the call needs %d" % (name, t.numel(), numel))
+
+
+def _chk_opt(t, dtype, name: str, device, numel: Optional[int] = None):
+    """Optional device tensor: None passes, anything else is checked like a mandatory one (the C side dereferences it)."""
+    if t is not None:
+        _chk(t, dtype, name, device, numel)
+
+
+def _host_array(a, dtype, name: str, numel: int):
+    """A host buffer handed to the C ABI by raw pointer: numpy array or CPU torch tensor of exactly this dtype, C-contiguous,
+    at least `numel` elements (the C side reinterprets the bytes: a float64 or strided view would be read as garbage)."""
+    if isinstance(a, torch.Tensor):
+        if a.device.type != "cpu" or a.dtype != getattr(torch, np.dtype(dtype).name) or not a.is_contiguous() or a.numel() < numel:
+            raise ValueError("%s must be a contiguous CPU %s tensor with >= %d elements (got %s on %s, %d)"
+                             % (name, np.dtype(dtype).name, numel, a.dtype, a.device, a.numel()))
+        return C.c_void_p(a.data_ptr())
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags["C_CONTIGUOUS"] or a.size < numel:
+        raise ValueError("%s must be a C-contiguous %s numpy array with >= %d elements (got %s)"
+                         % (name, np.dtype(dtype).name, numel, getattr(a, "dtype", type(a))))
+    return C.c_void_p(a.ctypes.data)
 
 
 class ScaleRecovery:
@@ -76,7 +98,8 @@ class ScaleRecovery:
         _chk(offsets, torch.int32, "offsets", dev)
         for n, t in (("cur_u", cur_u), ("cur_v", cur_v), ("ref_u", ref_u), ("ref_v", ref_v)):
             _chk(t, torch.float32, n, dev)
-        _chk(poses, torch.float64, "poses", dev)
+        _chk(poses, torch.float64, "poses", dev, 12 * F)
+        _chk_opt(e_mask, torch.uint8, "e_mask", dev, cur_u.numel())
         M = cur_u.numel()
         out = {k: torch.empty(M, dtype=torch.float32, device=dev) for k in "xyzuv"}
         n_out = torch.zeros(F, dtype=torch.int32, device=dev)
@@ -118,7 +141,8 @@ class ScaleRecovery:
         _chk(offsets, torch.int32, "offsets", dev)
         for n, t in (("cur_u", cur_u), ("cur_v", cur_v), ("ref_u", ref_u), ("ref_v", ref_v)):
             _chk(t, torch.float32, n, dev)
-        _chk(essential, torch.float64, "essential", dev)
+        _chk(essential, torch.float64, "essential", dev, 9 * F)
+        _chk_opt(e_mask, torch.uint8, "e_mask", dev, cur_u.numel())
         poses = torch.empty((F, 12), dtype=torch.float64, device=dev)
         n_good = torch.zeros((F, 4), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
@@ -136,6 +160,7 @@ class ScaleRecovery:
         _chk(offsets, torch.int32, "offsets", dev)
         for n, t in (("x", x), ("y", y), ("z", z), ("u", u), ("v", v)):
             _chk(t, torch.float32, n, dev)
+        _chk_opt(counts, torch.int32, "counts", dev, F)
         M = x.numel()
         raw = torch.empty(F, dtype=torch.float64, device=dev)
         status = torch.zeros(F, dtype=torch.uint8, device=dev)
@@ -163,7 +188,8 @@ class ScaleRecovery:
         _chk(offsets, torch.int32, "offsets", dev)
         for n, t in (("cur_u", cur_u), ("cur_v", cur_v), ("ref_u", ref_u), ("ref_v", ref_v)):
             _chk(t, torch.float32, n, dev)
-        _chk(poses, torch.float64, "poses", dev)
+        _chk(poses, torch.float64, "poses", dev, 12 * F)
+        _chk_opt(e_mask, torch.uint8, "e_mask", dev, cur_u.numel())
         raw = torch.empty(F, dtype=torch.float64, device=dev)
         status = torch.zeros(F, dtype=torch.uint8, device=dev)
         nfeat = torch.zeros(F, dtype=torch.int32, device=dev)
@@ -201,7 +227,8 @@ class ScaleRecovery:
         _chk(offsets, torch.int32, "offsets", dev)
         for n, t in (("cur_u", cur_u), ("cur_v", cur_v), ("ref_u", ref_u), ("ref_v", ref_v)):
             _chk(t, torch.float32, n, dev)
-        _chk(poses, torch.float64, "poses", dev)
+        _chk(poses, torch.float64, "poses", dev, 12 * F)
+        _chk_opt(e_mask, torch.uint8, "e_mask", dev, cur_u.numel())
         mask = torch.zeros(cur_u.numel(), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             N.check(self.lib.mvosr_pose_mask_frames(self._h, F, _ptr(offsets), _ptr(cur_u), _ptr(cur_v), _ptr(ref_u), _ptr(ref_v), _ptr(e_mask),
@@ -223,6 +250,48 @@ class ScaleRecovery:
         out.update(essential=ess["essential"], e_mask=ess["e_mask"], n_inliers=ess["n_inliers"], hyps_used=ess["hyps_used"], poses=pose["poses"])
         return out
 
+    def scale_shard_from_correspondences(self, offsets, cur_u, cur_v, ref_u, ref_v, poses, max_features: int, records,
+                                         frame_seq=None, frame_index=None, frame_index0: int = 0, seq_id: int = 0, order=None,
+                                         e_mask=None, seed: int = 0):
+        """Stages 1-5 over one rank's shard of a fleet in ONE launch (mvosr_scale_shard_from_correspondences): the frame range may
+        span sequences -- ``frame_seq`` / ``frame_index`` (int32 [F]) carry every frame's Philox stream --, ``order`` (int32 [F]) is
+        the processing order (largest frames first), and the results land as 16-byte records in ``records`` (uint8 [>= F, 16], e.g.
+        this rank's block of the all-gather buffer, so the collective runs in place)."""
+        dev = self.device
+        F = offsets.numel() - 1
+        _chk(offsets, torch.int32, "offsets", dev)
+        for n, t in (("cur_u", cur_u), ("cur_v", cur_v), ("ref_u", ref_u), ("ref_v", ref_v)):
+            _chk(t, torch.float32, n, dev)
+        _chk(poses, torch.float64, "poses", dev, 12 * F)
+        _chk(records, torch.uint8, "records", dev, N.RECORD_BYTES * F)
+        _chk_opt(frame_seq, torch.int32, "frame_seq", dev, F)
+        _chk_opt(frame_index, torch.int32, "frame_index", dev, F)
+        _chk_opt(order, torch.int32, "order", dev, F)
+        _chk_opt(e_mask, torch.uint8, "e_mask", dev, cur_u.numel())
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_scale_shard_from_correspondences(
+                self._h, F, _ptr(offsets), _ptr(cur_u), _ptr(cur_v), _ptr(ref_u), _ptr(ref_v), _ptr(e_mask), _ptr(poses), int(max_features),
+                _ptr(frame_seq), _ptr(frame_index), int(frame_index0), int(seq_id), _ptr(order), C.c_uint64(int(seed)), _ptr(records),
+                self._stream()))
+        return records
+
+    def filter_records(self, seq_offsets, records, slot=None, move_flags=None, filter10: bool = True, out=None):
+        """Stage 6 straight from gathered records (mvosr_filter_records): frame f of the global order is records[slot[f]]."""
+        dev = self.device
+        _chk(seq_offsets, torch.int32, "seq_offsets", dev)
+        _chk(records, torch.uint8, "records", dev)
+        S = seq_offsets.numel() - 1
+        F = slot.numel() if slot is not None else records.numel() // N.RECORD_BYTES
+        _chk_opt(slot, torch.int32, "slot", dev)
+        _chk_opt(move_flags, torch.uint8, "move_flags", dev, F)
+        if out is None:
+            out = dict(scale=torch.empty(F, dtype=torch.float64, device=dev),
+                       filter10=torch.empty(F, dtype=torch.float64, device=dev) if filter10 else None)
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_filter_records(self._h, S, _ptr(seq_offsets), _ptr(records), _ptr(slot), _ptr(move_flags),
+                                                  _ptr(out["scale"]), _ptr(out.get("filter10")), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ stage 6
     def filter_sequences(self, seq_offsets, raw_scale, status, move_flags=None, n_features=None, filter10: bool = True):
         """Replaces the gating of main_offline.py:57-88 + rescale.py:168-178, then evaluate_scale.filter(...,10)."""
@@ -232,6 +301,9 @@ class ScaleRecovery:
         _chk(status, torch.uint8, "status", dev)
         S = seq_offsets.numel() - 1
         F = raw_scale.numel()
+        _chk(status, torch.uint8, "status", dev, F)
+        _chk_opt(move_flags, torch.uint8, "move_flags", dev, F)
+        _chk_opt(n_features, torch.int32, "n_features", dev, F)
         out = torch.empty(F, dtype=torch.float64, device=dev)
         f10 = torch.empty(F, dtype=torch.float64, device=dev) if filter10 else None
         with torch.cuda.device(dev):
@@ -335,28 +407,37 @@ class ScaleRecovery:
                             seq_id: int = 0, seed: int = 0, out=None, seq_offsets=None):
         """Host (ideally pinned) numpy/torch-CPU buffers in, filtered scales out: copies + stages 1-6 inside.
         ``seq_offsets`` (int32 (S+1,), host): the batch holds S sequences (mvosr_recover_fleet_host; sequence ids seq_id + s)."""
-        def hp(a):
-            if a is None:
-                return None
-            if isinstance(a, torch.Tensor):
-                return C.c_void_p(a.data_ptr())
-            return C.c_void_p(a.ctypes.data)
+        if not isinstance(offsets, (np.ndarray, torch.Tensor)) or offsets.ndim != 1 or offsets.shape[0] < 1:
+            raise ValueError("offsets must be a 1-D int32 array of F + 1 entries")
         F = int(offsets.shape[0] - 1)
+        p_off = _host_array(offsets, np.int32, "offsets", F + 1)
+        o = offsets.numpy() if isinstance(offsets, torch.Tensor) else offsets
+        if F and (int(o[0]) != 0 or bool(np.any(np.diff(o) < 0))):
+            raise ValueError("offsets must start at 0 and be non-decreasing")
+        M = int(o[-1]) if F else 0
+        p_cu, p_cv = _host_array(cur_u, np.float32, "cur_u", M), _host_array(cur_v, np.float32, "cur_v", M)
+        p_ru, p_rv = _host_array(ref_u, np.float32, "ref_u", M), _host_array(ref_v, np.float32, "ref_v", M)
+        p_pose = _host_array(poses, np.float64, "poses", 12 * F)
+        p_move = None if move_flags is None else _host_array(move_flags, np.uint8, "move_flags", F)
         if out is None:
             out = dict(scale=np.empty(F, np.float64), raw_scale=np.empty(F, np.float64), status=np.empty(F, np.uint8))
+        p_scale = _host_array(out["scale"], np.float64, "out['scale']", F)
+        p_raw = None if out.get("raw_scale") is None else _host_array(out["raw_scale"], np.float64, "out['raw_scale']", F)
+        p_st = None if out.get("status") is None else _host_array(out["status"], np.uint8, "out['status']", F)
         if not max_features:
-            o = offsets.numpy() if isinstance(offsets, torch.Tensor) else offsets
             max_features = int(np.max(np.diff(o))) if F else 0
         with torch.cuda.device(self.device):
             if seq_offsets is None:
-                N.check(self.lib.mvosr_recover_scales_host(self._h, F, hp(offsets), hp(cur_u), hp(cur_v), hp(ref_u), hp(ref_v), hp(poses),
-                                                           hp(move_flags), int(max_features), int(seq_id), C.c_uint64(int(seed)),
-                                                           hp(out["scale"]), hp(out["raw_scale"]), hp(out["status"])))
+                N.check(self.lib.mvosr_recover_scales_host(self._h, F, p_off, p_cu, p_cv, p_ru, p_rv, p_pose,
+                                                           p_move, int(max_features), int(seq_id), C.c_uint64(int(seed)),
+                                                           p_scale, p_raw, p_st))
             else:
                 so = np.ascontiguousarray(seq_offsets.numpy() if isinstance(seq_offsets, torch.Tensor) else seq_offsets, dtype=np.int32)
-                N.check(self.lib.mvosr_recover_fleet_host(self._h, int(so.shape[0] - 1), hp(so), hp(offsets), hp(cur_u), hp(cur_v), hp(ref_u), hp(ref_v),
-                                                          hp(poses), hp(move_flags), int(max_features), int(seq_id), C.c_uint64(int(seed)),
-                                                          hp(out["scale"]), hp(out["raw_scale"]), hp(out["status"])))
+                if so.ndim != 1 or so.shape[0] < 1 or int(so[0]) != 0 or int(so[-1]) != F or bool(np.any(np.diff(so) < 0)):
+                    raise ValueError("seq_offsets must run from 0 to the number of frames, non-decreasing")
+                N.check(self.lib.mvosr_recover_fleet_host(self._h, int(so.shape[0] - 1), C.c_void_p(so.ctypes.data), p_off, p_cu, p_cv, p_ru, p_rv,
+                                                          p_pose, p_move, int(max_features), int(seq_id), C.c_uint64(int(seed)),
+                                                          p_scale, p_raw, p_st))
         return out
 
 

@@ -40,8 +40,10 @@ struct mvosr_handle {
     int64_t launches;
     // host-API staging (grown on demand)
     void *d_stage; size_t stage_bytes;
-    void *d_ws; size_t ws_bytes;   // large-frame staging (frames beyond the shared-memory capacity)
-    cudaEvent_t ev_ws; int ev_ws_ready;   // the staging is one buffer: launches that use it are chained through this event
+    // large-frame staging (frames beyond the shared-memory capacity): two sets of per-CTA slabs used alternately, so that two
+    // launches in flight (the two compute streams of the host pipeline) never share one; a launch waits for the previous user
+    // of its set through that set's event
+    void *d_ws[2]; size_t ws_bytes[2]; cudaEvent_t ev_ws[2]; int ev_ws_ready[2]; int ws_slot;
     long long *phase_cycles;     // optional profiling sink (device), set by mvosr_set_phase_timing
 };
 
@@ -104,94 +106,150 @@ __device__ __forceinline__ double median_window(const double *w, int n) {
 }
 
 // Stage 6: driver gating (main_offline.py:57-88) + slew limiter + median of the last window_size states
-// (rescale.py:168-178), then filter(data, 10) of script/evaluate_scale.py:25-29.  One CTA per sequence, frames in chunks
-// staged in shared memory: thread 0 runs the strictly sequential recurrences (slew limiter, "repeat the last output"),
-// everything else -- the windowed medians -- is computed by all threads in parallel.
+// (rescale.py:168-178), then filter(data, 10) of script/evaluate_scale.py:25-29.  One CTA per sequence, frames staged in shared
+// memory in chunks of FCH.  Only the slew limiter is a true recurrence (state_i = f(state_{i-1}, raw_i), unbounded memory); it is
+// run SPECULATIVELY by one warp: every lane advances FL consecutive frames from a guessed start state -- the raw scale of the last
+// updated frame before its segment, which is the exact state whenever that frame did not hit the +-0.3 limit --, then the lanes
+// compare their start with the end state of the lane before and the wrong ones recompute, lowest first, until none changes (the
+// arithmetic of every step is the sequential one, so the result is bit-identical to the loop; a slewing stretch costs one round
+// per lane it crosses).  Everything else is a scan or a window and runs on all threads: the push counter of the deque, the
+// medians, "repeat the last output" (a last-valid-index scan), filter_10.
 constexpr int FCH = 1024;            // frames per chunk
 constexpr int FHIST = 32;            // history carried between chunks (window_size <= 31, filter_10 needs 9)
-__global__ void __launch_bounds__(256) filter_kernel(int n_seq, const int32_t *seq_offsets, const double *raw, const uint8_t *status,
-                              const uint8_t *move, const int32_t *n_features, mvosr_config cfg, double *out, double *out10) {
+constexpr int FT = 256;              // threads; each owns FCH / FT consecutive frames in the scans
+constexpr int FL = 8;                // frames per lane and round of the speculative recurrence
+
+// inclusive block scan over FCH elements, 4 consecutive per thread: OP = 0 sum, 1 max.  v[4]: in/out.
+template <int OP>
+__device__ __forceinline__ void filter_scan4(int v[4], int *wtmp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) v[k] = OP ? max(v[k], v[k - 1]) : v[k] + v[k - 1];
+    int tot = v[3];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, tot, o); if (lane >= o) tot = OP ? max(tot, u) : tot + u; }
+    if (lane == 31) wtmp[warp] = tot;
+    __syncthreads();
+    int excl = __shfl_up_sync(0xFFFFFFFFu, tot, 1);
+    if (lane == 0) excl = OP ? -0x40000000 : 0;
+    for (int w = 0; w < warp; ++w) excl = OP ? max(excl, wtmp[w]) : excl + wtmp[w];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = OP ? max(v[k], excl) : v[k] + excl;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(FT) filter_kernel(int n_seq, const int32_t *seq_offsets, const double *raw, const uint8_t *status,
+                              const uint8_t *move, const int32_t *n_features, const mvosr_frame_record *rec, const int32_t *slot,
+                              mvosr_config cfg, double *out, double *out10) {
     __shared__ double P[FHIST + FCH];       // pushed states: [0,FHIST) = tail of the earlier chunks
     __shared__ double O[FHIST + FCH];       // outputs, same layout
-    __shared__ double R[FCH];               // raw scales, then the medians
+    __shared__ double R[FCH];               // raw scales
+    __shared__ double S[FCH];               // slew-limited state after every frame, then the deque medians
     __shared__ int pidx[FCH];               // number of states pushed up to and including this frame (chunk-local, + FHIST)
     __shared__ uint8_t kind[FCH], flags[FCH];
-    __shared__ double s_scale, s_last; __shared__ int s_npush, s_nhist, s_ohist;
-    const int tid = threadIdx.x;
+    __shared__ int wtmp[FT / 32];
+    __shared__ double s_scale, s_last; __shared__ int s_nhist, s_ohist;
+    static_assert(FCH == 4 * FT, "the scans give every thread four consecutive frames");
+    const int tid = threadIdx.x, lane = tid & 31;
     const int win = cfg.window_size < 1 ? 1 : (cfg.window_size > 31 ? 31 : cfg.window_size);
+    const double lim = cfg.slew_limit;
     for (int s = blockIdx.x; s < n_seq; s += gridDim.x) {
         const int f0 = seq_offsets[s], f1 = seq_offsets[s + 1];
         if (tid == 0) { s_scale = 1.0; s_last = 0.0; s_nhist = 0; s_ohist = 0; }     // self.scale = 1 (rescale.py:27), scales = [0] (main_offline.py:45)
         __syncthreads();
         for (int c0 = f0; c0 < f1; c0 += FCH) {
             const int n = min(FCH, f1 - c0);
-            for (int i = tid; i < n; i += blockDim.x) {
-                const int f = c0 + i;
-                R[i] = raw[f];
-                int fl = (status[f] & MVOSR_ST_UPDATED) ? 1 : 0;
-                if (move && !move[f]) fl |= 2;                                        // not moving -> 0 (:64-68)
-                else if (n_features && n_features[f] <= cfg.min_features) fl |= 4;    // too few features -> repeat (:73,84-86)
-                flags[i] = (uint8_t)fl;
+            // ---- 1. load; kind: 0 not moving -> 0 (:64-68), 1 too few features -> repeat (:73,84-86), 2 estimator called
+            for (int i = tid; i < FCH; i += FT) {
+                int kd = 1, fl = 0; double r = 0.0;          // padding frames repeat: they change nothing
+                if (i < n) {
+                    const int f = c0 + i;
+                    int nfeat = 0x7FFFFFFF;
+                    if (rec) {                                                            // gathered records, consumed in place
+                        const mvosr_frame_record q = rec[slot ? slot[f] : f];
+                        r = q.raw_scale; fl = (q.status & MVOSR_ST_UPDATED) ? 1 : 0; nfeat = q.n_features;
+                    } else {
+                        r = raw[f]; fl = (status[f] & MVOSR_ST_UPDATED) ? 1 : 0;
+                        if (n_features) nfeat = n_features[f];
+                    }
+                    kd = (move && !move[f]) ? 0 : (nfeat <= cfg.min_features ? 1 : 2);
+                }
+                R[i] = r; kind[i] = (uint8_t)kd; flags[i] = (uint8_t)(kd == 2 && fl);
             }
             __syncthreads();
-            if (tid == 0) {
-                // the slew limiter is a strict recurrence: inputs are fetched eight frames ahead so that only its own
-                // arithmetic is on the dependent path
-                double scale = s_scale; int np = FHIST;
-                for (int i0 = 0; i0 < n; i0 += 8) {
-                    double r8[8]; int f8[8];
+            // ---- 2. push counter of the deque (one push per estimator call)
+            int v4[4];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) { const int i = min(i0 + k, n - 1); r8[k] = R[i]; f8[k] = flags[i]; }
+            for (int k = 0; k < 4; ++k) v4[k] = kind[4 * tid + k] == 2;
+            filter_scan4<0>(v4, wtmp);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int i = i0 + k;
-                        if (i >= n) break;
-                        const int fl = f8[k];
-                        int kd = 2;
-                        if (fl & 2) kd = 0;
-                        else if (fl & 4) kd = 1;
-                        else {
-                            if (fl & 1) {
-                                const double r = r8[k];
-                                if (r - scale > cfg.slew_limit) scale += cfg.slew_limit;
-                                else if (r - scale < -cfg.slew_limit) scale -= cfg.slew_limit;
-                                else scale = r;
+            for (int k = 0; k < 4; ++k) pidx[4 * tid + k] = FHIST + v4[k];
+            // ---- 3. the slew limiter, speculatively (warp 0)
+            if (tid < 32) {
+                double carry = s_scale;
+                for (int base = 0; base < n; base += 32 * FL) {
+                    const int a = min(base + lane * FL, n), b = min(a + FL, n);
+                    // guess: the raw scale of the last updated frame before this lane's segment, else the carried state
+                    double lastv = 0.0; bool has = false;
+                    for (int i = a; i < b; ++i) if (flags[i]) { lastv = R[i]; has = true; }
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double uv = __shfl_up_sync(0xFFFFFFFFu, lastv, o); const bool uh = __shfl_up_sync(0xFFFFFFFFu, (int)has, o) != 0;
+                        if (lane >= o && !has) { lastv = uv; has = uh; }
+                    }
+                    double gv = __shfl_up_sync(0xFFFFFFFFu, lastv, 1); const bool gh = __shfl_up_sync(0xFFFFFFFFu, (int)has, 1) != 0;
+                    double start = (lane == 0 || !gh) ? carry : gv, end = start;
+                    bool run = true;
+                    for (;;) {
+                        if (run) {
+                            double sc = start;
+                            for (int i = a; i < b; ++i) {
+                                if (flags[i]) {                                        // rescale.py:168-174
+                                    const double r = R[i];
+                                    if (r - sc > lim) sc += lim;
+                                    else if (r - sc < -lim) sc -= lim;
+                                    else sc = r;
+                                }
+                                S[i] = sc;
                             }
-                            P[np++] = scale;
+                            end = sc;
                         }
-                        kind[i] = (uint8_t)kd; pidx[i] = np;
+                        double prev = __shfl_up_sync(0xFFFFFFFFu, end, 1);
+                        if (lane == 0) prev = carry;
+                        run = __double_as_longlong(prev) != __double_as_longlong(start);
+                        if (!__any_sync(0xFFFFFFFFu, run)) break;
+                        if (run) start = prev;
                     }
+                    carry = __shfl_sync(0xFFFFFFFFu, end, 31);
                 }
-                s_scale = scale; s_npush = np;
+                if (lane == 0) s_scale = carry;
             }
             __syncthreads();
+            // ---- 4. the pushed states, in push order
             const int nhist = s_nhist;
-            for (int i = tid; i < n; i += blockDim.x) {
-                if (kind[i] != 2) continue;
-                const int e = pidx[i];                                   // window = the last `win` pushed states
-                int b = e - win; if (b < FHIST - nhist) b = FHIST - nhist;
-                R[i] = median_window(P + b, e - b);
-            }
+            for (int i = tid; i < n; i += FT) if (kind[i] == 2) P[pidx[i] - 1] = S[i];
             __syncthreads();
-            if (tid == 0) {
-                double last = s_last;
-                for (int i0 = 0; i0 < n; i0 += 8) {
-                    double r8[8]; int k8[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { const int i = min(i0 + k, n - 1); r8[k] = R[i]; k8[k] = kind[i]; }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int i = i0 + k;
-                        if (i >= n) break;
-                        const double o = k8[k] == 0 ? 0.0 : (k8[k] == 1 ? last : r8[k]);
-                        O[FHIST + i] = o; last = o;
-                    }
+            // ---- 5. median of the last `win` pushed states (rescale.py:175-178); S becomes the per-frame value 0 / median
+            for (int i = tid; i < n; i += FT) {
+                double m = 0.0;
+                if (kind[i] == 2) {
+                    const int e = pidx[i];
+                    int b = e - win; if (b < FHIST - nhist) b = FHIST - nhist;
+                    m = median_window(P + b, e - b);
                 }
-                s_last = last;
+                S[i] = m;
             }
+            // ---- 6. outputs: "repeat the last output" = the value at the last frame that was not a repeat
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v4[k] = kind[4 * tid + k] != 1 ? 4 * tid + k : -1;
+            __syncthreads();
+            filter_scan4<1>(v4, wtmp);
+            const double last = s_last;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int i = 4 * tid + k; if (i < n) O[FHIST + i] = v4[k] >= 0 ? S[v4[k]] : last; }
             __syncthreads();
             const int ohist = s_ohist;
-            for (int i = tid; i < n; i += blockDim.x) {
+            for (int i = tid; i < n; i += FT) {
                 out[c0 + i] = O[FHIST + i];
                 if (out10) {                                             // causal running median over the last 10 outputs
                     int b = FHIST + i - 9; if (b < FHIST - ohist) b = FHIST - ohist;
@@ -199,16 +257,17 @@ __global__ void __launch_bounds__(256) filter_kernel(int n_seq, const int32_t *s
                 }
             }
             __syncthreads();
-            // carry the tails into the history slots
-            const int np = s_npush, keepP = min(FHIST, nhist + (np - FHIST)), keepO = min(FHIST, ohist + n);
+            // ---- carry the tails into the history slots
+            const int np = pidx[n - 1], keepP = min(FHIST, nhist + (np - FHIST)), keepO = min(FHIST, ohist + n);
             double tp = 0, to = 0;
             if (tid < FHIST) {
                 if (tid >= FHIST - keepP) tp = P[np - FHIST + tid];
                 if (tid >= FHIST - keepO) to = O[n + tid];
             }
+            const double newlast = O[FHIST + n - 1];
             __syncthreads();
             if (tid < FHIST) { P[tid] = tp; O[tid] = to; }
-            if (tid == 0) { s_nhist = keepP; s_ohist = keepO; }
+            if (tid == 0) { s_nhist = keepP; s_ohist = keepO; s_last = newlast; }
             __syncthreads();
         }
     }
@@ -294,22 +353,35 @@ int mvosr_create(const mvosr_config *cfg, int device, mvosr_handle **out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MVOSR_E_NO_DEVICE;
     if (device < 0 || device >= ndev) return MVOSR_E_INVALID;
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
     CK(cudaSetDevice(device));
     mvosr_handle *h = new (std::nothrow) mvosr_handle();
     if (!h) return MVOSR_E_NOMEM;
     memset(h, 0, sizeof(*h));
     if (cfg) h->cfg = *cfg; else mvosr_default_config(&h->cfg);
     h->device = device;
+    // any failure below releases what was acquired and leaves *out untouched
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    h->num_sms = prop.multiProcessorCount;
-    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    int cap = 256;
-    while (make_plan(cap + 64).total + (int)sizeof(Ctl) + 1024 <= h->smem_optin) cap += 64;
-    h->cap_max = cap;
-    CK(cudaMalloc(&h->work_counter, NCOUNTERS * sizeof(int)));
-    CK(cudaFuncSetAttribute(frame_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512));
-    CK(cudaFuncSetAttribute(frame_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512));
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) {
+        h->num_sms = prop.multiProcessorCount;
+        h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+        int cap = 256;
+        while (make_plan(cap + 64).total + (int)sizeof(Ctl) + 1024 <= h->smem_optin) cap += 64;
+        h->cap_max = cap;
+        e = cudaMalloc(&h->work_counter, NCOUNTERS * sizeof(int));
+    }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512);
+    if (e != cudaSuccess) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "%s in mvosr_create", cudaGetErrorString(e));
+        if (h->work_counter) cudaFree(h->work_counter);
+        delete h;
+        cudaSetDevice(prev_dev);
+        return MVOSR_E_CUDA;
+    }
+    cudaSetDevice(prev_dev);
     *out = h;
     return MVOSR_OK;
 }
@@ -319,8 +391,7 @@ int mvosr_destroy(mvosr_handle *h) {
     cudaSetDevice(h->device);
     if (h->work_counter) cudaFree(h->work_counter);
     if (h->d_stage) cudaFree(h->d_stage);
-    if (h->d_ws) cudaFree(h->d_ws);
-    if (h->ev_ws_ready) cudaEventDestroy(h->ev_ws);
+    for (int k = 0; k < 2; ++k) { if (h->d_ws[k]) cudaFree(h->d_ws[k]); if (h->ev_ws_ready[k]) cudaEventDestroy(h->ev_ws[k]); }
     if (h->streams_ready) {
         cudaStreamDestroy(h->s_copy); cudaStreamDestroy(h->s_comp[0]); cudaStreamDestroy(h->s_comp[1]);
         for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_copy[i]);
@@ -363,26 +434,27 @@ static int launch_frames(mvosr_handle *h, FrameParams &P, int max_features, cuda
     int grid = P.n_frames < h->num_sms ? P.n_frames : h->num_sms;
     size_t dyn = (size_t)pl.total;
     P.workspace = nullptr; P.ws_stride = 0;
+    int ws = -1;
     if (cap > h->cap_max) {
         // large-frame mode: the staging lives in global memory, one slab per CTA
+        ws = h->ws_slot; h->ws_slot ^= 1;
         size_t stride = ((size_t)pl.total + 255) & ~(size_t)255, need = stride * (size_t)grid;
-        if (need > h->ws_bytes) {
+        if (need > h->ws_bytes[ws]) {
             CK(cudaDeviceSynchronize());                     // earlier launches on any stream may still use the old buffer
-            if (h->d_ws) cudaFree(h->d_ws);
-            h->d_ws = nullptr; h->ws_bytes = 0;
-            if (cudaMalloc(&h->d_ws, need) != cudaSuccess) { cudaGetLastError(); return MVOSR_E_NOMEM; }
-            h->ws_bytes = need;
+            if (h->d_ws[ws]) cudaFree(h->d_ws[ws]);
+            h->d_ws[ws] = nullptr; h->ws_bytes[ws] = 0;
+            if (cudaMalloc(&h->d_ws[ws], need) != cudaSuccess) { cudaGetLastError(); return MVOSR_E_NOMEM; }
+            h->ws_bytes[ws] = need;
         }
-        P.workspace = (unsigned char *)h->d_ws; P.ws_stride = stride;
+        P.workspace = (unsigned char *)h->d_ws[ws]; P.ws_stride = stride;
         dyn = 0;
-        // two launches in flight (e.g. the two compute streams of the host pipeline) must not share the slabs
-        if (!h->ev_ws_ready) { CK(cudaEventCreateWithFlags(&h->ev_ws, cudaEventDisableTiming)); h->ev_ws_ready = 1; }
-        else CK(cudaStreamWaitEvent(st, h->ev_ws, 0));
+        if (!h->ev_ws_ready[ws]) { CK(cudaEventCreateWithFlags(&h->ev_ws[ws], cudaEventDisableTiming)); h->ev_ws_ready[ws] = 1; }
+        else CK(cudaStreamWaitEvent(st, h->ev_ws[ws], 0));
     }
     CK(cudaMemsetAsync(P.work_counter, 0, sizeof(int), st));
     frame_kernel<FROM_CORR><<<grid, NT, dyn, st>>>(P);
     CK(cudaGetLastError());
-    if (P.workspace) CK(cudaEventRecord(h->ev_ws, st));
+    if (ws >= 0) CK(cudaEventRecord(h->ev_ws[ws], st));
     h->launches += 1;
     return MVOSR_OK;
 }
@@ -459,26 +531,64 @@ int mvosr_filter_sequences(mvosr_handle *h, int32_t n_sequences, const int32_t *
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = n_sequences < 4 * h->num_sms ? n_sequences : 4 * h->num_sms;
-    filter_kernel<<<grid, 256, 0, st>>>(n_sequences, seq_offsets, raw_scale, status, move_flags, n_features, h->cfg, scale_out, filter10_out);
+    filter_kernel<<<grid, 256, 0, st>>>(n_sequences, seq_offsets, raw_scale, status, move_flags, n_features, nullptr, nullptr, h->cfg, scale_out, filter10_out);
     CK(cudaGetLastError());
     h->launches += 1;
     return MVOSR_OK;
 }
 
+int mvosr_filter_records(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets,
+                         const mvosr_frame_record *records, const int32_t *slot, const uint8_t *move_flags,
+                         double *scale_out, double *filter10_out, void *stream) {
+    if (!h || n_sequences < 0 || !seq_offsets || !records || !scale_out) return MVOSR_E_INVALID;
+    if (n_sequences == 0) return MVOSR_OK;
+    CK(cudaSetDevice(h->device));
+    const int grid = n_sequences < 4 * h->num_sms ? n_sequences : 4 * h->num_sms;
+    filter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_sequences, seq_offsets, nullptr, nullptr, move_flags, nullptr, records, slot, h->cfg,
+                                                         scale_out, filter10_out);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return MVOSR_OK;
+}
+
+int mvosr_scale_shard_from_correspondences(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
+                        const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
+                        const uint8_t *e_mask, const double *poses, int32_t max_features,
+                        const int32_t *frame_seq, const int32_t *frame_index, int32_t frame_index0, int32_t seq_id,
+                        const int32_t *order, uint64_t seed, mvosr_frame_record *records, void *stream) {
+    if (!h || n_frames < 0 || !offsets || !cur_u || !cur_v || !ref_u || !ref_v || !poses || !records || max_features < 0)
+        return MVOSR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    FrameParams P; memset(&P, 0, sizeof(P));
+    P.n_frames = n_frames; P.offsets = offsets;
+    P.cur_u = cur_u; P.cur_v = cur_v; P.ref_u = ref_u; P.ref_v = ref_v; P.e_mask = e_mask; P.poses = poses;
+    P.mode = MODE_FULL; P.gate = 1;
+    P.frame_seq = frame_seq; P.frame_index = frame_index; P.frame_index0 = frame_index0; P.seq_id = seq_id; P.order = order; P.seed = seed;
+    P.records = records;
+    return launch_frames<true>(h, P, max_features, (cudaStream_t)stream);
+}
+
 // Host-buffer pipeline shared by the two _host entry points: S sequences (frame ranges seq_off[0..S], Philox sequence ids
-// seq_id0 + s, frame counters restarting at every sequence) packed in one CSR batch.
+// seq_id0 + s, frame counters restarting at every sequence) packed in one CSR batch.  The batch is cut into about eight chunks
+// regardless of the sequence boundaries (per-frame Philox tables carry them): chunk k+1 is copied while chunk k is processed, and
+// consecutive chunks run on two compute streams so that the tail of one launch overlaps the head of the next.
 static int recover_host(mvosr_handle *h, int32_t n_frames, const int32_t *offsets_host,
                         const float *cur_u_host, const float *cur_v_host, const float *ref_u_host, const float *ref_v_host,
                         const double *poses_host, const uint8_t *move_flags_host, int32_t max_features,
                         int32_t n_sequences, const int32_t *seq_off, int32_t seq_id0, uint64_t seed,
                         double *scale_out_host, double *raw_scale_out_host, uint8_t *status_out_host) {
+    // the sized copies below trust offsets_host: check it first (a wrong dtype or a non-monotone table would read out of bounds)
+    if (offsets_host[0] != 0) return MVOSR_E_INVALID;
+    for (int f = 0; f < n_frames; ++f) if (offsets_host[f + 1] < offsets_host[f]) return MVOSR_E_INVALID;
     CK(cudaSetDevice(h->device));
     const size_t M = (size_t)offsets_host[n_frames];
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const bool tables = n_sequences > 1;
     size_t o_off = 0, o_cu = o_off + al(4 * (size_t)(n_frames + 1)), o_cv = o_cu + al(4 * M), o_ru = o_cv + al(4 * M),
            o_rv = o_ru + al(4 * M), o_pose = o_rv + al(4 * M), o_move = o_pose + al(96 * (size_t)n_frames),
            o_raw = o_move + al((size_t)n_frames), o_st = o_raw + al(8 * (size_t)n_frames), o_nf = o_st + al((size_t)n_frames),
-           o_out = o_nf + al(4 * (size_t)n_frames), o_seq = o_out + al(8 * (size_t)n_frames), total = o_seq + al(4 * (size_t)(n_sequences + 1));
+           o_out = o_nf + al(4 * (size_t)n_frames), o_seq = o_out + al(8 * (size_t)n_frames), o_tab = o_seq + al(4 * (size_t)(n_sequences + 1)),
+           total = o_tab + (tables ? al(8 * (size_t)n_frames) : 0);
     if (total > h->stage_bytes) {
         CK(cudaDeviceSynchronize());
         if (h->d_stage) cudaFree(h->d_stage);
@@ -494,47 +604,53 @@ static int recover_host(mvosr_handle *h, int32_t n_frames, const int32_t *offset
         for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
         h->streams_ready = 1;
     }
-    // Pipeline: every sequence is cut into chunks; chunk k+1 is copied while chunk k is processed, and consecutive chunks
-    // run on two compute streams so that the tail of one launch overlaps the head of the next.
     cudaStream_t sc = h->s_copy;
     CK(cudaMemcpyAsync(d + o_off, offsets_host, 4 * (size_t)(n_frames + 1), cudaMemcpyHostToDevice, sc));
     CK(cudaMemcpyAsync(d + o_pose, poses_host, 96 * (size_t)n_frames, cudaMemcpyHostToDevice, sc));
     if (move_flags_host) CK(cudaMemcpyAsync(d + o_move, move_flags_host, (size_t)n_frames, cudaMemcpyHostToDevice, sc));
     CK(cudaMemcpyAsync(d + o_seq, seq_off, 4 * (size_t)(n_sequences + 1), cudaMemcpyHostToDevice, sc));
-    int launch = 0;
-    for (int s = 0; s < n_sequences; ++s) {
-        const int s0 = seq_off[s], sn = seq_off[s + 1] - s0;
-        // about 8 chunks over the whole call, the first chunk of the call small so that the GPU starts early
-        int n_chunks = (int)((long long)8 * sn / (n_frames > 0 ? n_frames : 1));
-        if (sn >= 2 * h->num_sms && n_chunks < 2) n_chunks = 2;
-        if (sn < 2 * h->num_sms || n_chunks < 1) n_chunks = 1;
-        if (n_chunks > 8) n_chunks = 8;
-        if (n_chunks > sn / h->num_sms) n_chunks = sn / h->num_sms > 0 ? sn / h->num_sms : 1;       // at least one frame per SM and chunk
-        for (int c = 0; c < n_chunks; ++c) {
-            int f0, f1;
-            if (s == 0 && n_chunks > 1) {
-                f0 = c == 0 ? 0 : (int)((long long)sn * (2 * c - 1) / (2 * n_chunks - 1));
-                f1 = (int)((long long)sn * (2 * c + 1) / (2 * n_chunks - 1));
-            } else { f0 = (int)((long long)sn * c / n_chunks); f1 = (int)((long long)sn * (c + 1) / n_chunks); }
-            if (f1 > sn) f1 = sn;
-            if (f1 <= f0) continue;
-            const size_t a0 = (size_t)offsets_host[s0 + f0], a1 = (size_t)offsets_host[s0 + f1];
-            CK(cudaMemcpyAsync(d + o_cu + 4 * a0, cur_u_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
-            CK(cudaMemcpyAsync(d + o_cv + 4 * a0, cur_v_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
-            CK(cudaMemcpyAsync(d + o_ru + 4 * a0, ref_u_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
-            CK(cudaMemcpyAsync(d + o_rv + 4 * a0, ref_v_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
-            cudaEvent_t ev = h->ev_copy[launch & 7];
-            // an event slot is reused after eight launches: by then its waiter (two compute streams, in order) has long consumed it
-            CK(cudaEventRecord(ev, sc));
-            cudaStream_t st = h->s_comp[launch & 1];
-            CK(cudaStreamWaitEvent(st, ev, 0));
-            const int g0 = s0 + f0;
-            int rc = mvosr_scale_frames_from_correspondences(h, f1 - f0, (const int32_t *)(d + o_off) + g0, (const float *)(d + o_cu),
-                        (const float *)(d + o_cv), (const float *)(d + o_ru), (const float *)(d + o_rv), nullptr, (const double *)(d + o_pose) + 12 * (size_t)g0,
-                        max_features, f0, seq_id0 + s, seed, (double *)(d + o_raw) + g0, (uint8_t *)(d + o_st) + g0, (int32_t *)(d + o_nf) + g0, nullptr, st);
-            if (rc != MVOSR_OK) return rc;
-            ++launch;
-        }
+    if (tables) {
+        // per-frame (sequence id, frame index inside the sequence): the Philox stream of a frame does not depend on the chunking
+        int32_t *tab = (int32_t *)malloc(8 * (size_t)n_frames);
+        if (!tab) return MVOSR_E_NOMEM;
+        for (int s = 0; s < n_sequences; ++s)
+            for (int f = seq_off[s]; f < seq_off[s + 1]; ++f) { tab[f] = seq_id0 + s; tab[n_frames + f] = f - seq_off[s]; }
+        // (pageable source: the call returns once the data is staged, so the table can be freed right away)
+        cudaError_t e = cudaMemcpyAsync(d + o_tab, tab, 8 * (size_t)n_frames, cudaMemcpyHostToDevice, sc);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sc);
+        free(tab);
+        CK(e);
+    }
+    // about 8 chunks over the whole call, the first one half-sized so that the GPU starts early; at least one frame per SM and chunk
+    int n_chunks = 8;
+    if (n_chunks > n_frames / h->num_sms) n_chunks = n_frames / h->num_sms > 0 ? n_frames / h->num_sms : 1;
+    for (int c = 0; c < n_chunks; ++c) {
+        int f0, f1;
+        if (n_chunks > 1) {
+            f0 = c == 0 ? 0 : (int)((long long)n_frames * (2 * c - 1) / (2 * n_chunks - 1));
+            f1 = (int)((long long)n_frames * (2 * c + 1) / (2 * n_chunks - 1));
+        } else { f0 = 0; f1 = n_frames; }
+        if (f1 > n_frames) f1 = n_frames;
+        if (f1 <= f0) continue;
+        const size_t a0 = (size_t)offsets_host[f0], a1 = (size_t)offsets_host[f1];
+        CK(cudaMemcpyAsync(d + o_cu + 4 * a0, cur_u_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+        CK(cudaMemcpyAsync(d + o_cv + 4 * a0, cur_v_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+        CK(cudaMemcpyAsync(d + o_ru + 4 * a0, ref_u_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+        CK(cudaMemcpyAsync(d + o_rv + 4 * a0, ref_v_host + a0, 4 * (a1 - a0), cudaMemcpyHostToDevice, sc));
+        cudaEvent_t ev = h->ev_copy[c & 7];
+        CK(cudaEventRecord(ev, sc));
+        cudaStream_t st = h->s_comp[c & 1];
+        CK(cudaStreamWaitEvent(st, ev, 0));
+        FrameParams P; memset(&P, 0, sizeof(P));
+        P.n_frames = f1 - f0; P.offsets = (const int32_t *)(d + o_off) + f0;
+        P.cur_u = (const float *)(d + o_cu); P.cur_v = (const float *)(d + o_cv); P.ref_u = (const float *)(d + o_ru); P.ref_v = (const float *)(d + o_rv);
+        P.poses = (const double *)(d + o_pose) + 12 * (size_t)f0;
+        P.mode = MODE_FULL; P.gate = 1; P.seed = seed;
+        if (tables) { P.frame_seq = (const int32_t *)(d + o_tab) + f0; P.frame_index = (const int32_t *)(d + o_tab) + n_frames + f0; }
+        else { P.frame_index0 = f0; P.seq_id = seq_id0; }
+        P.raw_scale = (double *)(d + o_raw) + f0; P.status = (uint8_t *)(d + o_st) + f0; P.n_features = (int32_t *)(d + o_nf) + f0;
+        int rc = launch_frames<true>(h, P, max_features, st);
+        if (rc != MVOSR_OK) return rc;
     }
     // join: the filter runs on compute stream 0 after both compute streams
     CK(cudaEventRecord(h->ev_copy[0], h->s_comp[1]));

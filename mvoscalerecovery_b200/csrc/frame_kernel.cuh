@@ -44,6 +44,10 @@ struct FrameParams {
     int mode;
     int gate;                       // 1: skip frames with n_features <= min_features (main_offline.py:73)
     int frame_index0, seq_id;
+    // shard mode (a frame range that spans sequences, fleet.py): per-frame Philox indices, processing order, packed outputs
+    const int32_t *frame_seq, *frame_index;      // optional [F]: sequence id / frame index inside its sequence (else seq_id, frame_index0 + f)
+    const int32_t *order;                        // optional [F]: work item i processes frame order[i] (largest frames first)
+    mvosr_frame_record *records;                 // optional [F]: (raw_scale, n_features, status) in one 16-byte record per frame
     uint64_t seed;
     mvosr_config cfg;
     double *raw_scale;
@@ -357,8 +361,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         __syncthreads();
         if (tid == 0) ctl.frame = atomicAdd(P.work_counter, 1);
         __syncthreads();
-        const int f = ctl.frame;
-        if (f >= P.n_frames) break;
+        if (ctl.frame >= P.n_frames) break;
+        const int f = P.order ? P.order[ctl.frame] : ctl.frame;
         if (tid == 0) {
             ctl.n_roi = ctl.n_feat = ctl.status = ctl.bad = ctl.n_dup = ctl.n_kept = ctl.T = 0; ctl.n_dup1 = -1;
             ctl.n_exact = ctl.n_deferred_total = 0; ctl.rcount = 0; ctl.n_todo = 0;
@@ -695,7 +699,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                     double nx = 0, ny = 0, nz = 0, dd = 0, n4 = 1;
                     if (h < H) {
                         uint32_t posv[3];
-                        sample3_positions(P.seed, (uint32_t)h, (uint32_t)(P.frame_index0 + f), (uint32_t)P.seq_id, (uint32_t)n_sel,
+                        sample3_positions(P.seed, (uint32_t)h, (uint32_t)(P.frame_index ? P.frame_index[f] : P.frame_index0 + f),
+                                          (uint32_t)(P.frame_seq ? P.frame_seq[f] : P.seq_id), (uint32_t)n_sel,
                                           posv[0], posv[1], posv[2]);
                         int vtx[3];
 #pragma unroll
@@ -822,7 +827,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                     height = (-m_d) / nn;                           // sign already normalised (b >= 0)
                     scale = cfg.absolute_reference / height;
                 }
-                P.raw_scale[f] = scale;
+                if (P.raw_scale) P.raw_scale[f] = scale;
+                if (P.records) P.records[f].raw_scale = scale;
                 if (P.stats) {
                     mvosr_frame_stats &s = P.stats[f];
                     s.model[0] = m_a; s.model[1] = m_b; s.model[2] = m_c; s.model[3] = m_d; s.height = height;
@@ -830,7 +836,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             }
         } else if (P.mode == MODE_FULL) {
             if (tid == 0) {
-                P.raw_scale[f] = CUDART_NAN;
+                if (P.raw_scale) P.raw_scale[f] = CUDART_NAN;
+                if (P.records) P.records[f].raw_scale = CUDART_NAN;
                 if (P.stats) { mvosr_frame_stats &s = P.stats[f]; s.model[0] = s.model[1] = s.model[2] = s.model[3] = CUDART_NAN; s.height = CUDART_NAN; }
             }
         }
@@ -840,6 +847,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         if (tid == 0) {
             if (P.status) P.status[f] = (uint8_t)status;
             if (P.n_features) P.n_features[f] = n_feat;
+            if (P.records) { P.records[f].n_features = n_feat; P.records[f].status = (uint8_t)status; }
             if (P.mode == MODE_DT_ONLY && (status & ~MVOSR_ST_SECOND_DT) && P.n_tri_out) P.n_tri_out[f] = 0;
             if (P.stats) {
                 mvosr_frame_stats &s = P.stats[f];

@@ -73,7 +73,7 @@ def _rodrigues(rx, ry, rz):
 
 def make_frame(seed: int, seq: int, frame: int, n_corr: int, true_scale: float,
                cam: Camera = Camera(), camera_h: float = 1.7, outlier_frac: float = 0.1,
-               upper_frac: float = 0.2, pixel_noise: float = 0.05, z_max: float = 60.0):
+               upper_frac: float = 0.2, pixel_noise: float = 0.05, z_max: float = 60.0, density: str = "uniform"):
     """One frame of correspondences.
 
     Returns (cur_uv (n,2) f32, ref_uv (n,2) f32, R (3,3) f64, t (3,) f64).
@@ -85,6 +85,11 @@ def make_frame(seed: int, seq: int, frame: int, n_corr: int, true_scale: float,
     them are lifted 0.2..1.5 m off the road (kerbs, cars) or given a corrupted
     depth; ``upper_frac`` of all correspondences lie above the horizon (facades)
     and are removed by the ROI cut (src/rescale.py:115).
+
+    ``density``: where the road features fall.  "uniform" -- uniform in the image (bucketed front-end, the default);
+    "ground" -- uniform on the GROUND, X in U(-8, 8) m, Z in U(5, 40) m (SURVEY.md section 8d verbatim): in the image the
+    density grows like 1/(v - cy)^3 towards the horizon; "clustered" -- 70 % of them in 12 Gaussian clusters (textured
+    patches: sigma 30 x 9 px) over a uniform background.
     """
     rng = np.random.Generator(np.random.Philox(key=[seed & 0xFFFFFFFFFFFFFFFF,
                                                     (seq << 32) | (frame & 0xFFFFFFFF)]))
@@ -99,8 +104,29 @@ def make_frame(seed: int, seq: int, frame: int, n_corr: int, true_scale: float,
     # ---- lower (road ROI) points: uniform in the image below the far-depth row
     v_top = cam.cy + cam.fy * h / z_max
     v_top = min(max(v_top, cam.cy + 6.0), cam.height - 40.0)
-    u = rng.uniform(0.0, cam.width - 1.0, size=n_low)
-    v = rng.uniform(v_top, cam.height - 1.0, size=n_low)
+    if density == "uniform":
+        u = rng.uniform(0.0, cam.width - 1.0, size=n_low)
+        v = rng.uniform(v_top, cam.height - 1.0, size=n_low)
+    elif density == "ground":
+        u = np.empty(0); v = np.empty(0)
+        while u.shape[0] < n_low:                               # rejection: keep what projects inside the image below the far row
+            Xg = rng.uniform(-8.0, 8.0, size=2 * n_low) / true_scale
+            Zg = rng.uniform(5.0, 40.0, size=2 * n_low) / true_scale
+            Yg = (h - nrm[0] * Xg - nrm[2] * Zg) / nrm[1]
+            ug, vg = Xg / Zg * cam.fx + cam.cx, Yg / Zg * cam.fy + cam.cy
+            ok = (ug >= 0.0) & (ug <= cam.width - 1.0) & (vg >= v_top) & (vg <= cam.height - 1.0)
+            u, v = np.concatenate([u, ug[ok]]), np.concatenate([v, vg[ok]])
+        u, v = u[:n_low], v[:n_low]
+    elif density == "clustered":
+        n_cl = int(round(0.7 * n_low))
+        cu = rng.uniform(40.0, cam.width - 41.0, size=12)
+        cv = rng.uniform(v_top + 10.0, cam.height - 11.0, size=12)
+        which = rng.integers(0, 12, size=n_cl)
+        u = np.concatenate([cu[which] + 30.0 * rng.standard_normal(n_cl), rng.uniform(0.0, cam.width - 1.0, size=n_low - n_cl)])
+        v = np.concatenate([cv[which] + 9.0 * rng.standard_normal(n_cl), rng.uniform(v_top, cam.height - 1.0, size=n_low - n_cl)])
+        u, v = np.clip(u, 0.0, cam.width - 1.0), np.clip(v, v_top, cam.height - 1.0)
+    else:
+        raise ValueError("density must be 'uniform', 'ground' or 'clustered'")
     rx = (u - cam.cx) / cam.fx
     ry = (v - cam.cy) / cam.fy
     denom = nrm[0] * rx + nrm[1] * ry + nrm[2]
@@ -139,6 +165,13 @@ def make_frame(seed: int, seq: int, frame: int, n_corr: int, true_scale: float,
     return cur.astype(np.float32), ref.astype(np.float32), R, t
 
 
+def sequence_sizes(seed: int, n_frames: int, n_corr: int = 2500, seq: int = 0, n_jitter: float = 0.05) -> np.ndarray:
+    """Correspondences per frame of ``make_sequence(seed, n_frames, n_corr, seq, n_jitter=...)`` without building the frames
+    (still frames aside): what a fleet scheduler needs to balance shards by work before any rank generates its data."""
+    rng = np.random.Generator(np.random.Philox(key=[seed & 0xFFFFFFFFFFFFFFFF, 0xC0FFEE + seq]))
+    return np.maximum(8, np.round(n_corr * (1 + rng.uniform(-n_jitter, n_jitter, n_frames)))).astype(np.int64)
+
+
 def make_sequence(seed: int, n_frames: int, n_corr: int = 2500, seq: int = 0,
                   cam: Camera = Camera(), camera_h: float = 1.7, outlier_frac: float = 0.1,
                   n_jitter: float = 0.05, still_every: int = 0, scales=None, frame_range=None, **kw) -> CorrespondenceBatch:
@@ -149,8 +182,7 @@ def make_sequence(seed: int, n_frames: int, n_corr: int = 2500, seq: int = 0,
     correspondences), the case of src/main_offline.py:64-68.
     """
     scales = true_scale_profile(n_frames, seed, seq) if scales is None else np.asarray(scales, dtype=np.float64)
-    rng = np.random.Generator(np.random.Philox(key=[seed & 0xFFFFFFFFFFFFFFFF, 0xC0FFEE + seq]))
-    sizes = np.maximum(8, np.round(n_corr * (1 + rng.uniform(-n_jitter, n_jitter, n_frames)))).astype(np.int64)
+    sizes = sequence_sizes(seed, n_frames, n_corr, seq, n_jitter)
     move = np.ones(n_frames, dtype=np.uint8)
     if still_every:
         move[still_every - 1::still_every] = 0

@@ -3,12 +3,17 @@
   profiles/traffic.json                     dram bytes of that launch (read by bench.py for roofline.traffic)
   profiles/ncu_r01_frame_kernel_regions.txt instruction / sample shares per source region
   profiles/launches_r01_summary.txt         per-kernel shares of the launch list (profiles/launches_r01.csv)
-usage: python scripts/summarize_profiles.py [report.ncu-rep] [launches.csv]"""
-import collections, csv, json, os, subprocess, sys
+traffic.json also records the warp-instruction count of the launch and the hash of the kernel sources the capture was taken from
+(bench.kernel_source_hash): bench.py refuses the counters when the sources have changed since.
+usage: python scripts/summarize_profiles.py [report.ncu-rep] [launches.csv] [round tag, e.g. r02]"""
+import collections, csv, datetime, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-rep = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "prof_r01_final.ncu-rep")
-launches = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "launches_r01.csv")
+sys.path.insert(0, ROOT)
+import bench                                                            # kernel_source_hash
+RT = sys.argv[3] if len(sys.argv) > 3 else "r02"
+rep = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "prof_%s_final.ncu-rep" % RT)
+launches = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "launches_%s.csv" % RT)
 P = os.path.join(ROOT, "profiles")
 WANT = ['Kernel Name', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'gpu__time_duration.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'launch__block_size', 'launch__grid_size',
@@ -30,16 +35,18 @@ for w in WANT:
 tob = lambda u, v: float(v.replace(',', '')) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}[u]
 r, w = tob(*d['dram__bytes_read.sum']), tob(*d['dram__bytes_write.sum'])
 out.append('traffic %.1f' % (r + w))
-open(os.path.join(P, 'ncu_r01_frame_kernel_bench.txt'), 'w').write('\n'.join(out) + '\n')
+open(os.path.join(P, 'ncu_%s_frame_kernel_bench.txt' % RT), 'w').write('\n'.join(out) + '\n')
 json.dump({'frame_kernel_dram_bytes_per_launch': r + w,
-           'source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, frame_kernel<FROM_CORR> on the bench workload '
-                     '(4541 frames x 2500 correspondences), profiles/ncu_r01_frame_kernel_bench.txt', 'read_bytes': r, 'write_bytes': w},
+           'frame_kernel_warp_instructions_per_launch': float(d['smsp__inst_executed.sum'][1].replace(',', '')),
+           'kernel_source_hash': bench.kernel_source_hash(), 'captured': datetime.date.today().isoformat(),
+           'source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum, frame_kernel<FROM_CORR> on the '
+                     'bench workload (4541 frames x 2500 correspondences), profiles/ncu_%s_frame_kernel_bench.txt' % RT, 'read_bytes': r, 'write_bytes': w},
           open(os.path.join(P, 'traffic.json'), 'w'), indent=1)
 
 lines = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_lines.py"), rep, "frame_kernel", "400"], capture_output=True, text=True).stdout
 open("/tmp/ncu_lines.txt", "w").write(lines)
 reg = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_regions.py"), "/tmp/ncu_lines.txt"], capture_output=True, text=True).stdout
-open(os.path.join(P, 'ncu_r01_frame_kernel_regions.txt'), 'w').write(reg)
+open(os.path.join(P, 'ncu_%s_frame_kernel_regions.txt' % RT), 'w').write(reg)
 
 rows = list(csv.reader(l for l in open(launches) if l.startswith('"')))
 h = rows[0]; ki, vi, ui = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Unit')
@@ -52,7 +59,7 @@ ls = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 80 python be
       "(cold-cache, serialised launches: compare SHARES)", ""]
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     ls.append('%-72s n=%3d  avg %10.1f us  share %5.2f%%' % (k[:72], len(v), sum(v) / len(v), 100 * sum(v) / tot))
-open(os.path.join(P, 'launches_r01_summary.txt'), 'w').write('\n'.join(ls) + '\n')
-if os.path.abspath(launches) != os.path.join(P, 'launches_r01.csv'):
-    open(os.path.join(P, 'launches_r01.csv'), 'w').write(open(launches).read())
+open(os.path.join(P, 'launches_%s_summary.txt' % RT), 'w').write('\n'.join(ls) + '\n')
+if os.path.abspath(launches) != os.path.join(P, 'launches_%s.csv' % RT):
+    open(os.path.join(P, 'launches_%s.csv' % RT), 'w').write(open(launches).read())
 print('\n'.join(out)); print(reg); print('\n'.join(ls[:6]))

@@ -42,4 +42,4 @@ def test_weak_scaling_workload_is_one_sequence_per_rank():
         assert wl["pieces"] == [(rank, 0, 5)] and wl["total_frames"] == 20 and list(wl["seq_off_host"]) == [0, 5, 10, 15, 20]
         ref = synth.make_sequence(seed=bench.SEED, n_frames=5, n_corr=80, seq=rank, outlier_frac=0.10)
         assert np.array_equal(wl["batch"].cur_u, ref.cur_u) and wl["shards"][rank] == (5 * rank, 5 * rank + 5)
-    assert set(bench.WORKLOADS) == {"kitti00", "dense", "fleet"} and sum(bench.KITTI_LENGTHS) == 23201
+    assert {"kitti00", "dense", "fleet", "kitti00-ground", "kitti00-clustered"} <= set(bench.WORKLOADS) and sum(bench.KITTI_LENGTHS) == 23201

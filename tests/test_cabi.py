@@ -25,7 +25,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib, n), "libmvosr.so does not export %s" % n
     assert sorted(N.SYMBOLS) == names, "python binding list and header disagree"
-    assert lib.mvosr_version() == 100
+    assert lib.mvosr_version() == 200
     assert lib.mvosr_error_string(0) == b"ok" and b"capacity" in lib.mvosr_error_string(-4)
 
 

@@ -90,3 +90,53 @@ def test_sharded_essential_estimation_world_size_2_gloo(tmp_path):
     mp.spawn(_essential_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(str(tmp_path), "ess_rank%d" % r)).read() == "ok"
+
+
+def test_slot_map_and_frame_tables():
+    from mvoscalerecovery_b200.fleet import frame_shards, frame_tables, slot_map
+    lens = [7, 3, 1, 9]
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    shards = frame_shards(int(starts[-1]), 3)
+    slot = slot_map(shards)
+    max_len = max(e - s for s, e in shards)
+    assert len(set(slot.tolist())) == int(starts[-1])                              # injective
+    for r, (s, e) in enumerate(shards):
+        assert slot[s:e].tolist() == list(range(r * max_len, r * max_len + e - s))
+    sq, fi = frame_tables(starts, 0, int(starts[-1]))
+    assert sq.tolist() == sum([[s] * n for s, n in enumerate(lens)], []) and fi.tolist() == sum([list(range(n)) for n in lens], [])
+    lo, hi = shards[1]
+    sq1, fi1 = frame_tables(starts, lo, hi)
+    assert np.array_equal(sq1, sq[lo:hi]) and np.array_equal(fi1, fi[lo:hi])       # a frame's stream does not depend on the cut
+
+
+def _record_rank_main(rank, world, port, tmp):
+    """RecordExchange over gloo: every rank writes its records into its block, ONE in-place all-gather, and frame f of the global
+    order is found at slot[f] -- for uneven shards (padded blocks) and even ones."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mvoscalerecovery_b200.fleet import RecordExchange, frame_shards, records_to_numpy
+    ok = True
+    dt = np.dtype([("raw_scale", np.float64), ("n_features", np.int32), ("status", np.uint8), ("pad", np.uint8, (3,))])
+    for total in (23, 24):
+        shards = frame_shards(total, world)
+        s, e = shards[rank]
+        rng = np.random.default_rng(7)
+        allrec = np.zeros(total, dt)
+        allrec["raw_scale"] = rng.uniform(0.5, 1.5, total); allrec["raw_scale"][3] = np.nan
+        allrec["n_features"] = rng.integers(0, 3000, total); allrec["status"] = rng.integers(0, 128, total)
+        ex = RecordExchange(shards, rank, torch.device("cpu"))
+        ex.mine[: e - s] = torch.from_numpy(allrec[s:e].view(np.uint8).reshape(-1, 16).copy())
+        got = records_to_numpy(ex.gather())[ex.slot.numpy()]
+        ok = ok and got.tobytes() == allrec.tobytes()
+    with open(os.path.join(tmp, "rec_rank%d" % rank), "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_record_exchange_world_size_2_gloo(tmp_path):
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_record_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rec_rank%d" % r)).read() == "ok"

@@ -138,6 +138,45 @@ def test_fleet_of_sequences_filter_vs_oracle(engine):
         assert np.array_equal(got10[a:e], P.filter10(ref)), "sequence %d filter_10" % s
 
 
+def test_filter_under_heavy_slewing_vs_oracle(engine):
+    """The slew limiter is run speculatively on the GPU (every lane starts its stretch of frames from a guessed state and the
+    wrong guesses are recomputed): long slewing stretches, held states, sequences around every chunk / lane boundary -- the
+    result must still be the sequential recurrence of rescale.py:168-178, bit for bit."""
+    import torch
+    from oracle import pipeline as P
+    rng = np.random.default_rng(11)
+    lens = [1, 2, 7, 8, 9, 31, 32, 33, 255, 256, 257, 1023, 1024, 1025, 3000, 0, 5000]
+    total = sum(lens)
+    seq_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    raw = 0.9 + 0.05 * rng.standard_normal(total)
+    level = np.cumsum(np.where(rng.random(total) < 0.03, rng.choice([-2.5, 2.5, 4.0, -4.0], size=total), 0.0))      # steps of many x 0.3
+    raw = np.abs(raw + level) + 0.05
+    status = np.where(rng.random(total) < 0.8, 1, 0).astype(np.uint8)
+    raw[status == 0] = np.nan
+    move = (rng.random(total) > 0.05).astype(np.uint8)
+    nfeat = np.where(rng.random(total) < 0.1, 80, 2200).astype(np.int32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(engine.device)
+    out = engine.filter_sequences(t(seq_off), t(raw), t(status), t(move), t(nfeat))
+    torch.cuda.synchronize()
+    got, got10 = out["scale"].cpu().numpy(), out["filter10"].cpu().numpy()
+    for s in range(len(lens)):
+        a, e = seq_off[s], seq_off[s + 1]
+        if a == e:
+            continue
+        stt = P.TemporalState(5)
+        scales = [0.0]
+        for f in range(a, e):
+            if not move[f]:
+                scales.append(0.0)
+            elif nfeat[f] > P.MIN_FEATURES:
+                scales.append(stt.step(raw[f], bool(status[f] & 1)))
+            else:
+                scales.append(scales[-1])
+        ref = np.asarray(scales[1:])
+        assert np.array_equal(got[a:e], ref), "sequence %d (length %d)" % (s, lens[s])
+        assert np.array_equal(got10[a:e], P.filter10(ref)), "sequence %d filter_10" % s
+
+
 def test_host_pipeline_with_large_frames(engine):
     """mvosr_recover_scales_host on frames beyond the shared-memory capacity: the chunks of the host pipeline run on two
     streams but share one global-memory staging buffer, so their launches must be chained; result == the device-resident
