@@ -44,9 +44,11 @@ extern "C" {
 #define MVOSR_ST_SECOND_DT    0x02   /* graph check kept > 10 features -> second Delaunay (rescale.py:133) */
 #define MVOSR_ST_FEW_ROI      0x04   /* < 3 ROI features or all collinear: reference raises QhullError */
 #define MVOSR_ST_NO_MODEL     0x08   /* every hypothesis had 0 inliers: reference crashes in np.matrix(None) */
-#define MVOSR_ST_BAD_INPUT    0x10   /* |u|,|v| >= 4096 or non-finite pixel coordinate in the ROI */
+#define MVOSR_ST_BAD_INPUT    0x10   /* |u|,|v| >= 4096, or a non-finite pixel coordinate or 3-D coordinate in the ROI */
 #define MVOSR_ST_OVERFLOW     0x20   /* frame exceeds the kernel capacity (ROI features or star degree) */
 #define MVOSR_ST_SKIPPED      0x40   /* frame not processed (not moving / too few features, main_offline.py:64,73) */
+#define MVOSR_ST_SINGULAR     0x80   /* a triangle's vertex matrix is singular (plane through the origin): the reference raises
+                                        LinAlgError in np.matrix(...).I (rescale.py:79); no RANSAC, the temporal state is held */
 
 /* ---- configuration (POD). Defaults = the constants hard-coded in the reference. ---- */
 typedef struct mvosr_config {
@@ -150,6 +152,24 @@ int  mvosr_scale_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offset
                         int32_t max_features, int32_t frame_index0, int32_t seq_id, uint64_t seed,
                         double *raw_scale, uint8_t *status, mvosr_frame_stats *stats,
                         const mvosr_debug_buffers *debug, void *stream);
+
+/* The same on the float64 arrays of the reference's own hand-off: feature3d [M][3], feature2d [M][2] (array-of-structures, as numpy
+ * holds what src/main.py:102-113 passes to scale_calculation), CSR by offsets.  The reference computes on these float64 values;
+ * rounding them to float32 first moves a gate in about one frame in ten, which changes N_sel and with it the hypotheses drawn
+ * (tests/test_f64_handoff.py).  Here the ROI cut, the depth-order votes, the planes, the gates and the RANSAC evaluate the float64
+ * values; only the Delaunay triangulations run on the float32 roundings of the pixel coordinates (points that differ only below
+ * float32 resolution count as duplicates). */
+int  mvosr_scale_frames_f64(mvosr_handle *h, int32_t n_frames, const int32_t *offsets, const double *feature3d, const double *feature2d,
+                        int32_t max_features, int32_t frame_index0, int32_t seq_id, uint64_t seed,
+                        double *raw_scale, uint8_t *status, mvosr_frame_stats *stats,
+                        const mvosr_debug_buffers *debug, void *stream);
+
+/* One frame, HOST pointers in and out -- what rescale.ScaleEstimator.scale_calculation(feature3d, feature2d) does per call
+ * (src/main.py:113, src/main_offline.py:75) up to the temporal state: the arrays are copied as they are, one launch of the float64
+ * variant above, one copy back; synchronises.  record_out_host receives (raw_scale, n_features, status); stats_out_host is optional. */
+int  mvosr_scale_frame_host_f64(mvosr_handle *h, int32_t n_features, const double *feature3d_host, const double *feature2d_host,
+                        int32_t frame_index, int32_t seq_id, uint64_t seed,
+                        mvosr_frame_record *record_out_host, mvosr_frame_stats *stats_out_host);
 
 /* Stages 1-5 fused: tracked correspondences + relative poses in, raw scales out; triangulated
  * features never leave the SM.  n_features[f] receives the post-mask feature count (needed by the

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libmvosr.so")
 
 OK = 0
-ST_UPDATED, ST_SECOND_DT, ST_FEW_ROI, ST_NO_MODEL, ST_BAD_INPUT, ST_OVERFLOW, ST_SKIPPED = 1, 2, 4, 8, 16, 32, 64
+ST_UPDATED, ST_SECOND_DT, ST_FEW_ROI, ST_NO_MODEL, ST_BAD_INPUT, ST_OVERFLOW, ST_SKIPPED, ST_SINGULAR = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 class Config(C.Structure):
@@ -57,7 +57,7 @@ SYMBOLS = [
     "mvosr_recover_scales_host", "mvosr_recover_fleet_host", "mvosr_launch_count", "mvosr_set_phase_timing",
     "mvosr_triangle_planes", "mvosr_triangle_votes", "mvosr_ransac_planes", "mvosr_integrate_paths", "mvosr_depth_from_mesh", "mvosr_recover_pose_frames",
     "mvosr_find_essential_frames", "mvosr_pose_mask_frames", "mvosr_bucket_frames",
-    "mvosr_scale_shard_from_correspondences", "mvosr_filter_records",
+    "mvosr_scale_shard_from_correspondences", "mvosr_filter_records", "mvosr_scale_frames_f64", "mvosr_scale_frame_host_f64",
 ]
 
 _lib = None
@@ -94,6 +94,8 @@ def lib():
     L.mvosr_filter_sequences.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.mvosr_scale_shard_from_correspondences.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp, u64, vp, vp]
     L.mvosr_filter_records.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.mvosr_scale_frames_f64.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, u64, vp, vp, vp, C.POINTER(DebugBuffers), vp]
+    L.mvosr_scale_frame_host_f64.argtypes = [vp, i32, vp, vp, i32, i32, u64, C.POINTER(FrameRecord), C.POINTER(FrameStats)]
     L.mvosr_delaunay_frames.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
     L.mvosr_recover_scales_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, u64, vp, vp, vp]
     L.mvosr_recover_fleet_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, u64, vp, vp, vp]

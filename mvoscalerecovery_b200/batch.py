@@ -180,6 +180,48 @@ class ScaleRecovery:
                                                 self._stream()))
         return dict(raw_scale=raw, status=status, stats=st, debug=dbg)
 
+    def scale_frames_f64(self, offsets, feature3d, feature2d, max_features: int, frame_index0: int = 0, seq_id: int = 0,
+                         seed: int = 0, stats: bool = True, debug: bool = False):
+        """scale_frames on the float64 arrays of the reference's own hand-off: feature3d (M,3), feature2d (M,2) float64 CUDA tensors
+        (array-of-structures, numpy's layout), CSR by offsets.  Gates, votes, planes and RANSAC evaluate the float64 values
+        (mvosr_scale_frames_f64)."""
+        dev = self.device
+        F = offsets.numel() - 1
+        _chk(offsets, torch.int32, "offsets", dev)
+        M = feature3d.shape[0]
+        _chk(feature3d, torch.float64, "feature3d", dev, 3 * M)
+        _chk(feature2d, torch.float64, "feature2d", dev, 2 * M)
+        raw = torch.empty(F, dtype=torch.float64, device=dev)
+        status = torch.zeros(F, dtype=torch.uint8, device=dev)
+        st = torch.zeros(F * C.sizeof(N.FrameStats), dtype=torch.uint8, device=dev) if stats else None
+        dbg_struct, dbg = None, {}
+        if debug:
+            dbg = dict(tri1=torch.full((2 * M, 3), -1, dtype=torch.int32, device=dev), n_tri1=torch.zeros(F, dtype=torch.int32, device=dev),
+                       keep=torch.zeros(M, dtype=torch.uint8, device=dev), tri2=torch.full((2 * M, 3), -1, dtype=torch.int32, device=dev),
+                       tri_flags=torch.zeros(2 * M, dtype=torch.uint8, device=dev), tri_height=torch.zeros(2 * M, dtype=torch.float64, device=dev),
+                       inlier=torch.zeros(M, dtype=torch.uint8, device=dev), data_id=torch.full((6 * M,), -1, dtype=torch.int32, device=dev))
+            dbg_struct = N.DebugBuffers(*[dbg[k].data_ptr() for k in ("tri1", "n_tri1", "keep", "tri2", "tri_flags", "tri_height", "inlier", "data_id")])
+        with torch.cuda.device(dev):
+            N.check(self.lib.mvosr_scale_frames_f64(self._h, F, _ptr(offsets), _ptr(feature3d), _ptr(feature2d), int(max_features),
+                                                    int(frame_index0), int(seq_id), C.c_uint64(int(seed)), _ptr(raw), _ptr(status), _ptr(st),
+                                                    C.byref(dbg_struct) if dbg_struct else None, self._stream()))
+        return dict(raw_scale=raw, status=status, stats=st, debug=dbg)
+
+    def scale_frame_host_f64(self, feature3d: np.ndarray, feature2d: np.ndarray, frame_index: int = 0, seq_id: int = 0, seed: int = 0,
+                             stats: bool = True):
+        """One frame, numpy float64 (n,3) / (n,2) in, (raw_scale, status, n_features, stats or None) out: the whole per-frame call
+        of the drop-in in one C-ABI call (mvosr_scale_frame_host_f64).  Synchronises."""
+        n = int(feature3d.shape[0])
+        p3 = _host_array(feature3d, np.float64, "feature3d", 3 * n)
+        p2 = _host_array(feature2d, np.float64, "feature2d", 2 * n)
+        if feature2d.shape[0] != n:
+            raise ValueError("feature3d and feature2d must hold the same number of features")
+        rec = N.FrameRecord()
+        st = N.FrameStats() if stats else None
+        N.check(self.lib.mvosr_scale_frame_host_f64(self._h, n, p3, p2, int(frame_index), int(seq_id), C.c_uint64(int(seed)),
+                                                    C.byref(rec), C.byref(st) if stats else None))
+        return rec.raw_scale, int(rec.status), int(rec.n_features), st
+
     def scale_frames_from_correspondences(self, offsets, cur_u, cur_v, ref_u, ref_v, poses, max_features: int, e_mask=None,
                                           frame_index0: int = 0, seq_id: int = 0, seed: int = 0, stats: bool = False):
         """Stages 1-5 fused (correspondences + poses -> raw scales)."""

@@ -96,14 +96,16 @@ class ScaleEstimator:
     # ---- the GPU path ----------------------------------------------------------------------------
     def _launch(self, feature3d, feature2d, debug):
         import torch
-        from mvoscalerecovery_b200.batch import pack_frames
         eng = _engine(self.absolute_reference, self.vanish)
-        f3 = np.asarray(feature3d, dtype=np.float64).reshape(-1, 3)
-        f2 = np.asarray(feature2d, dtype=np.float64).reshape(-1, 2)
-        b = pack_frames([f3], [f2], eng.device)              # copies: the caller's arrays are never modified
-        out = eng.scale_frames(b["offsets"], b["x"], b["y"], b["z"], b["u"], b["v"], max(b["max_features"], 1),
-                               frame_index0=self.frame_index, seq_id=self.sequence_id, seed=self.seed, stats=True, debug=debug)
-        torch.cuda.synchronize(eng.device)
+        f3 = np.ascontiguousarray(feature3d, dtype=np.float64).reshape(-1, 3)
+        f2 = np.ascontiguousarray(feature2d, dtype=np.float64).reshape(-1, 2)
+        n = f3.shape[0]
+        dev = eng.device
+        off = torch.tensor([0, n], dtype=torch.int32, device=dev)
+        out = eng.scale_frames_f64(off, torch.from_numpy(f3).to(dev), torch.from_numpy(f2).to(dev), max(n, 1),      # device copies: the
+                                   frame_index0=self.frame_index, seq_id=self.sequence_id, seed=self.seed,            # caller's arrays are
+                                   stats=True, debug=debug)                                                           # never modified
+        torch.cuda.synchronize(dev)
         return eng, out
 
     def feature_selection(self, feature3d, feature2d):
@@ -158,12 +160,14 @@ class ScaleEstimator:
         return self.scale, 0
 
     def scale_calculation(self, feature3d, feature2d, img=None):
+        """One C-ABI call per frame (mvosr_scale_frame_host_f64): the caller's float64 arrays are copied as they are -- the ROI cut,
+        the votes, the gates and the RANSAC evaluate the float64 values, as the reference does --, one launch, one copy back."""
         from mvoscalerecovery_b200 import _native as N
-        from mvoscalerecovery_b200.batch import stats_to_numpy
-        _, out = self._launch(feature3d, feature2d, debug=False)
-        status = int(out["status"].cpu().numpy()[0])
-        raw = float(out["raw_scale"].cpu().numpy()[0])
-        self.height_level = float(stats_to_numpy(out["stats"])[0]["height_level"])
+        eng = _engine(self.absolute_reference, self.vanish)
+        f3 = np.ascontiguousarray(feature3d, dtype=np.float64).reshape(-1, 3)        # no copy when the caller passes float64 C arrays
+        f2 = np.ascontiguousarray(feature2d, dtype=np.float64).reshape(-1, 2)
+        raw, status, _, st = eng.scale_frame_host_f64(f3, f2, frame_index=self.frame_index, seq_id=self.sequence_id, seed=self.seed)
+        self.height_level = float(st.height_level)
         self.last_status = status
         self.frame_index += 1
         return self._apply_state(raw, bool(status & N.ST_UPDATED))

@@ -8,44 +8,14 @@
 #include <string.h>
 #include <new>
 
+#include "handle.h"
 #include "frame_kernel.cuh"
 #include "aux_kernels.cuh"
-#include "five_point_kernel.cuh"
 #include "bucket_kernel.cuh"
 
 using namespace mvosr;
 
-static thread_local char g_cuda_err[256] = "";
-
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
-            return MVOSR_E_CUDA;                                                                   \
-        }                                                                                          \
-    } while (0)
-
-static const int NCOUNTERS = 16;
-
-struct mvosr_handle {
-    mvosr_config cfg;
-    int device;
-    int num_sms;
-    int smem_optin;
-    int cap_max;
-    int *work_counter;           // device: NCOUNTERS dynamic-scheduler counters (one per in-flight launch)
-    int counter_slot;            // round-robin
-    cudaStream_t s_copy, s_comp[2]; cudaEvent_t ev_copy[8]; int streams_ready;    // host-buffer pipeline
-    int64_t launches;
-    // host-API staging (grown on demand)
-    void *d_stage; size_t stage_bytes;
-    // large-frame staging (frames beyond the shared-memory capacity): two sets of per-CTA slabs used alternately, so that two
-    // launches in flight (the two compute streams of the host pipeline) never share one; a launch waits for the previous user
-    // of its set through that set's event
-    void *d_ws[2]; size_t ws_bytes[2]; cudaEvent_t ev_ws[2]; int ev_ws_ready[2]; int ws_slot;
-    long long *phase_cycles;     // optional profiling sink (device), set by mvosr_set_phase_timing
-};
+thread_local char g_cuda_err[256] = "";
 
 // -------------------------------------------------------------------------------------------------
 // small kernels
@@ -372,8 +342,9 @@ int mvosr_create(const mvosr_config *cfg, int device, mvosr_handle **out) {
         h->cap_max = cap;
         e = cudaMalloc(&h->work_counter, NCOUNTERS * sizeof(int));
     }
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_kernel<SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_kernel<SRC_CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_kernel<SRC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin - (int)sizeof(Ctl) - 512);
     if (e != cudaSuccess) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "%s in mvosr_create", cudaGetErrorString(e));
         if (h->work_counter) cudaFree(h->work_counter);
@@ -391,6 +362,8 @@ int mvosr_destroy(mvosr_handle *h) {
     cudaSetDevice(h->device);
     if (h->work_counter) cudaFree(h->work_counter);
     if (h->d_stage) cudaFree(h->d_stage);
+    if (h->d_frame) cudaFree(h->d_frame);
+    if (h->h_frame) cudaFreeHost(h->h_frame);
     for (int k = 0; k < 2; ++k) { if (h->d_ws[k]) cudaFree(h->d_ws[k]); if (h->ev_ws_ready[k]) cudaEventDestroy(h->ev_ws[k]); }
     if (h->streams_ready) {
         cudaStreamDestroy(h->s_copy); cudaStreamDestroy(h->s_comp[0]); cudaStreamDestroy(h->s_comp[1]);
@@ -419,7 +392,7 @@ int mvosr_set_phase_timing(mvosr_handle *h, int64_t *phase_cycles_device) {
 // largest capacity the 16-bit indices of the frame kernel allow (triangle blocks are addressed below 2*cap < 65536)
 static const int CAP_LIMIT = 32704;
 
-template <bool FROM_CORR>
+template <int SRC>
 static int launch_frames(mvosr_handle *h, FrameParams &P, int max_features, cudaStream_t st) {
     if (P.n_frames <= 0) return MVOSR_OK;
     int cap = (max_features + 63) / 64 * 64;
@@ -452,7 +425,7 @@ static int launch_frames(mvosr_handle *h, FrameParams &P, int max_features, cuda
         else CK(cudaStreamWaitEvent(st, h->ev_ws[ws], 0));
     }
     CK(cudaMemsetAsync(P.work_counter, 0, sizeof(int), st));
-    frame_kernel<FROM_CORR><<<grid, NT, dyn, st>>>(P);
+    frame_kernel<SRC><<<grid, NT, dyn, st>>>(P);
     CK(cudaGetLastError());
     if (ws >= 0) CK(cudaEventRecord(h->ev_ws[ws], st));
     h->launches += 1;
@@ -492,7 +465,63 @@ int mvosr_scale_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets
     P.frame_index0 = frame_index0; P.seq_id = seq_id; P.seed = seed;
     P.raw_scale = raw_scale; P.status = status; P.stats = stats;
     if (debug) { P.dbg = *debug; P.has_dbg = 1; }
-    return launch_frames<false>(h, P, max_features, (cudaStream_t)stream);
+    return launch_frames<SRC_F32>(h, P, max_features, (cudaStream_t)stream);
+}
+
+int mvosr_scale_frames_f64(mvosr_handle *h, int32_t n_frames, const int32_t *offsets, const double *feature3d, const double *feature2d,
+                           int32_t max_features, int32_t frame_index0, int32_t seq_id, uint64_t seed,
+                           double *raw_scale, uint8_t *status, mvosr_frame_stats *stats, const mvosr_debug_buffers *debug, void *stream) {
+    if (!h || n_frames < 0 || !offsets || !feature3d || !feature2d || !raw_scale || !status || max_features < 0) return MVOSR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    FrameParams P; memset(&P, 0, sizeof(P));
+    P.n_frames = n_frames; P.offsets = offsets; P.f3d = feature3d; P.f2d = feature2d;
+    P.mode = MODE_FULL; P.gate = 0;
+    P.frame_index0 = frame_index0; P.seq_id = seq_id; P.seed = seed;
+    P.raw_scale = raw_scale; P.status = status; P.stats = stats;
+    if (debug) { P.dbg = *debug; P.has_dbg = 1; }
+    return launch_frames<SRC_F64>(h, P, max_features, (cudaStream_t)stream);
+}
+
+// One frame from host memory, the call behind the per-frame drop-in (compat/rescale.py): the two numpy arrays go to the device
+// as they are (one copy each through a pinned staging buffer), one launch, and ONE small copy back (stats + record).
+int mvosr_scale_frame_host_f64(mvosr_handle *h, int32_t n_features, const double *feature3d_host, const double *feature2d_host,
+                               int32_t frame_index, int32_t seq_id, uint64_t seed,
+                               mvosr_frame_record *record_out_host, mvosr_frame_stats *stats_out_host) {
+    if (!h || n_features < 0 || (n_features > 0 && (!feature3d_host || !feature2d_host)) || !record_out_host) return MVOSR_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)n_features;
+    // device staging: [offsets 2 x int32 | pad][record 16][stats][f3 3n doubles][f2 2n doubles]; the same layout pinned on the host
+    const size_t o_rec = 16, o_stats = 32, o_f3 = 32 + ((sizeof(mvosr_frame_stats) + 15) & ~(size_t)15), o_f2 = o_f3 + 24 * n, total = o_f2 + 16 * n;
+    if (total > h->frame_bytes) {
+        CK(cudaDeviceSynchronize());
+        if (h->d_frame) cudaFree(h->d_frame);
+        if (h->h_frame) cudaFreeHost(h->h_frame);
+        h->d_frame = nullptr; h->h_frame = nullptr; h->frame_bytes = 0;
+        const size_t cap = total + total / 2 + 4096;
+        if (cudaMalloc(&h->d_frame, cap) != cudaSuccess) { cudaGetLastError(); return MVOSR_E_NOMEM; }
+        if (cudaMallocHost(&h->h_frame, cap) != cudaSuccess) { cudaGetLastError(); cudaFree(h->d_frame); h->d_frame = nullptr; return MVOSR_E_NOMEM; }
+        h->frame_bytes = cap;
+    }
+    if (!h->s_frame_ready) { CK(cudaStreamCreateWithFlags(&h->s_frame, cudaStreamNonBlocking)); h->s_frame_ready = 1; }
+    char *hp = (char *)h->h_frame, *dp = (char *)h->d_frame;
+    int32_t *off = (int32_t *)hp; off[0] = 0; off[1] = n_features;
+    memcpy(hp + o_f3, feature3d_host, 24 * n);
+    memcpy(hp + o_f2, feature2d_host, 16 * n);
+    cudaStream_t st = h->s_frame;
+    CK(cudaMemcpyAsync(dp, hp, 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dp + o_f3, hp + o_f3, 40 * n, cudaMemcpyHostToDevice, st));
+    FrameParams P; memset(&P, 0, sizeof(P));
+    P.n_frames = 1; P.offsets = (const int32_t *)dp; P.f3d = (const double *)(dp + o_f3); P.f2d = (const double *)(dp + o_f2);
+    P.mode = MODE_FULL; P.gate = 0;
+    P.frame_index0 = frame_index; P.seq_id = seq_id; P.seed = seed;
+    P.records = (mvosr_frame_record *)(dp + o_rec); P.stats = (mvosr_frame_stats *)(dp + o_stats);
+    int rc = launch_frames<SRC_F64>(h, P, n_features > 0 ? n_features : 1, st);
+    if (rc != MVOSR_OK) return rc;
+    CK(cudaMemcpyAsync(hp + o_rec, dp + o_rec, o_f3 - o_rec, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(record_out_host, hp + o_rec, sizeof(mvosr_frame_record));
+    if (stats_out_host) memcpy(stats_out_host, hp + o_stats, sizeof(mvosr_frame_stats));
+    return MVOSR_OK;
 }
 
 int mvosr_scale_frames_from_correspondences(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
@@ -509,7 +538,7 @@ int mvosr_scale_frames_from_correspondences(mvosr_handle *h, int32_t n_frames, c
     P.mode = MODE_FULL; P.gate = 1;
     P.frame_index0 = frame_index0; P.seq_id = seq_id; P.seed = seed;
     P.raw_scale = raw_scale; P.status = status; P.n_features = n_features; P.stats = stats;
-    return launch_frames<true>(h, P, max_features, (cudaStream_t)stream);
+    return launch_frames<SRC_CORR>(h, P, max_features, (cudaStream_t)stream);
 }
 
 int mvosr_delaunay_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets, const float *u, const float *v,
@@ -520,7 +549,7 @@ int mvosr_delaunay_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offs
     P.n_frames = n_frames; P.offsets = offsets; P.u = u; P.v = v;
     P.mode = MODE_DT_ONLY;
     P.tri_out = tri; P.n_tri_out = n_tri; P.status = status;
-    return launch_frames<false>(h, P, max_features, (cudaStream_t)stream);
+    return launch_frames<SRC_F32>(h, P, max_features, (cudaStream_t)stream);
 }
 
 int mvosr_filter_sequences(mvosr_handle *h, int32_t n_sequences, const int32_t *seq_offsets,
@@ -565,7 +594,7 @@ int mvosr_scale_shard_from_correspondences(mvosr_handle *h, int32_t n_frames, co
     P.mode = MODE_FULL; P.gate = 1;
     P.frame_seq = frame_seq; P.frame_index = frame_index; P.frame_index0 = frame_index0; P.seq_id = seq_id; P.order = order; P.seed = seed;
     P.records = records;
-    return launch_frames<true>(h, P, max_features, (cudaStream_t)stream);
+    return launch_frames<SRC_CORR>(h, P, max_features, (cudaStream_t)stream);
 }
 
 // Host-buffer pipeline shared by the two _host entry points: S sequences (frame ranges seq_off[0..S], Philox sequence ids
@@ -649,7 +678,7 @@ static int recover_host(mvosr_handle *h, int32_t n_frames, const int32_t *offset
         if (tables) { P.frame_seq = (const int32_t *)(d + o_tab) + f0; P.frame_index = (const int32_t *)(d + o_tab) + n_frames + f0; }
         else { P.frame_index0 = f0; P.seq_id = seq_id0; }
         P.raw_scale = (double *)(d + o_raw) + f0; P.status = (uint8_t *)(d + o_st) + f0; P.n_features = (int32_t *)(d + o_nf) + f0;
-        int rc = launch_frames<true>(h, P, max_features, st);
+        int rc = launch_frames<SRC_CORR>(h, P, max_features, st);
         if (rc != MVOSR_OK) return rc;
     }
     // join: the filter runs on compute stream 0 after both compute streams
@@ -802,23 +831,6 @@ int mvosr_pose_mask_frames(mvosr_handle *h, int32_t n_frames, const int32_t *off
     if (n_frames == 0) return MVOSR_OK;
     CK(cudaSetDevice(h->device));
     pose_mask_kernel<<<min(n_frames, 8 * h->num_sms), 256, 0, (cudaStream_t)stream>>>(n_frames, offsets, cur_u, cur_v, ref_u, ref_v, e_mask, poses, h->cfg, mask_out);
-    CK(cudaGetLastError());
-    h->launches += 1;
-    return MVOSR_OK;
-}
-
-int mvosr_find_essential_frames(mvosr_handle *h, int32_t n_frames, const int32_t *offsets,
-                                const float *cur_u, const float *cur_v, const float *ref_u, const float *ref_v,
-                                int32_t hypotheses, double threshold_px, double confidence, uint64_t seed, const int32_t *frame_index, int32_t seq_id,
-                                double *essential, uint8_t *e_mask_out, int32_t *n_inliers, int32_t *best_hyp, int32_t *hyps_used, void *stream) {
-    if (!h || n_frames < 0 || !offsets || !cur_u || !cur_v || !ref_u || !ref_v || !essential || hypotheses < 1 || hypotheses > (1 << 24) ||
-        !(threshold_px > 0.0) || !(confidence >= 0.0))
-        return MVOSR_E_INVALID;
-    if (n_frames == 0) return MVOSR_OK;
-    CK(cudaSetDevice(h->device));
-    const int grid = min(n_frames, 16 * h->num_sms);
-    find_essential_kernel<<<grid, FP5_THREADS, 0, (cudaStream_t)stream>>>(n_frames, offsets, cur_u, cur_v, ref_u, ref_v,
-        h->cfg.fx, h->cfg.fy, h->cfg.cx, h->cfg.cy, hypotheses, threshold_px, confidence, seed, frame_index, seq_id, essential, e_mask_out, n_inliers, best_hyp, hyps_used);
     CK(cudaGetLastError());
     h->launches += 1;
     return MVOSR_OK;

@@ -29,6 +29,9 @@
 namespace mvosr {
 
 enum { MODE_FULL = 0, MODE_DT_ONLY = 1 };
+// where a frame's features come from: float32 structure-of-arrays (x,y,z,u,v), tracked correspondences + pose (stage 1 fused), or
+// the float64 arrays of the reference's own hand-off -- feature3d (n,3) / feature2d (n,2) as numpy holds them (src/main.py:102-113)
+enum { SRC_F32 = 0, SRC_CORR = 1, SRC_F64 = 2 };
 
 struct FrameParams {
     int n_frames;
@@ -36,7 +39,11 @@ struct FrameParams {
     const int32_t *counts;          // optional
     // triangulated features (FROM_CORR == false)
     const float *x, *y, *z, *u, *v;
-    // correspondences (FROM_CORR == true)
+    // float64 features, array-of-structures (SRC_F64): f3d[M][3], f2d[M][2].  The Delaunay runs on the float32 roundings of the
+    // pixel coordinates; the ROI cut, the depth-order votes (ties of the roundings resolved in float64), the planes, the gates
+    // and the RANSAC evaluate the float64 values, as the reference does.
+    const double *f3d, *f2d;
+    // correspondences (SRC_CORR)
     const float *cur_u, *cur_v, *ref_u, *ref_v;
     const uint8_t *e_mask;
     const double *poses;
@@ -97,7 +104,7 @@ __host__ __device__ inline SmemPlan make_plan(int cap) {   // cap: multiple of 6
 
 struct Ctl {                         // static shared control block
     StarCtl sc;
-    int n_roi, n_feat, status, bad, n_dup, n_dup1, n_kept, T, n_exact, n_deferred_total, rcount, n_todo;
+    int n_roi, n_feat, status, bad, singular, n_dup, n_dup1, n_kept, T, n_exact, n_deferred_total, rcount, n_todo;
     int n_loose, n_tight, n_valid, best_hyp, best_ic, hyps_used, n_degenerate;
     int warp_cnt[NWARP], warp_cnt2[NWARP];
     float red[4][NWARP];
@@ -325,8 +332,9 @@ __device__ __forceinline__ unsigned long long block_select_next(const double *h,
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool FROM_CORR>
+template <int SRC>
 __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
+    constexpr bool FROM_CORR = SRC == SRC_CORR, F64 = SRC == SRC_F64;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ Ctl ctl;
     // frames beyond the shared-memory capacity are staged in a per-CTA slab of global memory (L2-resident): same code
@@ -348,6 +356,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
     fv.Z = Z; fv.pflag = pflag; fv.tri = (uint16_t *)(smem + pl.off_T);
     fv.tbase = (uint16_t *)(smem + pl.off_tbase); fv.tcnt = smem + pl.off_tcnt;
     fv.T = &ctl.T; fv.status = &ctl.status; fv.pass_mask = P.cfg.graph_pass_mask; fv.tri_cap = 2 * cap;
+    fv.f3d = nullptr; fv.f2d = nullptr; fv.srcidx = nullptr;
+    uint32_t *const SRCI = (uint32_t *)X;                        // SRC_F64: X's storage holds the feature's index in the frame's float64 arrays (X, Y unused)
     fv.rpool = nullptr; fv.rinfo = (uint32_t *)(smem + pl.off_rinfo); fv.rcount = &ctl.rcount; fv.rpool_cap = 6 * cap; fv.oldof = nullptr;
     uint16_t *const inv = (uint16_t *)(smem + pl.off_scr), *const oldof = inv + cap;     // new index -> sorted position / old index (scr is free between the grid build and the planes)
     uint16_t *const rpool = (uint16_t *)(smem + pl.off_rpool);
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         if (ctl.frame >= P.n_frames) break;
         const int f = P.order ? P.order[ctl.frame] : ctl.frame;
         if (tid == 0) {
-            ctl.n_roi = ctl.n_feat = ctl.status = ctl.bad = ctl.n_dup = ctl.n_kept = ctl.T = 0; ctl.n_dup1 = -1;
+            ctl.n_roi = ctl.n_feat = ctl.status = ctl.bad = ctl.singular = ctl.n_dup = ctl.n_kept = ctl.T = 0; ctl.n_dup1 = -1;
             ctl.n_exact = ctl.n_deferred_total = 0; ctl.rcount = 0; ctl.n_todo = 0;
             ctl.n_loose = ctl.n_tight = ctl.n_valid = 0; ctl.best_hyp = -1; ctl.best_ic = 0; ctl.hyps_used = 0;
             ctl.n_degenerate = 0; ctl.height_level = CUDART_NAN;
@@ -376,6 +386,12 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         __syncthreads();
         const int base = P.offsets[f];
         const int n_in = P.counts ? P.counts[f] : (P.offsets[f + 1] - base);
+        if (F64) { fv.f3d = P.f3d; fv.f2d = P.f2d; fv.srcidx = SRCI; fv.fbase = base; }
+        // feature i of the staged frame as float64 (x, y, z): the staged float32 values, or the caller's float64 ones
+        auto point3 = [&](int i, double &px, double &py, double &pz) {
+            if (F64) { const double *q = P.f3d + 3 * ((size_t)base + SRCI[i]); px = q[0]; py = q[1]; pz = q[2]; }
+            else { px = X[i]; py = Y[i]; pz = Z[i]; }
+        };
 
         // ---------------- load + (stage 1) + ROI cut, order preserving ----------------
         Pose pose;
@@ -396,12 +412,24 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                                              cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.triangulation_max_depth, X3, Y3, Z3, uu, vv);
                     if (P.e_mask) feat = feat && P.e_mask[base + i] != 0;
                     fx3 = (float)X3; fy3 = (float)Y3; fz3 = (float)Z3; fu = (float)uu; fv_ = (float)vv;
+                } else if (F64) {
+                    feat = true;
+                    const double v64 = P.f2d[2 * (size_t)(base + i) + 1];
+                    ok = v64 > (double)cfg.vanish;                  // the ROI cut on the float64 value (rescale.py:115)
+                    fv_ = (float)v64;
+                    if (ok) {
+                        fu = (float)P.f2d[2 * (size_t)(base + i)];
+                        const double *p3 = P.f3d + 3 * (size_t)(base + i);
+                        fz3 = (float)p3[2];
+                        if (!isfinite(p3[0]) || !isfinite(p3[1]) || !isfinite(p3[2])) ctl.bad = 1;
+                        fx3 = __uint_as_float((unsigned)i);          // -> SRCI
+                    }
                 } else {
                     feat = true;
                     fv_ = P.v[base + i];
                 }
-                ok = feat && (P.mode == MODE_DT_ONLY || fv_ > cfg.vanish);
-                if (ok && !FROM_CORR) {
+                if (!F64) ok = feat && (P.mode == MODE_DT_ONLY || fv_ > cfg.vanish);
+                if (ok && SRC == SRC_F32) {
                     fu = P.u[base + i];
                     if (P.mode != MODE_DT_ONLY) { fx3 = P.x[base + i]; fy3 = P.y[base + i]; fz3 = P.z[base + i]; }
                 }
@@ -415,6 +443,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             if (ok) {
                 int pos = total + woff + __popc(bal & ((1u << lane) - 1u));
                 if (!(fabsf(fu) < 4096.f) || !(fabsf(fv_) < 4096.f)) ctl.bad = 1;
+                if (!F64 && P.mode != MODE_DT_ONLY && !(isfinite(fx3) && isfinite(fy3) && isfinite(fz3))) ctl.bad = 1;   // NaN / inf depth
                 if (fabsf(fu) < 7.62939453125e-06f) fu = 0.f;       // 2^-17: keeps every difference exact in float64
                 if (fabsf(fv_) < 7.62939453125e-06f) fv_ = 0.f;
                 if (pos < cap) { U[pos] = fu; V[pos] = fv_; X[pos] = fx3; Y[pos] = fy3; Z[pos] = fz3; pflag[pos] = 0; }
@@ -618,12 +647,14 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             int c_loose = 0, c_tight = 0;
             for (int t = tid; t < T; t += NT) {
                 int i0 = fv.tri[3 * t], i1 = fv.tri[3 * t + 1], i2 = fv.tri[3 * t + 2];
-                double p0x = X[i0], p0y = Y[i0], p0z = Z[i0];
-                double e1x = (double)X[i1] - p0x, e1y = (double)Y[i1] - p0y, e1z = (double)Z[i1] - p0z;
-                double e2x = (double)X[i2] - p0x, e2y = (double)Y[i2] - p0y, e2z = (double)Z[i2] - p0z;
+                double p0x, p0y, p0z, p1x, p1y, p1z, p2x, p2y, p2z;
+                point3(i0, p0x, p0y, p0z); point3(i1, p1x, p1y, p1z); point3(i2, p2x, p2y, p2z);
+                double e1x = p1x - p0x, e1y = p1y - p0y, e1z = p1z - p0z;
+                double e2x = p2x - p0x, e2y = p2y - p0y, e2z = p2z - p0z;
                 // n = P^-1 . 1 = (e1 x e2) / (p0 . (e1 x e2))
                 double cx = e1y * e2z - e1z * e2y, cy = e1z * e2x - e1x * e2z, cz = e1x * e2y - e1y * e2x;
                 double det = p0x * cx + p0y * cy + p0z * cz;
+                if (det == 0.0) ctl.singular = 1;                 // the reference's np.matrix(...).I raises LinAlgError (rescale.py:79)
                 double clen = sqrt(cx * cx + cy * cy + cz * cz);
                 double hgt = fabs(det) / clen;                     // 1/|n|
                 double s = -(det < 0 ? -cy : cy) / clen;          // -n_y/|n| = sin(pitch)
@@ -639,6 +670,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             }
             if (lane == 0) { atomicAdd(&ctl.n_loose, c_loose); atomicAdd(&ctl.n_tight, c_tight); }
             __syncthreads();
+            if (ctl.singular) status |= MVOSR_ST_SINGULAR;
             TMARK(10);
             const int n_loose = ctl.n_loose;
             // height_level = 0.9 * median(height[loose])  (np.median: mean of the two middle values for even counts)
@@ -688,7 +720,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
             // sequential bookkeeping of run_ransac over that round's counts (keep the first strictly larger ic,
             // stop at the first ic > goal), so the result is the one the sequential loop returns.
             double m_a = CUDART_NAN, m_b = CUDART_NAN, m_c = CUDART_NAN, m_d = CUDART_NAN;
-            if (n_sel >= cfg.min_selected) {
+            if (n_sel >= cfg.min_selected && !(status & MVOSR_ST_SINGULAR)) {
                 const double goal = (double)n_sel * cfg.ransac_goal_fraction;
                 const int H = cfg.ransac_iterations;
                 int h_done = 0, best = -1, best_ic = 0, ndeg = 0, used = 0;
@@ -716,9 +748,10 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                         }
                         int ic = 0;
                         bool degenerate = (vtx[0] == vtx[1]) || (vtx[0] == vtx[2]) || (vtx[1] == vtx[2]);
-                        double p0x = X[vtx[0]], p0y = Y[vtx[0]], p0z = Z[vtx[0]];
-                        double e1x = (double)X[vtx[1]] - p0x, e1y = (double)Y[vtx[1]] - p0y, e1z = (double)Z[vtx[1]] - p0z;
-                        double e2x = (double)X[vtx[2]] - p0x, e2y = (double)Y[vtx[2]] - p0y, e2z = (double)Z[vtx[2]] - p0z;
+                        double p0x, p0y, p0z, p1x, p1y, p1z, p2x, p2y, p2z;
+                        point3(vtx[0], p0x, p0y, p0z); point3(vtx[1], p1x, p1y, p1z); point3(vtx[2], p2x, p2y, p2z);
+                        double e1x = p1x - p0x, e1y = p1y - p0y, e1z = p1z - p0z;
+                        double e2x = p2x - p0x, e2y = p2y - p0y, e2z = p2z - p0z;
                         // null vector of [p 1] (3x4) in closed form: (n, -n.p0), n = e1 x e2 (estimate_road_norm.py:13-15)
                         nx = e1y * e2z - e1z * e2y; ny = e1z * e2x - e1x * e2z; nz = e1x * e2y - e1y * e2x;
                         dd = -(nx * p0x + ny * p0y + nz * p0z);
@@ -730,8 +763,10 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                             for (int q = lane; q < n; q += 64) {
                                 const int q2 = q + 32 < n ? q + 32 : q;
                                 const int w0 = mult[q], w1 = q + 32 < n ? mult[q2] : 0;
-                                const double r0 = nx * (double)X[q] + ny * (double)Y[q] + nz * (double)Z[q] + dd;
-                                const double r1 = nx * (double)X[q2] + ny * (double)Y[q2] + nz * (double)Z[q2] + dd;
+                                double ax, ay, az, bx, by, bz;
+                                point3(q, ax, ay, az); point3(q2, bx, by, bz);
+                                const double r0 = nx * ax + ny * ay + nz * az + dd;
+                                const double r1 = nx * bx + ny * by + nz * bz + dd;
                                 ic += (fabs(r0) < thr ? w0 : 0) + (fabs(r1) < thr ? w1 : 0);
                             }
 #pragma unroll
@@ -773,7 +808,9 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                     if (P.has_dbg && P.dbg.inlier) {
                         const double thr = cfg.ransac_threshold * b_n4;
                         for (int q = tid; q < n; q += NT) {
-                            double r = b_nx * (double)X[q] + b_ny * (double)Y[q] + b_nz * (double)Z[q] + b_dd;
+                            double qx, qy, qz;
+                            point3(q, qx, qy, qz);
+                            double r = b_nx * qx + b_ny * qy + b_nz * qz + b_dd;
                             P.dbg.inlier[base + q] = (mult[q] && fabs(r) < thr) ? 1 : 0;
                         }
                     }

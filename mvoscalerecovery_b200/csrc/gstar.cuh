@@ -92,20 +92,26 @@ struct FrameView {
     // seeds (emit pass of Delaunay #2): oldof[new feature index] = index in Delaunay #1; the rings of the stars to rebuild have
     // been rewritten as sorted positions of the new grid, RING_DROPPED marking the neighbours the graph check removed
     const uint16_t *oldof;
+    // float64 inputs (SRC_F64 of the frame kernel): the votes compare the float32 roundings (rounding is monotone, so an order seen
+    // in float32 is the order of the float64 values) and fall back to the float64 values of feature o -- f2d[2*(fbase+srcidx[o])+1],
+    // f3d[3*(fbase+srcidx[o])+2] -- when two roundings tie.  NULL: float32 inputs.
+    const double *f3d, *f2d; const uint32_t *srcidx; int fbase;
 };
 constexpr uint16_t RING_DROPPED = 0xFFFE;
 
-__device__ __forceinline__ bool edge_consistent(float va, float za, float vb, float zb) {
+template <typename T>
+__device__ __forceinline__ bool edge_consistent(T va, T za, T vb, T zb) {
     // check_triangle (graph.py:124-129): (v_a - v_b) * (d_a - d_b) < 0 in float64 on float32-exact values --
     // the product of two exact non-zero differences cannot underflow, so the sign rule is exact
     return (va < vb && za > zb) || (va > vb && za < zb);
 }
 
 // graph vote (graph.py:131-145) of triangle (p,a,b) for vertex p; vertices ordered by feature index
-__device__ __forceinline__ bool graph_vote(int op, float vp, float zp, int oa, float va, float za, int ob, float vb, float zb,
+template <typename T>
+__device__ __forceinline__ bool graph_vote(int op, T vp, T zp, int oa, T va, T za, int ob, T vb, T zb,
                                            uint32_t pass_mask) {
-    int i0 = op, i1 = oa, i2 = ob; float v0 = vp, v1 = va, v2 = vb, z0 = zp, z1 = za, z2 = zb;
-#define MVOSR_SWAP(A, B, C, D, E, F) { int ti = A; A = B; B = ti; float tf = C; C = D; D = tf; tf = E; E = F; F = tf; }
+    int i0 = op, i1 = oa, i2 = ob; T v0 = vp, v1 = va, v2 = vb, z0 = zp, z1 = za, z2 = zb;
+#define MVOSR_SWAP(A, B, C, D, E, F) { int ti = A; A = B; B = ti; T tf = C; C = D; D = tf; tf = E; E = F; F = tf; }
     if (i0 > i1) MVOSR_SWAP(i0, i1, v0, v1, z0, z1)
     if (i1 > i2) MVOSR_SWAP(i1, i2, v1, v2, z1, z2)
     if (i0 > i1) MVOSR_SWAP(i0, i1, v0, v1, z0, z1)
@@ -116,6 +122,18 @@ __device__ __forceinline__ bool graph_vote(int op, float vp, float zp, int oa, f
     return (pass_mask >> (idx * 3 + k)) & 1u;
 }
 
+// the vote of star triangle (p, sid, nid) (sorted positions) for p
+__device__ __forceinline__ bool graph_vote_at(const SortedSet &ps, const FrameView &fv, int p, int sid, int nid) {
+    const int op = ps.orig[p], oa = ps.orig[sid], ob = ps.orig[nid];
+    const float vp = ps.y[p], va = ps.y[sid], vb = ps.y[nid], zp = fv.Z[op], za = fv.Z[oa], zb = fv.Z[ob];
+    if (fv.f3d && (vp == va || vp == vb || va == vb || zp == za || zp == zb || za == zb)) {
+        const size_t ip = (size_t)fv.fbase + fv.srcidx[op], ia = (size_t)fv.fbase + fv.srcidx[oa], ib = (size_t)fv.fbase + fv.srcidx[ob];
+        return graph_vote<double>(op, fv.f2d[2 * ip + 1], fv.f3d[3 * ip + 2], oa, fv.f2d[2 * ia + 1], fv.f3d[3 * ia + 2],
+                                  ob, fv.f2d[2 * ib + 1], fv.f3d[3 * ib + 2], fv.pass_mask);
+    }
+    return graph_vote<float>(op, vp, zp, oa, va, za, ob, vb, zb, fv.pass_mask);
+}
+
 // keep = (#incident triangles with p>0.6)/(#incident) > 0.5 (graph.py:33-35,131-132); 0/0 -> False
 template <int W>
 __device__ __forceinline__ void consume_vote(unsigned mask, int gl, int d, int p, int sid, int nid,
@@ -123,10 +141,7 @@ __device__ __forceinline__ void consume_vote(unsigned mask, int gl, int d, int p
     const bool tri = gl < d && sid != INF16 && nid != INF16;
     bool vote = false;
     const int op = ps.orig[p];
-    if (tri) {
-        int oa = ps.orig[sid], ob = ps.orig[nid];
-        vote = graph_vote(op, ps.y[p], fv.Z[op], oa, ps.y[sid], fv.Z[oa], ob, ps.y[nid], fv.Z[ob], fv.pass_mask);
-    }
+    if (tri) vote = graph_vote_at(ps, fv, p, sid, nid);
     unsigned bt = __ballot_sync(mask, tri) & mask, bv = __ballot_sync(mask, vote) & mask;
     if (gl == 0 && 2 * __popc(bv) > __popc(bt)) fv.pflag[op] |= 2;
     if (fv.rpool && d > 0) {
@@ -1188,9 +1203,8 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
         } else {
             bool vote = false; int oa_ring = INF16;
             if (tri) {
-                const int oa = ps.orig[sid], ob = ps.orig[nid];
-                oa_ring = oa;
-                vote = graph_vote(op, ps.y[p], fv.Z[op], oa, ps.y[sid], fv.Z[oa], ob, ps.y[nid], fv.Z[ob], fv.pass_mask);
+                oa_ring = ps.orig[sid];
+                vote = graph_vote_at(ps, fv, p, sid, nid);
             }
             const unsigned bt = GBALLOT(tri), bv = GBALLOT(vote);
             if (gl == 0 && d > 0 && 2 * __popc(bv) > __popc(bt)) fv.pflag[op] |= 2;

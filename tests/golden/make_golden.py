@@ -100,7 +100,38 @@ def pack_sequence(name, b, store_stage1_frames=()):
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), "scales[:5] =", scales[:5])
 
 
+def pack_unrounded(name, b):
+    """The reference on the float64 values its own front-end hands over (cv2.recoverPose's output and main.py:102-104's
+    reprojection, NOT rounded to float32): what a caller of the per-frame drop-in actually passes.  The CUDA path stages
+    float32; this golden quantifies what that rounding changes (tests/test_f64_handoff.py)."""
+    ns = H.load_reference(seed=SEED)
+    f3s, f2s = [], []
+    for f in range(b.n_frames):
+        a, e = b.offsets[f], b.offsets[f + 1]
+        cur = np.stack([b.cur_u[a:e], b.cur_v[a:e]], 1)
+        ref = np.stack([b.ref_u[a:e], b.ref_v[a:e]], 1)
+        P = b.poses[f].reshape(3, 4)
+        _, _, mask, X = reference_stage1(cur, ref, P[:, :3], P[:, 3])
+        Xm = X[mask]
+        uv = Xm[:, 0:2].copy()
+        uv[:, 0] = uv[:, 0] * CAM.fx / Xm[:, 2] + CAM.cx
+        uv[:, 1] = uv[:, 1] * CAM.fx / Xm[:, 2] + CAM.cy
+        f3s.append(Xm); f2s.append(uv)
+    scales, recs = H.run_offline_loop(ns, f3s, f2s, b.move_flags, absolute_reference=1.7, window_size=5, seq=0)
+    out = dict(seed=np.uint64(SEED), n_frames=np.int32(b.n_frames), scales=scales)
+    for f in range(b.n_frames):
+        r = recs[f]
+        out["f%d_f3" % f] = f3s[f]; out["f%d_f2" % f] = f2s[f]                    # float64
+        out["f%d_scalars" % f] = np.array([r["raw_scale"], r["best_ic"], r["data_id"].shape[0], int(r["keep"].sum()), r["tri2"].shape[0],
+                                           r["height_level"], r["scale_out"]])
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), "scales[:5] =", scales[:5])
+
+
 def main():
+    # G0: the unrounded float64 hand-off (8 frames of the headline shape)
+    pack_unrounded("seq_f64", synth.make_sequence(seed=404, n_frames=8, n_corr=2500, outlier_frac=0.10))
     # G1: the headline shape -- ~2.5k correspondences / ~2k ROI features per frame, 10 % outliers
     b = synth.make_sequence(seed=101, n_frames=10, n_corr=2500, outlier_frac=0.10)
     pack_sequence("seq_2k", b, store_stage1_frames=(0, 5))

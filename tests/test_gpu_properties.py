@@ -285,7 +285,7 @@ def test_hostile_frames_are_flagged_and_do_not_disturb_their_neighbours(engine):
     st = out["status"].cpu().numpy(); raw = out["raw_scale"].cpu().numpy()
     assert st[0] & N.ST_UPDATED and st[3] & N.ST_UPDATED and st[10] & N.ST_UPDATED
     assert st[1] & N.ST_BAD_INPUT and st[2] & N.ST_BAD_INPUT and np.isnan(raw[1]) and np.isnan(raw[2])
-    assert not (st[4] & N.ST_UPDATED) or np.isfinite(raw[4])                # non-finite depths: gates fail or a finite model, never a crash
+    assert st[4] & N.ST_BAD_INPUT and not (st[4] & N.ST_UPDATED) and np.isnan(raw[4])       # non-finite 3-D coordinates in the ROI: flagged, state held
     for f in (5, 6, 7, 8, 9):
         assert st[f] & N.ST_FEW_ROI and np.isnan(raw[f]), (f, st[f])
     # the good frames alone, same frame indices for the hypothesis stream
@@ -293,6 +293,17 @@ def test_hostile_frames_are_flagged_and_do_not_disturb_their_neighbours(engine):
         bb = pack_frames([a3], [a2], engine.device)
         o = engine.scale_frames(bb["offsets"], bb["x"], bb["y"], bb["z"], bb["u"], bb["v"], bb["max_features"], frame_index0=f, seed=4)
         assert float(o["raw_scale"].cpu().numpy()[0]) == raw[f] and int(o["status"].cpu().numpy()[0]) == st[f]
+    # features on a plane THROUGH the camera centre (Y = Z / 4, dyadic coordinates: every product below is exact): every triangle's
+    # vertex matrix is singular, the reference raises LinAlgError in np.matrix(P).I (rescale.py:79) -> MVOSR_ST_SINGULAR, no
+    # RANSAC, NaN raw scale, state held.  Depth falls strictly with the pixel row, so the graph check keeps everything.
+    k = np.arange(40)
+    Zs = 50.0 - 0.5 * k
+    s3 = np.stack([np.where(k % 2 == 0, 1.0, -2.0) * (1 + k % 5), Zs / 4, Zs], 1).astype(np.float32)
+    s2 = np.stack([(37.0 * k * k + 11.0 * k) % 1200.0 + 10.0, 200.0 + 3.0 * k], 1).astype(np.float32)
+    bb = pack_frames([s3], [s2], engine.device)
+    o = engine.scale_frames(bb["offsets"], bb["x"], bb["y"], bb["z"], bb["u"], bb["v"], bb["max_features"], seed=4)
+    so = int(o["status"].cpu().numpy()[0])
+    assert so & N.ST_SINGULAR and not (so & N.ST_UPDATED) and np.isnan(float(o["raw_scale"].cpu().numpy()[0])), so
     # the filter holds its state over flagged frames (reference: uncaught exception -> undefined; here: hold)
     seq = torch.tensor([0, len(f3)], dtype=torch.int32, device=engine.device)
     nf = torch.tensor([a.shape[0] for a in f3], dtype=torch.int32, device=engine.device)

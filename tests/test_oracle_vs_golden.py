@@ -85,6 +85,11 @@ def test_oracle_intermediates_equal_reference(golden):
             assert rec["ic"] == sc["best_ic"]
             np.testing.assert_allclose(rec["height"], sc["height"], rtol=1e-9)
             np.testing.assert_allclose(rec["raw_scale"], sc["raw_scale"], rtol=1e-9)
+            # the returned model's inlier set over the vertex list == the reference's own is_inlier (estimate_road_norm.py:17-18)
+            ref_inl = np.unpackbits(g.get(f, "inlier"))[: rec["n_sel"]].astype(bool)
+            aug = np.hstack([rec["point_selected"], np.ones((rec["n_sel"], 1))])
+            assert np.array_equal(np.abs(aug @ rec["model"]) < 0.005, ref_inl), "frame %d inlier set" % f
+            assert int(ref_inl.sum()) == sc["best_ic"]
         n += 1
     assert n > 0
 
