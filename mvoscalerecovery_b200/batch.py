@@ -63,6 +63,8 @@ class ScaleRecovery:
         cfg = N.default_config()
         if "grid_density" in config:            # tuning knob of the Delaunay stage: mean points per grid cell (reserved[0] = x100)
             cfg.reserved[0] = int(round(100 * float(config.pop("grid_density"))))
+        if "window_factor" in config:           # tuning knob of the strip index: half-width of the candidate window in cell sides (reserved[1] = x100)
+            cfg.reserved[1] = int(round(100 * float(config.pop("window_factor"))))
         for k, v in config.items():
             if not hasattr(cfg, k):
                 raise TypeError("unknown config field %r" % k)

@@ -22,7 +22,11 @@
 #include <stdint.h>
 #include <math_constants.h>
 #include "../../include/mvosr.h"
-#include "gstar.cuh"
+#ifdef MVOSR_UNIFORM_GRID
+#include "gstar.cuh"            // round-1 spatial index: uniform grid tuned to image-uniform features
+#else
+#include "gstrip.cuh"           // density-adaptive strips (round 2)
+#endif
 #include "philox.cuh"
 #include "triangulate.cuh"
 
@@ -158,7 +162,8 @@ __device__ __forceinline__ void block_excl_scan(uint32_t *a, int n, int *warp_tm
 // ---------------------------------------------------------------------------------------------
 struct GridArrays { float *sx, *sy; uint16_t *sorig, *cell_start; uint32_t *scr; };
 
-__device__ __forceinline__ void build_grid(int n, const float *U, const float *V, uint8_t *pflag, GridArrays ga, int cap, Ctl *ctl, float density) {
+#ifdef MVOSR_UNIFORM_GRID
+__device__ __forceinline__ void build_grid(int n, const float *U, const float *V, uint8_t *pflag, GridArrays ga, int cap, Ctl *ctl, float density, uint16_t *, int, float) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float xmn = CUDART_INF_F, xmx = -CUDART_INF_F, ymn = CUDART_INF_F, ymx = -CUDART_INF_F;
     for (int i = tid; i < n; i += NT) {
@@ -244,6 +249,127 @@ __device__ __forceinline__ void build_grid(int n, const float *U, const float *V
     }
     __syncthreads();
 }
+
+#else
+// Strip build (gstrip.cuh): y-histogram with the x-extent of every bin -> strips grown until count x height >= k x extent ->
+// every strip cut into uniform sub-cells of about two points -> counting sort by (strip, sub-cell) -> rank sort by (x, feature
+// index) inside each sub-cell -> exact duplicates become holes in place.
+// tmp: 2 cap uint16 of scratch (the sorted feature list, then the sub-cell starts).  scr: cap + 4 uint32.
+__device__ __forceinline__ void build_grid(int n, const float *U, const float *V, uint8_t *pflag, GridArrays ga, int cap, Ctl *ctl, float density,
+                                           uint16_t *tmp, int win_m, float wfac) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float xmn = CUDART_INF_F, xmx = -CUDART_INF_F, ymn = CUDART_INF_F, ymx = -CUDART_INF_F;
+    for (int i = tid; i < n; i += NT) {
+        float a = U[i], b = V[i];
+        xmn = fminf(xmn, a); xmx = fmaxf(xmx, a); ymn = fminf(ymn, b); ymx = fmaxf(ymx, b);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        xmn = fminf(xmn, __shfl_xor_sync(0xFFFFFFFFu, xmn, o)); xmx = fmaxf(xmx, __shfl_xor_sync(0xFFFFFFFFu, xmx, o));
+        ymn = fminf(ymn, __shfl_xor_sync(0xFFFFFFFFu, ymn, o)); ymx = fmaxf(ymx, __shfl_xor_sync(0xFFFFFFFFu, ymx, o));
+    }
+    if (lane == 0) { ctl->red[0][warp] = xmn; ctl->red[1][warp] = xmx; ctl->red[2][warp] = ymn; ctl->red[3][warp] = ymx; }
+    __syncthreads();
+    const int NB = min(256, cap / 8);
+    uint16_t *row_start = ga.cell_start, *row_bin = row_start + (NB + 1), *bin_row = row_bin + (NB + 1);
+    uint32_t *cnt = ga.scr, *bxmin = cnt + NB + 1, *bxmax = bxmin + NB + 1, *cc = bxmax + NB + 1;      // cc: sub-cell counters, <= cap/2 + NB + 1 entries
+    // per strip, written over the histogram as it is consumed (strip r <= its first bin): first sub-cell, x origin, 1 / sub-cell width
+    int *rowoff = (int *)cnt; float *rowx0 = (float *)bxmin, *rowinv = (float *)bxmax;
+    uint16_t *cstart = tmp + cap;                                 // sub-cell starts (the counters serve as cursors during the scatter)
+    if (warp == 0) {
+        const int wl = lane < NWARP ? lane : 0;
+        xmn = ctl->red[0][wl]; xmx = ctl->red[1][wl]; ymn = ctl->red[2][wl]; ymx = ctl->red[3][wl];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            xmn = fminf(xmn, __shfl_xor_sync(0xFFFFFFFFu, xmn, o)); xmx = fmaxf(xmx, __shfl_xor_sync(0xFFFFFFFFu, xmx, o));
+            ymn = fminf(ymn, __shfl_xor_sync(0xFFFFFFFFu, ymn, o)); ymx = fmaxf(ymx, __shfl_xor_sync(0xFFFFFFFFu, ymx, o));
+        }
+        if (lane == 0) {
+            SortedSet &ps = ctl->ps;
+            float bh = (ymx - ymn) / (float)NB;
+            if (!(bh > 0.f)) bh = 1.f;                             // all points on one horizontal line: one bin, one strip
+            ps.x = ga.sx; ps.y = ga.sy; ps.orig = ga.sorig; ps.row_start = row_start; ps.row_bin = row_bin; ps.bin_row = bin_row;
+            ps.n = n; ps.NB = NB; ps.R = 0; ps.win_m = win_m; ps.kdens = density; ps.wfac = wfac;
+            ps.xmin = xmn; ps.xmax = xmx; ps.ymin = ymn; ps.bh = bh; ps.inv_bh = 1.f / bh;
+        }
+    }
+    for (int i = tid; i < NB; i += NT) { cnt[i] = 0; bxmin[i] = 0xFFFFFFFFu; bxmax[i] = 0u; }
+    __syncthreads();
+    const SortedSet &ps = ctl->ps;
+    for (int i = tid; i < n; i += NT) {
+        const int b = bin_of(ps, V[i]);
+        const unsigned kx = fkey(U[i]);
+        atomicAdd(&cnt[b], 1u); atomicMin(&bxmin[b], kx); atomicMax(&bxmax[b], kx);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // a strip is closed once a cell of `density` points would be at least as tall as it is wide: count x height >= k x extent
+        const float Lmin = 0.2f * (ps.xmax - ps.xmin);
+        int R = 0, b = 0, ncell = 0;
+        while (b < NB) {
+            const int start = b;
+            unsigned c = 0, klo = 0xFFFFFFFFu, khi = 0u;
+            float need;
+            do {
+                c += cnt[b]; klo = min(klo, bxmin[b]); khi = max(khi, bxmax[b]); ++b;
+                const float L = c ? fmaxf(funkey(khi) - funkey(klo), Lmin) : Lmin;
+                need = density * L - (float)c * ((float)(b - start) * ps.bh);
+            } while (b < NB && need > 0.f);
+            row_bin[R] = (uint16_t)start;
+            for (int q = start; q < b; ++q) bin_row[q] = (uint16_t)R;
+            const int nc = (int)(c >> 1) + 1;                      // sub-cells of about two points
+            const float x0 = funkey(klo), ext = funkey(khi) - x0;
+            rowoff[R] = ncell; rowx0[R] = x0; rowinv[R] = ext > 0.f ? (float)nc / ext : 0.f;
+            ncell += nc;
+            ++R;
+        }
+        row_bin[R] = (uint16_t)NB; rowoff[R] = ncell;
+        ctl->ps.R = R;
+    }
+    __syncthreads();
+    const int R = ps.R, NC = rowoff[R];
+    // sub-cell of a point: strips in order, sub-cells left to right inside a strip
+    auto subcell = [&](float x, float y) {
+        const int r = bin_row[bin_of(ps, y)];
+        const int nc = rowoff[r + 1] - rowoff[r];
+        int c = (int)((x - rowx0[r]) * rowinv[r]);
+        c = c < 0 ? 0 : (c >= nc ? nc - 1 : c);
+        return rowoff[r] + c;
+    };
+    for (int i = tid; i <= NC; i += NT) cc[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) atomicAdd(&cc[subcell(U[i], V[i])], 1u);
+    __syncthreads();
+    block_excl_scan(cc, NC, ctl->warp_cnt);
+    for (int i = tid; i <= NC; i += NT) cstart[i] = (uint16_t)cc[i];
+    for (int r = tid; r <= R; r += NT) row_start[r] = (uint16_t)cc[rowoff[r]];
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) tmp[atomicAdd(&cc[subcell(U[i], V[i])], 1u)] = (uint16_t)i;
+    __syncthreads();
+    for (int a = tid; a < n; a += NT) {
+        const int i = tmp[a];
+        const float xi = U[i], yi = V[i];
+        const int sc = subcell(xi, yi), b0 = cstart[sc], e0 = cstart[sc + 1];
+        int rank = 0;
+        for (int j = b0; j < e0; ++j) { const int q = tmp[j]; const float xq = U[q]; rank += (xq < xi) || (xq == xi && q < i); }
+        ga.sorig[b0 + rank] = (uint16_t)i; ga.sx[b0 + rank] = xi; ga.sy[b0 + rank] = yi;
+    }
+    __syncthreads();
+    // exact duplicates (same strip, equal x: adjacent up to other points of that x): all but the lowest index become holes
+    // (Qhull drops duplicates too, into .coplanar)
+    for (int a = tid; a < n; a += NT) {
+        const int b0 = row_start[bin_row[bin_of(ps, ga.sy[a])]];
+        bool dup = false;
+        for (int c = a - 1; c >= b0 && ga.sx[c] == ga.sx[a]; --c) if (ga.sy[c] == ga.sy[a]) { dup = true; break; }
+        tmp[a] = dup;
+    }
+    __syncthreads();
+    int ndup = 0;
+    for (int a = tid; a < n; a += NT) if (tmp[a]) { pflag[ga.sorig[a]] |= 1; ga.sorig[a] = INF16; ++ndup; }
+    if (ndup) atomicAdd(&ctl->n_dup, ndup);
+    __syncthreads();
+}
+#endif
 
 // write this frame's triangle list to global memory in canonical order
 __device__ __forceinline__ void write_canonical(int n, const FrameView &fv, uint32_t *scr, int *warp_tmp,
@@ -364,6 +490,12 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
     uint16_t *const todo = (uint16_t *)(smem + pl.off_tflags);   // list of the stars Delaunay #2 must rebuild (tflags is free until the planes)
     const mvosr_config &cfg = P.cfg;
     const float density = cfg.reserved[0] > 0 ? 0.01f * (float)cfg.reserved[0] : GRID_DENSITY;     // tuning knob: mean points per grid cell x 100
+#ifdef MVOSR_UNIFORM_GRID
+    const int win_m = 0; const float wfac = 0.f;
+#else
+    const int win_m = WIN_M;
+    const float wfac = cfg.reserved[1] > 0 ? 0.01f * (float)cfg.reserved[1] : WIN_FACTOR;            // tuning knob: half-width of the candidate window in cell sides x 100
+#endif
 
     long long tlast = 0;
 #define TMARK(k) do { if (tid == 0) { long long tn_ = clock64(); ctl.tphase[k] += tn_ - tlast; tlast = tn_; } } while (0)
@@ -465,7 +597,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
         int n_exact = 0;
         if (!status) {
             // ---------------- Delaunay #1 -> graph vote (or triangles in DT-only mode) ----------------
-            build_grid(n, U, V, pflag, ga, cap, &ctl, density);
+            build_grid(n, U, V, pflag, ga, cap, &ctl, density, defer, win_m, wfac);
             TMARK(1);
             if (P.mode == MODE_DT_ONLY) {
                 for (int i = tid; i < n; i += NT) { fv.tcnt[i] = 0; fv.tbase[i] = 0; }
@@ -535,7 +667,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 for (int i = tid; i < n; i += NT) pflag[i] = 0;
                 if (tid == 0) { ctl.n_dup1 = ctl.n_dup; ctl.n_dup = 0; }
                 __syncthreads();
-                build_grid(n, U, V, pflag, ga, cap, &ctl, density);
+                build_grid(n, U, V, pflag, ga, cap, &ctl, density, defer, win_m, wfac);
             } else {
                 for (int i = tid; i < n; i += NT) pflag[i] &= 1;
                 __syncthreads();
@@ -610,7 +742,11 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 __syncthreads();
                 // the stars to rebuild, as sorted positions, hull rows first (see stars_pair)
                 const SortedSet &ps = ctl.ps;
+#ifdef MVOSR_UNIFORM_GRID
                 const int rot = ps.cell_start[(ps.gy - 1) * ps.gx];
+#else
+                const int rot = ps.row_start[ps.R - 1];
+#endif
                 int run = 0;
                 for (int c0 = 0; c0 < n; c0 += NT) {
                     const int j = c0 + tid;

@@ -13,8 +13,8 @@ os.makedirs(tmp, exist_ok=True)
 for f in os.listdir(tmp):
     os.remove(os.path.join(tmp, f))
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL)
-cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+dis = "\n".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+                for f in sorted(os.listdir(tmp)) if f.endswith(".cubin"))          # one cubin per translation unit
 cur_f, cur_line, table = None, None, collections.defaultdict(list)
 norm = lambda t: re.sub(r"\s+", " ", re.sub(r"`\([^)]*\)|0x[0-9a-f]+", "#", t.strip().rstrip(";"))).strip()
 for ln in dis.splitlines():

@@ -2,17 +2,19 @@
 import re, collections, sys, os
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = open(sys.argv[1]).read()
-lines = open(os.path.join(root, 'mvoscalerecovery_b200/csrc/gstar.cuh')).read().splitlines()
-def find(pat):
-    for i,l in enumerate(lines):
-        if pat in l: return i+1
-    raise KeyError(pat)
+GS = sys.argv[2] if len(sys.argv) > 2 else 'gstrip.cuh'          # the spatial-index header the build used (gstrip.cuh, or gstar.cuh with -DMVOSR_UNIFORM_GRID)
+lines = open(os.path.join(root, 'mvoscalerecovery_b200/csrc', GS)).read().splitlines()
+def find(*pats):
+    for pat in pats:
+        for i,l in enumerate(lines):
+            if pat in l: return i+1
+    raise KeyError(pats)
 marks = {
  'consume': (find('struct FrameView'), find('// exact conflict of candidate')),
  'group path+fallback': (find('// exact conflict of candidate'), find('// wrap path: one warp per star')),
  'w_eval/key/circle': (find('struct WEval'), find('// One batch of candidates (one per lane)')),
- 'w_batch': (find('// One batch of candidates (one per lane)'), find('// Stream the grid cells that the left cap')),
- 'w_stream': (find('// Stream the grid cells that the left cap'), find('// The stars of list[0..n_list) (sorted positions), one per warp')),
+ 'w_batch': (find('// One batch of candidates (one per lane)'), find('// Stream the grid cells that the left cap', '// Stream the strips')),
+ 'w_stream': (find('// Stream the grid cells that the left cap', '// Stream the strips'), find('// The stars of list[0..n_list) (sorted positions), one per warp')),
  'wrap:fetch+load': (find('// The stars of list[0..n_list) (sorted positions), one per warp'), find('// ---- one step of the walk')),
  'wrap:step': (find('// ---- one step of the walk'), find('// ---- the star: lane i keeps')),
  'wrap:seeded walk': (find('// ---- the star: lane i keeps'), find('// ---- q0 = the nearest point')),
@@ -28,7 +30,7 @@ for l in out.splitlines():
     if not m: continue
     f, ln, s, w = m.group(1), int(m.group(2)), float(m.group(3)), float(m.group(4))
     key = f
-    if f == 'gstar.cuh':
+    if f == GS:
         key = 'gstar:other'
         for k,(a,b) in marks.items():
             if a <= ln < b: key = k

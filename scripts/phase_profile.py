@@ -17,10 +17,12 @@ NAMES = {0: "load+stage1+roi", 1: "grid1", 2: "stars1", 3: "stars1_pair", 6: "ke
 def main():
     n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 592
     n_corr = int(sys.argv[2]) if len(sys.argv) > 2 else 2500
-    b = synth.make_sequence(seed=20261017, n_frames=n_frames, n_corr=n_corr, outlier_frac=0.10)
+    b = synth.make_sequence(seed=20261017, n_frames=n_frames, n_corr=n_corr, outlier_frac=0.10, **({'density': os.environ['MVOSR_DATA']} if os.environ.get('MVOSR_DATA') else {}))
     kw = {}
     if os.environ.get('MVOSR_DENSITY'):
         kw['grid_density'] = float(os.environ['MVOSR_DENSITY'])
+    if os.environ.get('MVOSR_WFAC'):
+        kw['window_factor'] = float(os.environ['MVOSR_WFAC'])
     eng = ScaleRecovery(absolute_reference=1.7, **kw)
     dev = eng.device
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
