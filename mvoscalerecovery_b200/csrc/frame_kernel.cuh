@@ -254,7 +254,7 @@ __device__ __forceinline__ void build_grid(int n, const float *U, const float *V
 // Strip build (gstrip.cuh): y-histogram with the x-extent of every bin -> strips grown until count x height >= k x extent ->
 // every strip cut into uniform sub-cells of about two points -> counting sort by (strip, sub-cell) -> rank sort by (x, feature
 // index) inside each sub-cell -> exact duplicates become holes in place.
-// tmp: 2 cap uint16 of scratch (the sorted feature list, then the sub-cell starts).  scr: cap + 4 uint32.
+// tmp: cap uint16 of scratch (the feature list in sub-cell order).  scr: cap + 4 uint32.
 __device__ __forceinline__ void build_grid(int n, const float *U, const float *V, uint8_t *pflag, GridArrays ga, int cap, Ctl *ctl, float density,
                                            uint16_t *tmp, int win_m, float wfac) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -270,12 +270,12 @@ __device__ __forceinline__ void build_grid(int n, const float *U, const float *V
     }
     if (lane == 0) { ctl->red[0][warp] = xmn; ctl->red[1][warp] = xmx; ctl->red[2][warp] = ymn; ctl->red[3][warp] = ymx; }
     __syncthreads();
-    const int NB = min(256, cap / 8);
-    uint16_t *row_start = ga.cell_start, *row_bin = row_start + (NB + 1), *bin_row = row_bin + (NB + 1);
-    uint32_t *cnt = ga.scr, *bxmin = cnt + NB + 1, *bxmax = bxmin + NB + 1, *cc = bxmax + NB + 1;      // cc: sub-cell counters, <= cap/2 + NB + 1 entries
-    // per strip, written over the histogram as it is consumed (strip r <= its first bin): first sub-cell, x origin, 1 / sub-cell width
-    int *rowoff = (int *)cnt; float *rowx0 = (float *)bxmin, *rowinv = (float *)bxmax;
-    uint16_t *cstart = tmp + cap;                                 // sub-cell starts (the counters serve as cursors during the scatter)
+    // tables kept with the sorted set (2 cap bytes at h_cell_start): row_start, row_bin, bin_row, row_cell, row_xi, cell_start
+    const int NB = max(1, min(128, (cap - 32) / 18));
+    uint16_t *row_start = ga.cell_start, *row_bin = row_start + (NB + 1), *bin_row = row_bin + (NB + 1), *rowoff = bin_row + NB;
+    float2 *rowxi = (float2 *)(((uintptr_t)(rowoff + (NB + 1)) + 7) & ~(uintptr_t)7);
+    uint16_t *cstart = (uint16_t *)(rowxi + NB);                  // <= cap / 2 + NB + 1 entries
+    uint32_t *cnt = ga.scr, *bxmin = cnt + NB, *bxmax = bxmin + NB, *cc = bxmax + NB;      // cc: sub-cell counters / cursors
     if (warp == 0) {
         const int wl = lane < NWARP ? lane : 0;
         xmn = ctl->red[0][wl]; xmx = ctl->red[1][wl]; ymn = ctl->red[2][wl]; ymx = ctl->red[3][wl];
@@ -289,6 +289,7 @@ __device__ __forceinline__ void build_grid(int n, const float *U, const float *V
             float bh = (ymx - ymn) / (float)NB;
             if (!(bh > 0.f)) bh = 1.f;                             // all points on one horizontal line: one bin, one strip
             ps.x = ga.sx; ps.y = ga.sy; ps.orig = ga.sorig; ps.row_start = row_start; ps.row_bin = row_bin; ps.bin_row = bin_row;
+            ps.row_cell = rowoff; ps.row_xi = rowxi; ps.cell_start = cstart;
             ps.n = n; ps.NB = NB; ps.R = 0; ps.win_m = win_m; ps.kdens = density; ps.wfac = wfac;
             ps.xmin = xmn; ps.xmax = xmx; ps.ymin = ymn; ps.bh = bh; ps.inv_bh = 1.f / bh;
         }
@@ -302,39 +303,45 @@ __device__ __forceinline__ void build_grid(int n, const float *U, const float *V
         atomicAdd(&cnt[b], 1u); atomicMin(&bxmin[b], kx); atomicMax(&bxmax[b], kx);
     }
     __syncthreads();
-    if (tid == 0) {
-        // a strip is closed once a cell of `density` points would be at least as tall as it is wide: count x height >= k x extent
+    if (warp == 0) {
+        // A strip is closed once a cell of `density` points would be at least as tall as it is wide: count x height >= k x extent.
+        // One warp grows the strips: lane l looks at "the strip ends with bin b + l" (running count / x-extent by warp scans).
+        const unsigned FULL = 0xFFFFFFFFu;
         const float Lmin = 0.2f * (ps.xmax - ps.xmin);
-        int R = 0, b = 0, ncell = 0;
+        int R = 0, b = 0, start = 0, ncell = 0;
+        unsigned c0 = 0, lo0 = 0xFFFFFFFFu, hi0 = 0u;              // carried over when a strip is longer than 32 bins
         while (b < NB) {
-            const int start = b;
-            unsigned c = 0, klo = 0xFFFFFFFFu, khi = 0u;
-            float need;
-            do {
-                c += cnt[b]; klo = min(klo, bxmin[b]); khi = max(khi, bxmax[b]); ++b;
-                const float L = c ? fmaxf(funkey(khi) - funkey(klo), Lmin) : Lmin;
-                need = density * L - (float)c * ((float)(b - start) * ps.bh);
-            } while (b < NB && need > 0.f);
-            row_bin[R] = (uint16_t)start;
-            for (int q = start; q < b; ++q) bin_row[q] = (uint16_t)R;
-            const int nc = (int)(c >> 1) + 1;                      // sub-cells of about two points
-            const float x0 = funkey(klo), ext = funkey(khi) - x0;
-            rowoff[R] = ncell; rowx0[R] = x0; rowinv[R] = ext > 0.f ? (float)nc / ext : 0.f;
-            ncell += nc;
-            ++R;
+            const int idx = b + lane; const bool in = idx < NB;
+            unsigned c = in ? cnt[idx] : 0u, lo = in ? bxmin[idx] : 0xFFFFFFFFu, hi = in ? bxmax[idx] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned uc = __shfl_up_sync(FULL, c, o), ul = __shfl_up_sync(FULL, lo, o), uh = __shfl_up_sync(FULL, hi, o);
+                if (lane >= o) { c += uc; lo = min(lo, ul); hi = max(hi, uh); }
+            }
+            c += c0; lo = min(lo, lo0); hi = max(hi, hi0);
+            const float L = c ? fmaxf(funkey(hi) - funkey(lo), Lmin) : Lmin;
+            const bool stop = in && (idx == NB - 1 || !(density * L - (float)c * ((float)(idx + 1 - start) * ps.bh) > 0.f));
+            const unsigned sm = __ballot_sync(FULL, stop);
+            if (!sm) { c0 = __shfl_sync(FULL, c, 31); lo0 = __shfl_sync(FULL, lo, 31); hi0 = __shfl_sync(FULL, hi, 31); b += 32; continue; }
+            const int e = __ffs(sm) - 1, end = b + e;            // the strip is bins start .. end
+            const unsigned cs = __shfl_sync(FULL, c, e), klo = __shfl_sync(FULL, lo, e), khi = __shfl_sync(FULL, hi, e);
+            for (int q = start + lane; q <= end; q += 32) bin_row[q] = (uint16_t)R;
+            if (lane == 0) {
+                const int nc = (int)(cs >> 1) + 1;                 // sub-cells of about two points
+                const float x0 = funkey(klo), ext = funkey(khi) - x0;
+                row_bin[R] = (uint16_t)start; rowoff[R] = (uint16_t)ncell; rowxi[R] = make_float2(x0, ext > 0.f ? (float)nc / ext : 0.f);
+            }
+            ncell += (int)(cs >> 1) + 1;
+            ++R; b = end + 1; start = b; c0 = 0; lo0 = 0xFFFFFFFFu; hi0 = 0u;
         }
-        row_bin[R] = (uint16_t)NB; rowoff[R] = ncell;
-        ctl->ps.R = R;
+        if (lane == 0) { row_bin[R] = (uint16_t)NB; rowoff[R] = (uint16_t)ncell; ctl->ps.R = R; }
     }
     __syncthreads();
     const int R = ps.R, NC = rowoff[R];
     // sub-cell of a point: strips in order, sub-cells left to right inside a strip
     auto subcell = [&](float x, float y) {
         const int r = bin_row[bin_of(ps, y)];
-        const int nc = rowoff[r + 1] - rowoff[r];
-        int c = (int)((x - rowx0[r]) * rowinv[r]);
-        c = c < 0 ? 0 : (c >= nc ? nc - 1 : c);
-        return rowoff[r] + c;
+        return rowoff[r] + strip_cell(rowxi[r], rowoff[r + 1] - rowoff[r], x);
     };
     for (int i = tid; i <= NC; i += NT) cc[i] = 0;
     __syncthreads();

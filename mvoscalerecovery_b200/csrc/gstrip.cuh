@@ -73,6 +73,11 @@ struct SortedSet {
     const uint16_t *row_start;           // [R+1] first entry of every strip
     const uint16_t *row_bin;             // [R+1] first histogram bin of every strip
     const uint16_t *bin_row;             // [NB] strip of every bin
+    // every strip is cut into uniform sub-cells of about two points (the unit of the counting sort that built it): the first
+    // position with x >= v is found in the sub-cell of v, cell_start[row_cell[r] + (int)((v - x0) * inv)], x0 / inv = row_xi[r]
+    const uint16_t *row_cell;            // [R+1] first sub-cell of every strip
+    const float2 *row_xi;                // [R] (x origin, 1 / sub-cell width) of every strip
+    const uint16_t *cell_start;          // [row_cell[R]+1] first entry of every sub-cell
     int n, R, NB, win_m;
     float xmin, xmax, ymin, bh, inv_bh, kdens, wfac;
 };
@@ -97,6 +102,21 @@ __device__ __forceinline__ int lower_x(const float *x, int b, int e, float v) {
 __device__ __forceinline__ int upper_x(const float *x, int b, int e, float v) {
     while (b < e) { const int m = (b + e) >> 1; if (x[m] <= v) b = m + 1; else e = m; }
     return b;
+}
+
+// sub-cell of x in a strip of nc sub-cells (monotone in x: the float product and the truncation are)
+__device__ __forceinline__ int strip_cell(float2 xi, int nc, float x) {
+    const int c = (int)((x - xi.x) * xi.y);                      // (the conversion saturates; NaN -> 0)
+    return c < 0 ? 0 : (c >= nc ? nc - 1 : c);
+}
+// first position of strip `row` whose x is >= v (row_lower) / > v (row_upper)
+__device__ __forceinline__ int row_lower(const SortedSet &ps, int row, float v) {
+    const int o = ps.row_cell[row], c = o + strip_cell(ps.row_xi[row], ps.row_cell[row + 1] - o, v);
+    return lower_x(ps.x, ps.cell_start[c], ps.cell_start[c + 1], v);
+}
+__device__ __forceinline__ int row_upper(const SortedSet &ps, int row, float v) {
+    const int o = ps.row_cell[row], c = o + strip_cell(ps.row_xi[row], ps.row_cell[row + 1] - o, v);
+    return upper_x(ps.x, ps.cell_start[c], ps.cell_start[c + 1], v);
 }
 
 // The candidate block of the point at sorted position p: its own strip and the two above and below (strips are about one local
@@ -439,8 +459,7 @@ __device__ __noinline__ void stars_fast(const SortedSet &ps, const FrameView &fv
                     if (k >= 3) { phase = 1; t = 0; continue; }
                     row = k == 0 ? g.pcy : (k == 1 ? g.pcy - 1 : g.pcy + 1); ++k;        // own strip first
                     if (row < 0 || row >= ps.R) continue;
-                    const int b = ps.row_start[row], e = ps.row_start[row + 1];
-                    ri = lower_x(ps.x, b, e, exlo); re = upper_x(ps.x, ri, e, exhi); dir = 1;
+                    ri = row_lower(ps, row, exlo); re = row_upper(ps, row, exhi); dir = 1;
                 } else {
                     if (g.dirty) g_regions(g, gl, ps);
                     int r0 = __reduce_min_sync(gmask, g.rowlo), r1 = __reduce_max_sync(gmask, g.rowhi);
@@ -467,8 +486,7 @@ __device__ __noinline__ void stars_fast(const SortedSet &ps, const FrameView &fv
                     float xa = gminf(la, gmask), xb = gmaxf(lb, gmask);
                     if (g.d == 0) { xa = -CUDART_INF_F; xb = CUDART_INF_F; }
                     if (xa > xb) continue;
-                    const int b = ps.row_start[row], e = ps.row_start[row + 1];
-                    const int ia = lower_x(ps.x, b, e, xa + g.ppx - 1.0e-3f), ib = upper_x(ps.x, ia, e, xb + g.ppx + 1.0e-3f);
+                    const int ia = row_lower(ps, row, xa + g.ppx - 1.0e-3f), ib = row_upper(ps, row, xb + g.ppx + 1.0e-3f);
                     if (ia >= ib) continue;
                     // split at p (in the three strips examined first: around the examined window): the left part is walked right to
                     // left, the right part left to right -- nearest points first
@@ -656,8 +674,7 @@ __device__ __noinline__ FbResult fb_build(const SortedSet &ps, int p) {
         const int r0 = row_of(ps, (float)(ppy - w)), r1 = row_of(ps, (float)(ppy + w));
         const float xlo = (float)(ppx - w) - 1.0e-3f, xhi = (float)(ppx + w) + 1.0e-3f;
         for (int row = r0; row <= r1 && rc == STAR_OK; ++row) {
-            const int b = ps.row_start[row], e = ps.row_start[row + 1];
-            const int ia = lower_x(ps.x, b, e, xlo), ib = upper_x(ps.x, ia, e, xhi);
+            const int ia = row_lower(ps, row, xlo), ib = row_upper(ps, row, xhi);
             int ea = ia, eb = ia;                                  // [ea, eb): seen in the previous round
             if (row >= pr0 && row <= pr1) { ea = lower_x(ps.x, ia, ib, pxlo); eb = upper_x(ps.x, ea, ib, pxhi); }
             scan(ia, ea);
@@ -831,8 +848,8 @@ __device__ __noinline__ bool w_stream(WBest &b, const SortedSet &ps, int p, floa
         if (on && lo <= hi) {
             const int rs0 = ps.row_start[row], re0 = ps.row_start[row + 1];
             // the strip's points with x in [lo, hi] (relative to p; padded for the rounding of the sum)
-            int ia = lo == -INF ? rs0 : lower_x(ps.x, rs0, re0, lo + ppx - 1.0e-3f);
-            int ib = hi == INF ? re0 : upper_x(ps.x, ia, re0, hi + ppx + 1.0e-3f);
+            int ia = lo == -INF ? rs0 : row_lower(ps, row, lo + ppx - 1.0e-3f);
+            int ib = hi == INF ? re0 : row_upper(ps, row, hi + ppx + 1.0e-3f);
             if (row >= by0 && row <= by1 && xbn > 0) {
                 // up to two runs: left and right of the block's own run
                 const int e1 = min(ib, xb0), a2 = max(ia, xb0 + xbn);
@@ -901,10 +918,7 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
         int rb = 0, rn = 0, posA = -1, posB = -1, M = 0;
         for (int attempt = 0; attempt < 6; ++attempt) {
             rb = 0; rn = 0;
-            if (lane <= by1 - by0) {
-                const int row = by0 + lane, b = ps.row_start[row], e = ps.row_start[row + 1];
-                rb = lower_x(ps.x, b, e, bk.xlo); rn = upper_x(ps.x, rb, e, bk.xhi) - rb;
-            }
+            if (lane <= by1 - by0) { rb = row_lower(ps, by0 + lane, bk.xlo); rn = row_upper(ps, by0 + lane, bk.xhi) - rb; }
             posA = -1; posB = -1; M = 0;
             int eA = lane, eB = lane + 32;
 #pragma unroll
@@ -1118,10 +1132,7 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
         {
             const int row = bk.r0 + (gl >> 1);
             int res = 0;
-            if (gl < 2 * BLOCK_ROWS && row <= bk.r1) {
-                const int b = ps.row_start[row], e = ps.row_start[row + 1];
-                res = (gl & 1) ? upper_x(ps.x, b, e, bk.xhi) : lower_x(ps.x, b, e, bk.xlo);
-            }
+            if (gl < 2 * BLOCK_ROWS && row <= bk.r1) res = (gl & 1) ? row_upper(ps, row, bk.xhi) : row_lower(ps, row, bk.xlo);
 #pragma unroll
             for (int r = 0; r < BLOCK_ROWS; ++r) {
                 const int lo = GSHFL(res, 2 * r), hi = GSHFL(res, 2 * r + 1);
