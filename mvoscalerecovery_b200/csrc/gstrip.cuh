@@ -450,6 +450,21 @@ __device__ __noinline__ void stars_fast(const SortedSet &ps, const FrameView &fv
                     if (rdir > 0) { bbase = ri; ri += GL; } else { bbase = re - 1; re -= GL; }
                     CNT(c_batch);
                     F = (__ballot_sync(gmask, v) >> gshift) & 0xFFFFu;
+                    if (F && phase == 1 && g.d > 0) {
+                        // sweep: screen the batch candidate-parallel (lane = candidate) against every triangle of the star as it is
+                        // now -- the regions only shrink while the star grows, so what is certainly outside all of them stays
+                        // outside.  Far from p nearly every candidate goes here, for d x 14 instructions per 16 instead of ~40 each.
+                        const float sl = fmaf(cx, cx, cy * cy);
+                        bool maybe = false;
+                        for (int kk = 0; kk < g.d; ++kk) {
+                            const float m0 = __shfl_sync(gmask, g.m0, kk, GL), m1 = __shfl_sync(gmask, g.m1, kk, GL), m2 = __shfl_sync(gmask, g.m2, kk, GL);
+                            const float e0 = __shfl_sync(gmask, g.e0, kk, GL), e1 = __shfl_sync(gmask, g.e1, kk, GL), e2 = __shfl_sync(gmask, g.e2, kk, GL);
+                            const float det = fmaf(m0, sl, fmaf(m1, cx, m2 * cy));
+                            const float err = fmaf(e0, sl, fmaf(e1, fabsf(cx), e2 * fabsf(cy))) + 1.0e-30f;
+                            maybe |= !(det > err);
+                        }
+                        F &= (__ballot_sync(gmask, v && maybe) >> gshift) & 0xFFFFu;
+                    }
                     if (F) break;
                     continue;
                 }
@@ -599,6 +614,23 @@ __device__ __noinline__ FbResult fb_build(const SortedSet &ps, int p) {
                 double sxl = 0, syl = 0, sll = 0;
                 if (v) { sxl = (double)ps.x[pos] - ppx; syl = (double)ps.y[pos] - ppy; sll = sxl * sxl + syl * syl; }
                 unsigned F = __ballot_sync(FULL, v && sll <= reach2);
+                if (F && d >= 2) {
+                    // screen the batch candidate-parallel (lane = candidate) with the float64 filters of the predicates: whatever is
+                    // certainly in conflict with no triangle of the star as it is now stays so while the star grows (the regions
+                    // only shrink).  An open star sweeps the whole set: nearly every far candidate goes here.
+                    bool maybe = false;
+                    for (int kk = 0; kk < d; ++kk) {
+                        const int ks = __shfl_sync(FULL, sid, kk), kn = __shfl_sync(FULL, nid, kk);
+                        const double ax = __shfl_sync(FULL, qx, kk), ay = __shfl_sync(FULL, qy, kk), al = __shfl_sync(FULL, ql, kk);
+                        const double cx = __shfl_sync(FULL, bx, kk), cy = __shfl_sync(FULL, by, kk), cl = __shfl_sync(FULL, bl, kk);
+                        bool out;
+                        if (kn == INF16) { const double l = ax * syl, r = ay * sxl; out = l - r < -3.3306690738754731e-16 * (fabs(l) + fabs(r)); }       // strictly right of p->a
+                        else if (ks == INF16) { const double l = cx * syl, r = cy * sxl; out = l - r > 3.3306690738754731e-16 * (fabs(l) + fabs(r)); }   // strictly left of p->b
+                        else out = det3_lift_sign_filter(ax, ay, al, cx, cy, cl, sxl, syl, sll) == 1;                                          // strictly outside the circle
+                        maybe |= !out;
+                    }
+                    F &= __ballot_sync(FULL, maybe);
+                }
                 while (F) {
                     const int j = __ffs(F) - 1; F &= F - 1;
                     const int s = base + j;
