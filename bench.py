@@ -573,6 +573,21 @@ def run_gpu_arm(args):
                        "status_hist": fhist}
         del frun
 
+    # ---- the same kernel on other feature densities (rank 0's GPU, one short sequence each): the bench line's own workload is
+    #      image-uniform, which is the easy case for any spatial index
+    density_block = None
+    if rank == 0 and args.workload == "kitti00" and not args.no_densities:
+        density_block = {}
+        for name in ("kitti00-ground", "kitti00-clustered"):
+            dwl = build_rank_workload(name, 0, 1, 1184, args.features)
+            drun = make_runner(eng, dwl, 0, dev)
+            dl = timed_leg(drun, max(3, min(args.steps, 5)), 3, 1, dev)
+            density_block[name] = {"workload": WORKLOADS[name][2], "frames": 1184, "value": 1184 / (dl["ms_step"] * 1e-3), "unit": "frames/s (1 GPU)",
+                                   "kernel_ms": dl["kernel_ms"], "status_hist": status_hist(drun)}
+            del drun
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.isfile(peaks_path):
@@ -633,6 +648,7 @@ def run_gpu_arm(args):
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api,
                         "pageable_value": (total_frames / page_s) if page_s else None, "dropin_fps": dropin},
                 "fleet": fleet_block,
+                "other_densities": density_block,
                 "gpu_launches": int(main["launches"]), "clocks": main["clocks"]}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -652,6 +668,7 @@ def main():
     ap.add_argument("--features", type=int, default=0, help="correspondences per frame (0 = the workload's own)")
     ap.add_argument("--cpu-sample", type=int, default=50, help="frames of the workload timed on one host core through the reference (0 = skip)")
     ap.add_argument("--dropin-frames", type=int, default=500, help="frames of the per-frame drop-in leg (0 = skip)")
+    ap.add_argument("--no-densities", action="store_true", help="skip the perspective / clustered feature-density legs of the kitti00 line")
     ap.add_argument("--no-fleet", action="store_true", help="skip the fleet block (BASELINE configs[3] in the same invocation)")
     ap.add_argument("--ref-cores", type=int, default=0, help="--impl reference: worker processes (0 = all host cores, at most 64)")
     ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per worker per step (0 = 2 for the reference, 6 for the port)")

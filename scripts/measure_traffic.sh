@@ -6,8 +6,8 @@
 RT=${1:-r02}
 mkdir -p gpurun_out
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$RT.csv \
-    python bench.py --steps 2 --warmup 1 --cpu-sample 0 --dropin-frames 0 > gpurun_out/ncu_launch_bench.log 2>&1
+    python bench.py --steps 2 --warmup 1 --cpu-sample 0 --dropin-frames 0 --no-densities > gpurun_out/ncu_launch_bench.log 2>&1
 tail -2 gpurun_out/ncu_launch_bench.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:frame_kernel -s 3 -c 1 -o gpurun_out/prof_${RT}_final -f \
-    python bench.py --steps 1 --warmup 3 --cpu-sample 0 --dropin-frames 0 --no-fleet > gpurun_out/ncu_full_bench.log 2>&1
+    python bench.py --steps 1 --warmup 3 --cpu-sample 0 --dropin-frames 0 --no-fleet --no-densities > gpurun_out/ncu_full_bench.log 2>&1
 tail -2 gpurun_out/ncu_full_bench.log
