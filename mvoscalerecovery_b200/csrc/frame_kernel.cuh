@@ -291,7 +291,7 @@ __device__ __forceinline__ void build_grid(int n, const float *U, const float *V
             ps.x = ga.sx; ps.y = ga.sy; ps.orig = ga.sorig; ps.row_start = row_start; ps.row_bin = row_bin; ps.bin_row = bin_row;
             ps.row_cell = rowoff; ps.row_xi = rowxi; ps.cell_start = cstart;
             ps.n = n; ps.NB = NB; ps.R = 0; ps.win_m = win_m; ps.kdens = density; ps.wfac = wfac;
-            ps.xmin = xmn; ps.xmax = xmx; ps.ymin = ymn; ps.bh = bh; ps.inv_bh = 1.f / bh;
+            ps.xmin = xmn; ps.xmax = xmx; ps.ymin = ymn; ps.ymax = ymx; ps.bh = bh; ps.inv_bh = 1.f / bh;
         }
     }
     for (int i = tid; i < NB; i += NT) { cnt[i] = 0; bxmin[i] = 0xFFFFFFFFu; bxmax[i] = 0u; }

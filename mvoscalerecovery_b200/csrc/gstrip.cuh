@@ -79,7 +79,7 @@ struct SortedSet {
     const float2 *row_xi;                // [R] (x origin, 1 / sub-cell width) of every strip
     const uint16_t *cell_start;          // [row_cell[R]+1] first entry of every sub-cell
     int n, R, NB, win_m;
-    float xmin, xmax, ymin, bh, inv_bh, kdens, wfac;
+    float xmin, xmax, ymin, ymax, bh, inv_bh, kdens, wfac;
 };
 // order-preserving float <-> uint (atomicMin / atomicMax on float coordinates, REDUX on float keys)
 __device__ __forceinline__ unsigned fkey(float t) { const unsigned k = __float_as_uint(t); return (k & 0x80000000u) ? ~k : (k | 0x80000000u); }
@@ -103,6 +103,10 @@ __device__ __forceinline__ int upper_x(const float *x, int b, int e, float v) {
     while (b < e) { const int m = (b + e) >> 1; if (x[m] <= v) b = m + 1; else e = m; }
     return b;
 }
+
+// single-instruction approximations (MUFU, 2 ulp); every use below is covered by explicit padding
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // sub-cell of x in a strip of nc sub-cells (monotone in x: the float product and the truncation are)
 __device__ __forceinline__ int strip_cell(float2 xi, int nc, float x) {
@@ -128,6 +132,8 @@ __device__ __forceinline__ int row_upper(const SortedSet &ps, int row, float v) 
 // up to eight in the sparse part of a thin one.  The noise of the local spacing then enters the candidate count squared; on all
 // three bench densities more stars left the pair path than with the fixed five strips.)
 constexpr int BLOCK_ROWS = 5;
+constexpr int WRAP_ROWS = 7;             // strips of the (larger) block of the one-warp-per-star path
+constexpr float WRAP_WIDEN = 1.35f;      // ... and its window relative to the pair path's
 struct Block { int row, r0, r1; float xlo, xhi; int open; };
 __device__ __forceinline__ Block block_of(const SortedSet &ps, int p, float ppx, float ppy) {
     Block k;
@@ -136,7 +142,8 @@ __device__ __forceinline__ Block block_of(const SortedSet &ps, int p, float ppx,
     const int rb = ps.row_start[k.row], re = ps.row_start[k.row + 1];
     const int ia = max(p - ps.win_m, rb), ib = min(p + ps.win_m, re - 1);
     const float span = ps.x[ib] - ps.x[ia], H = row_yhi(ps, k.row) - row_ylo(ps, k.row);
-    const float side = (ib > ia && span > 0.f) ? sqrtf(ps.kdens * H * span / (float)(ib - ia)) : H;
+    // (the window is a heuristic: single-instruction reciprocal and square root; the box and its candidates both follow from it)
+    const float side = (ib > ia && span > 0.f) ? sqrt_approx(ps.kdens * H * span * rcp_approx((float)(ib - ia))) : H;
     const float w = ps.wfac * fmaxf(side, 1.0e-3f);
     k.xlo = ppx - w; k.xhi = ppx + w;
     k.open = (k.xlo <= ps.xmin ? 1 : 0) | (k.xhi >= ps.xmax ? 2 : 0) | (k.r0 == 0 ? 4 : 0) | (k.r1 == ps.R - 1 ? 8 : 0);
@@ -144,7 +151,7 @@ __device__ __forceinline__ Block block_of(const SortedSet &ps, int p, float ppx,
 }
 
 struct StarCtl {                         // shared-memory work queues of one Delaunay pass
-    int next_pos, n_defer, n_defer2, n_wrap;
+    int next_pos, n_defer, n_defer_hi, n_defer2, n_wrap;    // n_defer_hi: stars queued from the END of defer[] (expected to be long: open / far-neighbour stars, taken first)
     unsigned long long cnt[8];           // profiling counters (MVOSR_STAR_COUNTERS): tests, splices, batches, rows, runs, exact, loop iterations, refill iterations
 };
 
@@ -180,20 +187,18 @@ __device__ __forceinline__ bool edge_consistent(T va, T za, T vb, T zb) {
     return (va < vb && za > zb) || (va > vb && za < zb);
 }
 
-// graph vote (graph.py:131-145) of triangle (p,a,b) for vertex p; vertices ordered by feature index
+// graph vote (graph.py:131-145) of triangle (p,a,b) for vertex p.  The reference orders the vertices by feature index (i0 < i1 < i2)
+// and looks up (consistent(0,1), consistent(1,2), consistent(0,2), position of p): with the rank of every vertex among the three, the
+// edge whose ranks sum to 1 is (0,1), to 3 is (1,2), to 2 is (0,2) -- no data movement.
 template <typename T>
 __device__ __forceinline__ bool graph_vote(int op, T vp, T zp, int oa, T va, T za, int ob, T vb, T zb,
                                            uint32_t pass_mask) {
-    int i0 = op, i1 = oa, i2 = ob; T v0 = vp, v1 = va, v2 = vb, z0 = zp, z1 = za, z2 = zb;
-#define MVOSR_SWAP(A, B, C, D, E, F) { int ti = A; A = B; B = ti; T tf = C; C = D; D = tf; tf = E; E = F; F = tf; }
-    if (i0 > i1) MVOSR_SWAP(i0, i1, v0, v1, z0, z1)
-    if (i1 > i2) MVOSR_SWAP(i1, i2, v1, v2, z1, z2)
-    if (i0 > i1) MVOSR_SWAP(i0, i1, v0, v1, z0, z1)
-#undef MVOSR_SWAP
-    int a = edge_consistent(v0, z0, v1, z1), b = edge_consistent(v1, z1, v2, z2), c = edge_consistent(v0, z0, v2, z2);
-    int idx = a * 4 + b * 2 + c;
-    int k = (op == i0) ? 0 : (op == i1 ? 1 : 2);
-    return (pass_mask >> (idx * 3 + k)) & 1u;
+    const int pa = op > oa, pb = op > ob, ab = oa > ob;
+    const int rp = pa + pb, ra = (1 - pa) + ab, rb = 3 - rp - ra;
+    // weight of an edge in idx = a*4 + b*2 + c by its rank sum s: s = 1 -> 4, s = 2 -> 1, s = 3 -> 2
+    const int wpa = (0x2140 >> (4 * (rp + ra))) & 7, wpb = (0x2140 >> (4 * (rp + rb))) & 7, wab = (0x2140 >> (4 * (ra + rb))) & 7;
+    const int idx = (edge_consistent(vp, zp, va, za) ? wpa : 0) + (edge_consistent(vp, zp, vb, zb) ? wpb : 0) + (edge_consistent(va, za, vb, zb) ? wab : 0);
+    return (pass_mask >> (idx * 3 + rp)) & 1u;
 }
 
 // the vote of star triangle (p, sid, nid) (sorted positions) for p
@@ -747,9 +752,6 @@ constexpr int WRAP_BLOCK = 2;                     // half-width of the candidate
 
 struct WEval { float t, eps; bool cand, susp; };
 
-// single-instruction approximations (MUFU, 2 ulp); every use below is covered by explicit padding
-__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // candidate s (relative to p) against edge (p,cur), orientation sigma (+1 counter-clockwise walk, -1 clockwise)
 __device__ __forceinline__ WEval w_eval(bool valid, float sx, float sy, float sl, float cx, float cy, float sigma) {
@@ -794,6 +796,15 @@ __device__ __forceinline__ void w_circle(WBest &b, float cx, float cy, float sig
 // ~40 stars per frame out of streaming but the extra instructions per step cost more than that saves (pair path +13 %,
 // wrap path +3 %), so both paths run with CLIP = false; the variant is kept for sparser inputs.
 struct WBox { float x0, x1, y0, y1; };
+#ifndef MVOSR_CAP_CLIP
+#define MVOSR_CAP_CLIP 0                 // 1: clip the cap test to the bounding box of the point set.  Measured again in round 2 behind the quick accept: uniform -0.5 %, perspective -2.5 %, clustered -5 % (fewer streaming stars, dearer slow path)
+#endif
+constexpr bool CAP_CLIP = MVOSR_CAP_CLIP != 0;
+// bounding box of the point set relative to p (a superset is safe)
+__device__ __forceinline__ WBox set_box(const SortedSet &ps, float ppx, float ppy) {
+    WBox G; G.x0 = ps.xmin - ppx - 1.0e-3f; G.x1 = ps.xmax - ppx + 1.0e-3f; G.y0 = ps.ymin - ppy - 1.0e-3f; G.y1 = ps.ymax - ppy + 1.0e-3f;
+    return G;
+}
 template <bool CLIP>
 __device__ __forceinline__ bool w_cap_inside(float cx, float cy, float sigma, float vx, float vy, float rs,
                                              float BX0, float BX1, float BY0, float BY1, const WBox &G) {
@@ -921,11 +932,15 @@ __device__ __noinline__ bool w_stream(WBest &b, const SortedSet &ps, int p, floa
 // The stars of list[0..n_list) (sorted positions), one per warp; stars that need the exact path are appended to
 // defer[] (sc->n_defer2).
 template <bool EMIT>
-__device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv, StarCtl *sc, const uint16_t *list, int n_list, uint16_t *defer) {
+__device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv, StarCtl *sc, const uint16_t *list, int n_list, uint16_t *defer,
+                                        const uint16_t *list_hi = nullptr, int n_hi = 0) {
+    // list_hi[0], list_hi[-1], ... list_hi[-(n_hi-1)]: the stars expected to take longest (something lay beyond the pair path's whole block:
+    // a hull edge or a far neighbour) are started first so that they do not form the tail of the pass
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
 #ifdef MVOSR_WRAP_COUNTERS
     unsigned w_steps = 0, w_out = 0, w_sstars = 0, w_hull = 0, w_big = 0, w_stars = 0, w_nocand = 0;
+    long long w_cyc = 0, w_cyc_open = 0, w_cyc_stream = 0, w_t0 = 0, w_ts = 0; unsigned w_open = 0;     // cycles: all stars / open stars / inside w_stream
 #define WCNT(x) ++x
 #else
 #define WCNT(x)
@@ -937,13 +952,21 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
             int i = 0;
             if (lane == 0) i = atomicAdd(&sc->next_pos, 1);
             i = __shfl_sync(FULL, i, 0);
-            if (i >= n_list) done = true; else p = list[i];
+            if (i >= n_list + n_hi) done = true; else p = i < n_hi ? list_hi[-i] : list[i - n_hi];
         }
         if (done) break;
         bool ok = true;
+#ifdef MVOSR_WRAP_COUNTERS
+        w_t0 = clock64();
+#endif
         const float ppx = ps.x[p], ppy = ps.y[p];
+        // The stars that come here have a circle that left the pair path's block (or a hull edge): a LARGER block -- one more strip
+        // on either side, the window widened -- settles most of them without streaming; two candidates per lane hold up to 64.
         Block bk = block_of(ps, p, ppx, ppy);
         const int pcy = bk.row;
+        bk.r0 = max(pcy - WRAP_ROWS / 2, 0); bk.r1 = min(pcy + WRAP_ROWS / 2, ps.R - 1);
+        bk.xlo = ppx - WRAP_WIDEN * (ppx - bk.xlo); bk.xhi = ppx + WRAP_WIDEN * (bk.xhi - ppx);
+        bk.open = (bk.xlo <= ps.xmin ? 1 : 0) | (bk.xhi >= ps.xmax ? 2 : 0) | (bk.r0 == 0 ? 4 : 0) | (bk.r1 == ps.R - 1 ? 8 : 0);
         int by0 = bk.r0, by1 = bk.r1;
         // ---- the block's candidates, two per lane: element e of the concatenated strip runs goes to lane e & 31.  A block that
         // holds more than 64 points (denser strips next to a sparse one) is narrowed: whatever lies beyond it is streamed anyway.
@@ -954,7 +977,7 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
             posA = -1; posB = -1; M = 0;
             int eA = lane, eB = lane + 32;
 #pragma unroll
-            for (int r = 0; r < BLOCK_ROWS; ++r) {
+            for (int r = 0; r < WRAP_ROWS; ++r) {
                 const int bb = __shfl_sync(FULL, rb, r), nn = __shfl_sync(FULL, rn, r);
                 if (posA < 0) { if (eA < nn) posA = bb + eA; else eA -= nn; }
                 if (posB < 0) { if (eB < nn) posB = bb + eB; else eB -= nn; }
@@ -976,6 +999,7 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
         const float slack = strip_slack(ps);
         const float BX0 = (bk.open & 1) ? -CUDART_INF_F : bk.xlo - ppx + slack, BX1 = (bk.open & 2) ? CUDART_INF_F : bk.xhi - ppx - slack;
         const float BY0 = (bk.open & 4) ? -CUDART_INF_F : row_ylo(ps, by0) - ppy + slack, BY1 = (bk.open & 8) ? CUDART_INF_F : row_yhi(ps, by1) - ppy - slack;
+        const WBox GB = set_box(ps, ppx, ppy);
         // ---- one step of the walk: the neighbour that follows cur (relative (cx,cy), position cpos) in direction sigma.
         // Block candidates first, then streaming if the winner's cap leaves the block (or nothing lies on the left).
         // false: a decision could not be certified.  b.have == false on return: hull edge.
@@ -999,13 +1023,20 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
                 if (__any_sync(FULL, clash)) return false;
                 w_circle(b, cx, cy, sigma);
                 if (!(fabsf(b.t) < 1.0e18f)) return false;
-                inside = w_cap_inside<false>(cx, cy, sigma, b.vx, b.vy, b.rs, BX0, BX1, BY0, BY1, WBox());
+                inside = w_cap_inside<CAP_CLIP>(cx, cy, sigma, b.vx, b.vy, b.rs, BX0, BX1, BY0, BY1, GB);
             }
             WCNT(w_steps);
             if (!inside) {
                 WCNT(w_out); if (!b.have) { WCNT(w_nocand); } if (!streamed) { streamed = true; WCNT(w_sstars); }
                 WBest bs = b;                                     // (a copy: keeps b itself in registers)
-                if (!w_stream(bs, ps, p, ppx, ppy, pcy, by0, by1, rb, rn, cx, cy, sigma, cpos)) return false;
+#ifdef MVOSR_WRAP_COUNTERS
+                w_ts = clock64();
+#endif
+                const bool sok = w_stream(bs, ps, p, ppx, ppy, pcy, by0, by1, rb, rn, cx, cy, sigma, cpos);
+#ifdef MVOSR_WRAP_COUNTERS
+                w_cyc_stream += clock64() - w_ts;
+#endif
+                if (!sok) return false;
                 b = bs;
             }
             return true;
@@ -1085,6 +1116,9 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
             if (sigma > 0.f) { if (lane == nC) sidC = b.pos; ++nC; } else { if (lane == nW) sidW = b.pos; ++nW; }
             cx = b.x; cy = b.y; cpos = b.pos;
         }
+#ifdef MVOSR_WRAP_COUNTERS
+        { const long long dt = clock64() - w_t0; w_cyc += dt; if (ok && !closed) { w_cyc_open += dt; ++w_open; } }
+#endif
         if (!ok) {
             if (lane == 0) { const int slot = atomicAdd(&sc->n_defer2, 1); defer[slot] = (uint16_t)p; }
             continue;
@@ -1104,9 +1138,9 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
 #ifdef MVOSR_WRAP_COUNTERS
     if (lane == 0) {
         atomicAdd(&sc->cnt[0], (unsigned long long)w_steps); atomicAdd(&sc->cnt[1], (unsigned long long)w_out);
-        atomicAdd(&sc->cnt[2], (unsigned long long)w_sstars); atomicAdd(&sc->cnt[3], (unsigned long long)w_hull);
-        atomicAdd(&sc->cnt[4], (unsigned long long)w_big); atomicAdd(&sc->cnt[5], (unsigned long long)w_stars);
-        atomicAdd(&sc->cnt[6], (unsigned long long)w_nocand);
+        atomicAdd(&sc->cnt[2], (unsigned long long)w_sstars); atomicAdd(&sc->cnt[3], (unsigned long long)w_open);
+        atomicAdd(&sc->cnt[4], (unsigned long long)w_cyc); atomicAdd(&sc->cnt[5], (unsigned long long)w_stars);
+        atomicAdd(&sc->cnt[6], (unsigned long long)w_cyc_open); atomicAdd(&sc->cnt[7], (unsigned long long)w_cyc_stream);
     }
 #endif
 #undef WCNT
@@ -1127,7 +1161,7 @@ __device__ __forceinline__ unsigned gmin_u32(unsigned v, int g) {
 }
 
 template <bool EMIT>
-__device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer,
+__device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, uint16_t *defer_hi,
                                         const uint16_t *todo, int n_todo) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, g = lane >> 4, gl = lane & (GL - 1), gshift = lane & GL;
@@ -1154,7 +1188,7 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
             p = i + g + rot; if (p >= ps.n) p -= ps.n; if (p >= ps.n) p -= ps.n;
             have = i + g < ps.n && ps.orig[p] != INF16;
         }
-        bool ok = have;
+        bool ok = have, far = false;
         const float ppx = ps.x[p], ppy = ps.y[p];
         const Block bk = block_of(ps, p, ppx, ppy);
         // ---- block candidates: the runs of the block's strips inside its x-window (lane 2r / 2r+1 of the half-warp searches the
@@ -1262,7 +1296,7 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
             const unsigned gsusp = GBALLOT(susp && walking);               // (ballots are executed by all 32 lanes)
             if (walking && gsusp) { PR(3); ok = false; walking = false; }
             const unsigned kmin = gmin_u32(walking ? kbest : 0xFFFFFFFFu, g);
-            if (walking && kmin == 0xFFFFFFFFu) { PR(4); ok = false; walking = false; }      // nothing on the left inside the block: hull edge or far neighbour
+            if (walking && kmin == 0xFFFFFFFFu) { PR(4); ok = false; walking = false; far = true; }      // nothing on the left inside the block: hull edge or far neighbour
             const int wl = max(__ffs(GBALLOT(walking && kbest == kmin)) - 1, 0);
             const float wt = GSHFL(tb, wl), we = GSHFL(eb, wl), wx = GSHFL(xb, wl), wy = GSHFL(yb, wl);
             const int wpos = GSHFL(pb, wl);
@@ -1278,7 +1312,7 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
             // (quick accept: the whole padded disk inside the block; the cap test proper only when some star needs it)
             const bool disk_in = vx - rs >= BX0 && vx + rs <= BX1 && vy - rs >= BY0 && vy + rs <= BY1;
             if (__any_sync(FULL, walking && !disk_in)) {
-                if (walking && !disk_in && !w_cap_inside<false>(cx, cy, 1.f, vx, vy, rs, BX0, BX1, BY0, BY1, WBox())) { PR(6); ok = false; walking = false; }
+                if (walking && !disk_in && !w_cap_inside<CAP_CLIP>(cx, cy, 1.f, vx, vy, rs, BX0, BX1, BY0, BY1, set_box(ps, ppx, ppy))) { PR(6); ok = false; walking = false; }
             }
             if (!EMIT) {
                 // vote pass: never seeded -- the plain walk from q0 back to q0
@@ -1309,7 +1343,10 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
         }
         const bool fin = ok && closed;
         if (have && ok && !closed) PR(2);
-        if (have && !fin && gl == 0) { const int slot = atomicAdd(&sc->n_defer, 1); defer[slot] = (uint16_t)p; }
+        if (have && !fin && gl == 0) {                              // (defer_hi: the last entry of defer[]; the two ends cannot meet, there are at most n stars)
+            if (far) { const int slot = atomicAdd(&sc->n_defer_hi, 1); defer_hi[-slot] = (uint16_t)p; }
+            else { const int slot = atomicAdd(&sc->n_defer, 1); defer[slot] = (uint16_t)p; }
+        }
         // ---- consumers, both half-warps in lock step (d = 0: nothing)
         const int d = fin ? nC : 0;
         const int nid = GSHFL(sid, gl + 1 < d ? gl + 1 : 0);
@@ -1365,17 +1402,18 @@ template <bool EMIT>
 __device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, uint16_t *defer2,
                                       int &n_exact, long long *t_fast, const uint16_t *todo = nullptr, int n_todo = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { sc->next_pos = 0; sc->n_defer = 0; sc->n_defer2 = 0; }
+    if (tid == 0) { sc->next_pos = 0; sc->n_defer = 0; sc->n_defer_hi = 0; sc->n_defer2 = 0; }
     __syncthreads();
     long long tc0 = clock64();
-    stars_pair<EMIT>(ps, fv, sc, defer, todo, n_todo);
+    uint16_t *const defer_hi = defer2 - 1;                       // defer[] is filled from both ends (defer2 = defer + cap)
+    stars_pair<EMIT>(ps, fv, sc, defer, defer_hi, todo, n_todo);
     __syncthreads();
     if (tid == 0 && t_fast) *t_fast += clock64() - tc0;
-    const int n1 = sc->n_defer;
+    const int n1l = sc->n_defer, n1h = sc->n_defer_hi, n1 = n1l + n1h;
     __syncthreads();
     if (tid == 0) sc->next_pos = 0;
     __syncthreads();
-    if (n1) stars_wrap<EMIT>(ps, fv, sc, defer, n1, defer2);
+    if (n1) stars_wrap<EMIT>(ps, fv, sc, defer, n1l, defer2, defer_hi, n1h);
     __syncthreads();
     const int n2 = sc->n_defer2;
     __syncthreads();
