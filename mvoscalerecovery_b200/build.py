@@ -11,7 +11,7 @@ LIB = os.path.join(CSRC, "libmvosr.so")
 # operation individually rounded, so its results are bit-reproducible on any IEEE-754 host (csrc/five_point_api.cu).
 UNITS = [("api.cu", []), ("five_point_api.cu", ["-fmad=false"])]
 SOURCES = [u for u, _ in UNITS]
-HEADERS = ["handle.h", "frame_kernel.cuh", "gstar.cuh", "predicates.cuh", "philox.cuh", "triangulate.cuh", "aux_kernels.cuh",
+HEADERS = ["handle.h", "frame_kernel.cuh", "gstar.cuh", "gstrip.cuh", "gindex.cuh", "gthread.cuh", "predicates.cuh", "philox.cuh", "triangulate.cuh", "aux_kernels.cuh",
            "five_point.cuh", "five_point_kernel.cuh", "five_point_tables.h", "bucket_kernel.cuh",
            os.path.join("..", "..", "include", "mvosr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]

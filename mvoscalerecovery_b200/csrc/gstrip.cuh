@@ -43,6 +43,8 @@
 #include <math_constants.h>
 #include <stdio.h>
 #include "predicates.cuh"
+#include "gindex.cuh"
+#include "gthread.cuh"
 
 namespace mvosr {
 
@@ -52,106 +54,10 @@ namespace mvosr {
 constexpr int NT = MVOSR_NT;             // threads per CTA of the fused frame kernel
 constexpr int NWARP = NT / 32;
 constexpr int GL = 16;                   // lanes per star on the fast path
-constexpr uint16_t INF16 = 0xFFFF;
-constexpr float GRID_DENSITY = 1.5f;     // k: a strip is closed when count x height >= k x extent (k points per square cell)
-constexpr int WIN_M = 4;                 // the local spacing in a point's own strip is measured over WIN_M neighbours on either side
-constexpr float WIN_FACTOR = 2.5f;       // half-width of the candidate window in local cell sides (the block is +-2 strips tall)
-// Forward error bound of the float32 in-circle evaluation: inputs are float32 roundings of exact
-// differences (relative error u = 2^-24); every term of the expanded determinant accumulates at most
-// 11u (4 inputs, <= 7 roundings), so |det_fl - det| <= 11u * perm.  KERR = 16u leaves room for the
-// rounding of the bound itself.
-constexpr float KERR = 9.5367431640625e-07f;   // 2^-20
-
 enum { STAR_OK = 0, STAR_DEFER = 1, STAR_OVERFLOW = 2, STAR_INCONSISTENT = 3, STAR_NONE = 4 };
 
-// The staged point set: entries sorted by strip (bottom-up in y), inside a strip by (x, original index); an exact duplicate
-// of an earlier point stays in place as a hole (orig == INF16).  Strip r is the union of the histogram bins row_bin[r] ..
-// row_bin[r+1]-1 of width bh starting at ymin; a point's strip is bin_row[bin_of(y)].
-struct SortedSet {
-    const float *x, *y;                  // [n] pixel coordinates (float32; |x| < 4096, multiples of 2^-40)
-    const uint16_t *orig;                // [n] index in the frame's feature order, INF16 for a hole
-    const uint16_t *row_start;           // [R+1] first entry of every strip
-    const uint16_t *row_bin;             // [R+1] first histogram bin of every strip
-    const uint16_t *bin_row;             // [NB] strip of every bin
-    // every strip is cut into uniform sub-cells of about two points (the unit of the counting sort that built it): the first
-    // position with x >= v is found in the sub-cell of v, cell_start[row_cell[r] + (int)((v - x0) * inv)], x0 / inv = row_xi[r]
-    const uint16_t *row_cell;            // [R+1] first sub-cell of every strip
-    const float2 *row_xi;                // [R] (x origin, 1 / sub-cell width) of every strip
-    const uint16_t *cell_start;          // [row_cell[R]+1] first entry of every sub-cell
-    int n, R, NB, win_m;
-    float xmin, xmax, ymin, ymax, bh, inv_bh, kdens, wfac;
-};
-// order-preserving float <-> uint (atomicMin / atomicMax on float coordinates, REDUX on float keys)
-__device__ __forceinline__ unsigned fkey(float t) { const unsigned k = __float_as_uint(t); return (k & 0x80000000u) ? ~k : (k | 0x80000000u); }
-__device__ __forceinline__ float funkey(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
-
-__device__ __forceinline__ int bin_of(const SortedSet &ps, float y) {
-    int b = (int)((y - ps.ymin) * ps.inv_bh);
-    return b < 0 ? 0 : (b >= ps.NB ? ps.NB - 1 : b);
-}
-__device__ __forceinline__ int row_of(const SortedSet &ps, float y) { return ps.bin_row[bin_of(ps, y)]; }
-// strip r holds exactly the points with ylo(r) <= y < yhi(r) up to the rounding of bin_of (callers shrink by STRIP_SLACK)
-__device__ __forceinline__ float row_ylo(const SortedSet &ps, int r) { return ps.ymin + (float)ps.row_bin[r] * ps.bh; }
-__device__ __forceinline__ float row_yhi(const SortedSet &ps, int r) { return ps.ymin + (float)ps.row_bin[r + 1] * ps.bh; }
-__device__ __forceinline__ float strip_slack(const SortedSet &ps) { return 1.0e-3f + 1.0e-4f * ps.bh; }
-// first position in [b, e) whose x is >= v (lower) / > v (upper); the strip is sorted by x
-__device__ __forceinline__ int lower_x(const float *x, int b, int e, float v) {
-    while (b < e) { const int m = (b + e) >> 1; if (x[m] < v) b = m + 1; else e = m; }
-    return b;
-}
-__device__ __forceinline__ int upper_x(const float *x, int b, int e, float v) {
-    while (b < e) { const int m = (b + e) >> 1; if (x[m] <= v) b = m + 1; else e = m; }
-    return b;
-}
-
-// single-instruction approximations (MUFU, 2 ulp); every use below is covered by explicit padding
-__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-
-// sub-cell of x in a strip of nc sub-cells (monotone in x: the float product and the truncation are)
-__device__ __forceinline__ int strip_cell(float2 xi, int nc, float x) {
-    const int c = (int)((x - xi.x) * xi.y);                      // (the conversion saturates; NaN -> 0)
-    return c < 0 ? 0 : (c >= nc ? nc - 1 : c);
-}
-// first position of strip `row` whose x is >= v (row_lower) / > v (row_upper)
-__device__ __forceinline__ int row_lower(const SortedSet &ps, int row, float v) {
-    const int o = ps.row_cell[row], c = o + strip_cell(ps.row_xi[row], ps.row_cell[row + 1] - o, v);
-    return lower_x(ps.x, ps.cell_start[c], ps.cell_start[c + 1], v);
-}
-__device__ __forceinline__ int row_upper(const SortedSet &ps, int row, float v) {
-    const int o = ps.row_cell[row], c = o + strip_cell(ps.row_xi[row], ps.row_cell[row + 1] - o, v);
-    return upper_x(ps.x, ps.cell_start[c], ps.cell_start[c + 1], v);
-}
-
-// The candidate block of the point at sorted position p: its own strip and the two above and below (strips are about one local
-// cell side tall by construction), cut to the x-window [xlo, xhi] (absolute coordinates) of half-width WIN_FACTOR local cell
-// sides -- the side c of the square that holds k points at the local density: c^2 = k x (strip height) x (spacing along x in
-// the strip, measured over the WIN_M neighbours on either side).  `open` bits (1 left, 2 right, 4 below, 8 above): no point of
-// the whole set lies beyond that side.
-// (Measured and dropped: choosing the NUMBER of strips from c as well -- fewer strips inside a dense cluster of a tall strip,
-// up to eight in the sparse part of a thin one.  The noise of the local spacing then enters the candidate count squared; on all
-// three bench densities more stars left the pair path than with the fixed five strips.)
-constexpr int BLOCK_ROWS = 5;
-constexpr int WRAP_ROWS = 7;             // strips of the (larger) block of the one-warp-per-star path
-constexpr float WRAP_WIDEN = 1.35f;      // ... and its window relative to the pair path's
-struct Block { int row, r0, r1; float xlo, xhi; int open; };
-__device__ __forceinline__ Block block_of(const SortedSet &ps, int p, float ppx, float ppy) {
-    Block k;
-    k.row = row_of(ps, ppy);
-    k.r0 = max(k.row - BLOCK_ROWS / 2, 0); k.r1 = min(k.row + BLOCK_ROWS / 2, ps.R - 1);
-    const int rb = ps.row_start[k.row], re = ps.row_start[k.row + 1];
-    const int ia = max(p - ps.win_m, rb), ib = min(p + ps.win_m, re - 1);
-    const float span = ps.x[ib] - ps.x[ia], H = row_yhi(ps, k.row) - row_ylo(ps, k.row);
-    // (the window is a heuristic: single-instruction reciprocal and square root; the box and its candidates both follow from it)
-    const float side = (ib > ia && span > 0.f) ? sqrt_approx(ps.kdens * H * span * rcp_approx((float)(ib - ia))) : H;
-    const float w = ps.wfac * fmaxf(side, 1.0e-3f);
-    k.xlo = ppx - w; k.xhi = ppx + w;
-    k.open = (k.xlo <= ps.xmin ? 1 : 0) | (k.xhi >= ps.xmax ? 2 : 0) | (k.r0 == 0 ? 4 : 0) | (k.r1 == ps.R - 1 ? 8 : 0);
-    return k;
-}
-
 struct StarCtl {                         // shared-memory work queues of one Delaunay pass
-    int next_pos, n_defer, n_defer_hi, n_defer2, n_wrap;    // n_defer_hi: stars queued from the END of defer[] (expected to be long: open / far-neighbour stars, taken first)
+    int next_pos, next_thread, n_defer, n_defer_hi, n_defer2, n_wrap;    // n_defer_hi: stars queued from the END of defer[] (expected to be long: open / far-neighbour stars, taken first)
     unsigned long long cnt[8];           // profiling counters (MVOSR_STAR_COUNTERS): tests, splices, batches, rows, runs, exact, loop iterations, refill iterations
 };
 
@@ -747,7 +653,6 @@ __device__ __noinline__ FbResult fb_build(const SortedSet &ps, int p) {
 // An edge with no left point anywhere is a hull edge: the walk restarts clockwise from q0 (mirrored orientation).
 // All decisions are certified by the error bounds; whenever one is not (ties, collinearities, crowded cells) the star
 // is handed to the exact path above, which decides with exact predicates.
-constexpr float WU = 5.9604644775390625e-08f;     // 2^-24, unit roundoff of float32
 constexpr int WRAP_BLOCK = 2;                     // half-width of the candidate block in cells
 
 struct WEval { float t, eps; bool cand, susp; };
@@ -786,45 +691,6 @@ __device__ __forceinline__ void w_circle(WBest &b, float cx, float cy, float sig
     const float r = sqrt_approx(fmaf(b.vx, b.vx, b.vy * b.vy));
     const float pad = b.eps * (fabsf(cx) + fabsf(cy)) * 0.51f + 1.0e-3f + 1.0e-4f * r;
     b.rs = r + 2.f * pad;
-}
-
-// Does the walk's-left cap of the padded circle (centre v, radius rs, through p = origin and cur) lie inside the box?
-// The cap's bounding box is spanned by p, cur and those axis-extreme points of the circle that lie on the left of p->cur.
-// CLIP: only the part of the cap inside the bounding box G of the point set matters (there is nothing to find outside it),
-// so the box is intersected with the box of (disk n G) -- this lets the flat triangles along the boundary of the point set
-// pass, whose circles are huge but only a thin sliver of them lies inside G.  Measured on the bench workload it keeps
-// ~40 stars per frame out of streaming but the extra instructions per step cost more than that saves (pair path +13 %,
-// wrap path +3 %), so both paths run with CLIP = false; the variant is kept for sparser inputs.
-struct WBox { float x0, x1, y0, y1; };
-#ifndef MVOSR_CAP_CLIP
-#define MVOSR_CAP_CLIP 0                 // 1: clip the cap test to the bounding box of the point set.  Measured again in round 2 behind the quick accept: uniform -0.5 %, perspective -2.5 %, clustered -5 % (fewer streaming stars, dearer slow path)
-#endif
-constexpr bool CAP_CLIP = MVOSR_CAP_CLIP != 0;
-// bounding box of the point set relative to p (a superset is safe)
-__device__ __forceinline__ WBox set_box(const SortedSet &ps, float ppx, float ppy) {
-    WBox G; G.x0 = ps.xmin - ppx - 1.0e-3f; G.x1 = ps.xmax - ppx + 1.0e-3f; G.y0 = ps.ymin - ppy - 1.0e-3f; G.y1 = ps.ymax - ppy + 1.0e-3f;
-    return G;
-}
-template <bool CLIP>
-__device__ __forceinline__ bool w_cap_inside(float cx, float cy, float sigma, float vx, float vy, float rs,
-                                             float BX0, float BX1, float BY0, float BY1, const WBox &G) {
-    const float tol = 1.0e-4f * (fabsf(cx) + fabsf(cy)) * (rs + fabsf(vx) + fabsf(vy));       // include when in doubt
-    float lox = fminf(0.f, cx), hix = fmaxf(0.f, cx), loy = fminf(0.f, cy), hiy = fmaxf(0.f, cy);
-    if (sigma * (cx * vy - cy * (vx - rs)) > -tol) lox = fminf(lox, vx - rs);
-    if (sigma * (cx * vy - cy * (vx + rs)) > -tol) hix = fmaxf(hix, vx + rs);
-    if (sigma * (cx * (vy - rs) - cy * vx) > -tol) loy = fminf(loy, vy - rs);
-    if (sigma * (cx * (vy + rs) - cy * vx) > -tol) hiy = fmaxf(hiy, vy + rs);
-    if (CLIP) {
-        if (rs < 1.0e6f) {
-            // half-widths of the disk inside the strips G.y0..G.y1 and G.x0..G.x1 ((rs-d)(rs+d): no cancellation)
-            const float dy = fmaxf(fmaxf(G.y0 - vy, vy - G.y1), 0.f), dx = fmaxf(fmaxf(G.x0 - vx, vx - G.x1), 0.f);
-            const float hwx = sqrt_approx(fmaxf((rs - dy) * (rs + dy), 0.f)) * 1.001f + 1.0e-3f;
-            const float hwy = sqrt_approx(fmaxf((rs - dx) * (rs + dx), 0.f)) * 1.001f + 1.0e-3f;
-            lox = fmaxf(lox, vx - hwx); hix = fminf(hix, vx + hwx); loy = fmaxf(loy, vy - hwy); hiy = fminf(hiy, vy + hwy);
-        }
-        lox = fmaxf(lox, G.x0); hix = fminf(hix, G.x1); loy = fmaxf(loy, G.y0); hiy = fminf(hiy, G.y1);
-    }
-    return lox >= BX0 && hix <= BX1 && loy >= BY0 && hiy <= BY1;
 }
 
 // One batch of candidates (one per lane) against the current best of the step.  Returns false if a decision could not
@@ -1394,6 +1260,61 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
 #undef PR
 }
 
+// ---------------------------------------------------------------------------------------------
+// thread path: one star per LANE (gthread.cuh), vote pass
+// ---------------------------------------------------------------------------------------------
+// A warp takes 32 consecutive stars of the pass order (the same rotated order as stars_pair: index i -> position i + rot), every lane
+// walks its own (thread_star), and the warp then consumes the certified ones together: graph vote per triangle, keep flag, the ring
+// store with ONE allocation per warp.  The stars it returns go where stars_pair's go: defer[] (from the end when nothing lay on the
+// left inside the block).  It covers the indices below `limit` (a multiple of 32); stars_pair takes the rest with its finer grain, so
+// that the warps that run out of 32-star tasks fill the tail of the pass.
+constexpr int THREAD_FILL = 192;         // stars left to the pair path to balance the last wave of 32-star tasks
+__device__ __noinline__ void stars_thread(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, uint16_t *defer_hi, int limit) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int rot = ps.row_start[ps.R - 1];
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&sc->next_thread, 32);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= limit) break;
+        int p = i + lane + rot; if (p >= ps.n) p -= ps.n; if (p >= ps.n) p -= ps.n;
+        const int op = ps.orig[p];
+        const bool have = op != INF16;
+        TRing ring; int deg = 0, st = TS_DEFER;
+        if (have) st = thread_star(ps, p, ring, deg);
+        __syncwarp();
+        const bool fin = have && st == TS_OK;
+        if (have && !fin) {
+            if (st == TS_NOCAND) { const int slot = atomicAdd(&sc->n_defer_hi, 1); defer_hi[-slot] = (uint16_t)p; }
+            else { const int slot = atomicAdd(&sc->n_defer, 1); defer[slot] = (uint16_t)p; }
+        }
+        // ---- consumers: the vote of every triangle (p, ring[k], ring[k+1]) for p, the keep flag, the ring store
+        const int d = fin ? deg : 0;
+        int nv = 0, prev = fin ? tring_get(ring, 0) : 0;
+        const int first = prev;
+        for (int k = 0; k < d; ++k) {
+            const int nxt = k + 1 < d ? tring_get(ring, k + 1) : first;
+            nv += graph_vote_at(ps, fv, p, prev, nxt) ? 1 : 0;
+            prev = nxt;
+        }
+        if (fin && 2 * nv > d) fv.pflag[op] |= 2;
+        if (fv.rpool) {
+            int inc = d;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+            int base = 0;
+            if (lane == 31 && inc) base = atomicAdd(fv.rcount, inc);
+            base = __shfl_sync(FULL, base, 31);
+            const int rb = base + inc - d;
+            if (fin && rb + d <= fv.rpool_cap) {
+                for (int k = 0; k < d; ++k) fv.rpool[rb + k] = ps.orig[tring_get(ring, k)];
+                fv.rinfo[op] = ((uint32_t)rb << 8) | (uint32_t)d;
+            }
+        }
+    }
+}
+
 // All stars of the staged point set.  EMIT: triangles into fv.tri; otherwise the graph vote into fv.pflag.
 // Block-wide; sc, defer[] and defer2[] are shared scratch.  Four levels: pair path (all stars) -> wrap path (hull stars,
 // circles leaving the block) -> exact half-warp path (what float32 could not certify) -> exact full-warp path (more than
@@ -1402,10 +1323,16 @@ template <bool EMIT>
 __device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, StarCtl *sc, uint16_t *defer, uint16_t *defer2,
                                       int &n_exact, long long *t_fast, const uint16_t *todo = nullptr, int n_todo = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { sc->next_pos = 0; sc->n_defer = 0; sc->n_defer_hi = 0; sc->n_defer2 = 0; }
+    // vote pass over all stars: 32-star tasks of the thread path first, the rest (and small frames) on the pair path
+    int limit = 0;
+#ifdef MVOSR_THREAD_PATH
+    if (!EMIT && !todo) limit = max(ps.n - THREAD_FILL, 0) & ~31;
+#endif
+    if (tid == 0) { sc->next_pos = limit; sc->next_thread = 0; sc->n_defer = 0; sc->n_defer_hi = 0; sc->n_defer2 = 0; }
     __syncthreads();
     long long tc0 = clock64();
     uint16_t *const defer_hi = defer2 - 1;                       // defer[] is filled from both ends (defer2 = defer + cap)
+    if (limit) stars_thread(ps, fv, sc, defer, defer_hi, limit);
     stars_pair<EMIT>(ps, fv, sc, defer, defer_hi, todo, n_todo);
     __syncthreads();
     if (tid == 0 && t_fast) *t_fast += clock64() - tc0;

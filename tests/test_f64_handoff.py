@@ -3,9 +3,11 @@
 The reference computes on the float64 values its front-end produces (cv2.recoverPose's output, the reprojection of
 src/main.py:102-104); the CUDA path stages float32 structure-of-arrays (compat/rescale.py -> batch.pack_frames).
 tests/golden/seq_f64.npz holds 8 frames of the headline shape as UNROUNDED float64 arrays together with what the unmodified
-reference makes of them (make_golden.pack_unrounded, Philox sampler).  Measured: the rounding moves no gate on these frames --
-same survivor / triangle / vertex-list / inlier counts -- and the raw scale by < 1e-6 relative (north star: 1e-5), so no float64
-entry point is needed for the bar; the tests below keep it that way."""
+reference makes of them (make_golden.pack_unrounded, Philox sampler).  Measured: rounding the inputs to float32 moves a gate in
+1 of the 8 frames (three more vertices pass the tight-pitch gate, the RANSAC consensus changes, 6.9e-4 on the raw scale); in the
+other frames every count is unchanged and the raw scale moves by < 1e-6 relative (north star: 1e-5).  Hence the float64 entry
+points (mvosr_scale_frames_f64 / mvosr_scale_frame_host_f64, what compat/rescale.ScaleEstimator calls): they evaluate the ROI cut,
+the votes, the gates and the RANSAC on the caller's float64 values, and the GPU test below holds them to the reference."""
 import os
 import sys
 
@@ -37,19 +39,27 @@ def test_oracle_on_the_unrounded_hand_off_equals_reference(z):
         np.testing.assert_allclose(rec["raw_scale"], sc["raw_scale"], rtol=1e-9)
 
 
-def test_float32_rounding_of_the_inputs_stays_inside_the_tolerance_on_the_cpu(z):
-    """Oracle on the float32-rounded copies of the same arrays (what the CUDA path stages) against the reference on the
-    unrounded ones: the fraction of frames beyond 1e-5 is zero, and no gate moves."""
-    worst, beyond = 0.0, 0
-    for f in range(int(z["n_frames"])):
+def test_float32_rounding_of_the_inputs_on_the_cpu(z):
+    """Oracle on the float32-rounded copies of the same arrays (what a float32 staging would compute) against the reference on the
+    unrounded ones.  Where no gate moves the raw scale stays within 1e-6; a frame whose counts change is exactly the case the
+    float64 entry points exist for -- at most a quarter of these frames, and this test says which."""
+    worst_same, moved = 0.0, []
+    n = int(z["n_frames"])
+    for f in range(n):
         f3 = z["f%d_f3" % f].astype(np.float32).astype(np.float64); f2 = z["f%d_f2" % f].astype(np.float32).astype(np.float64)
         rec = P.frame_raw_scale(f3, f2, int(z["seed"]), f, 0, absolute_reference=1.7)
         sc = _scalars(z, f)
         rel = abs(rec["raw_scale"] - sc["raw_scale"]) / sc["raw_scale"]
-        worst = max(worst, rel); beyond += rel > TOL
-        assert (rec["ic"], rec["n_sel"], int(rec["keep"].sum()), rec["tri2"].shape[0]) == (sc["best_ic"], sc["n_sel"], sc["n_kept"], sc["n_tri"]), f
-    print("float32 staging vs float64 reference: %d of %d frames beyond %g, worst %.2e" % (beyond, int(z["n_frames"]), TOL, worst))
-    assert beyond == 0 and worst < 1e-6
+        same = (rec["ic"], rec["n_sel"], int(rec["keep"].sum()), rec["tri2"].shape[0]) == (sc["best_ic"], sc["n_sel"], sc["n_kept"], sc["n_tri"])
+        if same:
+            worst_same = max(worst_same, rel)
+        else:
+            moved.append((f, rel))
+    print("float32-rounded inputs vs float64 reference: a gate moved in %d of %d frames %s; elsewhere worst %.2e"
+          % (len(moved), n, ["frame %d: %.1e" % m for m in moved], worst_same))
+    assert worst_same < 1e-6
+    assert len(moved) <= n // 4
+    assert all(rel < 5e-3 for _, rel in moved)
 
 
 @pytest.mark.gpu
