@@ -618,6 +618,8 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 int nd = run_stars<false>(ctl.ps, fv, &ctl.sc, defer, defer2, n_exact, &ctl.tphase[3]);
                 fv.rpool = nullptr;
                 if (tid == 0) ctl.n_deferred_total += nd;
+                __syncthreads();
+                votes_from_rings(n, V, fv, rpool);                 // the graph votes of the stored stars, one star per thread
             }
             __syncthreads();
             status |= ctl.status;

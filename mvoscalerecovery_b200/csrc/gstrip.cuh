@@ -119,16 +119,26 @@ __device__ __forceinline__ bool graph_vote_at(const SortedSet &ps, const FrameVi
     return graph_vote<float>(op, vp, zp, oa, va, za, ob, vb, zb, fv.pass_mask);
 }
 
-// keep = (#incident triangles with p>0.6)/(#incident) > 0.5 (graph.py:33-35,131-132); 0/0 -> False
+// the same vote by feature indices (V: the frame's v by feature index -- the values the sorted copy holds)
+__device__ __forceinline__ bool graph_vote_orig(const FrameView &fv, const float *V, int op, int oa, int ob) {
+    const float vp = V[op], va = V[oa], vb = V[ob], zp = fv.Z[op], za = fv.Z[oa], zb = fv.Z[ob];
+    if (fv.f3d && (vp == va || vp == vb || va == vb || zp == za || zp == zb || za == zb)) {
+        const size_t ip = (size_t)fv.fbase + fv.srcidx[op], ia = (size_t)fv.fbase + fv.srcidx[oa], ib = (size_t)fv.fbase + fv.srcidx[ob];
+        return graph_vote<double>(op, fv.f2d[2 * ip + 1], fv.f3d[3 * ip + 2], oa, fv.f2d[2 * ia + 1], fv.f3d[3 * ia + 2],
+                                  ob, fv.f2d[2 * ib + 1], fv.f3d[3 * ib + 2], fv.pass_mask);
+    }
+    return graph_vote<float>(op, vp, zp, oa, va, za, ob, vb, zb, fv.pass_mask);
+}
+
+// keep = (#incident triangles with p>0.6)/(#incident) > 0.5 (graph.py:33-35,131-132); 0/0 -> False.
+// With the ring store on (vote pass of the full pipeline) a finished star only STORES its ring here: the votes of all stored rings
+// are taken afterwards by votes_from_rings, one star per thread -- in the star builders the triangles of a star sit on 6 of the 16
+// (or 32) lanes that built it, and the vote was 6.5 % of the kernel's instructions at 10-14 active lanes.  A star whose ring does
+// not fit the pool votes here.
 template <int W>
 __device__ __forceinline__ void consume_vote(unsigned mask, int gl, int d, int p, int sid, int nid,
                                              const SortedSet &ps, const FrameView &fv) {
-    const bool tri = gl < d && sid != INF16 && nid != INF16;
-    bool vote = false;
     const int op = ps.orig[p];
-    if (tri) vote = graph_vote_at(ps, fv, p, sid, nid);
-    unsigned bt = __ballot_sync(mask, tri) & mask, bv = __ballot_sync(mask, vote) & mask;
-    if (gl == 0 && 2 * __popc(bv) > __popc(bt)) fv.pflag[op] |= 2;
     if (fv.rpool && d > 0) {
         int rb = 0;
         if (gl == 0) rb = atomicAdd(fv.rcount, d);
@@ -136,7 +146,32 @@ __device__ __forceinline__ void consume_vote(unsigned mask, int gl, int d, int p
         if (rb + d <= fv.rpool_cap) {
             if (gl < d) fv.rpool[rb + gl] = sid != INF16 ? ps.orig[sid] : INF16;
             if (gl == 0) fv.rinfo[op] = ((uint32_t)rb << 8) | (uint32_t)d;
+            return;
         }
+    }
+    const bool tri = gl < d && sid != INF16 && nid != INF16;
+    bool vote = false;
+    if (tri) vote = graph_vote_at(ps, fv, p, sid, nid);
+    unsigned bt = __ballot_sync(mask, tri) & mask, bv = __ballot_sync(mask, vote) & mask;
+    if (gl == 0 && 2 * __popc(bv) > __popc(bt)) fv.pflag[op] |= 2;
+}
+
+// The graph votes of every star whose ring is in the store: thread o walks the ring of feature o (feature indices, counter-clockwise,
+// INF16 = the hull gap) and sets its keep flag.  Block-wide; the caller synchronises.
+__device__ __forceinline__ void votes_from_rings(int n, const float *V, const FrameView &fv, const uint16_t *rpool) {
+    for (int o = threadIdx.x; o < n; o += NT) {
+        const uint32_t info = fv.rinfo[o];
+        if (!info) continue;
+        const int d = (int)(info & 0xFFu);
+        const uint16_t *r = rpool + (info >> 8);
+        const int first = r[0];
+        int prev = first, nt = 0, nv = 0;
+        for (int k = 0; k < d; ++k) {
+            const int nxt = k + 1 < d ? (int)r[k + 1] : first;
+            if (prev != INF16 && nxt != INF16) { ++nt; nv += graph_vote_orig(fv, V, o, prev, nxt) ? 1 : 0; }
+            prev = nxt;
+        }
+        if (2 * nv > nt) fv.pflag[o] |= 2;
     }
 }
 
@@ -1237,21 +1272,23 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
             if (own && !over) { uint16_t *t = fv.tri + 3 * (base + rk); t[0] = (uint16_t)op; t[1] = (uint16_t)(key >> 16); t[2] = (uint16_t)(key & 0xFFFFu); }
             if (gl == 0 && k && !over) { fv.tbase[op] = (uint16_t)base; fv.tcnt[op] = (uint8_t)k; }
         } else {
-            bool vote = false; int oa_ring = INF16;
-            if (tri) {
-                oa_ring = ps.orig[sid];
-                vote = graph_vote_at(ps, fv, p, sid, nid);
-            }
-            const unsigned bt = GBALLOT(tri), bv = GBALLOT(vote);
-            if (gl == 0 && d > 0 && 2 * __popc(bv) > __popc(bt)) fv.pflag[op] |= 2;
-            if (fv.rpool) {                                                  // ring store (see FrameView)
+            // ring store first (see consume_vote): the votes of a stored ring are taken by votes_from_rings
+            bool stored = false;
+            if (fv.rpool) {
                 int rb = 0;
                 if (gl == 0 && d > 0) rb = atomicAdd(fv.rcount, d);
                 rb = GSHFL(rb, 0);
-                if (rb + d <= fv.rpool_cap) {
-                    if (tri) fv.rpool[rb + gl] = (uint16_t)oa_ring;
+                stored = rb + d <= fv.rpool_cap;
+                if (stored) {
+                    if (tri) fv.rpool[rb + gl] = ps.orig[sid];
                     if (gl == 0 && d > 0) fv.rinfo[op] = ((uint32_t)rb << 8) | (uint32_t)d;
                 }
+            }
+            if (__any_sync(FULL, d > 0 && !stored)) {                           // pool full (or no store): vote here
+                bool vote = false;
+                if (tri && !stored) vote = graph_vote_at(ps, fv, p, sid, nid);
+                const unsigned bt = GBALLOT(tri), bv = GBALLOT(vote);
+                if (gl == 0 && d > 0 && !stored && 2 * __popc(bv) > __popc(bt)) fv.pflag[op] |= 2;
             }
         }
     }

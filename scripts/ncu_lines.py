@@ -1,6 +1,8 @@
 """Aggregate an ncu source-page CSV (SASS level) per CUDA source line using nvdisasm line info.
 The SASS listing of a kernel in ncu is the kernel followed by its callees; functions are aligned by
-matching instruction text.  usage: ncu_lines.py <report.ncu-rep> <kernel-substring> [top] [sass]"""
+matching instruction text.  usage: ncu_lines.py <report.ncu-rep> <kernel-substring> [top] [sass]
+MVOSR_CALLER=1: instructions inlined from CUDA's own headers (shuffles, ballots, reductions, atomics) are attributed to the line
+of OUR source that called them (nvdisasm -gi prints the inlining chain)."""
 import csv, io, os, re, subprocess, sys, collections
 
 rep, kname = sys.argv[1], sys.argv[2]
@@ -13,9 +15,11 @@ os.makedirs(tmp, exist_ok=True)
 for f in os.listdir(tmp):
     os.remove(os.path.join(tmp, f))
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL)
-dis = "\n".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+CALLER = bool(os.environ.get("MVOSR_CALLER"))
+dis = "\n".join(subprocess.run(["nvdisasm", "-gi" if CALLER else "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
                 for f in sorted(os.listdir(tmp)) if f.endswith(".cubin"))          # one cubin per translation unit
 cur_f, cur_line, table = None, None, collections.defaultdict(list)
+cur_path, in_chain = "", False
 norm = lambda t: re.sub(r"\s+", " ", re.sub(r"`\([^)]*\)|0x[0-9a-f]+", "#", t.strip().rstrip(";"))).strip()
 for ln in dis.splitlines():
     m = re.match(r"\.text\.(\S+):", ln)
@@ -23,7 +27,12 @@ for ln in dis.splitlines():
         cur_f = m.group(1); continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
-        cur_line = (os.path.basename(m.group(1)), int(m.group(2))); continue
+        # -gi: the chain innermost -> outermost on consecutive lines; keep the innermost frame that is not a CUDA header
+        if not (CALLER and in_chain and "/cuda/" not in cur_path):
+            cur_path = m.group(1); cur_line = (os.path.basename(cur_path), int(m.group(2)))
+        in_chain = True
+        continue
+    in_chain = False
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(\S.*);", ln)
     if m and cur_f:
         table[cur_f].append((int(m.group(1), 16), cur_line, norm(m.group(2))))
