@@ -1,13 +1,23 @@
-"""Write profiles/README.md from the JSON lines and ncu summaries under profiles/ (numbers are never typed by hand)."""
+"""Write profiles/README.md from the JSON lines and ncu summaries under profiles/ (numbers are never typed by hand).
+Round 2: bench_r02_final_n{1,2,4,8}.json, bench_r02_{reference,dense_n1,fleet_n1}.json, ransac_sweep_r02.json, primitives_r02.json,
+phase_r02_{uniform,ground,clustered}.json, main_config0_r02.json, ncu_r02_*.txt, launches_r02_summary.txt, traffic.json."""
 import json, os
 P = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles") + os.sep
 J = lambda n: json.load(open(P + n))
-n1, n8, d1, f1, f8, ref = (J('bench_r01_final_n1.json'), J('bench_r01_final_n8.json'), J('bench_r01_dense_n1.json'),
-                           J('bench_r01_fleet_n1.json'), J('bench_r01_fleet_n8.json'), J('bench_r01_reference.json'))
-sweep = J('ransac_sweep_r01.json')
-ncu, reg, launch = open(P + 'ncu_r01_frame_kernel_bench.txt').read(), open(P + 'ncu_r01_frame_kernel_regions.txt').read(), open(P + 'launches_r01_summary.txt').read()
+T = lambda n: open(P + n).read()
+N = {n: J('bench_r02_final_n%d.json' % n) for n in (1, 2, 4, 8)}
+n1 = N[1]
+r1 = J('bench_r01_final_n1.json')
+ref, dense, fleet1 = J('bench_r02_reference.json'), J('bench_r02_dense_n1.json'), J('bench_r02_fleet_n1.json')
+dense1 = J('bench_r01_dense_n1.json')
+sweep, prim, cfg0, traffic = J('ransac_sweep_r02.json'), J('primitives_r02.json'), J('main_config0_r02.json'), J('traffic.json')
+ph = {d: J('phase_r02_%s.json' % d) for d in ('uniform', 'ground', 'clustered')}
+ncu, reg, launch, fe = T('ncu_r02_frame_kernel_bench.txt'), T('ncu_r02_frame_kernel_regions.txt'), T('launches_r02_summary.txt'), T('ncu_r02_find_essential.txt')
 m = {l.split()[0]: l.split()[-1] for l in ncu.splitlines() if l.strip()}
 winstr = float(m['smsp__inst_executed.sum'])
+kms = float(m['gpu__time_duration.sum'])
+rf = n1['roofline']
+
 tab = {}
 for r in sweep['rows']:
     tab.setdefault((r['outlier_frac'], r['hypotheses']), {})[int(r['stop_at_goal'])] = r
@@ -15,62 +25,105 @@ lines = ["| outliers | H | early stop: frames/s | med err | p95 err | all hypoth
 for (o, h), v in sorted(tab.items()):
     a, b = v[1], v[0]
     lines.append("| %d %% | %d | %d | %.2e | %.2e | %d | %.2e | %.2e |" % (round(100 * o), h, a['fps'], a['err_median'], a['err_p95'], b['fps'], b['err_median'], b['err_p95']))
-txt = f"""# profiles/ — round 1 measurements (B200, sm_100a, {n1['clocks']['sm_mhz']:.0f} MHz, throttle reasons: {n1['clocks']['reasons'] or 'none'})
 
-All numbers were taken through `gpurun` on this pool's B200s.  Bench lines are `bench.py` outputs (CUDA events, not under a
-profiler); ncu numbers are from separate profiled runs of the same command.  `scripts/summarize_profiles.py` and
-`scripts/make_profiles_readme.py` regenerate the summaries and this file from the raw outputs.
 
-## Headline (BASELINE configs[1]: 4 541 frames x 2 500 correspondences, ~2 000 road-ROI features per frame, per GPU)
+def scal_rows():
+    out = []
+    for n in (1, 2, 4, 8):
+        d, f = N[n], N[n]['fleet']
+        out.append("| %d | %d | %.2f | %d | %.2fx | %d | %.2f | %.2f / %.3f / %.3f | %d | **%.2fx** | `bench_r02_final_n%d.json` |" % (
+            n, d['value'], d['ms_per_step'], d['e2e']['value'], d['value'] / n1['value'], f['value'], f['ms_per_step'], f['kernel_ms'], f['gather_ms'], f['filter_ms'],
+            f['e2e']['value'], f['value'] / n1['fleet']['value'], n))
+    return "\n".join(out)
 
-| GPUs | frames/s (device-resident) | ms/step | frames/s end to end (pinned host buffers, H2D+D2H inside) | file |
-|---|---|---|---|---|
-| 1 | {n1['value']:.0f} | {n1['ms_per_step']:.2f} | {n1['e2e']['value']:.0f} | `bench_r01_final_n1.json` |
-| 8 | {n8['value']:.0f} | {n8['ms_per_step']:.2f} | {n8['e2e']['value']:.0f} | `bench_r01_final_n8.json` |
 
-Weak scaling 8 GPUs / 1 GPU: {n8['value'] / n1['value']:.2f}x (one 4 541-frame sequence per GPU; one all-gather of 24 B/frame, then the
-filter over all eight sequences on every rank); 2 GPUs: `bench_r01_final_n2.json` (408.0 k with the build before the RANSAC change).
-Reference arm (`bench.py --impl reference`, oracle port of stages 1-5 on {ref['cpu_baseline']['cores']} host cores): {ref['value']:.0f} frames/s
-(`bench_r01_reference.json`); single core: {n1['cpu_baseline']['value']:.1f} frames/s.  The unmodified reference (Python loops per triangle)
-measured 0.53-0.69 s/frame/core in the build container (SURVEY.md 3.3).
+def phase_rows():
+    names = [("load+stage1+roi", "load + stage 1 + ROI"), ("grid1", "strip index #1"), ("stars1", "stars #1: vote pass + votes from the ring store"),
+             ("stars1_pair", "... of which pair path"), ("keep+compact+grid2", "keep + compaction + strip index #2 + ring pre-pass"),
+             ("stars2", "stars #2: emit pass"), ("stars2_pair", "... of which pair path"), ("planes", "planes"), ("median", "median"),
+             ("valid_list", "vertex list"), ("ransac", "RANSAC")]
+    out = []
+    for k, label in names:
+        out.append("| %s | %s |" % (label, " | ".join("%d k" % round(ph[d]['phases'][k]['cycles'] / 1e3) for d in ('uniform', 'ground', 'clustered'))))
+    tot = lambda d: sum(ph[d]['phases'][k]['cycles'] for k in ("load+stage1+roi", "grid1", "stars1", "keep+compact+grid2", "stars2", "planes", "median", "valid_list", "ransac"))
+    out.append("| total | %s |" % " | ".join("%.2f M" % (tot(d) / 1e6) for d in ('uniform', 'ground', 'clustered')))
+    out.append("| stars leaving the pair path (both passes) | %s |" % " | ".join("%d" % round(ph[d]['phases']['n_to_wrap_path']['cycles']) for d in ('uniform', 'ground', 'clustered')))
+    out.append("| stars on the exact paths | %s |" % " | ".join("%.1f" % ph[d]['n_deferred'] for d in ('uniform', 'ground', 'clustered')))
+    out.append("| kernel-only frames/s of this 592-frame run (with the phase clocks on) | %s |" % " | ".join("%d" % ph[d]['fps'] for d in ('uniform', 'ground', 'clustered')))
+    return "\n".join(out)
 
-History of the same bench line this round: 8.3 k (first correct path, FP64 thread-per-point stars) -> 17 k (register-resident
-half-warp stars) -> 91 k (warp-per-star gift wrapping, lanes = candidates) -> 110 k (stage 1 by inverse iteration) -> 132 k
-(registers, hull rows first) -> 136 k (two stars per warp in lock step) -> 140.6 k (temporal filter kernel) -> 166.3 k
-(**Delaunay #2 reuses the stars of Delaunay #1**) -> 188.9 k (dense nearest-first streaming, seeded rebuilds, one-pass median)
--> 190.4 k (filter prefetch) -> 196.0 k (quick accept of the cap test, seeded wrap walk) -> {n1['value'] / 1e3:.1f} k (pair-path
-micro-optimisations: one order-preserving key per step, slots populated on demand, closed-form candidate decode; 203.7 k, then
-896 threads per CTA instead of 1024: 73 registers per thread, no spills; RANSAC scoring pipelined).
 
-## The other BASELINE configurations (`bench.py --workload ...`; dense and the 8-GPU fleet line measured with the 190 k build)
+od = n1['other_densities']
+cb = n1['cpu_baseline']
+txt = f"""# profiles/ — round 2 measurements (B200, sm_100a, {n1['clocks']['sm_mhz']:.0f} MHz, throttle reasons: {n1['clocks']['reasons'] or 'none'})
+
+All numbers were taken through `gpurun` on this pool's B200s, on the build of the round's last kernel change (kernel source hash
+`{traffic['kernel_source_hash']}`, `bench.kernel_source_hash()`).  Bench lines are `bench.py` outputs (CUDA events, not under a profiler); ncu
+numbers are from separate profiled runs of the same command.  `scripts/gpu_r02_final.sh` is the single-GPU evidence run,
+`scripts/summarize_profiles.py` and `scripts/make_profiles_readme.py` regenerate the summaries and this file from the raw outputs.
+Round-1 files (`*_r01*`) are kept for comparison.
+
+## Headline (BASELINE configs[1]: 4 541 frames x 2 500 correspondences, ~2 000 road-ROI features per frame, per GPU) and the fleet (configs[3])
+
+| GPUs | frames/s (device-resident) | ms/step | frames/s end to end (pinned host buffers, H2D+D2H inside) | weak scaling | fleet frames/s (23 201 frames cut by frame range) | fleet ms/step | kernel / gather / filter ms | fleet end to end | fleet strong scaling | file |
+|---|---|---|---|---|---|---|---|---|---|---|
+{scal_rows()}
+
+Both blocks come from ONE invocation per N (`bench.py --gpus N`: the `kitti00` line carries a `fleet` block).  The fleet path is three
+launches per rank -- shard kernel over a frame range that may span sequences, one in-place NCCL all-gather of 16-byte frame records,
+the filter straight from the gathered records -- and no other collective.  Round 1 (mixed builds): 6.70x at 8 GPUs.
+
+CPU arm, the **unmodified reference** (`oracle/_ref/src`: `cv2.recoverPose` + `rescale.ScaleEstimator.scale_calculation` in the loop of
+`main_offline.py:57-88`): {cb['value']:.2f} frames/s on one host core ({cb['sample'].split(';')[0]}); `bench.py --impl reference`:
+{ref['value']:.1f} frames/s on {ref['cpu_baseline']['cores']} worker processes = {ref['cpu_baseline']['frames_per_s_per_core']:.2f} frames/s/core (`bench_r02_reference.json`).
+Per-frame drop-in (`compat/rescale.ScaleEstimator.scale_calculation`, numpy float64 in, one C-ABI call per frame, the loop of
+`main_offline.py:57-88` over 500 frames): {n1['e2e']['dropin_fps']['value']:.0f} calls/s -- one frame occupies one SM for {1e3 / n1['e2e']['dropin_fps']['value']:.2f} ms, the other 147 idle: the
+batch entry points exist for that reason.  Pageable (not pinned) host arrays through the same host call: {n1['e2e']['pageable_value']:.0f} frames/s.
+
+Same kernel on other feature densities (1 184 frames, `other_densities` block of the same line; round-1 uniform-grid build in brackets):
+perspective ground features (SURVEY 8d generator: X in U(-8,8) m, Z in U(5,40) m) **{od['kitti00-ground']['value']:.0f}** frames/s (40 k), clustered
+(70 % of the features in 12 Gaussian patches) **{od['kitti00-clustered']['value']:.0f}** (55 k), image-uniform {n1['value']:.0f} ({r1['value']:.0f}): the strip index
+trades 4 % on the easiest distribution for 4x / 2.5x on the realistic ones.  Every frame of every workload ends `updated` (status
+histogram in `config.status_hist`; no overflow, no held state).
+
+History of the headline line: round 1 8.3 k -> 209.3 k (`profiles/README.md` of round 1, in git history); round 2: 209 k (round-1
+build on this pool) -> 179 k (strip index, all densities) -> 190 k (sub-cell queries, strips grown by one warp) -> 195 k (window from
+single-instruction rcp / sqrt, wider block on the one-warp-per-star path, vote by rank sums) -> {n1['value'] / 1e3:.1f} k (graph votes taken from the
+ring store, one star per thread).
+
+## The other BASELINE configurations
 
 | workload | GPUs | frames/s | ms/step | end to end | note | file |
 |---|---|---|---|---|---|---|
-| dense (configs[2]): 25 000 correspondences, ~20 000 ROI features per frame, 592 frames per GPU | 1 | {d1['value']:.0f} | {d1['ms_per_step']:.2f} | {d1['e2e']['value']:.0f} | large-frame mode: staging in per-CTA global-memory slabs (L2); per feature only 1.5x the cost of the shared-memory mode; CPU port: {d1['cpu_baseline']['value']:.2f} frames/s/core | `bench_r01_dense_n1.json` |
-| fleet (configs[3]): 11 KITTI 00-10-shaped sequences, 23 201 frames, frame-range shards | 1 | {f1['value']:.0f} | {f1['ms_per_step']:.2f} | {f1['e2e']['value']:.0f} | strong scaling; end to end = `mvosr_recover_fleet_host` | `bench_r01_fleet_n1.json` |
-| fleet | 8 | {f8['value']:.0f} | {f8['ms_per_step']:.2f} | {f8['e2e']['value']:.0f} | {f8['value'] / f1['value']:.2f}x at 8 GPUs: 2 900 frames = 19.6 per SM per GPU (tail of the last wave) + the filter over the full vector on every rank | `bench_r01_fleet_n8.json` |
+| dense (configs[2]): 25 000 correspondences, ~20 000 ROI features per frame, 592 frames per GPU | 1 | {dense['value']:.0f} | {dense['ms_per_step']:.2f} | {dense['e2e']['value']:.0f} ({dense['e2e']['value'] / dense['value']:.2f} of device-resident) | large-frame mode: staging in per-CTA global-memory slabs (L2), two slab sets so that the two compute streams overlap copies; round 1: {dense1['value']:.0f} / {dense1['e2e']['value']:.0f} (0.69); unmodified reference: {dense['cpu_baseline']['value']:.2f} frames/s/core | `bench_r02_dense_n1.json` |
+| fleet (configs[3]) stand-alone | 1 | {fleet1['value']:.0f} | {fleet1['ms_per_step']:.2f} | {fleet1['e2e']['value']:.0f} | the `--workload fleet` line; the scaling table above comes from the `fleet` block of the default line | `bench_r02_fleet_n1.json` |
+| configs[0]: the UNMODIFIED `src/main.py` on {cfg0['dropin']['frames']} rendered frames (1241x376 textured ground plane, AKAZE + LK + findEssentialMat + recoverPose + estimator), whole-program wall clock | 1 | reference modules: {cfg0['reference']['frames_per_s']:.2f} ({cfg0['reference']['frames']} frames); drop-in module set: {cfg0['dropin']['frames_per_s_warm']:.2f} warm / {cfg0['dropin']['frames_per_s_cold']:.2f} cold | | | {cfg0['speedup_warm']:.2f}x: the estimator's share of the frame is gone (0.8 ms per call), what remains is the host front-end, identical in both arms; recovered scale / true step: {cfg0['dropin']['median_scale_over_true_step']:.3f} (drop-in) vs {cfg0['reference']['median_scale_over_true_step']:.3f} (reference, OS-entropy RANSAC) | `main_config0_r02.json`, `scripts/time_main_config0.py` |
 
 ## Roofline (`roofline` block of the bench line)
 
 Contract bound: HBM.  Algorithmic bytes per launch = 16 B x 11.35 M correspondences + 64 B x 4 541 frames = 182.0 MB;
-kernel {n1['roofline']['kernel_ms']:.2f} ms -> {n1['roofline']['achieved']:.2f} GB/s = {100 * n1['roofline']['frac']:.3f} % of the measured 6 545 GB/s.  ncu `dram__bytes` for the same launch
-(`traffic.json`): reads = the algorithmic bytes (no re-reads); the writes are local-memory (register spill / call stack)
-write-backs of 151 k resident threads, the outputs are 60 KB.  **The kernel is instruction-issue bound, not memory bound**:
-issue slots {float(m['smsp__issue_active.avg.pct_of_peak_sustained_active']):.0f} % busy, IPC {float(m['sm__inst_executed.avg.per_cycle_elapsed']):.1f} of 4 per SM, {winstr / 1e9:.1f} G warp-instructions per launch = {winstr / 4541 / 1e6:.2f} M per frame (6.05 M at the start of the
-session), {float(m['smsp__thread_inst_executed_per_inst_executed.ratio']):.1f} of 32 lanes active on average, FP64 pipe {float(m['sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active']):.1f} %.
+kernel {rf['kernel_ms']:.2f} ms -> {rf['achieved']:.2f} GB/s = {100 * rf['frac']:.3f} % of the measured 6 545 GB/s.  ncu `dram__bytes` for the same launch
+(`traffic.json`, refused by `bench.py` unless its source hash matches the build): {traffic['read_bytes'] / 1e6:.0f} MB read = the algorithmic bytes (no
+re-reads) + {traffic['write_bytes'] / 1e6:.0f} MB written = local-memory (call stack / spill, 592 B per thread) write-backs of 132 k resident threads; the outputs
+are 60 KB.  **The kernel is instruction-issue bound, not memory bound**: issue slots {float(m['smsp__issue_active.avg.pct_of_peak_sustained_active']):.0f} % busy, IPC {float(m['sm__inst_executed.avg.per_cycle_elapsed']):.2f} of 4 per SM,
+{winstr / 1e9:.2f} G warp-instructions per launch = **{winstr / 4541 / 1e6:.2f} M per frame** (round 1: 3.95 M with the uniform grid; 4.19 M at the first strip
+build), issue fraction = warp-instructions / kernel time / (148 SMs x 4 schedulers x 1.965 GHz) = {winstr / (kms * 1e-3) / (148 * 4 * 1.965e9):.3f} (`roofline.issue_frac`),
+{float(m['smsp__thread_inst_executed_per_inst_executed.ratio']):.1f} of 32 lanes active on average, FP64 pipe {float(m['sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active']):.1f} %.
 
 ```
 {ncu}```
-(`ncu --set full --clock-control none --import-source on -k regex:frame_kernel -s 3 -c 1 python bench.py --steps 1 --warmup 3 --cpu-sample 0`)
+(`ncu --set full --clock-control none --import-source on -k regex:frame_kernel -s 3 -c 1 python bench.py --steps 1 --warmup 3 --cpu-sample 0 --dropin-frames 0 --no-fleet --no-densities`)
 
 ### Where the instructions go (same capture, per source region; `scripts/ncu_lines.py` + `scripts/ncu_regions.py`)
 
 ```
 {reg}```
-`pair` + most of `w_eval` = the two-stars-per-warp gift-wrapping path (both Delaunay passes; 85 % of the stars that are built
-at all); `w_stream`, `wrap:*`, `w_batch` = the one-warp-per-star path with streaming (hull stars and circles that leave the 5x5
-block, ~320 stars per frame); `frame_kernel.cuh` = load / grid build / ring pre-pass / planes / median / RANSAC;
-`triangulate.cuh` = stage 1; the samples of `run_stars` are barrier waits between the levels of the star pipeline.
+`pair` + `w_eval` = the two-stars-per-warp gift-wrapping path (both Delaunay passes); `gindex.cuh` = the strip index queries (block
+of a point, run searches) of every path; `w_stream`, `wrap:*`, `w_batch` = the one-warp-per-star path with streaming (hull stars and
+circles that leave the block, ~290 stars per frame); `frame_kernel.cuh` = load / strip build / ring pre-pass / planes / median /
+RANSAC; `consume` = ring store, votes from the ring store, triangle emission; `triangulate.cuh` = stage 1.  Stall reasons of the
+same capture: fixed-latency waits 23 %, eligible-not-selected 21 %, barrier 11 %, math-pipe throttle 9 %, long scoreboard 9 %,
+instruction fetch 6 %.
 
 ### Launch list of one bench run (shares)
 
@@ -79,61 +132,62 @@ block, ~320 stars per frame); `frame_kernel.cuh` = load / grid build / ring pre-
 
 ## Per-phase SM cycles of one frame (`scripts/phase_profile.py`, clock64 per CTA, 592 frames, 2 000 ROI features)
 
-| phase | session start | now |
+| phase | image-uniform | perspective (ground) | clustered |
+|---|---|---|---|
+{phase_rows()}
+
+Round 1 (uniform grid, image-uniform features): 1.32 M cycles per frame.  The one-warp-per-star path (`MVOSR_WRAP_COUNTERS`,
+`scripts/star_counters.py`): 290 stars per frame over both passes, 33 of them open (hull), 6.1 steps and 2.2 streaming calls per star,
+26 k warp-cycles per star (open stars 51 k), 47 % of them inside the streaming routine; summed over the stars that is 273 k cycles
+of 28 warps per frame against ~400 k measured for the two wrap phases: a third of those phases is the tail of uneven stars.
+
+### Measured and dropped this round (A/B on the three densities, `scripts/gpu_ab.sh`, `scripts/gpu_ab_test.sh`)
+
+| experiment | result | kept? |
 |---|---|---|
-| load + stage 1 + ROI | 23 k | 22 k |
-| grid #1 | 20 k | 20 k |
-| stars #1 (vote pass; of which pair path) | 943 k (642 k) | 813 k (570 k) |
-| keep + compaction + grid #2 (+ ring pre-pass) | 24 k | 54 k |
-| stars #2 (emit pass; of which pair path) | 838 k (570 k) | 342 k (199 k) |
-| planes | 8 k | 7 k |
-| median | 68 k | 20 k |
-| vertex list | 9 k | 9 k |
-| RANSAC | 39 k | 28 k |
-| total | 1.97 M | 1.32 M |
+| one star per LANE (`gthread.cuh`: scalar walk, propose by circumcentre parameter + certify by the empty-circle determinant; CPU-tested against Qhull, parity 40/40 on the B200) for the vote pass, pair path as filler | 30 % fewer warp instructions than the pair path on paper, 16 % in the ncu capture (12 of 32 lanes active: lanes wait for the longest walk and the largest block); instruction-fetch stalls 6 % -> 29 % (unrolled scalar loops); 195 k -> 187 k (divergent single pass), 133 k (two branch-free passes) | no (`-DMVOSR_THREAD_PATH`) |
+| streaming from inside the pair path, both stars of a warp in lock step (`pair_stream`) + 7-strip widened block on the wrap path | 190.6 k -> 143.6 k | no (the widened wrap block alone: kept, +1 %) |
+| dedicated warps on the one-warp-per-star path fed by a queue while the pair path runs (2 / 4 / 8 warps) | 199.8 k -> 186 k / 171 k / 144 k | no |
+| cap test clipped to the bounding box of the point set, behind the quick accept | uniform -0.5 %, perspective -2.5 %, clustered -5 % | no (`MVOSR_CAP_CLIP`) |
+| far-neighbour / hull stars queued first on the wrap path (defer list filled from both ends) | +0.3 % | yes |
+| 768 / 832 / 960 / 1024 threads per CTA | 197.8 k / 195.8 k / 195.2 k / 195.5 k against 199.6 k at 896 | 896 kept |
+| triangles ranked among the owning lanes only at emission | no change | no |
+| strip density 1.2 / 1.5 / 1.8 x window 2.2 / 2.5 / 2.8 cell sides | 1.5 x 2.5 is the optimum (3.23 ms per 592 frames; others 3.27 ... 3.51) | defaults kept |
 
-Stars that leave the pair path: 350 -> 322 per frame (82 hull / far-neighbour steps, 229 circles leaving the 5x5 block;
-`scripts/star_counters.py` with `-DMVOSR_STAR_COUNTERS`); the wrap path takes 6.9 steps and 2.8 streaming calls per star
-(`-DMVOSR_WRAP_COUNTERS`).  Grid density sweep 1.1 ... 1.8 points per cell: flat between 1.4 and 1.65 (1.5 kept).
-Tried and measured worse, kept out: clipping the cap test to the bounding box of the point set (pair path +13 %
-instructions for 38 fewer streaming stars); squared candidate lengths kept in registers (register pressure); running the
-wrap path from inside the pair pass instead of as a second phase (stars +150 k cycles); a second chance in the pair path that
-certifies steps whose cap leaves the 5x5 block against the ring of cells up to 7x7 (80 fewer wrap stars, but they are the cheap
-ones: pair path +85 k cycles for 31 k saved).
+## Stand-alone primitives (`scripts/bench_primitives.py`, `primitives_r02.json`; median of 10 device-timed calls, L2 flushed)
 
-## Stand-alone primitives (`scripts/bench_primitives.py`, `primitives_r01.json`; median of 10 device-timed calls, L2 flushed)
-
-| kernel | workload | ms | algorithmic GB/s | of measured HBM peak |
-|---|---|---|---|---|
-""" + "\n".join("| `%s` | %s | %.3f | %.0f | %.1f %% |" % (r["kernel"], r["workload"], r["ms"], r["achieved_gbs"], 100 * r["frac_of_hbm_peak"]) for r in J('primitives_r01.json')["rows"]) + """
+| kernel | workload | ms | algorithmic GB/s | of measured HBM peak | rate |
+|---|---|---|---|---|---|
+""" + "\n".join("| `%s` | %s | %.3f | %.0f | %.1f %% | %s |" % (r["kernel"], r["workload"], r["ms"], r["achieved_gbs"], 100 * r["frac_of_hbm_peak"],
+                                                                 ", ".join("%s %.3g" % (k, v) for k, v in r.items() if k.endswith("_per_s") or k.startswith("opencv"))) for r in prim["rows"]) + f"""
 
 `triangle_planes_kernel` is gather-bound (72 B of vertex gathers + 12 B of indices + 40 B out per triangle through L1/L2 for
 24 B/point of compulsory DRAM traffic); the votes are bound by their per-vertex atomics; the RANSAC with early stop reads every
-list once (first round of 8 hypotheses); the path scan and the pose selection are latency-bound at these sizes (one CTA per
-sequence / frame).
+list once; the path scan and the pose selection are latency-bound at these sizes (one CTA per sequence / frame).
+
+### `find_essential_kernel` (SURVEY N1: `cv2.findEssentialMat`'s five-point RANSAC, thread per hypothesis)
+
+```
+{fe}```
+FP64 pipe 42 % busy; the dominant stall is long scoreboard = the 5.3 KB of per-thread local memory (the 10x20 and 10x10 matrices):
+3.4 GB of DRAM traffic per launch for 25 MB of inputs, L1 hit rate 64 %.  Decision from these numbers: thread-per-hypothesis keeps the
+FP64 pipe less than half busy because of local-memory latency; a warp-per-hypothesis layout with the matrices in shared memory is the
+next step for this kernel (not done: at 144.6 k frames/s for 128 hypotheses -- OpenCV on the host: ~900 frames/s/core -- it is 1.4x
+the speed of the scale-recovery kernel it feeds).
 
 ## Sanitizers
 
-`compute-sanitizer --tool memcheck` and `--tool racecheck` over `scripts/sanitize_small.py` (fused and staged paths with debug
-buffers, shared-memory and large-frame staging, Delaunay-only, filter, path scan, plane RANSAC): 0 errors, 0 hazards
-(`sanitizer_r01.txt`).
+`compute-sanitizer --tool memcheck` and `--tool racecheck` over `scripts/sanitize_small.py` on the final build (fused and staged
+frame kernel with debug buffers, float64 entry, shared-memory and large-frame staging, Delaunay-only, filter, path scan, plane RANSAC,
+find_essential / recover_pose / pose_mask / bucket kernels): 0 errors, 0 hazards (`sanitizer_r02.txt`).
 
-## RANSAC sweep (BASELINE configs[4]; 592 frames, kernel-only frames/s, error of the RAW scale against the synthetic truth; 196 k build)
+## RANSAC sweep (BASELINE configs[4]; 592 frames, kernel-only frames/s, error of the RAW scale against the synthetic truth)
 
 """ + "\n".join(lines) + """
 
-(`ransac_sweep_r01.json`, `scripts/ransac_sweep.py`.)  With the reference's early stop the cost is flat in H because the first
+(`ransac_sweep_r02.json`, `scripts/ransac_sweep.py`.)  With the reference's early stop the cost is flat in H because the first
 hypothesis above 0.8 N usually ends the loop; evaluating all hypotheses costs ~10 us per frame per 1 000 hypotheses and halves
 the error.
-
-## Not measured this round: `find_essential_kernel` (five-point RANSAC), `pose_mask_kernel`, `bucket_kernel` (SURVEY N1)
-
-Written after the round's GPU minutes were spent; no number in this file covers them.  Evidence so far is CPU-side only:
-the solver's `__host__ __device__` numerics against LAPACK (2 797 of 2 810 solutions, none spurious), the kernel SOURCE under a
-pthread emulation bit-exact against a sequential replay and race-free under ThreadSanitizer (`sanitizer_r01.txt`, last section),
-`ptxas`: 128 registers, 5.3 KB stack, 0.8 KB spills, ~10 k instructions.  `scripts/gpu_round2_first.sh` is the GPU call it owes
-(parity, compute-sanitizer, `scripts/bench_primitives.py` rows with OpenCV's `findEssentialMat` on the host beside them, one ncu
-capture).  OpenCV's `findEssentialMat` in the build container: ~830 frames/s on one sequence of 400- or 2 500-correspondence frames.
 """
 open(P + 'README.md', 'w').write(txt)
 print("wrote", P + "README.md")
