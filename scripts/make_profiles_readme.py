@@ -152,6 +152,7 @@ of 28 warps per frame against ~400 k measured for the two wrap phases: a third o
 | far-neighbour / hull stars queued first on the wrap path (defer list filled from both ends) | +0.3 % | yes |
 | 768 / 832 / 960 / 1024 threads per CTA | 197.8 k / 195.8 k / 195.2 k / 195.5 k against 199.6 k at 896 | 896 kept |
 | triangles ranked among the owning lanes only at emission | no change | no |
+| pair path follows the edges a FINISHED neighbour's stored ring already settles (the successor of a in p's ring precedes p in a's ring) instead of evaluating them | 2 934 of ~12 000 steps per frame answered that way, parity 40/40, but 199.7 k -> 194.2 k: each look-up costs volatile loads + a fence, the writers a `MEMBAR` per star, and the two stars of a warp rarely skip the same step; cross-warp reads of the ring store without a barrier would also show up as racecheck hazards | no |
 | strip density 1.2 / 1.5 / 1.8 x window 2.2 / 2.5 / 2.8 cell sides | 1.5 x 2.5 is the optimum (3.23 ms per 592 frames; others 3.27 ... 3.51) | defaults kept |
 
 ## Stand-alone primitives (`scripts/bench_primitives.py`, `primitives_r02.json`; median of 10 device-timed calls, L2 flushed)

@@ -365,3 +365,36 @@ def test_ransac_configurations_vs_oracle(iters, stop):
         assert (st["best_hyp"][f], st["best_ic"][f], st["hyps_used"][f]) == (rr["best_hyp"], rr["ic"], rr["hyps_used"]), (f, iters, stop)
         np.testing.assert_allclose(raw[f], 1.7 / P.height_from_model(rr["model"]), rtol=1e-9)
     eng.close()
+
+
+@pytest.mark.parametrize("density", ["ground", "clustered"])
+def test_other_feature_densities_vs_oracle(engine, density):
+    """The bench's perspective (SURVEY 8d ground generator) and clustered feature distributions at the headline size (2 500
+    correspondences, ~2 000 ROI features), full pipeline against the oracle frame by frame: survivor count, triangle count of
+    Delaunay #2, vertex-list length, chosen hypothesis, inlier count, hypotheses used exactly, raw scale to 1e-9 -- the strip index
+    and the star paths see very uneven candidate blocks here (the round-1 uniform grid sent most of these stars to its slow paths)."""
+    import torch
+    from mvoscalerecovery_b200 import synth
+    from mvoscalerecovery_b200.batch import stats_to_numpy
+    from oracle import pipeline as P
+    b = synth.make_sequence(seed=4242, n_frames=4, n_corr=2500, outlier_frac=0.10, density=density)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(engine.device)
+    s1 = engine.triangulate_frames(t(b.offsets), t(b.cur_u), t(b.cur_v), t(b.ref_u), t(b.ref_v), t(b.poses))
+    maxf = int(np.max(np.diff(b.offsets)))
+    out = engine.scale_frames(t(b.offsets), s1["x"], s1["y"], s1["z"], s1["u"], s1["v"], maxf, counts=s1["n_out"], seed=5, seq_id=1, stats=True)
+    fused = engine.scale_frames_from_correspondences(t(b.offsets), t(b.cur_u), t(b.cur_v), t(b.ref_u), t(b.ref_v), t(b.poses),
+                                                     max_features=maxf, seed=5, seq_id=1)
+    torch.cuda.synchronize()
+    st = stats_to_numpy(out["stats"]); raw = out["raw_scale"].cpu().numpy(); n_out = s1["n_out"].cpu().numpy()
+    assert np.array_equal(raw, fused["raw_scale"].cpu().numpy(), equal_nan=True)
+    assert (out["status"].cpu().numpy() & 1).all()
+    for f in range(b.n_frames):
+        a = int(b.offsets[f]); m = int(n_out[f])
+        f3 = np.stack([s1[k][a:a + m].cpu().numpy() for k in "xyz"], 1).astype(np.float64)
+        f2 = np.stack([s1[k][a:a + m].cpu().numpy() for k in "uv"], 1).astype(np.float64)
+        rec = P.frame_raw_scale(f3, f2, 5, f, 1, absolute_reference=1.7)
+        assert st["n_kept"][f] == int(rec["keep"].sum()), (density, f)
+        assert st["n_tri"][f] == rec["tri2"].shape[0], (density, f)
+        assert 3 * st["n_valid"][f] == rec["n_sel"], (density, f)
+        assert (st["best_ic"][f], st["hyps_used"][f]) == (rec["ic"], rec["hyps_used"]), (density, f)
+        np.testing.assert_allclose(raw[f], rec["raw_scale"], rtol=1e-9)
