@@ -378,6 +378,59 @@ __device__ __forceinline__ void build_grid(int n, const float *U, const float *V
 }
 #endif
 
+#ifndef MVOSR_UNIFORM_GRID
+#ifndef MVOSR_FILTER_MIN_PCT
+#define MVOSR_FILTER_MIN_PCT 75
+#endif
+constexpr int FILTER_MIN_PCT = MVOSR_FILTER_MIN_PCT;       // filter the index of Delaunay #1 when at least this share of the points survives, else build anew
+// Strip index of a SUBSET of the indexed points (Delaunay #2 runs over the survivors of the graph check): instead of building it
+// again from the feature arrays -- histogram, strips, counting sort, rank sort, duplicates: 31 k cycles per frame -- the sorted copy
+// is filtered in place.  Strips, bins and sub-cells stay as they are (an order-preserving filter keeps every run sorted by (x,
+// index): the new feature indices are monotone in the old ones); row_start / cell_start become the survivor counts before their old
+// values.  The bounding box stays the old one (a superset: only used conservatively).  newidx[old feature] = new feature index or
+// INF16; tmp: cap + 1 uint16 of scratch.  The caller uses this while most points survive (the strips were sized for the old density).
+__device__ __forceinline__ void filter_grid(int n_old, int n_new, const uint16_t *newidx, GridArrays ga, Ctl *ctl, uint16_t *tmp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    SortedSet &ps = ctl->ps;
+    uint16_t *row_start = (uint16_t *)ps.row_start, *cstart = (uint16_t *)ps.cell_start;
+    // tmp[i] = survivors among the sorted positions before i
+    int run = 0;
+    for (int c0 = 0; c0 < n_old; c0 += NT) {
+        const int i = c0 + tid;
+        bool k = false;
+        if (i < n_old) { const int o = ga.sorig[i]; k = o != INF16 && newidx[o] != INF16; }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, k);
+        if (lane == 0) ctl->warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int woff, tot;
+        warp_offsets(ctl->warp_cnt, warp, lane, woff, tot);
+        if (i < n_old) tmp[i] = (uint16_t)(run + woff + __popc(bal & ((1u << lane) - 1u)));
+        run += tot;
+        __syncthreads();
+    }
+    if (tid == 0) tmp[n_old] = (uint16_t)run;
+    __syncthreads();
+    const int NC = ps.row_cell[ps.R];
+    for (int c = tid; c <= NC; c += NT) cstart[c] = tmp[cstart[c]];
+    for (int r = tid; r <= ps.R; r += NT) row_start[r] = tmp[row_start[r]];
+    // the sorted copy, in place: every chunk is read before any of its (smaller or equal) target positions is written
+    for (int c0 = 0; c0 < n_old; c0 += NT) {
+        const int i = c0 + tid;
+        float x = 0.f, y = 0.f; int no = INF16, pos = 0;
+        if (i < n_old) {
+            const int o = ga.sorig[i];
+            if (o != INF16) no = newidx[o];
+            if (no != INF16) { x = ga.sx[i]; y = ga.sy[i]; pos = tmp[i]; }
+        }
+        __syncthreads();
+        if (no != INF16) { ga.sx[pos] = x; ga.sy[pos] = y; ga.sorig[pos] = (uint16_t)no; }
+        __syncthreads();
+    }
+    if (tid == 0) ps.n = n_new;
+    __syncthreads();
+}
+#endif
+
 // write this frame's triangle list to global memory in canonical order
 __device__ __forceinline__ void write_canonical(int n, const FrameView &fv, uint32_t *scr, int *warp_tmp,
                                                 int32_t *out, int32_t *n_out) {
@@ -619,7 +672,9 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 fv.rpool = nullptr;
                 if (tid == 0) ctl.n_deferred_total += nd;
                 __syncthreads();
+#ifndef MVOSR_UNIFORM_GRID
                 votes_from_rings(n, V, fv, rpool);                 // the graph votes of the stored stars, one star per thread
+#endif
             }
             __syncthreads();
             status |= ctl.status;
@@ -676,6 +731,10 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                 for (int i = tid; i < n; i += NT) pflag[i] = 0;
                 if (tid == 0) { ctl.n_dup1 = ctl.n_dup; ctl.n_dup = 0; }
                 __syncthreads();
+#ifndef MVOSR_UNIFORM_GRID
+                if (100 * n_kept >= FILTER_MIN_PCT * n1) filter_grid(n1, n, mult, ga, &ctl, defer);          // most points survive: filter the index
+                else
+#endif
                 build_grid(n, U, V, pflag, ga, cap, &ctl, density, defer, win_m, wfac);
             } else {
                 for (int i = tid; i < n; i += NT) pflag[i] &= 1;
