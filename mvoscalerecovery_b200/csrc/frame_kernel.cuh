@@ -380,7 +380,7 @@ __device__ __forceinline__ void build_grid(int n, const float *U, const float *V
 
 #ifndef MVOSR_UNIFORM_GRID
 #ifndef MVOSR_FILTER_MIN_PCT
-#define MVOSR_FILTER_MIN_PCT 75
+#define MVOSR_FILTER_MIN_PCT 60
 #endif
 constexpr int FILTER_MIN_PCT = MVOSR_FILTER_MIN_PCT;       // filter the index of Delaunay #1 when at least this share of the points survives, else build anew
 // Strip index of a SUBSET of the indexed points (Delaunay #2 runs over the survivors of the graph check): instead of building it
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(NT, 1) frame_kernel(FrameParams P) {
                     int np = INF16, d = 0, dfull = 0;
                     if (o < n1) np = mult[o];
                     uint32_t info = 0;
-                    if (np != INF16) { info = fv.rinfo[o]; dfull = d = (int)(info & 0xFFu); if (d > RD) d = 0; oldof[np] = (uint16_t)o; }
+                    if (np != INF16) { info = fv.rinfo[o]; if (info & RING_PARTIAL) info = 0; dfull = d = (int)(info & 0xFFu); if (d > RD) d = 0; oldof[np] = (uint16_t)o; }
                     uint16_t *ring = rpool + (info >> 8);
                     int nb[RD];                                    // new index of ring entry j; INF16: hull gap; -1: dropped
                     bool clean = d > 0;

@@ -85,6 +85,9 @@ struct FrameView {
     const double *f3d, *f2d; const uint32_t *srcidx; int fbase;
 };
 constexpr uint16_t RING_DROPPED = 0xFFFE;
+// rinfo degree field, bit 7: a PARTIAL ring (vote pass) -- the counter-clockwise part of a star that stars_pair certified before it had to
+// give the star up, as sorted positions from the nearest neighbour on; stars_wrap resumes the walk there and clears the word
+constexpr uint32_t RING_PARTIAL = 0x80u;
 
 template <typename T>
 __device__ __forceinline__ bool edge_consistent(T va, T za, T vb, T zb) {
@@ -161,7 +164,7 @@ __device__ __forceinline__ void consume_vote(unsigned mask, int gl, int d, int p
 __device__ __forceinline__ void votes_from_rings(int n, const float *V, const FrameView &fv, const uint16_t *rpool) {
     for (int o = threadIdx.x; o < n; o += NT) {
         const uint32_t info = fv.rinfo[o];
-        if (!info) continue;
+        if (!info || (info & RING_PARTIAL)) continue;
         const int d = (int)(info & 0xFFu);
         const uint16_t *r = rpool + (info >> 8);
         const int first = r[0];
@@ -983,9 +986,24 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
                 if (ok && !fallback) { closed = true; sidC = sid; nC = n; }
             }
         }
-        // ---- q0 = the nearest point: certified by the distance to the block's boundary, unique up to rounding
+        // ---- a partial ring from stars_pair (vote pass): q0 and the counter-clockwise neighbours up to cur are certified already
         int q0 = -1; float q0x = 0.f, q0y = 0.f;
-        if (ok && !closed) {
+        int resume = 0, rcur = -1;
+        if (!EMIT && fv.rpool && ok) {
+            const int op = ps.orig[p];
+            const uint32_t info = fv.rinfo[op];
+            if (info & RING_PARTIAL) {
+                resume = (int)(info & 0x7Fu);
+                const int e = lane < resume ? (int)fv.rpool[(info >> 8) + lane] : (int)INF16;
+                __syncwarp();
+                if (lane == 0) fv.rinfo[op] = 0u;
+                sidC = e; nC = resume;
+                q0 = __shfl_sync(FULL, e, 0); rcur = __shfl_sync(FULL, e, resume - 1);
+                q0x = ps.x[q0] - ppx; q0y = ps.y[q0] - ppy;
+            }
+        }
+        // ---- q0 = the nearest point: certified by the distance to the block's boundary, unique up to rounding
+        if (ok && !closed && !resume) {
             const unsigned kA = vA ? __float_as_uint(al) : 0xFFFFFFFFu, kB = vB ? __float_as_uint(bl) : 0xFFFFFFFFu;
             const unsigned kmin = __reduce_min_sync(FULL, min(kA, kB));
             const float lmin = __uint_as_float(kmin);
@@ -1001,8 +1019,9 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
             }
         }
         // ---- the plain walk: counter-clockwise from q0 until it closes or meets a hull edge, then clockwise from q0
-        if (!closed) { sidC = lane == 0 ? q0 : (int)INF16; nC = 1; }
+        if (!closed && !resume) { sidC = lane == 0 ? q0 : (int)INF16; nC = 1; }
         float sigma = 1.f, cx = q0x, cy = q0y; int cpos = q0;
+        if (resume) { cpos = rcur; cx = ps.x[rcur] - ppx; cy = ps.y[rcur] - ppy; }
         while (ok && !closed) {
             WBest b;
             if (!step(cx, cy, sigma, cpos, b)) { ok = false; break; }
@@ -1244,6 +1263,22 @@ __device__ __noinline__ void stars_pair(const SortedSet &ps, const FrameView &fv
         }
         const bool fin = ok && closed;
         if (have && ok && !closed) PR(2);
+#ifndef MVOSR_NO_WRAP_RESUME
+        if (!EMIT && fv.rpool) {
+            // what was certified of a star that is given up is handed over: its neighbours from the nearest one to cur (the step from
+            // cur failed), as sorted positions; stars_wrap continues the walk from cur instead of starting over
+            const bool part = have && !fin && nC >= 2;
+            if (__any_sync(FULL, part)) {
+                int rb = 0;
+                if (gl == 0 && part) rb = atomicAdd(fv.rcount, nC);
+                rb = GSHFL(rb, 0);
+                if (part && rb + nC <= fv.rpool_cap) {
+                    if (gl < nC) fv.rpool[rb + gl] = (uint16_t)sid;
+                    if (gl == 0) fv.rinfo[ps.orig[p]] = ((uint32_t)rb << 8) | RING_PARTIAL | (uint32_t)nC;
+                }
+            }
+        }
+#endif
         if (have && !fin && gl == 0) {                              // (defer_hi: the last entry of defer[]; the two ends cannot meet, there are at most n stars)
             if (far) { const int slot = atomicAdd(&sc->n_defer_hi, 1); defer_hi[-slot] = (uint16_t)p; }
             else { const int slot = atomicAdd(&sc->n_defer, 1); defer[slot] = (uint16_t)p; }
