@@ -991,11 +991,12 @@ __device__ __noinline__ void stars_wrap(const SortedSet &ps, const FrameView &fv
         int resume = 0, rcur = -1;
         if (!EMIT && fv.rpool && ok) {
             const int op = ps.orig[p];
-            const uint32_t info = fv.rinfo[op];
+            uint32_t info = 0u;
+            if (lane == 0) info = fv.rinfo[op];                       // (one lane reads, clears and -- in the consumer -- rewrites this word)
+            info = __shfl_sync(FULL, info, 0);
             if (info & RING_PARTIAL) {
                 resume = (int)(info & 0x7Fu);
                 const int e = lane < resume ? (int)fv.rpool[(info >> 8) + lane] : (int)INF16;
-                __syncwarp();
                 if (lane == 0) fv.rinfo[op] = 0u;
                 sidC = e; nC = resume;
                 q0 = __shfl_sync(FULL, e, 0); rcur = __shfl_sync(FULL, e, resume - 1);

@@ -88,8 +88,9 @@ histogram in `config.status_hist`; no overflow, no held state).
 
 History of the headline line: round 1 8.3 k -> 209.3 k (`profiles/README.md` of round 1, in git history); round 2: 209 k (round-1
 build on this pool) -> 179 k (strip index, all densities) -> 190 k (sub-cell queries, strips grown by one warp) -> 195 k (window from
-single-instruction rcp / sqrt, wider block on the one-warp-per-star path, vote by rank sums) -> {n1['value'] / 1e3:.1f} k (graph votes taken from the
-ring store, one star per thread).
+single-instruction rcp / sqrt, wider block on the one-warp-per-star path, vote by rank sums) -> 200.0 k (graph votes taken from the
+ring store, one star per thread) -> 202 k (index of Delaunay #2 by filtering the sorted copy) -> {n1['value'] / 1e3:.1f} k (the pair path hands the
+certified part of a star it gives up to the one-warp-per-star path).
 
 ## The other BASELINE configurations
 
@@ -150,6 +151,8 @@ of 28 warps per frame against ~400 k measured for the two wrap phases: a third o
 | dedicated warps on the one-warp-per-star path fed by a queue while the pair path runs (2 / 4 / 8 warps) | 199.8 k -> 186 k / 171 k / 144 k | no |
 | cap test clipped to the bounding box of the point set, behind the quick accept | uniform -0.5 %, perspective -2.5 %, clustered -5 % | no (`MVOSR_CAP_CLIP`) |
 | far-neighbour / hull stars queued first on the wrap path (defer list filled from both ends) | +0.3 % | yes |
+| index of Delaunay #2: filter the sorted copy of Delaunay #1 in place instead of building anew (threshold 75 / 60 / 50 % survivors) | uniform 199.4 k -> 202.2 k, clustered +1.9 %; perspective (72 % survive) +0.7 % at 60 % | yes, from 60 % |
+| partial ring handed from the pair path to the one-warp-per-star path (vote pass) | uniform 202.4 k -> 204.2 k, perspective 172.3 k -> 175.8 k | yes |
 | 768 / 832 / 960 / 1024 threads per CTA | 197.8 k / 195.8 k / 195.2 k / 195.5 k against 199.6 k at 896 | 896 kept |
 | triangles ranked among the owning lanes only at emission | no change | no |
 | pair path follows the edges a FINISHED neighbour's stored ring already settles (the successor of a in p's ring precedes p in a's ring) instead of evaluating them | 2 934 of ~12 000 steps per frame answered that way, parity 40/40, but 199.7 k -> 194.2 k: each look-up costs volatile loads + a fence, the writers a `MEMBAR` per star, and the two stars of a warp rarely skip the same step; cross-warp reads of the ring store without a barrier would also show up as racecheck hazards | no |
