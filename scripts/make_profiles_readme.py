@@ -83,7 +83,7 @@ batch entry points exist for that reason.  Pageable (not pinned) host arrays thr
 Same kernel on other feature densities (1 184 frames, `other_densities` block of the same line; round-1 uniform-grid build in brackets):
 perspective ground features (SURVEY 8d generator: X in U(-8,8) m, Z in U(5,40) m) **{od['kitti00-ground']['value']:.0f}** frames/s (40 k), clustered
 (70 % of the features in 12 Gaussian patches) **{od['kitti00-clustered']['value']:.0f}** (55 k), image-uniform {n1['value']:.0f} ({r1['value']:.0f}): the strip index
-trades 4 % on the easiest distribution for 4x / 2.5x on the realistic ones.  Every frame of every workload ends `updated` (status
+trades 3 % on the easiest distribution for 4x / 2.5x on the realistic ones.  Every frame of every workload ends `updated` (status
 histogram in `config.status_hist`; no overflow, no held state).
 
 History of the headline line: round 1 8.3 k -> 209.3 k (`profiles/README.md` of round 1, in git history); round 2: 209 k (round-1
@@ -138,7 +138,7 @@ instruction fetch 6 %.
 {phase_rows()}
 
 Round 1 (uniform grid, image-uniform features): 1.32 M cycles per frame.  The one-warp-per-star path (`MVOSR_WRAP_COUNTERS`,
-`scripts/star_counters.py`): 290 stars per frame over both passes, 33 of them open (hull), 6.1 steps and 2.2 streaming calls per star,
+`scripts/star_counters.py`, measured before the partial-ring hand-over): 290 stars per frame over both passes, 33 of them open (hull), 6.1 steps and 2.2 streaming calls per star,
 26 k warp-cycles per star (open stars 51 k), 47 % of them inside the streaming routine; summed over the stars that is 273 k cycles
 of 28 warps per frame against ~400 k measured for the two wrap phases: a third of those phases is the tail of uneven stars.
 
