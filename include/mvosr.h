@@ -45,7 +45,7 @@ extern "C" {
 #define MVOSR_ST_FEW_ROI      0x04   /* < 3 ROI features or all collinear: reference raises QhullError */
 #define MVOSR_ST_NO_MODEL     0x08   /* every hypothesis had 0 inliers: reference crashes in np.matrix(None) */
 #define MVOSR_ST_BAD_INPUT    0x10   /* |u|,|v| >= 4096, or a non-finite pixel coordinate or 3-D coordinate in the ROI */
-#define MVOSR_ST_OVERFLOW     0x20   /* frame exceeds the kernel capacity (ROI features or star degree) */
+#define MVOSR_ST_OVERFLOW     0x20   /* frame exceeds the kernel capacity (ROI features per frame; a point with more than 254 Delaunay neighbours) */
 #define MVOSR_ST_SKIPPED      0x40   /* frame not processed (not moving / too few features, main_offline.py:64,73) */
 #define MVOSR_ST_SINGULAR     0x80   /* a triangle's vertex matrix is singular (plane through the origin): the reference raises
                                         LinAlgError in np.matrix(...).I (rescale.py:79); no RANSAC, the temporal state is held */

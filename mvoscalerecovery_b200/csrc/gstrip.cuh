@@ -31,6 +31,7 @@
 //                  Bowyer-Watson restricted to one star held in registers, float32 filter + exact float64/integer
 //                  predicates, strip sweep bounded by the union of circumdisks.
 //   4. fb_build    exact full-warp path, 32 slots, collinear bootstrap, scan in growing square windows.
+//   5. hub_star    stars of more than 32 neighbours, kept in memory instead of on the lanes of a warp (up to 254 neighbours).
 //
 // Two passes per frame.  The vote pass (Delaunay #1, EMIT = false) feeds every finished star to the depth-order graph vote
 // (consume_vote) and stores its ring of neighbours (FrameView::rpool).  The emit pass (Delaunay #2, EMIT = true) runs over
@@ -57,7 +58,7 @@ constexpr int GL = 16;                   // lanes per star on the fast path
 enum { STAR_OK = 0, STAR_DEFER = 1, STAR_OVERFLOW = 2, STAR_INCONSISTENT = 3, STAR_NONE = 4 };
 
 struct StarCtl {                         // shared-memory work queues of one Delaunay pass
-    int next_pos, next_thread, n_defer, n_defer_hi, n_defer2, n_wrap;    // n_defer_hi: stars queued from the END of defer[] (expected to be long: open / far-neighbour stars, taken first)
+    int next_pos, next_thread, n_defer, n_defer_hi, n_defer2, n_hub, n_wrap;    // n_defer_hi: stars queued from the END of defer[] (expected to be long: open / far-neighbour stars, taken first)
     unsigned long long cnt[8];           // profiling counters (MVOSR_STAR_COUNTERS): tests, splices, batches, rows, runs, exact, loop iterations, refill iterations
 };
 
@@ -1388,6 +1389,182 @@ __device__ __noinline__ void stars_thread(const SortedSet &ps, const FrameView &
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// level 5: stars of any degree (hubs)
+// ---------------------------------------------------------------------------------------------
+// fb_build keeps a star on the 32 lanes of a warp; a point with more neighbours -- the centre of a ring of features -- used to fail
+// its frame (MVOSR_ST_OVERFLOW), which Qhull never does.  Such stars are rebuilt here by one warp with the star in MEMORY (scratch:
+// two rings of dmax sorted positions + dmax conflict flags), the same exact incremental insertion: every point of the set is examined
+// (growing windows, nearest first), screened candidate-parallel with the float64 filters against all triangles of the star, and the
+// survivors inserted one by one with the exact predicates -- the conflict set of a candidate is a contiguous run of the ring, replaced
+// by the candidate.  Cost O(n x degree) filter evaluations: a cold path for a rare case.  Returns STAR_OK / STAR_NONE, or
+// STAR_OVERFLOW beyond dmax neighbours (dmax <= 254: 8-bit triangle counts per feature).
+template <bool EMIT>
+__device__ __noinline__ int hub_star(const SortedSet &ps, const FrameView &fv, int p, uint16_t *scratch, int dmax, int &n_exact) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    uint16_t *A = scratch, *B = scratch + dmax, *flag = scratch + 2 * dmax;
+    const double ppx = ps.x[p], ppy = ps.y[p];
+    const int op = ps.orig[p];
+    int d = 0, rc = STAR_OK;
+    int qpos = -1, qneg = -1;                                      // collinear bootstrap, as in fb_build
+    auto rel = [&](int pos, double &x, double &y, double &l) { x = (double)ps.x[pos] - ppx; y = (double)ps.y[pos] - ppy; l = x * x + y * y; };
+    auto scan = [&](int b, int e) {
+        for (int base = b; base < e && rc == STAR_OK; base += 32) {
+            const int pos = base + lane;
+            const bool v = pos < e && pos != p && ps.orig[pos] != INF16;
+            double sxl = 0, syl = 0, sll = 0;
+            if (v) rel(pos, sxl, syl, sll);
+            unsigned F = __ballot_sync(FULL, v);
+            if (F && d >= 2) {
+                bool maybe = false;
+                for (int kk = 0; kk < d; ++kk) {                  // (every lane reads the same ring entries: broadcasts)
+                    const int ks = A[kk], kn = A[kk + 1 < d ? kk + 1 : 0];
+                    double ax = 0, ay = 0, al = 0, cx = 0, cy = 0, cl = 0;
+                    if (ks != INF16) rel(ks, ax, ay, al);
+                    if (kn != INF16) rel(kn, cx, cy, cl);
+                    bool out;
+                    if (kn == INF16) { const double l = ax * syl, r = ay * sxl; out = l - r < -3.3306690738754731e-16 * (fabs(l) + fabs(r)); }
+                    else if (ks == INF16) { const double l = cx * syl, r = cy * sxl; out = l - r > 3.3306690738754731e-16 * (fabs(l) + fabs(r)); }
+                    else out = det3_lift_sign_filter(ax, ay, al, cx, cy, cl, sxl, syl, sll) == 1;
+                    maybe |= !out;
+                }
+                F &= __ballot_sync(FULL, maybe);
+            }
+            while (F && rc == STAR_OK) {
+                const int j = __ffs(F) - 1; F &= F - 1;
+                const int s = base + j;
+                double sx, sy, sl; rel(s, sx, sy, sl);
+                if (d == 0) {
+                    // ---- bootstrap (warp-uniform): the first point off the line through p and the first candidate
+                    if (qpos < 0) { qpos = s; continue; }
+                    double ux, uy, ul; rel(qpos, ux, uy, ul);
+                    const int o = cross_sign(ux, uy, sx, sy, n_exact);
+                    if (o == 0) {
+                        const bool same = (fabs(ux) >= fabs(uy)) ? ((sx > 0) == (ux > 0)) : ((sy > 0) == (uy > 0));
+                        if (same) { if (fabs(sx) + fabs(sy) < fabs(ux) + fabs(uy)) qpos = s; }
+                        else if (qneg < 0) qneg = s;
+                        else { double nx, ny, nl; rel(qneg, nx, ny, nl); if (fabs(sx) + fabs(sy) < fabs(nx) + fabs(ny)) qneg = s; }
+                        continue;
+                    }
+                    int ids[4], dd = 0;
+                    if (o > 0) { ids[dd++] = qpos; ids[dd++] = s; if (qneg >= 0) ids[dd++] = qneg; ids[dd++] = INF16; }
+                    else { if (qneg >= 0) ids[dd++] = qneg; ids[dd++] = s; ids[dd++] = qpos; ids[dd++] = INF16; }
+                    if (lane == 0) for (int i = 0; i < dd; ++i) A[i] = (uint16_t)ids[i];
+                    d = dd;
+                    __syncwarp();
+                    continue;
+                }
+                // ---- conflicts of s with every triangle (lanes stride over the ring), exact
+                int cnt = 0, starts = 0, i0 = 0x7FFFFFFF;
+                for (int k0 = 0; k0 < d; k0 += 32) {
+                    const int k = k0 + lane;
+                    bool c = false;
+                    if (k < d) {
+                        const int code = exact_conflict(ps.x, ps.y, ps.orig, p, A[k], A[k + 1 < d ? k + 1 : 0], s);
+                        c = code & 1; n_exact += code >> 2;
+                        flag[k] = (uint16_t)c;
+                    }
+                    cnt += __popc(__ballot_sync(FULL, c));
+                }
+                __syncwarp();
+                if (!cnt) continue;
+                for (int k0 = 0; k0 < d; k0 += 32) {
+                    const int k = k0 + lane;
+                    const bool st = k < d && flag[k] && !flag[k > 0 ? k - 1 : d - 1];
+                    const unsigned m = __ballot_sync(FULL, st);
+                    starts += __popc(m);
+                    if (m) i0 = min(i0, k0 + __ffs(m) - 1);
+                }
+                if (starts != 1 || cnt >= d) { rc = STAR_INCONSISTENT; break; }
+                const int nd = d - cnt + 2;
+                if (nd > dmax) { rc = STAR_OVERFLOW; break; }
+                for (int t = lane; t < nd; t += 32) {
+                    int src = i0 + cnt + t - 1; if (src >= d) src -= d;
+                    B[t] = t == 0 ? (uint16_t)s : A[src];
+                }
+                __syncwarp();
+                uint16_t *tswap = A; A = B; B = tswap;
+                d = nd;
+            }
+        }
+    };
+    // every point, in growing square windows around p (nearest first keeps the intermediate stars small)
+    const int prow = row_of(ps, (float)ppy);
+    double w = fmax((double)(row_yhi(ps, prow) - row_ylo(ps, prow)), 1.0e-2);
+    int pr0 = 1, pr1 = 0; float pxlo = 0.f, pxhi = 0.f;
+    for (int round = 0; round < 64 && rc == STAR_OK; ++round, w *= 2.0) {
+        const int r0 = row_of(ps, (float)(ppy - w)), r1 = row_of(ps, (float)(ppy + w));
+        const float xlo = (float)(ppx - w) - 1.0e-3f, xhi = (float)(ppx + w) + 1.0e-3f;
+        for (int row = r0; row <= r1 && rc == STAR_OK; ++row) {
+            const int ia = row_lower(ps, row, xlo), ib = row_upper(ps, row, xhi);
+            int ea = ia, eb = ia;
+            if (row >= pr0 && row <= pr1) { ea = lower_x(ps.x, ia, ib, pxlo); eb = upper_x(ps.x, ea, ib, pxhi); }
+            scan(ia, ea);
+            if (rc == STAR_OK) scan(eb, ib);
+        }
+        pr0 = r0; pr1 = r1; pxlo = xlo; pxhi = xhi;
+        if (xlo <= ps.xmin && xhi >= ps.xmax && r0 == 0 && r1 == ps.R - 1) break;
+    }
+    if (rc != STAR_OK) return rc;
+    if (d == 0) return STAR_NONE;
+    // ---- consumers, from the ring in memory
+    auto nxt = [&](int k) { return (int)A[k + 1 < d ? k + 1 : 0]; };
+    if (!EMIT) {
+        bool stored = false;
+        if (fv.rpool && d < (int)RING_PARTIAL) {
+            int rb = 0;
+            if (lane == 0) rb = atomicAdd(fv.rcount, d);
+            rb = __shfl_sync(FULL, rb, 0);
+            if (rb + d <= fv.rpool_cap) {
+                for (int k = lane; k < d; k += 32) fv.rpool[rb + k] = A[k] != INF16 ? ps.orig[A[k]] : INF16;
+                __syncwarp();
+                if (lane == 0) fv.rinfo[op] = ((uint32_t)rb << 8) | (uint32_t)d;
+                stored = true;                                     // votes_from_rings takes the votes
+            }
+        }
+        if (!stored) {
+            int nt = 0, nv = 0;
+            for (int k0 = 0; k0 < d; k0 += 32) {
+                const int k = k0 + lane;
+                const bool tri = k < d && A[k] != INF16 && nxt(k) != INF16;
+                const bool vote = tri && graph_vote_at(ps, fv, p, A[k], nxt(k));
+                nt += __popc(__ballot_sync(FULL, tri)); nv += __popc(__ballot_sync(FULL, vote));
+            }
+            if (lane == 0 && 2 * nv > nt) fv.pflag[op] |= 2;
+        }
+    } else {
+        // triangles (op < oa, ob) as one block sorted by (min, max) of the other two vertices; keys go through the flag array
+        int kown = 0;
+        for (int k0 = 0; k0 < d; k0 += 32) {
+            const int k = k0 + lane;
+            bool own = false;
+            if (k < d && A[k] != INF16 && nxt(k) != INF16) { const int oa = ps.orig[A[k]], ob = ps.orig[nxt(k)]; own = op < oa && op < ob; }
+            if (k < d) flag[k] = (uint16_t)own;
+            kown += __popc(__ballot_sync(FULL, own));
+        }
+        __syncwarp();
+        if (kown) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(fv.T, kown);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + kown > fv.tri_cap) { if (lane == 0) atomicOr(fv.status, MVOSR_ST_OVERFLOW); }
+            else {
+                auto keyof = [&](int k) { const unsigned oa = ps.orig[A[k]], ob = ps.orig[nxt(k)]; return (min(oa, ob) << 16) | max(oa, ob); };
+                for (int k = lane; k < d; k += 32) {
+                    if (!flag[k]) continue;
+                    const unsigned key = keyof(k);
+                    int r = 0;
+                    for (int j = 0; j < d; ++j) if (flag[j] && keyof(j) < key) ++r;
+                    uint16_t *t = fv.tri + 3 * (base + r); t[0] = (uint16_t)op; t[1] = (uint16_t)(key >> 16); t[2] = (uint16_t)(key & 0xFFFFu);
+                }
+                if (lane == 0) { fv.tbase[op] = (uint16_t)base; fv.tcnt[op] = (uint8_t)kown; }
+            }
+        }
+    }
+    return STAR_OK;
+}
+
 // All stars of the staged point set.  EMIT: triangles into fv.tri; otherwise the graph vote into fv.pflag.
 // Block-wide; sc, defer[] and defer2[] are shared scratch.  Four levels: pair path (all stars) -> wrap path (hull stars,
 // circles leaving the block) -> exact half-warp path (what float32 could not certify) -> exact full-warp path (more than
@@ -1401,7 +1578,7 @@ __device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, 
 #ifdef MVOSR_THREAD_PATH
     if (!EMIT && !todo) limit = max(ps.n - THREAD_FILL, 0) & ~31;
 #endif
-    if (tid == 0) { sc->next_pos = limit; sc->next_thread = 0; sc->n_defer = 0; sc->n_defer_hi = 0; sc->n_defer2 = 0; }
+    if (tid == 0) { sc->next_pos = limit; sc->next_thread = 0; sc->n_defer = 0; sc->n_defer_hi = 0; sc->n_defer2 = 0; sc->n_hub = 0; }
     __syncthreads();
     long long tc0 = clock64();
     uint16_t *const defer_hi = defer2 - 1;                       // defer[] is filled from both ends (defer2 = defer + cap)
@@ -1429,11 +1606,24 @@ __device__ __noinline__ int run_stars(const SortedSet &ps, const FrameView &fv, 
         if (r.rc == STAR_OK) {
             if (EMIT) consume_emit<32>(0xFFFFFFFFu, lane, r.d, p, r.sid, r.nid, ps, fv);
             else consume_vote<32>(0xFFFFFFFFu, lane, r.d, p, r.sid, r.nid, ps, fv);
+        } else if (r.rc == STAR_OVERFLOW) {                          // more than 32 neighbours: level 5, below
+            if (lane == 0) { const int slot = atomicAdd(&sc->n_hub, 1); defer[n3 + slot] = (uint16_t)p; }
         } else if (r.rc != STAR_NONE && lane == 0) {
             atomicOr(fv.status, MVOSR_ST_OVERFLOW);
 #ifdef MVOSR_DEBUG_PRINT
             printf("fb_build failed: rc=%d p=%d orig=%d d=%d n=%d\n", r.rc, p, (int)ps.orig[p], r.d, ps.n);
 #endif
+        }
+    }
+    __syncthreads();
+    const int n4 = sc->n_hub;
+    if (n4 && warp == 0) {
+        // hubs, one after the other on warp 0: the star lives in defer2[] (dead by now), two rings and the conflict flags
+        const int dmax = min(254, (int)(defer2 - defer) / 3);
+        for (int k = 0; k < n4; ++k) {
+            const int p = defer[n3 + k];
+            const int rc = hub_star<EMIT>(ps, fv, p, defer2, dmax, n_exact);
+            if (rc != STAR_OK && rc != STAR_NONE && lane == 0) atomicOr(fv.status, MVOSR_ST_OVERFLOW);
         }
     }
     __syncthreads();

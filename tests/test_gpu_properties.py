@@ -398,3 +398,74 @@ def test_other_feature_densities_vs_oracle(engine, density):
         assert 3 * st["n_valid"][f] == rec["n_sel"], (density, f)
         assert (st["best_ic"][f], st["hyps_used"][f]) == (rec["ic"], rec["hyps_used"]), (density, f)
         np.testing.assert_allclose(raw[f], rec["raw_scale"], rtol=1e-9)
+
+
+def _hub_points(rng, spokes, n_bg, integer=False):
+    """A hub: one feature in the middle of a ring of `spokes` features (its Delaunay star has that many neighbours) over a random
+    background that stays outside the ring.  integer=True: the ring on an exact circle of integer radius around an integer centre is not
+    possible in general, so the ring points are rounded -- ties and near-ties among the spokes go through the exact predicates."""
+    c = np.array([620.0, 285.0])
+    ang = (np.arange(spokes) + rng.uniform(-0.2, 0.2, spokes)) * (2 * np.pi / spokes)          # (a spoke set back by more than the sag of its
+    r = 70.0 + rng.uniform(-0.002, 0.002, spokes)                                                  # neighbours' chord would lose its edge to the centre)
+    ring = c + np.stack([r * np.cos(ang), r * np.sin(ang)], 1)
+    bg = np.stack([rng.uniform(0, 1240, 4 * n_bg), rng.uniform(186, 375, 4 * n_bg)], 1)
+    bg = bg[np.linalg.norm(bg - c, axis=1) > 78.0][:n_bg]
+    pts = np.concatenate([c[None], ring, bg], 0)
+    if integer:
+        pts = np.round(pts)
+        pts = pts[np.sort(np.unique(pts, axis=0, return_index=True)[1])]
+    return pts[rng.permutation(pts.shape[0])].astype(np.float32)
+
+
+@pytest.mark.parametrize("spokes", [20, 40, 100, 230])
+def test_hub_stars_any_degree_vs_qhull(engine, spokes):
+    """A star of more than 32 neighbours used to end its frame with MVOSR_ST_OVERFLOW (fb_build keeps a star on the 32 lanes of a warp);
+    Qhull has no such limit.  Level 5 (hub_star) builds such stars in memory: triangulations with hubs of 20 ... 230 spokes equal
+    Qhull's, and the rounded (tie-laden) variants equal the exact-arithmetic oracle's."""
+    import torch
+    from scipy.spatial import Delaunay
+    from oracle import ref_harness as H
+    rng = np.random.default_rng(1000 + spokes)
+    sets = [_hub_points(rng, spokes, 400), _hub_points(rng, spokes, 1500), _hub_points(rng, spokes, 60)]
+    off = np.zeros(len(sets) + 1, np.int32)
+    np.cumsum([p.shape[0] for p in sets], out=off[1:])
+    allp = np.concatenate(sets, 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(engine.device)
+    out = engine.delaunay_frames(t(off), t(allp[:, 0]), t(allp[:, 1]), int(np.max(np.diff(off))))
+    torch.cuda.synchronize()
+    tri = out["tri"].cpu().numpy(); ntri = out["n_tri"].cpu().numpy(); st = out["status"].cpu().numpy()
+    for i, p in enumerate(sets):
+        assert st[i] == 0, (spokes, i, st[i])
+        want = H.canonicalise(Delaunay(p.astype(np.float64)).simplices)
+        got = tri[2 * off[i]: 2 * off[i] + ntri[i]]
+        assert ntri[i] == want.shape[0] and np.array_equal(got, want), (spokes, i)
+        deg = np.bincount(want.reshape(-1), minlength=p.shape[0]).max()
+        assert deg >= 0.9 * spokes, (spokes, deg)
+
+
+def test_hub_frames_full_pipeline_vs_oracle(engine):
+    """The same through the whole estimator (vote pass, ring store, second Delaunay, planes, RANSAC): frames whose road features
+    contain a 60-spoke hub against the oracle, and the status byte stays clean."""
+    import torch
+    from mvoscalerecovery_b200.batch import pack_frames, stats_to_numpy
+    from oracle import pipeline as P
+    rng = np.random.default_rng(77)
+    fx, cx, cy = 718.856, 607.1928, 185.2157
+    f3s, f2s = [], []
+    for f in range(3):
+        p = _hub_points(rng, 60, 900).astype(np.float64)
+        u, v = p[:, 0], p[:, 1]
+        z = 1.7 * fx / (v - cy + 1e-3) * (1 + 0.01 * rng.standard_normal(u.shape[0]))
+        bad = rng.random(u.shape[0]) < 0.15
+        z[bad] *= rng.uniform(0.4, 0.95, bad.sum())
+        f2s.append(np.stack([u, v], 1).astype(np.float32)); f3s.append(np.stack([(u - cx) * z / fx, (v - cy) * z / fx, z], 1).astype(np.float32))
+    b = pack_frames(f3s, f2s, engine.device)
+    out = engine.scale_frames(b["offsets"], b["x"], b["y"], b["z"], b["u"], b["v"], b["max_features"], seed=3, seq_id=0, stats=True)
+    torch.cuda.synchronize()
+    st = stats_to_numpy(out["stats"]); raw = out["raw_scale"].cpu().numpy(); status = out["status"].cpu().numpy()
+    for f in range(3):
+        assert not (status[f] & 32), (f, status[f])
+        rec = P.frame_raw_scale(f3s[f].astype(np.float64), f2s[f].astype(np.float64), 3, f, 0, absolute_reference=1.7)
+        assert st["n_kept"][f] == int(rec["keep"].sum()) and st["n_tri"][f] == rec["tri2"].shape[0], f
+        assert (st["best_ic"][f], st["hyps_used"][f], 3 * st["n_valid"][f]) == (rec["ic"], rec["hyps_used"], rec["n_sel"]), f
+        np.testing.assert_allclose(raw[f], rec["raw_scale"], rtol=1e-9)
