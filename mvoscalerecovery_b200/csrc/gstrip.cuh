@@ -1408,6 +1408,7 @@ __device__ __noinline__ int hub_star(const SortedSet &ps, const FrameView &fv, i
     const int op = ps.orig[p];
     int d = 0, rc = STAR_OK;
     int qpos = -1, qneg = -1;                                      // collinear bootstrap, as in fb_build
+    __syncwarp();
     auto rel = [&](int pos, double &x, double &y, double &l) { x = (double)ps.x[pos] - ppx; y = (double)ps.y[pos] - ppy; l = x * x + y * y; };
     auto scan = [&](int b, int e) {
         for (int base = b; base < e && rc == STAR_OK; base += 32) {
@@ -1562,6 +1563,7 @@ __device__ __noinline__ int hub_star(const SortedSet &ps, const FrameView &fv, i
             }
         }
     }
+    __syncwarp();                                                  // the next hub of the frame reuses the scratch
     return STAR_OK;
 }
 
