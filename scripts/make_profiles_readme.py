@@ -105,8 +105,8 @@ certified part of a star it gives up to the one-warp-per-star path).
 Contract bound: HBM.  Algorithmic bytes per launch = 16 B x 11.35 M correspondences + 64 B x 4 541 frames = 182.0 MB;
 kernel {rf['kernel_ms']:.2f} ms -> {rf['achieved']:.2f} GB/s = {100 * rf['frac']:.3f} % of the measured 6 545 GB/s.  ncu `dram__bytes` for the same launch
 (`traffic.json`, refused by `bench.py` unless its source hash matches the build): {traffic['read_bytes'] / 1e6:.0f} MB read = the algorithmic bytes (no
-re-reads) + {traffic['write_bytes'] / 1e6:.0f} MB written = local-memory (call stack / spill, 592 B per thread) write-backs of 132 k resident threads; the outputs
-are 60 KB.  **The kernel is instruction-issue bound, not memory bound**: issue slots {float(m['smsp__issue_active.avg.pct_of_peak_sustained_active']):.0f} % busy, IPC {float(m['sm__inst_executed.avg.per_cycle_elapsed']):.2f} of 4 per SM,
+re-reads) + {traffic['write_bytes'] / 1e6:.0f} MB written = local-memory (call stack / spill, 592 B per thread) write-backs of 132 k resident threads (120 ... 250 MB
+from capture to capture: it follows the eviction pattern of the L2, not the algorithm); the outputs are 60 KB.  **The kernel is instruction-issue bound, not memory bound**: issue slots {float(m['smsp__issue_active.avg.pct_of_peak_sustained_active']):.0f} % busy, IPC {float(m['sm__inst_executed.avg.per_cycle_elapsed']):.2f} of 4 per SM,
 {winstr / 1e9:.2f} G warp-instructions per launch = **{winstr / 4541 / 1e6:.2f} M per frame** (round 1: 3.95 M with the uniform grid; 4.19 M at the first strip
 build), issue fraction = warp-instructions / kernel time / (148 SMs x 4 schedulers x 1.965 GHz) = {winstr / (kms * 1e-3) / (148 * 4 * 1.965e9):.3f} (`roofline.issue_frac`),
 {float(m['smsp__thread_inst_executed_per_inst_executed.ratio']):.1f} of 32 lanes active on average, FP64 pipe {float(m['sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active']):.1f} %.
@@ -183,7 +183,7 @@ the speed of the scale-recovery kernel it feeds).
 
 `compute-sanitizer --tool memcheck` and `--tool racecheck` over `scripts/sanitize_small.py` on the final build (fused and staged
 frame kernel with debug buffers, float64 entry, shared-memory and large-frame staging, Delaunay-only, filter, path scan, plane RANSAC,
-find_essential / recover_pose / pose_mask / bucket kernels): 0 errors, 0 hazards; the 42 parity + property GPU tests themselves under memcheck and under racecheck: 0 errors, 0 hazards (`sanitizer_r02.txt`).
+find_essential / recover_pose / pose_mask / bucket kernels): 0 errors, 0 hazards; the 42 parity + property GPU tests and the 5 hub tests themselves under memcheck and under racecheck: 0 errors, 0 hazards (`sanitizer_r02.txt`).
 
 ## RANSAC sweep (BASELINE configs[4]; 592 frames, kernel-only frames/s, error of the RAW scale against the synthetic truth)
 
