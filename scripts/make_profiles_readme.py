@@ -12,6 +12,7 @@ ref, dense, fleet1 = J('bench_r02_reference.json'), J('bench_r02_dense_n1.json')
 dense1 = J('bench_r01_dense_n1.json')
 sweep, prim, cfg0, traffic = J('ransac_sweep_r02.json'), J('primitives_r02.json'), J('main_config0_r02.json'), J('traffic.json')
 ph = {d: J('phase_r02_%s.json' % d) for d in ('uniform', 'ground', 'clustered')}
+FS = [json.loads(l) for l in open(P + 'feature_sweep_r02.jsonl') if l.strip()]
 ncu, reg, launch, fe = T('ncu_r02_frame_kernel_bench.txt'), T('ncu_r02_frame_kernel_regions.txt'), T('launches_r02_summary.txt'), T('ncu_r02_find_essential.txt')
 m = {l.split()[0]: l.split()[-1] for l in ncu.splitlines() if l.strip()}
 winstr = float(m['smsp__inst_executed.sum'])
@@ -100,6 +101,18 @@ certified part of a star it gives up to the one-warp-per-star path).
 | fleet (configs[3]) stand-alone | 1 | {fleet1['value']:.0f} | {fleet1['ms_per_step']:.2f} | {fleet1['e2e']['value']:.0f} | the `--workload fleet` line; the scaling table above comes from the `fleet` block of the default line | `bench_r02_fleet_n1.json` |
 | configs[0]: the UNMODIFIED `src/main.py` on {cfg0['dropin']['frames']} rendered frames (1241x376 textured ground plane, AKAZE + LK + findEssentialMat + recoverPose + estimator), whole-program wall clock | 1 | reference modules: {cfg0['reference']['frames_per_s']:.2f} ({cfg0['reference']['frames']} frames); drop-in module set: {cfg0['dropin']['frames_per_s_warm']:.2f} warm / {cfg0['dropin']['frames_per_s_cold']:.2f} cold | | | {cfg0['speedup_warm']:.2f}x: the estimator's share of the frame is gone (0.8 ms per call), what remains is the host front-end, identical in both arms; recovered scale / true step: {cfg0['dropin']['median_scale_over_true_step']:.3f} (drop-in) vs {cfg0['reference']['median_scale_over_true_step']:.3f} (reference, OS-entropy RANSAC) | `main_config0_r02.json`, `scripts/time_main_config0.py` |
 
+### Correspondences per frame (`scripts/gpu_feature_sweep.sh`, `feature_sweep_r02.jsonl`; one GPU, kernel-only and end to end)
+
+| correspondences per frame | frames | frames/s | correspondences/s | end to end frames/s | staging |
+|---|---|---|---|---|---|
+""" + "\n".join("| %d | %d | %d | %.0f M | %d | %s |" % (r['correspondences_per_frame'], r['frames'], r['frames_per_s'], r['correspondences_per_s'] / 1e6, r['e2e_frames_per_s'],
+                                                     "shared memory" if r['correspondences_per_frame'] <= 3264 else "global-memory slab per CTA (L2)") for r in FS) + """
+
+The cost per correspondence is flat from 2 500 to 12 500 per frame (480 ... 512 M/s) across the two staging modes -- frames too large for
+shared memory lose at most 6 % per feature in the L2-resident slabs (the headline workload forced onto slabs: 204.0 k -> 191.5 k frames/s),
+so a cluster of CTAs sharing a frame through distributed shared memory (SURVEY H2) has little to win here and was not built; 600 per frame pays the fixed per-frame phases, 25 000 the last wave (454 frames
+on 148 CTAs).
+
 ## Roofline (`roofline` block of the bench line)
 
 Contract bound: HBM.  Algorithmic bytes per launch = 16 B x 11.35 M correspondences + 64 B x 4 541 frames = 182.0 MB;
@@ -156,6 +169,7 @@ of 28 warps per frame against ~400 k measured for the two wrap phases: a third o
 | 768 / 832 / 960 / 1024 threads per CTA | 197.8 k / 195.8 k / 195.2 k / 195.5 k against 199.6 k at 896 | 896 kept |
 | triangles ranked among the owning lanes only at emission | no change | no |
 | pair path follows the edges a FINISHED neighbour's stored ring already settles (the successor of a in p's ring precedes p in a's ring) instead of evaluating them | 2 934 of ~12 000 steps per frame answered that way, parity 40/40, but 199.7 k -> 194.2 k: each look-up costs volatile loads + a fence, the writers a `MEMBAR` per star, and the two stars of a warp rarely skip the same step; cross-warp reads of the ring store without a barrier would also show up as racecheck hazards | no |
+| two or more frames in flight per SM: 2 x 448 / 3 x 288 / 4 x 224 threads per SM, every CTA staging its frame in a global-memory slab (the shared-memory plan of 68 B per feature only admits one frame per SM) | slabs alone at 896 x 1: 204.0 k -> 191.5 k; 2 / 3 / 4 CTAs per SM: 137 k / 100 k / 91 k (the slabs of 296 ... 592 CTAs are 54 ... 108 MB beside 182 MB of streaming input in a 126 MB L2) | no |
 | strip density 1.2 / 1.5 / 1.8 x window 2.2 / 2.5 / 2.8 cell sides | 1.5 x 2.5 is the optimum (3.23 ms per 592 frames; others 3.27 ... 3.51) | defaults kept |
 
 ## Stand-alone primitives (`scripts/bench_primitives.py`, `primitives_r02.json`; median of 10 device-timed calls, L2 flushed)
