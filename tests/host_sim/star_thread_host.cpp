@@ -72,15 +72,44 @@ void build(HostSet &H, int n, const float *U, const float *V, int cap, float den
     }
     for (int a = 0; a < n; ++a) if (dup[a]) H.orig[a] = INF16;
 }
+
+// The index of a SUBSET by filtering (filter_grid of csrc/frame_kernel.cuh, restated sequentially): strips, bins and sub-cells stay,
+// the sorted copy is compacted in order, row_start / cell_start become survivor counts.  newidx[old feature] = new index or INF16.
+void filter(HostSet &H, const uint16_t *newidx, int n_new) {
+    const int n_old = H.ps.n;
+    std::vector<uint16_t> before(n_old + 1, 0);
+    int run = 0;
+    for (int i = 0; i < n_old; ++i) { before[i] = (uint16_t)run; const int o = H.orig[i]; if (o != INF16 && newidx[o] != INF16) ++run; }
+    before[n_old] = (uint16_t)run;
+    for (auto &c : H.cell_start) c = before[c];
+    for (auto &r : H.row_start) r = before[r];
+    for (int i = 0; i < n_old; ++i) {
+        const int o = H.orig[i];
+        if (o == INF16 || newidx[o] == INF16) continue;
+        const int pos = before[i];
+        H.x[pos] = H.x[i]; H.y[pos] = H.y[i]; H.orig[pos] = newidx[o];
+    }
+    H.ps.n = n_new;
+}
 }  // namespace
 
 // status / deg / ring by FEATURE index (ring: 16 feature indices per star, counter-clockwise from the nearest neighbour).
 // cost[0..2]: candidate evaluations, steps, stars; cost[3]: sum over groups of 32 consecutive sorted positions of 32 x (max evaluations
 // of a lane) -- what a warp executes when its lanes run in lock step; cost[4]: the same for steps; cost[5]: strips R; cost[6]: warp iterations of the step loops in the lock-step model (sum over groups and steps of the largest candidate count among the lanes still walking); cost[7]: largest candidate count of a star.
+
+// keep != nullptr: the index is built over all n points and then FILTERED to the points with keep[i] != 0 (new feature index = rank
+// among the kept ones); status / deg / ring are then by NEW feature index.
 extern "C" int star_thread_run(int n, const float *u, const float *v, int cap, float density, int win_m, float wfac,
-                               int32_t *status, int32_t *deg, int32_t *ring, uint64_t *cost) {
+                               int32_t *status, int32_t *deg, int32_t *ring, uint64_t *cost, const uint8_t *keep) {
     HostSet H;
     build(H, n, u, v, cap, density, win_m, wfac);
+    if (keep) {
+        std::vector<uint16_t> newidx(n, INF16);
+        int m = 0;
+        for (int i = 0; i < n; ++i) if (keep[i]) newidx[i] = (uint16_t)m++;
+        filter(H, newidx.data(), m);
+        n = m;
+    }
     for (int k = 0; k < 8; ++k) cost[k] = 0;
     cost[5] = (uint64_t)H.ps.R;
     unsigned gmax_e = 0, gmax_s = 0;

@@ -23,7 +23,7 @@ def sim():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-DMVOSR_THREAD_COST", "-o", so, src])
     lib = C.CDLL(so)
     lib.star_thread_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -42,11 +42,13 @@ def points(kind, n, rng):
     return u.astype(np.float32), v.astype(np.float32)
 
 
-def run(sim, u, v, cap=None):
+def run(sim, u, v, cap=None, keep=None):
     n = u.shape[0]
     cap = cap or ((n + 63) // 64) * 64
     status = np.full(n, -1, np.int32); deg = np.zeros(n, np.int32); ring = np.full((n, 16), -1, np.int32); cost = np.zeros(8, np.uint64)
-    sim.star_thread_run(n, u.ctypes.data, v.ctypes.data, cap, 1.5, 4, 2.5, status.ctypes.data, deg.ctypes.data, ring.ctypes.data, cost.ctypes.data)
+    k = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+    sim.star_thread_run(n, u.ctypes.data, v.ctypes.data, cap, 1.5, 4, 2.5, status.ctypes.data, deg.ctypes.data, ring.ctypes.data, cost.ctypes.data,
+                        None if k is None else k.ctypes.data)
     return status, deg, ring, cost
 
 
@@ -107,3 +109,28 @@ def test_degenerate_sets_never_certify_wrongly(sim):
             det = m0 * sl + (A[1] * bl - al * B[1]) * P0[:, 0] + (al * B[0] - A[0] * bl) * P0[:, 1]
             inside = det < 0
             assert not inside.any(), (p, a, b)
+
+
+@pytest.mark.parametrize("kind,frac", [("uniform", 0.84), ("ground", 0.72), ("clustered", 0.62)])
+def test_filtered_index_serves_the_subset(sim, kind, frac):
+    """Delaunay #2 runs over the survivors of the graph check on the index of Delaunay #1 FILTERED in place (filter_grid,
+    csrc/frame_kernel.cuh: strips, bins and sub-cells kept, starts replaced by survivor counts) instead of a new build.  The same
+    filter, restated sequentially in the host simulation: every star certified over the filtered index equals Qhull's star in the
+    triangulation of the SURVIVORS, and about as many stars are certified as over an index built for them."""
+    rng = np.random.default_rng(sum(map(ord, kind)))
+    u, v = points(kind, 2000, rng)
+    keep = rng.random(2000) < frac
+    status, deg, ring, cost = run(sim, u, v, keep=keep)
+    us, vs = u[keep], v[keep]
+    m = us.shape[0]
+    rings, hull = qhull_rings(us, vs)
+    ok = np.flatnonzero(status[:m] == 0)
+    for p in ok:
+        mine = ring[p, :deg[p]]
+        ref = rings[p]
+        assert deg[p] == ref.size and set(mine.tolist()) == set(ref.tolist()), (kind, p, mine, ref)
+        k = int(np.flatnonzero(ref == mine[0])[0])
+        assert np.array_equal(np.roll(ref, -k), mine), (kind, p)
+    fresh = run(sim, us, vs)[0]
+    print("\n%s, %d of 2000 kept: certified over the filtered index %.1f %%, over a fresh one %.1f %%" % (kind, m, 100.0 * ok.size / m, 100.0 * np.count_nonzero(fresh == 0) / m))
+    assert ok.size > 0.6 * m and ok.size > 0.85 * np.count_nonzero(fresh == 0)
