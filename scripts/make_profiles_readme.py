@@ -106,7 +106,7 @@ certified part of a star it gives up to the one-warp-per-star path).
 | correspondences per frame | frames | frames/s | correspondences/s | end to end frames/s | staging |
 |---|---|---|---|---|---|
 """ + "\n".join("| %d | %d | %d | %.0f M | %d | %s |" % (r['correspondences_per_frame'], r['frames'], r['frames_per_s'], r['correspondences_per_s'] / 1e6, r['e2e_frames_per_s'],
-                                                     "shared memory" if r['correspondences_per_frame'] <= 3264 else "global-memory slab per CTA (L2)") for r in FS) + """
+                                                     "shared memory" if r['correspondences_per_frame'] <= 3264 else "global-memory slab per CTA (L2)") for r in FS) + f"""
 
 The cost per correspondence is flat from 2 500 to 12 500 per frame (480 ... 512 M/s) across the two staging modes -- frames too large for
 shared memory lose at most 6 % per feature in the L2-resident slabs (the headline workload forced onto slabs: 204.0 k -> 191.5 k frames/s),
