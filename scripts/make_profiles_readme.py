@@ -76,7 +76,8 @@ the filter straight from the gathered records -- and no other collective.  Round
 
 CPU arm, the **unmodified reference** (`oracle/_ref/src`: `cv2.recoverPose` + `rescale.ScaleEstimator.scale_calculation` in the loop of
 `main_offline.py:57-88`): {cb['value']:.2f} frames/s on one host core ({cb['sample'].split(';')[0]}); `bench.py --impl reference`:
-{ref['value']:.1f} frames/s on {ref['cpu_baseline']['cores']} worker processes = {ref['cpu_baseline']['frames_per_s_per_core']:.2f} frames/s/core (`bench_r02_reference.json`).
+{ref['value']:.1f} frames/s wall clock with {ref['cpu_baseline']['cores']} worker processes, {ref['cpu_baseline']['frames_per_s_per_core']:.2f} frames per second of worker busy time (`bench_r02_reference.json`; the
+pool's dispatch and the box's share of free cores are inside the wall-clock figure).
 Per-frame drop-in (`compat/rescale.ScaleEstimator.scale_calculation`, numpy float64 in, one C-ABI call per frame, the loop of
 `main_offline.py:57-88` over 500 frames): {n1['e2e']['dropin_fps']['value']:.0f} calls/s -- one frame occupies one SM for {1e3 / n1['e2e']['dropin_fps']['value']:.2f} ms, the other 147 idle: the
 batch entry points exist for that reason.  Pageable (not pinned) host arrays through the same host call: {n1['e2e']['pageable_value']:.0f} frames/s.
