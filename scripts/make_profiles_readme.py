@@ -153,8 +153,8 @@ The same counters on the other workloads (one `ncu --set full` capture each, `sc
 |---|---|---|---|---|---|---|
 {wl_rows()}
 
-(~2 000 warp-instructions per ROI feature on every workload; perspective and clustered features cost more because more stars leave the
-pair path -- 399 and 927 per frame against 300.)
+(Per ROI feature: 1 990 warp-instructions on the image-uniform headline and on the dense workload alike, 2 220 on perspective and 2 660
+on clustered features, where more stars leave the pair path -- 399 and 927 per frame against 300.)
 
 ### Where the instructions go (same capture, per source region; `scripts/ncu_lines.py` + `scripts/ncu_regions.py`)
 
