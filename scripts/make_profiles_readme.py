@@ -178,6 +178,11 @@ instruction fetch 6 %.
 |---|---|---|---|
 {phase_rows()}
 
+Why stars leave the pair path (`-DMVOSR_STAR_COUNTERS`, per frame, both passes; uniform / perspective / clustered): the left cap of a
+circle leaves the block 222 / 308 / 354, nothing on the left inside the block (hull edge, far neighbour) 77 / 84 / 53, crowded block
+(more than 64 candidates) 1.6 / 7.7 / 518, everything else (uncertain side, interval clash, nearest point not certified, more than 16
+neighbours) below 2.
+
 Round 1 (uniform grid, image-uniform features): 1.32 M cycles per frame.  The one-warp-per-star path (`MVOSR_WRAP_COUNTERS`,
 `scripts/star_counters.py`, measured before the partial-ring hand-over): 290 stars per frame over both passes, 33 of them open (hull), 6.1 steps and 2.2 streaming calls per star,
 26 k warp-cycles per star (open stars 51 k), 47 % of them inside the streaming routine; summed over the stars that is 273 k cycles
@@ -198,6 +203,7 @@ of 28 warps per frame against ~400 k measured for the two wrap phases: a third o
 | triangles ranked among the owning lanes only at emission | no change | no |
 | pair path follows the edges a FINISHED neighbour's stored ring already settles (the successor of a in p's ring precedes p in a's ring) instead of evaluating them | 2 934 of ~12 000 steps per frame answered that way, parity 40/40, but 199.7 k -> 194.2 k: each look-up costs volatile loads + a fence, the writers a `MEMBAR` per star, and the two stars of a warp rarely skip the same step; cross-warp reads of the ring store without a barrier would also show up as racecheck hazards | no |
 | two or more frames in flight per SM: 2 x 448 / 3 x 288 / 4 x 224 threads per SM, every CTA staging its frame in a global-memory slab (the shared-memory plan of 68 B per feature only admits one frame per SM) | slabs alone at 896 x 1: 204.0 k -> 191.5 k; 2 / 3 / 4 CTAs per SM: 137 k / 100 k / 91 k (the slabs of 296 ... 592 CTAs are 54 ... 108 MB beside 182 MB of streaming input in a 126 MB L2) | no |
+| pair path narrows a crowded block (> 64 candidates: 1.6 / 7.7 / 518 stars per frame on uniform / perspective / clustered features, `scripts/star_counters.py`) instead of giving the star up | clustered 141.3 k -> 148.2 k, but uniform 204.6 k -> 202.0 k and perspective 176.3 k -> 173.7 k even with the retry in a cold branch (it perturbs the hot loop's code) | no: the headline workload decides; the obvious next step for clustered inputs |
 | strip density 1.2 / 1.5 / 1.8 x window 2.2 / 2.5 / 2.8 cell sides | 1.5 x 2.5 is the optimum (3.23 ms per 592 frames; others 3.27 ... 3.51) | defaults kept |
 
 ## Stand-alone primitives (`scripts/bench_primitives.py`, `primitives_r02.json`; median of 10 device-timed calls, L2 flushed)
