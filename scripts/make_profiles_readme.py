@@ -231,7 +231,7 @@ the speed of the scale-recovery kernel it feeds).
 
 `compute-sanitizer --tool memcheck` and `--tool racecheck` over `scripts/sanitize_small.py` on the final build (fused and staged
 frame kernel with debug buffers, float64 entry, shared-memory and large-frame staging, Delaunay-only, filter, path scan, plane RANSAC,
-find_essential / recover_pose / pose_mask / bucket kernels): 0 errors, 0 hazards; the 42 parity + property GPU tests and the 5 hub tests themselves under memcheck and under racecheck: 0 errors, 0 hazards (`sanitizer_r02.txt`).
+find_essential / recover_pose / pose_mask / bucket kernels): 0 errors, 0 hazards; all 47 parity + property GPU tests (hubs included) themselves under racecheck on the final build and under memcheck: 0 errors, 0 hazards (`sanitizer_r02.txt`).
 
 ## RANSAC sweep (BASELINE configs[4]; 592 frames, kernel-only frames/s, error of the RAW scale against the synthetic truth)
 
